@@ -1,0 +1,172 @@
+/* stuffing_b200.h — C ABI of the B200-native collision-and-fit engine.
+ *
+ * Drop-in boundary for the hot path of guo-yong-zhi/Stuffing.jl v0.10.4.  Every entry point
+ * names the reference interface it replaces (file:line under /root/reference/src/).  The
+ * reference is pure Julia; the binding a maintainer adds is a `ccall` per function
+ * (julia/StuffingB200.jl).  No torch types, no C++ types: plain pointers,
+ * sizes and int32 status codes.
+ *
+ * Conventions
+ *  - labels and (l,a,b) are 1-based, exactly as the reference prints them;
+ *  - matrices are column-major (row index fastest), like Julia's Matrix{UInt8};
+ *  - node codes: EMPTY=1, FULL=2, MIX=3 (qtrees.jl:56);
+ *  - a context owns device copies of one vector of ShiftedQTrees ("objects") that share a
+ *    canvas; the device is authoritative for shifts and levels >= 2 after upload;
+ *  - every call is synchronous with respect to its outputs; calls on one context must be
+ *    serialised by the caller;
+ *  - result lists use the two-call pattern: if `cap` is too small the call returns
+ *    STF_E_CAPACITY, stores the needed size in *count, and keeps the result on the device for
+ *    stf_fetch_result();
+ *  - there is no CPU fallback: without a CUDA device stf_create fails with STF_E_CUDA.
+ */
+#ifndef STUFFING_B200_H
+#define STUFFING_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STF_EMPTY 1
+#define STF_FULL 2
+#define STF_MIX 3
+
+#define STF_OK 0
+#define STF_E_CUDA (-1)      /* CUDA runtime error (text in stf_last_error) */
+#define STF_E_ARG (-2)       /* bad argument */
+#define STF_E_CAPACITY (-3)  /* output buffer too small; *count holds the needed size */
+#define STF_E_BADCODE (-4)   /* a node code outside 1..3 was uploaded */
+#define STF_E_RANGE (-5)     /* a spatial cell coordinate left the representable window */
+#define STF_E_STATE (-6)     /* call not valid in this state (nothing uploaded, ...) */
+
+typedef struct stf_ctx stf_ctx;
+
+/* CoItem = Pair{Tuple{Int,Int},Index}: (i1,i2) => (l,a,b)   qtree_functions.jl:52 */
+typedef struct { int32_t i1, i2, l, a, b; } stf_item;
+/* one spatial-tree entry: `label` sits in cell (l,a,b)       qtrees.jl:411-415,501-524 */
+typedef struct { int32_t l, a, b, label; } stf_cellrec;
+
+/* optimiser kinds (fit_helper.jl:13-38, fit.jl:25) */
+#define STF_OPT_DEFAULT 0 /* (t, Δ) -> Δ ./ 6 */
+#define STF_OPT_SGD 1
+#define STF_OPT_MOMENTUM 2
+
+/* counters of the last many-body call */
+typedef struct {
+    int64_t records;  /* located (cell,label) records          */
+    int64_t items;    /* narrow-phase items (the reference's itemlist) */
+    int64_t direct;   /* default-FULL direct hits (qtree_functions.jl:212-218) */
+    int64_t hits;     /* results before unique                  */
+    int64_t overflow; /* items that needed the large-frontier path */
+    int64_t moved;    /* objects moved by the last batchsteps   */
+    int64_t visited;  /* child nodes tested by the narrow phase */
+    int64_t reserved;
+} stf_counters_t;
+
+/* ---- lifetime ---- */
+int32_t stf_create(int32_t device, stf_ctx** out);
+void stf_destroy(stf_ctx* ctx);
+const char* stf_last_error(const stf_ctx* ctx);
+/* the context's CUDA stream (cudaStream_t) so that callers can time with events on it */
+void* stf_stream(stf_ctx* ctx);
+
+/* ---- construction: qtree / maskqtree / qtrees (Stuffing.jl:16-63) + ShiftedQTree constructors
+ * (qtrees.jl:176-209) + buildqtree! (qtrees.jl:221-237).
+ * pics[i] points at the kh[i] x kw[i] level-1 payload (codes 1..3), column-major with leading
+ * dimension pitch[i] (Julia: pointer(kernel, 2,2) with pitch kh+3, or the pic itself).
+ * rshift/cshift: level-1 shifts (maskqtree centres the mask; qtree uses 0).  dflt: EMPTY for
+ * objects, FULL for the mask.  canvas: power of two >= 2.  is_mask (nullable): which objects
+ * step_index! treats as the mask (default: label 1 only, fit.jl:58-67 — pass all zeros for
+ * scenes without a mask).  scene (nullable): scene id per object for batches of independent
+ * scenes that share a canvas size; objects of different scenes never interact.
+ * All levels are built on the device before the call returns. */
+int32_t stf_upload_objects(stf_ctx* ctx, int32_t n, const uint8_t* const* pics, const int32_t* kh,
+                           const int32_t* kw, const int32_t* pitch, const int32_t* rshift,
+                           const int32_t* cshift, const uint8_t* dflt, int32_t canvas,
+                           const uint8_t* is_mask, const int32_t* scene);
+/* same, with all level-1 payloads packed back to back (kh[i]*kw[i] bytes each, pitch = kh[i]) in one
+ * buffer that is ALREADY IN DEVICE MEMORY (bench "inputs resident in HBM" leg) or in host memory */
+int32_t stf_upload_packed(stf_ctx* ctx, int32_t n, const uint8_t* payload, int32_t payload_on_device,
+                          const int32_t* kh, const int32_t* kw, const int32_t* rshift,
+                          const int32_t* cshift, const uint8_t* dflt, int32_t canvas,
+                          const uint8_t* is_mask, const int32_t* scene);
+int32_t stf_num_objects(const stf_ctx* ctx);
+int32_t stf_num_levels(const stf_ctx* ctx); /* length(t)  qtrees.jl:217 */
+
+/* ---- tree state ---- */
+/* out = {kh, kw, rshift, cshift, canvas size} of level l: kernelsize / getshift / size  qtrees.jl:152,288-289 */
+int32_t stf_get_level_info(stf_ctx* ctx, int32_t label, int32_t l, int32_t out[5]);
+/* kh*kw payload bytes of level l, column-major: t[l].kernel[2:end-2,2:end-2] */
+int32_t stf_download_level(stf_ctx* ctx, int32_t label, int32_t l, uint8_t* out);
+/* t[l, a, b] for n coordinates: PaddedMat getindex, `default` outside the kernel  qtrees.jl:156-162 */
+int32_t stf_read_nodes(stf_ctx* ctx, int32_t n, const int32_t* labels, const int32_t* l,
+                       const int32_t* a, const int32_t* b, uint8_t* out);
+int32_t stf_get_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level, int32_t* rs, int32_t* cs);
+/* mode 0: setshift!(t, level, rs, cs) (qtrees.jl:277-285); mode 1: shift!(t, level, rs, cs) (:267-275).
+ * Levels <= level move, levels > level are rebuilt.  labels == NULL: objects 1..n */
+int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level,
+                       const int32_t* rs, const int32_t* cs, int32_t mode);
+/* setrshift!(t[l], v) / setcshift!(t[l], v) on one PaddedMat, no rebuild  qtrees.jl:134-135 */
+int32_t stf_set_level_shift(stf_ctx* ctx, int32_t label, int32_t l, int32_t rs, int32_t cs);
+/* buildqtree!(t, layer) for the given labels (NULL: all)  qtrees.jl:221-237 */
+int32_t stf_build(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t layer);
+
+/* ---- narrow phase ---- */
+/* collision(Q1,Q2)  qtree_functions.jl:43-51.  out = (l,a,b); l < 0: no collision */
+int32_t stf_collision(stf_ctx* ctx, int32_t i1, int32_t i2, int32_t out[3]);
+/* _collision_randbfs from explicit start nodes for n pairs, canonical child order; returns EVERY
+ * result (hit or (-l,a,b) miss) in item order  qtree_functions.jl:21-42 */
+int32_t stf_collision_bfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out);
+/* collision_dfs(Q1,Q2,i)  qtree_functions.jl:2-20, n pairs */
+int32_t stf_collision_dfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out);
+/* _totalcollisions_native(qtrees, coitems, colist)  qtree_functions.jl:89-110: hits only */
+int32_t stf_collide_items(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out, int64_t cap, int64_t* count);
+
+/* ---- many-body collision ---- */
+/* totalcollisions_native(qtrees, labels)  qtree_functions.jl:111-131 (labels == NULL: 1..n) */
+int32_t stf_totalcollisions_native(stf_ctx* ctx, int32_t nl, const int32_t* labels, stf_item* out, int64_t cap, int64_t* count);
+/* locate!(qtrees[, labels], HashSpacialQTree)  qtree_functions.jl:159-201: records sorted by cell
+ * (level, a, b), labels of one cell in `labels` order */
+int32_t stf_locate(stf_ctx* ctx, int32_t nl, const int32_t* labels, stf_cellrec* out, int64_t cap, int64_t* count);
+/* totalcollisions_spacial(qtrees[, labels]; unique)  qtree_functions.jl:225-263.
+ * unique != 0: sorted by ((i1,i2),(l,a,b)), first entry per unordered pair (:252).
+ * unique == 0: all hits, same sort order (the reference's order is arbitrary). */
+int32_t stf_totalcollisions_spacial(stf_ctx* ctx, int32_t nl, const int32_t* labels, int32_t unique,
+                                    stf_item* out, int64_t cap, int64_t* count);
+/* the narrow-phase item list of the last spacial/partial call (the reference's `itemlist`), unordered */
+int32_t stf_fetch_items(stf_ctx* ctx, stf_item* out, int64_t cap, int64_t* count);
+int32_t stf_fetch_result(stf_ctx* ctx, stf_item* out, int64_t cap, int64_t* count);
+
+/* LinkedSpacialQTree state kept in the context (qtrees.jl:424-552; linked_spacial_qtree):
+ * locate!(qtrees, labels, linkedtree) relocates `labels` (cells outside the root are dropped, :506) */
+int32_t stf_linked_reset(stf_ctx* ctx);
+int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* labels);
+int32_t stf_linked_clear(stf_ctx* ctx, int32_t nl, const int32_t* labels); /* clear!(t,label) :530-538 */
+int32_t stf_linked_collect(stf_ctx* ctx, stf_cellrec* out, int64_t cap, int64_t* count); /* collect_tree */
+/* partialcollisions(qtrees, linkedtree, labels; unique)  qtree_functions.jl:277-330 */
+int32_t stf_partialcollisions(stf_ctx* ctx, int32_t nl, const int32_t* labels, int32_t unique,
+                              stf_item* out, int64_t cap, int64_t* count);
+
+/* ---- fit step ---- */
+/* grad2d(t, l, a, b) -> (gh, gw) for n queries  fit_helper.jl:51-66; out = 2n int32 */
+int32_t stf_grad2d(stf_ctx* ctx, int32_t n, const int32_t* labels, const int32_t* l, const int32_t* a,
+                   const int32_t* b, int32_t* out);
+int32_t stf_set_optimiser(stf_ctx* ctx, int32_t kind, double eta, double rho); /* Momentum/SGD; eta! */
+int32_t stf_reset_velocity(stf_ctx* ctx, int32_t n, const int32_t* labels);    /* reset!(o, x); NULL: all */
+int32_t stf_get_velocity(stf_ctx* ctx, int32_t n, const int32_t* labels, double* v /*2n*/, uint8_t* has);
+/* batchsteps!(qtrees, colist, optimiser)  fit.jl:58-75 in canonical mode: the result equals the
+ * sequential loop over `colist` in list order with the draws of stuffing_b200_rng.h keyed
+ * (seed, iteration, k).  Steps that share no movable object run concurrently. */
+int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colist, uint64_t seed, uint64_t iteration);
+/* one device-resident fit iteration = the body of trainepoch_E!'s rounds (fit.jl:87-96):
+ * totalcollisions(qtrees[, labels]; unique=false) followed by batchsteps! on its result, without
+ * copying the hit list to the host.  mode 0: spacial over `labels` (NULL: all); mode 1:
+ * partialcollisions over `labels`.  *nhits = length(colist). */
+int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels,
+                      uint64_t seed, uint64_t iteration, int64_t* nhits);
+
+int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -91,6 +91,7 @@ def lib():
             "orc_opt_reset": (None, [vp, i32]),
             "orc_opt_velocity": (None, [vp, i32, vp, vp]),
             "orc_batchsteps": (None, [vp, i32, vp, i64, vp, u64, u64]),
+            "orc_batchsteps_masks": (None, [vp, i32, vp, i64, vp, u64, u64, vp]),
             "orc_place": (i32, [vp, i32, u64]),
             "orc_overlap": (None, [vp, vp]),
         }
@@ -460,9 +461,10 @@ class Opt:
         return (float(out[0]), float(out[1])), bool(has.value)
 
 
-def batchsteps(qts, colist, opt: Opt | None, seed=0, iteration=0):
+def batchsteps(qts, colist, opt: Opt | None, seed=0, iteration=0, is_mask=None):
     arr = colist if isinstance(colist, np.ndarray) else items_array(colist)
-    lib().orc_batchsteps(_handles(qts), len(qts), _ptr(arr), len(arr), opt.h if opt else None, seed, iteration)
+    im = None if is_mask is None else np.ascontiguousarray(is_mask, np.uint8)
+    lib().orc_batchsteps_masks(_handles(qts), len(qts), _ptr(arr), len(arr), opt.h if opt else None, seed, iteration, _ptr(im))
 
 
 def place(qts, seed=1):

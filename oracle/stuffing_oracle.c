@@ -288,6 +288,8 @@ static Idx positionlower(const OrcTree* qt, Idx ind) {
             Idx ci = child(ind, i);
             if (rdi(qt, ci) != ORC_EMPTY) { if (flag) return ind; flag = 1; cind = ci; }
         }
+        if (!flag) return ind; /* non-EMPTY node without a non-EMPTY child (inconsistent pyramid): the
+                                  reference would spin forever on `ind = cind`; oracle and device stop here */
         ind = cind;
     }
     return ind;
@@ -602,17 +604,23 @@ static void step_mask_(OrcTree* const* trees, int im, int i2, Idx cp, OrcOpt* op
     double d[2] = { (ll * g2[0] - ll * g1[0]) / 2, (ll * g2[1] - ll * g1[1]) / 2 };
     opt_apply(opt, i2, d); move_(t2, d, seed, iter, k, 2);
 }
-void orc_batchsteps(OrcTree* const* trees, int n, const OrcItem* colist, int64_t nh, OrcOpt* opt, uint64_t seed, uint64_t iter) {
+void orc_batchsteps_masks(OrcTree* const* trees, int n, const OrcItem* colist, int64_t nh, OrcOpt* opt, uint64_t seed, uint64_t iter,
+                          const uint8_t* is_mask) {
     /* batchsteps! + step_index!  fit.jl:58-75.  The reference shuffles colist first; canonical mode
-     * takes the list order as the (already arbitrary) order. */
+     * takes the list order as the (already arbitrary) order.  is_mask == NULL: label 1 is the mask
+     * (fit.jl:60-63); a non-NULL array generalises that convention to batches of scenes. */
     (void)n;
     for (int64_t k = 0; k < nh; k++) {
         Idx cp = { colist[k].l, colist[k].a, colist[k].b };
         int i1 = colist[k].i1, i2 = colist[k].i2;
-        if (i1 == 1) step_mask_(trees, i1, i2, cp, opt, seed, iter, (uint64_t)k);
-        else if (i2 == 1) step_mask_(trees, i2, i1, cp, opt, seed, iter, (uint64_t)k);
+        int m1 = is_mask ? is_mask[i1 - 1] : i1 == 1, m2 = is_mask ? is_mask[i2 - 1] : i2 == 1;
+        if (m1) step_mask_(trees, i1, i2, cp, opt, seed, iter, (uint64_t)k);
+        else if (m2) step_mask_(trees, i2, i1, cp, opt, seed, iter, (uint64_t)k);
         else step_(trees, i1, i2, cp, opt, seed, iter, (uint64_t)k);
     }
+}
+void orc_batchsteps(OrcTree* const* trees, int n, const OrcItem* colist, int64_t nh, OrcOpt* opt, uint64_t seed, uint64_t iter) {
+    orc_batchsteps_masks(trees, n, colist, nh, opt, seed, iter, NULL);
 }
 
 /* ------------------------------------------------------------------ place! (input generation) */

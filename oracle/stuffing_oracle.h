@@ -107,6 +107,9 @@ void orc_opt_velocity(const OrcOpt* o, int label, double out[2], int32_t* has);
 /* batchsteps! in list order (canonical mode), draws keyed (seed, iter, k, slot) */
 void orc_batchsteps(OrcTree* const* trees, int n, const OrcItem* colist, int64_t nh, OrcOpt* opt,
                     uint64_t seed, uint64_t iter);
+/* same with an explicit mask flag per label (batches of scenes); is_mask == NULL: label 1 */
+void orc_batchsteps_masks(OrcTree* const* trees, int n, const OrcItem* colist, int64_t nh, OrcOpt* opt,
+                          uint64_t seed, uint64_t iter, const uint8_t* is_mask);
 
 /* ---- input generation (not on the hot path) ---- */
 /* place!(qtrees) of Stuffing.jl:64-68: trees[0] is the mask; returns 0, or -1 "no room" */

@@ -1,0 +1,458 @@
+// stf_collide.cuh — subsystems (2) broad phase and (3) narrow phase.
+//  (2) locate!/positionlower (qtree_functions.jl:141-201), the spatial trees as sorted (cell,label)
+//      records, candidate generation of totalcollisions_spacial (:230-249), collisions_boundsfilter
+//      (:203-223) and partialcollisions (:285-326).
+//  (3) _collision_randbfs / collision / collision_dfs (:2-51) as a level-synchronous frontier.
+#pragma once
+#include <cooperative_groups.h>
+#include "stf_common.cuh"
+namespace cg = cooperative_groups;
+
+// =============================================================================================
+// (2) broad phase
+// =============================================================================================
+
+// one thread per label: <= 4 cells, written to slots 4*slot..4*slot+3 (unused slots = INVALID key).
+// linked != 0: LinkedSpacialQTree semantics — slot = object, cells outside the root (L,1,1) dropped
+// (qtrees.jl:506).  linked == 0: HashSpacialQTree semantics — slot = position in `labels`.
+__global__ void k_locate(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
+                         int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                         int* __restrict__ err) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nl) return;
+    int o = labels ? labels[j] - 1 : j;
+    int slot = linked ? o : j;
+    const LevelMeta* olm = lm + (size_t)o * L;
+    LevelMeta top = olm[L - 1]; // sizelevel(qt) == length(qt)  qtrees.jl:191-193
+    int scene = om[o].scene;
+    int cnt = 0;
+    for (int k = 0; k < 4; k++) { // (1,1),(1,2),(2,1),(2,2)  qtree_functions.jl:167-170
+        int l = L, a = top.rs + 1 + (k >> 1), b = top.cs + 1 + (k & 1);
+        if (node_code<false>(words, top, a, b) == CODE_EMPTY) continue;
+        while (l > 2) { // positionlower  :141-158
+            LevelMeta cm = olm[l - 2];
+            int ca = a, cb = b, flag = 0, stop = 0;
+            for (int i = 0; i < 4; i++) {
+                int xa = 2 * a - (i & 1), xb = 2 * b - (i >> 1);
+                if (node_code<false>(words, cm, xa, xb) != CODE_EMPTY) {
+                    if (flag) { stop = 1; break; }
+                    flag = 1; ca = xa; cb = xb;
+                }
+            }
+            if (stop || !flag) break; // !flag: inconsistent pyramid; the reference would not terminate (oracle: same stop)
+            l = l - 1; a = ca; b = cb;
+        }
+        bool keep = true;
+        if (linked) { int r = 1 << (L - l); keep = (a >= 1 && a <= r && b >= 1 && b <= r); }
+        if (a <= -STF_CELL_BIAS || a >= STF_CELL_BIAS || b <= -STF_CELL_BIAS || b >= STF_CELL_BIAS) { atomicOr(err, 2); keep = false; }
+        if (keep) { keys[4 * (size_t)slot + cnt] = cell_key(scene, l, a, b); vals[4 * (size_t)slot + cnt] = (uint32_t)(o + 1); cnt++; }
+    }
+    for (int k = cnt; k < 4; k++) { keys[4 * (size_t)slot + k] = STF_KEY_INVALID; vals[4 * (size_t)slot + k] = (uint32_t)(o + 1); }
+}
+
+__global__ void k_fill_invalid(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = STF_KEY_INVALID; vals[i] = (uint32_t)(i / 4 + 1); }
+}
+__global__ void k_clear_slots(uint64_t* __restrict__ keys, int nl, const int32_t* __restrict__ labels) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nl) { size_t o = (size_t)(labels[j] - 1); for (int k = 0; k < 4; k++) keys[4 * o + k] = STF_KEY_INVALID; }
+}
+
+__device__ __forceinline__ int64_t lower_bound_u64(const uint64_t* __restrict__ keys, int64_t n, uint64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+struct EmitOut {
+    Item16* items; int64_t item_cap;
+    Item16* direct; int64_t direct_cap;
+    unsigned long long* counts; // [0] items, [1] direct hits
+};
+__device__ __forceinline__ void emit_push(Item16* buf, int64_t cap, unsigned long long* counter, const Item16& it) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
+    base = g.shfl(base, 0);
+    unsigned long long slot = base + g.thread_rank();
+    if ((int64_t)slot < cap) buf[slot] = it;
+}
+
+// candidate generation.  One thread per (sorted record r, k): k == 0 pairs r with the later records of its
+// own cell (qtree_functions.jl:233-239); k >= 1 looks the k-th ancestor cell up by binary search and runs
+// collisions_boundsfilter (:203-223) against every label stored there (:241-248).
+// moved_pos != NULL selects partialcollisions semantics (:285-326): a pair is generated iff at least one
+// side is in `labels` (moved_pos[o] >= 0); two moved labels of one cell are oriented (later, earlier).
+__global__ void k_emit_items(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t nrec, int L,
+                             const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const int32_t* __restrict__ moved_pos,
+                             EmitOut out) {
+    int K = L - 1;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r = t / K; int k = (int)(t - r * K);
+    if (r >= nrec) return;
+    uint64_t key = keys[r];
+    if (key == STF_KEY_INVALID) return;
+    int low = (int)vals[r];
+    int l, a, b; cell_unkey(key, &l, &a, &b);
+    int mp_low = moved_pos ? moved_pos[low - 1] : 0;
+    if (k == 0) {
+        for (int64_t h = r + 1; h < nrec && keys[h] == key; h++) {
+            int other = (int)vals[h];
+            int i1 = low, i2 = other;
+            if (moved_pos) {
+                int mp_o = moved_pos[other - 1];
+                if (mp_low < 0 && mp_o < 0) continue;
+                if (mp_low < 0 || (mp_o >= 0 && mp_o > mp_low)) { i1 = other; i2 = low; }
+            }
+            emit_push(out.items, out.item_cap, out.counts, make_item(i1, i2, l, a, b));
+        }
+        return;
+    }
+    if (l + k > L) return;
+    int pa = a, pb = b;
+    for (int i = 0; i < k; i++) { pa = (pa + 1) / 2; pb = (pb + 1) / 2; } // parent(): ÷ truncates toward zero
+    uint64_t scene_bits = key >> (5 + 2 * STF_CELL_W);
+    uint64_t akey = (scene_bits << (5 + 2 * STF_CELL_W)) | ((uint64_t)(uint32_t)(l + k) << (2 * STF_CELL_W)) |
+                    ((uint64_t)(uint32_t)(pa + STF_CELL_BIAS) << STF_CELL_W) | (uint64_t)(uint32_t)(pb + STF_CELL_BIAS);
+    int64_t h = lower_bound_u64(keys, nrec, akey);
+    LevelMeta lowm = lm[(size_t)(low - 1) * L + (l - 1)];
+    int lowcode = -1;
+    for (; h < nrec && keys[h] == akey; h++) {
+        int high = (int)vals[h];
+        if (moved_pos && mp_low < 0 && moved_pos[high - 1] < 0) continue;
+        LevelMeta hm = lm[(size_t)(high - 1) * L + (l - 1)];
+        int rr = a - hm.rs - 1, cc = b - hm.cs - 1;
+        if ((unsigned)rr < (unsigned)lm_kh(hm) && (unsigned)cc < (unsigned)lm_kw(hm)) {
+            emit_push(out.items, out.item_cap, out.counts, make_item(low, high, l, a, b));
+        } else if (lm_dflt(hm) == CODE_FULL) {
+            if (lowcode < 0) lowcode = (int)node_code<false>(words, lowm, a, b);
+            if (lowcode != (int)CODE_EMPTY) emit_push(out.direct, out.direct_cap, out.counts + 1, make_item(low, high, l, a, b));
+        }
+    }
+}
+
+// totalcollisions_native (qtree_functions.jl:111-131): labels whose top kernel covers (L,1,1), in order
+__global__ void k_native_filter(const LevelMeta* __restrict__ lm, int L, int nl, const int32_t* __restrict__ labels,
+                                int32_t* __restrict__ flt, int* __restrict__ m_out) {
+    __shared__ int wcnt[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j0 = 0; j0 < nl; j0 += blockDim.x) {
+        int j = j0 + threadIdx.x;
+        int o = 0; bool keep = false;
+        if (j < nl) {
+            o = labels ? labels[j] - 1 : j;
+            LevelMeta m = lm[(size_t)o * L + (L - 1)];
+            int rr = 1 - m.rs - 1, cc = 1 - m.cs - 1;
+            keep = (unsigned)rr < (unsigned)lm_kh(m) && (unsigned)cc < (unsigned)lm_kw(m);
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcnt[w] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int i = 0; i < w; i++) off += wcnt[i];
+        if (keep) flt[off + __popc(bal & ((1u << lane) - 1))] = o + 1;
+        __syncthreads();
+        if (threadIdx.x == 0) { int s = 0; for (int i = 0; i < nw; i++) s += wcnt[i]; base += s; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *m_out = base;
+}
+// pairs (labels[i], labels[j]) for i in 1:l for j in l:-1:i+1 (:120), start node (L,1,1)
+__global__ void k_native_pairs(const int32_t* __restrict__ flt, const int* __restrict__ m_in, int nl, int L, Item16* __restrict__ items,
+                               int64_t cap, unsigned long long* __restrict__ counts) {
+    int m = *m_in;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) counts[0] = (unsigned long long)m * (unsigned long long)(m - 1 > 0 ? m - 1 : 0) / 2;
+    int64_t i = t / nl, j = t - i * nl;
+    if (i < j && j < m) {
+        int64_t idx = i * (2 * (int64_t)m - i - 1) / 2 + (m - 1 - j);
+        if (idx < cap) items[idx] = make_item(flt[i], flt[j], L, 1, 1);
+    }
+}
+
+// =============================================================================================
+// (3) narrow phase: _collision_randbfs (qtree_functions.jl:21-42) in canonical child order
+// =============================================================================================
+// The FIFO queue of the reference visits the tree level by level, so the BFS is run as a
+// level-synchronous frontier.  The frontier (nodes whose code is MIX in both trees) is kept in BFS
+// order; the 4*count child tests of one level are spread over the lanes of a group in that same
+// order; a ballot finds the first FULL code (= the node the sequential BFS returns) and an ordered
+// ballot/popc compaction appends the MIX children to the next frontier.
+// Frontier entries are (alpha,beta) offsets below the start node: a = at.a*2^d - alpha.
+#define NP_GROUP 8
+#define NP_FCAP 64
+#define NP_THREADS 128
+
+struct NarrowArgs {
+    const uint32_t* words; const LevelMeta* lm; int L;
+    const Item16* items; const unsigned long long* n_items_dev; int64_t n_items_host; // device count if non-null
+    int4* res;                       // per item (l,a,b,0); l < 0 = miss
+    unsigned long long* counts;      // [2] overflow count, [3] visited
+    uint32_t* overflow;              // item indices that need the big path
+    int64_t overflow_cap;
+};
+
+__global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
+    __shared__ uint32_t fr[NP_THREADS / NP_GROUP][2][NP_FCAP];
+    cg::thread_block_tile<NP_GROUP> g = cg::tiled_partition<NP_GROUP>(cg::this_thread_block());
+    int gl = g.thread_rank();
+    int gib = threadIdx.x / NP_GROUP;
+    int64_t n = A.n_items_dev ? (int64_t)*A.n_items_dev : A.n_items_host;
+    if (n > A.n_items_host && A.n_items_host >= 0 && A.n_items_dev) n = A.n_items_host; // clamp to buffer capacity
+    int64_t ngroups = (int64_t)gridDim.x * (NP_THREADS / NP_GROUP);
+    unsigned long long visited = 0;
+    for (int64_t it = (int64_t)blockIdx.x * (NP_THREADS / NP_GROUP) + gib; it < n; it += ngroups) {
+        Item16 item = A.items[it];
+        int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
+        int lev = item_l(item), ata = item.a, atb = item.b;
+        int cnt = 1, cur = 0, depth = 0;
+        if (gl == 0) fr[gib][0][0] = 0;
+        g.sync();
+        int4 result = make_int4(-lev, ata, atb, 0);
+        bool overflow = false;
+        for (;;) {
+            LevelMeta m1 = A.lm[(size_t)o1 * A.L + (lev - 2)], m2 = A.lm[(size_t)o2 * A.L + (lev - 2)];
+            int basea = ata << (depth + 1), baseb = atb << (depth + 1);
+            int ncnt = 0; bool hit = false;
+            int ntest = 4 * cnt;
+            for (int t0 = 0; t0 < ntest; t0 += NP_GROUP) {
+                int t = t0 + gl;
+                bool valid = t < ntest;
+                uint32_t code = 0, ab = 0; int a = 0, b = 0;
+                if (valid) {
+                    uint32_t node = fr[gib][cur][t >> 2]; int cn = t & 3;
+                    uint32_t al = ((node >> 16) << 1) + (cn & 1), be = ((node & 0xffffu) << 1) + (cn >> 1);
+                    ab = (al << 16) | be;
+                    a = basea - (int)al; b = baseb - (int)be;
+                    code = node_code<false>(A.words, m1, a, b) & node_code<false>(A.words, m2, a, b);
+                }
+                visited += valid;
+                unsigned hm = g.ballot(valid && code == CODE_FULL);
+                if (hm) {
+                    int src = __ffs(hm) - 1;
+                    result = make_int4(lev - 1, g.shfl(a, src), g.shfl(b, src), 0);
+                    hit = true; break;
+                }
+                bool push = valid && code == CODE_MIX && lev - 1 > 1;
+                unsigned pm = g.ballot(push);
+                int np = __popc(pm);
+                if (ncnt + np > NP_FCAP) { overflow = true; break; }
+                if (push) fr[gib][cur ^ 1][ncnt + __popc(pm & ((1u << gl) - 1))] = ab;
+                ncnt += np;
+            }
+            if (hit || overflow) break;
+            if (ncnt == 0) { // miss: -(level) and coordinates of the last node popped (:41)
+                uint32_t node = fr[gib][cur][cnt - 1];
+                result = make_int4(-lev, (ata << depth) - (int)(node >> 16), (atb << depth) - (int)(node & 0xffffu), 0);
+                break;
+            }
+            g.sync();
+            cur ^= 1; cnt = ncnt; lev -= 1; depth += 1;
+        }
+        if (gl == 0) {
+            if (overflow) {
+                unsigned long long s = atomicAdd(A.counts + 2, 1ull);
+                if ((int64_t)s < A.overflow_cap) A.overflow[s] = (uint32_t)it;
+                result = make_int4(-1, 0, 0, -1);
+            }
+            A.res[it] = result;
+        }
+        g.sync();
+    }
+    // visited-node counter (algorithmic bytes of the roofline)
+    for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, o);
+    if ((threadIdx.x & 31) == 0 && visited) atomicAdd(A.counts + 3, visited);
+}
+
+// large-frontier path: one CTA per overflowed item, frontier double-buffered in global scratch
+#define NPB_THREADS 256
+__global__ void __launch_bounds__(NPB_THREADS) k_collide_big(NarrowArgs A, uint32_t* __restrict__ scratch, int64_t cap_per_cta, int* __restrict__ err) {
+    __shared__ int w_push[NPB_THREADS / 32];
+    __shared__ int w_hit[NPB_THREADS / 32];
+    __shared__ int4 s_result;
+    __shared__ int s_flag;
+    int64_t nov = (int64_t)A.counts[2];
+    if (nov > A.overflow_cap) nov = A.overflow_cap;
+    uint32_t* f0 = scratch + (size_t)blockIdx.x * 2 * cap_per_cta;
+    uint32_t* fbuf[2] = { f0, f0 + cap_per_cta };
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long visited = 0;
+    for (int64_t ov = blockIdx.x; ov < nov; ov += gridDim.x) {
+        int64_t it = A.overflow[ov];
+        Item16 item = A.items[it];
+        int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
+        int lev = item_l(item), ata = item.a, atb = item.b;
+        int64_t cnt = 1; int cur = 0, depth = 0;
+        if (threadIdx.x == 0) fbuf[0][0] = 0;
+        __syncthreads();
+        int4 result = make_int4(-lev, ata, atb, 0);
+        for (;;) {
+            LevelMeta m1 = A.lm[(size_t)o1 * A.L + (lev - 2)], m2 = A.lm[(size_t)o2 * A.L + (lev - 2)];
+            int basea = ata << (depth + 1), baseb = atb << (depth + 1);
+            int64_t ncnt = 0; int done = 0;
+            int64_t ntest = 4 * cnt;
+            for (int64_t t0 = 0; t0 < ntest; t0 += NPB_THREADS) {
+                int64_t t = t0 + threadIdx.x;
+                bool valid = t < ntest;
+                uint32_t code = 0, ab = 0; int a = 0, b = 0;
+                if (valid) {
+                    uint32_t node = fbuf[cur][t >> 2]; int cn = (int)(t & 3);
+                    uint32_t al = ((node >> 16) << 1) + (cn & 1), be = ((node & 0xffffu) << 1) + (cn >> 1);
+                    ab = (al << 16) | be;
+                    a = basea - (int)al; b = baseb - (int)be;
+                    code = node_code<false>(A.words, m1, a, b) & node_code<false>(A.words, m2, a, b);
+                }
+                visited += valid;
+                unsigned hm = __ballot_sync(0xffffffffu, valid && code == CODE_FULL);
+                bool push = valid && code == CODE_MIX && lev - 1 > 1;
+                unsigned pm = __ballot_sync(0xffffffffu, push);
+                if (lane == 0) { w_hit[w] = hm ? __ffs(hm) - 1 : -1; w_push[w] = __popc(pm); }
+                __syncthreads();
+                int first_w = -1; int off = 0, tot = 0;
+                for (int i = 0; i < NPB_THREADS / 32; i++) {
+                    if (first_w < 0 && w_hit[i] >= 0) first_w = i;
+                    if (i < w) off += w_push[i];
+                    tot += w_push[i];
+                }
+                if (first_w >= 0) {
+                    if (w == first_w && lane == w_hit[w]) s_result = make_int4(lev - 1, a, b, 0);
+                    done = 1;
+                } else {
+                    if (ncnt + tot > cap_per_cta) { if (threadIdx.x == 0) atomicOr(err, 4); done = 2; }
+                    else if (push) fbuf[cur ^ 1][ncnt + off + __popc(pm & ((1u << lane) - 1))] = ab;
+                    ncnt += tot;
+                }
+                __syncthreads();
+                if (done) break;
+            }
+            if (done == 1) { result = s_result; break; }
+            if (done == 2) { result = make_int4(-1, 0, 0, -2); break; }
+            if (ncnt == 0) {
+                uint32_t node = fbuf[cur][cnt - 1];
+                result = make_int4(-lev, (ata << depth) - (int)(node >> 16), (atb << depth) - (int)(node & 0xffffu), 0);
+                break;
+            }
+            __syncthreads();
+            cur ^= 1; cnt = ncnt; lev -= 1; depth += 1;
+        }
+        if (threadIdx.x == 0) { A.res[it] = result; s_flag = 0; }
+        __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, o);
+    if (lane == 0 && visited) atomicAdd(A.counts + 3, visited);
+}
+
+// hits = results with l >= 0 (cp[1] >= 0, qtree_functions.jl:104-106), appended after `base` entries
+__global__ void k_compact_hits(const Item16* __restrict__ items, const int4* __restrict__ res, const unsigned long long* __restrict__ n_dev, int64_t n_host,
+                               Item16* __restrict__ hits, int64_t cap, unsigned long long* __restrict__ nhits) {
+    int64_t n = n_dev ? min((int64_t)*n_dev, n_host) : n_host;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 r = res[i];
+    if (r.x >= 0) {
+        Item16 it = items[i];
+        emit_push(hits, cap, nhits, make_item(it.i1, item_i2(it), r.x, r.y, r.z));
+    }
+}
+
+// collision_dfs (qtree_functions.jl:2-20): one thread per pair, explicit stack
+__global__ void k_collision_dfs(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, const Item16* __restrict__ items, int64_t n, int4* __restrict__ res) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Item16 item = items[i];
+    int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
+    int sa[STF_MAX_LEVELS + 1], sb[STF_MAX_LEVELS + 1], sc[STF_MAX_LEVELS + 1];
+    int l = item_l(item), top = l;
+    sa[l] = item.a; sb[l] = item.b; sc[l] = -1;
+    int4 r = make_int4(-l, item.a, item.b, 0);
+    while (l <= top) {
+        if (sc[l] < 0) { // entering node (l, sa[l], sb[l])
+            uint32_t code = node_code<false>(words, lm[(size_t)o1 * L + (l - 1)], sa[l], sb[l]) & node_code<false>(words, lm[(size_t)o2 * L + (l - 1)], sa[l], sb[l]);
+            if (code == CODE_FULL) { r = make_int4(l, sa[l], sb[l], 0); break; }
+            r = make_int4(-l, sa[l], sb[l], 0);
+            if (code == CODE_MIX && l > 1) sc[l] = 0; else { l++; continue; }
+        }
+        if (sc[l] < 4) { int cn = sc[l]++; sa[l - 1] = 2 * sa[l] - (cn & 1); sb[l - 1] = 2 * sb[l] - (cn >> 1); sc[l - 1] = -1; l--; }
+        else l++;
+    }
+    res[i] = r;
+}
+
+// =============================================================================================
+// result ordering: sort!(r) and unique!(minmax∘first, ·)  (qtree_functions.jl:252)
+// =============================================================================================
+__global__ void k_hit_keys(const Item16* __restrict__ hits, int64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = ((uint64_t)(uint32_t)hits[i].i1 << 32) | (uint32_t)item_i2(hits[i]); vals[i] = (uint32_t)i; }
+}
+__global__ void k_gather_hits(const Item16* __restrict__ hits, const uint32_t* __restrict__ vals, int64_t n, Item16* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = hits[vals[i]];
+}
+__device__ __forceinline__ bool lab_less(const Item16& x, const Item16& y) {
+    int lx = item_l(x), ly = item_l(y);
+    if (lx != ly) return lx < ly; if (x.a != y.a) return x.a < y.a; return x.b < y.b;
+}
+// hits of one ordered pair (i1,i2) are adjacent after the radix sort; order them by (l,a,b) and mark what
+// unique! keeps: the first entry of a run, unless the swapped pair (i2,i1) sorts earlier (i1 > i2 and it exists)
+__global__ void k_fix_ties(Item16* __restrict__ hits, const uint64_t* __restrict__ keys, int64_t n, int unique, uint32_t* __restrict__ keep) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i];
+    bool head = (i == 0) || keys[i - 1] != key;
+    uint32_t kp = 1;
+    if (unique) {
+        kp = head;
+        uint32_t i1 = (uint32_t)(key >> 32), i2 = (uint32_t)key;
+        if (kp && i1 > i2) {
+            uint64_t sw = ((uint64_t)i2 << 32) | i1;
+            int64_t p = lower_bound_u64(keys, n, sw);
+            if (p < n && keys[p] == sw) kp = 0;
+        }
+    }
+    keep[i] = kp;
+    if (!head) return;
+    int64_t e = i + 1; while (e < n && keys[e] == key) e++;
+    for (int64_t x = i + 1; x < e; x++) { // insertion sort of a (short) run
+        Item16 v = hits[x]; int64_t y = x - 1;
+        while (y >= i && lab_less(v, hits[y])) { hits[y + 1] = hits[y]; y--; }
+        hits[y + 1] = v;
+    }
+}
+__global__ void k_export_hits(const Item16* __restrict__ hits, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, int64_t n, int32_t* __restrict__ out /*5 ints each*/) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    int32_t* o = out + 5 * (size_t)pos[i];
+    Item16 h = hits[i];
+    o[0] = h.i1; o[1] = item_i2(h); o[2] = item_l(h); o[3] = h.a; o[4] = h.b;
+}
+__global__ void k_import_items(const int32_t* __restrict__ in, int64_t n, Item16* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int32_t* p = in + 5 * (size_t)i; out[i] = make_item(p[0], p[1], p[2], p[3], p[4]); }
+}
+__global__ void k_export_results(const Item16* __restrict__ items, const int4* __restrict__ res, int64_t n, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t* o = out + 5 * (size_t)i;
+    o[0] = items[i].i1; o[1] = item_i2(items[i]); o[2] = res[i].x; o[3] = res[i].y; o[4] = res[i].z;
+}
+__global__ void k_export_items(const Item16* __restrict__ items, int64_t n, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t* o = out + 5 * (size_t)i;
+    o[0] = items[i].i1; o[1] = item_i2(items[i]); o[2] = item_l(items[i]); o[3] = items[i].a; o[4] = items[i].b;
+}
+__global__ void k_export_cells(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, int32_t* __restrict__ out, unsigned long long* __restrict__ nvalid) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = keys[i];
+    if (k == STF_KEY_INVALID) return;
+    if (i + 1 == n || keys[i + 1] == STF_KEY_INVALID) *nvalid = (unsigned long long)(i + 1);
+    int l, a, b; cell_unkey(k, &l, &a, &b);
+    int32_t* o = out + 4 * (size_t)i;
+    o[0] = l; o[1] = a; o[2] = b; o[3] = (int32_t)vals[i];
+}

@@ -1,0 +1,782 @@
+// stuffing_b200.cu — the C ABI (include/stuffing_b200.h) over the sm_100a kernels.
+// Host-side orchestration only: buffer management, launches, the few count read-backs the
+// reference's own control flow needs (length(itemlist), length(colist)).  No CPU fallback.
+#include "../../include/stuffing_b200.h"
+#include "stf_common.cuh"
+#include "stf_pyramid.cuh"
+#include "stf_sort.cuh"
+#include "stf_collide.cuh"
+#include "stf_step.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t st = 0) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = std::max(bytes, cap + cap / 2) + 256;
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap);
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) { e = cudaMemcpyAsync(q, p, cap, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; cudaStreamSynchronize(st); }
+        if (p) cudaFree(p);
+        p = q; cap = ncap; return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct stf_ctx {
+    int device = 0; cudaStream_t st = nullptr; std::string err;
+    int n = 0, L = 0, canvas = 0; uint64_t total_words = 0;
+    int scene_bits = 0, label_bits = 1; bool multi_scene = false, sizelevel_ok = true, has_big = false;
+    std::vector<ObjMeta> h_om; std::vector<uint32_t> h_off; // h_off[o*L + l-1]: word offsets (static)
+    std::vector<int> big_objs;
+    DevBuf words, lm, om, payload, poff, woff1, work, lab, lab2, lab3, lab4, bytes_tmp;
+    DevBuf rk, rv, rk2, rv2, hist, lkk, lkv;
+    DevBuf items, direct, res, overflow, hits, hits2, hk, hv, hk2, hv2, keep, out32, scratch;
+    DevBuf counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m;
+    unsigned long long* h_counts = nullptr; int* h_err = nullptr; // pinned
+    OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
+    int64_t last_result = 0, last_items = 0; bool items_valid = false;
+    int64_t big_cap = 0; int big_ctas = 1;
+    stf_counters_t ctr = {};
+};
+
+#define CK(call)                                                                                         \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return STF_E_CUDA; } } while (0)
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+#define KCHECK() CK(cudaGetLastError())
+static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n + t - 1) / t); }
+
+enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_NVALID = 7, C_N = 8 };
+
+static int32_t sync_counts(stf_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (*ctx->h_err & 1) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st); FAIL(STF_E_BADCODE, "node code outside 1..3 in uploaded payload"); }
+    if (*ctx->h_err & 2) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st); FAIL(STF_E_RANGE, "spatial cell coordinate outside +-2^21"); }
+    if (*ctx->h_err & 4) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st); FAIL(STF_E_CUDA, "internal: frontier scratch too small"); }
+    return STF_OK;
+}
+static int32_t upload_labels(stf_ctx* ctx, DevBuf& buf, int32_t nl, const int32_t* labels, const int32_t** dev) {
+    *dev = nullptr;
+    if (!labels) return STF_OK;
+    for (int i = 0; i < nl; i++) if (labels[i] < 1 || labels[i] > ctx->n) FAIL(STF_E_ARG, "label out of range");
+    CK(buf.ensure(sizeof(int32_t) * (size_t)std::max(nl, 1)));
+    CK(cudaMemcpyAsync(buf.p, labels, sizeof(int32_t) * (size_t)nl, cudaMemcpyHostToDevice, ctx->st));
+    *dev = buf.as<int32_t>();
+    return STF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ lifetime
+extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
+    if (!out) return STF_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return STF_E_CUDA;
+    stf_ctx* ctx = new stf_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || cudaMallocHost(&ctx->h_err, sizeof(int)) != cudaSuccess ||
+        ctx->counts.ensure(C_N * sizeof(unsigned long long)) != cudaSuccess || ctx->errflag.ensure(sizeof(int)) != cudaSuccess) {
+        delete ctx; return STF_E_CUDA;
+    }
+    cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st);
+    cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st);
+    *out = ctx;
+    return STF_OK;
+}
+extern "C" void stf_destroy(stf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
+                      &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
+                      &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m };
+    for (DevBuf* b : all) b->release();
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+extern "C" const char* stf_last_error(const stf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" void* stf_stream(stf_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
+extern "C" int32_t stf_num_objects(const stf_ctx* ctx) { return ctx ? ctx->n : 0; }
+extern "C" int32_t stf_num_levels(const stf_ctx* ctx) { return ctx ? ctx->L : 0; }
+
+// ------------------------------------------------------------------------------------------------ build helpers
+static int32_t build_worklist(stf_ctx* ctx, int nwork) { // ctx->work holds (object, from) pairs
+    int blocks = std::min(nblk((int64_t)nwork * 32, 256), 148 * 8);
+    k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), nwork, ctx->om.as<ObjMeta>(), 0);
+    KCHECK();
+    return STF_OK;
+}
+static int32_t build_big(stf_ctx* ctx, int o, int from) { // levels from+1..L of one big object, many CTAs per level
+    for (int l = from + 1; l <= ctx->L; l++) {
+        k_set_parent_shift<<<1, 1, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, o, l);
+        int kh = ((ctx->h_om[o].kh1 - 2) >> (l - 1)) + 2, kw = ((ctx->h_om[o].kw1 - 2) >> (l - 1)) + 2;
+        int64_t nw = (int64_t)wpc_of(kh) * kw;
+        k_build_level_wide<<<std::min(nblk(nw, 256), 148 * 16), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l);
+    }
+    KCHECK();
+    return STF_OK;
+}
+
+static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics, const int32_t* pitch, const uint8_t* packed, int packed_on_device,
+                             const int32_t* kh, const int32_t* kw, const int32_t* rshift, const int32_t* cshift, const uint8_t* dflt, int32_t canvas,
+                             const uint8_t* is_mask, const int32_t* scene) {
+    if (!ctx) return STF_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n < 0 || canvas < 2 || (canvas & (canvas - 1)) || canvas > 65536) FAIL(STF_E_ARG, "canvas must be a power of two in [2, 65536]");
+    int L = 1; for (int s = canvas; s > 1; s >>= 1) L++;
+    ctx->n = n; ctx->L = L; ctx->canvas = canvas; ctx->items_valid = false; ctx->last_result = 0;
+    ctx->label_bits = 1; while ((1ll << ctx->label_bits) <= n) ctx->label_bits++;
+    if (n >= (1 << 26)) FAIL(STF_E_ARG, "too many objects");
+    ctx->h_om.assign(n, ObjMeta());
+    ctx->h_off.assign((size_t)n * L, 0);
+    std::vector<LevelMeta> h_lm((size_t)n * L);
+    std::vector<uint64_t> poff(n + 1, 0), woff1(n + 1, 0);
+    uint64_t words = 0; int max_scene = 0;
+    ctx->big_objs.clear(); ctx->sizelevel_ok = true;
+    std::vector<int64_t> n2(n, 0);
+    for (int o = 0; o < n; o++) {
+        if (kh[o] < 0 || kw[o] < 0 || kh[o] > 32767 || kw[o] > 32767) FAIL(STF_E_ARG, "kernel size must be in [0, 32767]");
+        if (dflt[o] != STF_EMPTY && dflt[o] != STF_FULL) FAIL(STF_E_ARG, "default must be EMPTY or FULL");
+        ObjMeta& m = ctx->h_om[o];
+        m.kh1 = kh[o]; m.kw1 = kw[o]; m.scene = scene ? scene[o] : 0; m.dflt = dflt[o];
+        m.is_mask = is_mask ? is_mask[o] : (o == 0);
+        if (m.scene < 0) FAIL(STF_E_ARG, "negative scene id");
+        max_scene = std::max(max_scene, m.scene);
+        int a = kh[o], b = kw[o];
+        for (int l = 1; l <= L; l++) {
+            LevelMeta& v = h_lm[(size_t)o * L + l - 1];
+            if (words > 0xFFFFFFF0ull) FAIL(STF_E_ARG, "pyramids exceed 2^32 words per context");
+            v.off = (uint32_t)words; ctx->h_off[(size_t)o * L + l - 1] = v.off;
+            v.rs = (l == 1 && rshift) ? rshift[o] : 0; v.cs = (l == 1 && cshift) ? cshift[o] : 0;
+            v.dims = (uint32_t)a | ((uint32_t)b << 15) | ((uint32_t)dflt[o] << 30);
+            uint64_t nw = (uint64_t)wpc_of(a) * b;
+            if (l == 1) { woff1[o + 1] = woff1[o] + nw; poff[o + 1] = poff[o] + (uint64_t)a * b; }
+            if (l == 2) { n2[o] = (int64_t)a * b; m.big = nw > 4096; }
+            if (l == L && (a > 2 || b > 2)) ctx->sizelevel_ok = false; // sizelevel == -1  qtrees.jl:182-193
+            words += nw;
+            a = a / 2 + 1; b = b / 2 + 1; // qtrees.jl:185
+        }
+        if (m.big) ctx->big_objs.push_back(o);
+    }
+    ctx->has_big = !ctx->big_objs.empty();
+    ctx->total_words = words;
+    ctx->multi_scene = max_scene > 0;
+    ctx->scene_bits = 0; while ((1ll << ctx->scene_bits) <= max_scene) ctx->scene_bits++;
+    if (!ctx->multi_scene) ctx->scene_bits = 0;
+    if (ctx->scene_bits > 64 - 5 - 2 * STF_CELL_W) FAIL(STF_E_ARG, "too many scenes");
+    // frontier bound of the large path: a frontier holds distinct nodes that are MIX in BOTH trees, hence at most the
+    // level-2 node count of the smaller tree; over all pairs that is the second largest level-2 count
+    std::vector<int64_t> s2 = n2; std::sort(s2.begin(), s2.end());
+    ctx->big_cap = std::max<int64_t>(1024, n >= 2 ? s2[n - 2] : 1024) + 64;
+    ctx->big_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(148, (512ll << 20) / (8 * ctx->big_cap)));
+
+    CK(ctx->words.ensure(sizeof(uint32_t) * (size_t)(words + 16)));
+    CK(ctx->lm.ensure(sizeof(LevelMeta) * (size_t)std::max<size_t>(1, (size_t)n * L)));
+    CK(ctx->om.ensure(sizeof(ObjMeta) * (size_t)std::max(1, n)));
+    CK(ctx->poff.ensure(sizeof(uint64_t) * (size_t)(n + 1)));
+    CK(ctx->woff1.ensure(sizeof(uint64_t) * (size_t)(n + 1)));
+    CK(ctx->work.ensure(sizeof(int2) * (size_t)std::max(1, n)));
+    CK(ctx->vel.ensure(sizeof(double) * 2 * (size_t)std::max(1, n)));
+    CK(ctx->has_vel.ensure((size_t)std::max(1, n)));
+    CK(ctx->moved_flag.ensure((size_t)std::max(1, n)));
+    CK(ctx->moved_pos.ensure(sizeof(int32_t) * (size_t)std::max(1, n)));
+    CK(ctx->lkk.ensure(sizeof(uint64_t) * 4 * (size_t)std::max(1, n)));
+    CK(ctx->lkv.ensure(sizeof(uint32_t) * 4 * (size_t)std::max(1, n)));
+    CK(cudaMemsetAsync(ctx->has_vel.p, 0, (size_t)std::max(1, n), ctx->st));
+    CK(cudaMemsetAsync(ctx->moved_flag.p, 0, (size_t)std::max(1, n), ctx->st));
+    if (n == 0) { CK(cudaStreamSynchronize(ctx->st)); return STF_OK; }
+    CK(cudaMemcpyAsync(ctx->lm.p, h_lm.data(), sizeof(LevelMeta) * (size_t)n * L, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->om.p, ctx->h_om.data(), sizeof(ObjMeta) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->poff.p, poff.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->woff1.p, woff1.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->st));
+    k_fill_invalid<<<nblk(4ll * n, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), 4ll * n);
+
+    const uint8_t* d_payload = nullptr;
+    std::vector<uint8_t> staging;
+    if (packed && packed_on_device) d_payload = packed; // needs >= 8 readable bytes of slack after the payload
+    else {
+        CK(ctx->payload.ensure((size_t)poff[n] + 64));
+        const uint8_t* src = packed;
+        if (!packed) {
+            staging.resize((size_t)poff[n] + 1);
+            for (int o = 0; o < n; o++)
+                for (int c = 0; c < kw[o]; c++) memcpy(staging.data() + poff[o] + (size_t)c * kh[o], pics[o] + (size_t)c * pitch[o], (size_t)kh[o]);
+            src = staging.data();
+        }
+        if (poff[n]) CK(cudaMemcpyAsync(ctx->payload.p, src, (size_t)poff[n], cudaMemcpyHostToDevice, ctx->st));
+        d_payload = ctx->payload.as<uint8_t>();
+    }
+    if (woff1[n]) {
+        k_pack_level1<<<nblk((int64_t)woff1[n], 256), 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), ctx->woff1.as<uint64_t>(), n, ctx->lm.as<LevelMeta>(), L,
+                                                                      ctx->words.as<uint32_t>(), woff1[n], ctx->errflag.as<int>());
+        KCHECK();
+    }
+    // buildqtree!(t) for every object: warp-per-object for small ones, level-by-level wide launches for big ones
+    k_fill_worklist<<<nblk(n, 256), 256, 0, ctx->st>>>(n, nullptr, 1, ctx->work.as<int2>());
+    {
+        int blocks = std::min(nblk((int64_t)n * 32, 256), 148 * 8);
+        k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), 1);
+        KCHECK();
+    }
+    for (int o : ctx->big_objs) { int32_t r = build_big(ctx, o, 1); if (r) return r; }
+    int32_t r = sync_counts(ctx); // staging must outlive the copy; also surfaces bad codes
+    return r;
+}
+
+extern "C" int32_t stf_upload_objects(stf_ctx* ctx, int32_t n, const uint8_t* const* pics, const int32_t* kh, const int32_t* kw, const int32_t* pitch,
+                                      const int32_t* rshift, const int32_t* cshift, const uint8_t* dflt, int32_t canvas, const uint8_t* is_mask, const int32_t* scene) {
+    if (!ctx || (n > 0 && (!pics || !kh || !kw || !pitch || !dflt))) return STF_E_ARG;
+    return upload_common(ctx, n, pics, pitch, nullptr, 0, kh, kw, rshift, cshift, dflt, canvas, is_mask, scene);
+}
+extern "C" int32_t stf_upload_packed(stf_ctx* ctx, int32_t n, const uint8_t* payload, int32_t payload_on_device, const int32_t* kh, const int32_t* kw,
+                                     const int32_t* rshift, const int32_t* cshift, const uint8_t* dflt, int32_t canvas, const uint8_t* is_mask, const int32_t* scene) {
+    if (!ctx || (n > 0 && (!payload || !kh || !kw || !dflt))) return STF_E_ARG;
+    return upload_common(ctx, n, nullptr, nullptr, payload, payload_on_device, kh, kw, rshift, cshift, dflt, canvas, is_mask, scene);
+}
+
+// ------------------------------------------------------------------------------------------------ tree state
+#define NEED_OBJS() do { if (!ctx) return STF_E_ARG; if (ctx->L == 0) FAIL(STF_E_STATE, "nothing uploaded"); CK(cudaSetDevice(ctx->device)); } while (0)
+#define CHECK_LABEL(x) do { if ((x) < 1 || (x) > ctx->n) FAIL(STF_E_ARG, "label out of range"); } while (0)
+
+extern "C" int32_t stf_get_level_info(stf_ctx* ctx, int32_t label, int32_t l, int32_t out[5]) {
+    NEED_OBJS(); CHECK_LABEL(label);
+    if (l < 1 || l > ctx->L || !out) FAIL(STF_E_ARG, "level out of range");
+    LevelMeta m;
+    CK(cudaMemcpyAsync(&m, ctx->lm.as<LevelMeta>() + (size_t)(label - 1) * ctx->L + (l - 1), sizeof(m), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    out[0] = lm_kh(m); out[1] = lm_kw(m); out[2] = m.rs; out[3] = m.cs; out[4] = ctx->canvas >> (l - 1);
+    return STF_OK;
+}
+extern "C" int32_t stf_download_level(stf_ctx* ctx, int32_t label, int32_t l, uint8_t* out) {
+    NEED_OBJS(); CHECK_LABEL(label);
+    if (l < 1 || l > ctx->L) FAIL(STF_E_ARG, "level out of range");
+    int o = label - 1;
+    int kh = ((ctx->h_om[o].kh1 - 2) >> (l - 1)) + 2, kw = ((ctx->h_om[o].kw1 - 2) >> (l - 1)) + 2;
+    if (l == 1) { kh = ctx->h_om[o].kh1; kw = ctx->h_om[o].kw1; }
+    size_t nb = (size_t)kh * kw;
+    if (!nb) return STF_OK;
+    CK(ctx->bytes_tmp.ensure(nb));
+    k_unpack_level<<<std::min(nblk((int64_t)nb, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l, ctx->bytes_tmp.as<uint8_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, nb, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+static int32_t upload_query(stf_ctx* ctx, int32_t n, const int32_t* labels, const int32_t* l, const int32_t* a, const int32_t* b) {
+    for (int i = 0; i < n; i++) { CHECK_LABEL(labels[i]); if (l[i] < 1 || l[i] > ctx->L) FAIL(STF_E_ARG, "level out of range"); }
+    size_t nb = sizeof(int32_t) * (size_t)n;
+    CK(ctx->lab.ensure(nb)); CK(ctx->lab2.ensure(nb)); CK(ctx->lab3.ensure(nb)); CK(ctx->lab4.ensure(nb));
+    CK(cudaMemcpyAsync(ctx->lab.p, labels, nb, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->lab2.p, l, nb, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->lab3.p, a, nb, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->lab4.p, b, nb, cudaMemcpyHostToDevice, ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_read_nodes(stf_ctx* ctx, int32_t n, const int32_t* labels, const int32_t* l, const int32_t* a, const int32_t* b, uint8_t* out) {
+    NEED_OBJS();
+    if (n <= 0) return STF_OK;
+    int32_t r = upload_query(ctx, n, labels, l, a, b); if (r) return r;
+    CK(ctx->bytes_tmp.ensure((size_t)n));
+    k_read_nodes<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, n, ctx->lab.as<int32_t>(), ctx->lab2.as<int32_t>(),
+                                                    ctx->lab3.as<int32_t>(), ctx->lab4.as<int32_t>(), ctx->bytes_tmp.as<uint8_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_grad2d(stf_ctx* ctx, int32_t n, const int32_t* labels, const int32_t* l, const int32_t* a, const int32_t* b, int32_t* out) {
+    NEED_OBJS();
+    if (n <= 0) return STF_OK;
+    int32_t r = upload_query(ctx, n, labels, l, a, b); if (r) return r;
+    CK(ctx->out32.ensure(sizeof(int32_t) * 2 * (size_t)n));
+    k_grad2d<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, n, ctx->lab.as<int32_t>(), ctx->lab2.as<int32_t>(),
+                                                ctx->lab3.as<int32_t>(), ctx->lab4.as<int32_t>(), ctx->out32.as<int32_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(int32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_get_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level, int32_t* rs, int32_t* cs) {
+    NEED_OBJS();
+    if (level < 1 || level > ctx->L) FAIL(STF_E_ARG, "level out of range");
+    std::vector<LevelMeta> all((size_t)ctx->n * ctx->L);
+    if (ctx->n) CK(cudaMemcpyAsync(all.data(), ctx->lm.p, sizeof(LevelMeta) * all.size(), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int i = 0; i < n; i++) {
+        int lb = labels ? labels[i] : i + 1; CHECK_LABEL(lb);
+        rs[i] = all[(size_t)(lb - 1) * ctx->L + level - 1].rs; cs[i] = all[(size_t)(lb - 1) * ctx->L + level - 1].cs;
+    }
+    return STF_OK;
+}
+static int32_t rebuild_after(stf_ctx* ctx, int n, const int32_t* labels_host, int from) { // ctx->work filled with (o, from)
+    if (from >= ctx->L) return STF_OK;
+    int blocks = std::min(nblk((int64_t)n * 32, 256), 148 * 8);
+    k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0);
+    KCHECK();
+    if (ctx->has_big)
+        for (int i = 0; i < n; i++) { int o = labels_host ? labels_host[i] - 1 : i; if (ctx->h_om[o].big) { int32_t r = build_big(ctx, o, from); if (r) return r; } }
+    return STF_OK;
+}
+extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level, const int32_t* rs, const int32_t* cs, int32_t mode) {
+    NEED_OBJS();
+    if (level < 1 || level > ctx->L || n < 0 || (!labels && n > ctx->n)) FAIL(STF_E_ARG, "bad level or count");
+    if (n == 0) return STF_OK;
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r;
+    CK(ctx->lab2.ensure(sizeof(int32_t) * (size_t)n)); CK(ctx->lab3.ensure(sizeof(int32_t) * (size_t)n));
+    CK(ctx->work.ensure(sizeof(int2) * (size_t)n));
+    CK(cudaMemcpyAsync(ctx->lab2.p, rs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->lab3.p, cs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+    k_apply_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, dl, level, ctx->lab2.as<int32_t>(), ctx->lab3.as<int32_t>(), mode, ctx->work.as<int2>());
+    KCHECK();
+    r = rebuild_after(ctx, n, labels, level); if (r) return r;
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_set_level_shift(stf_ctx* ctx, int32_t label, int32_t l, int32_t rs, int32_t cs) {
+    NEED_OBJS(); CHECK_LABEL(label);
+    if (l < 1 || l > ctx->L) FAIL(STF_E_ARG, "level out of range");
+    int32_t v[2] = { rs, cs };
+    CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->lm.as<LevelMeta>() + (size_t)(label - 1) * ctx->L + (l - 1)) + 4, v, 8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_build(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t layer) {
+    NEED_OBJS();
+    if (layer < 2) FAIL(STF_E_ARG, "layer must be >= 2");
+    if (!labels) n = ctx->n;
+    if (n == 0 || layer > ctx->L) return STF_OK;
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r;
+    CK(ctx->work.ensure(sizeof(int2) * (size_t)n));
+    k_fill_worklist<<<nblk(n, 256), 256, 0, ctx->st>>>(n, dl, layer - 1, ctx->work.as<int2>());
+    r = rebuild_after(ctx, n, labels, layer - 1); if (r) return r;
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ narrow phase
+// runs the BFS over ctx->items[0..n) into ctx->res; n is host-known
+static int32_t narrow_phase(stf_ctx* ctx, int64_t n) {
+    CK(ctx->res.ensure(sizeof(int4) * (size_t)std::max<int64_t>(1, n)));
+    CK(ctx->overflow.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, n)));
+    if (n == 0) return STF_OK;
+    NarrowArgs A;
+    A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.L = ctx->L;
+    A.items = ctx->items.as<Item16>(); A.n_items_dev = nullptr; A.n_items_host = n;
+    A.res = ctx->res.as<int4>(); A.counts = ctx->counts.as<unsigned long long>();
+    A.overflow = ctx->overflow.as<uint32_t>(); A.overflow_cap = n;
+    int64_t groups = (n + 0) ; int per_block = NP_THREADS / NP_GROUP;
+    int blocks = (int)std::min<int64_t>((groups + per_block - 1) / per_block, 148 * 32);
+    k_collide_small<<<blocks, NP_THREADS, 0, ctx->st>>>(A);
+    KCHECK();
+    CK(ctx->scratch.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->big_cap * ctx->big_ctas));
+    k_collide_big<<<ctx->big_ctas, NPB_THREADS, 0, ctx->st>>>(A, ctx->scratch.as<uint32_t>(), ctx->big_cap, ctx->errflag.as<int>());
+    KCHECK();
+    return STF_OK;
+}
+static int32_t import_items(stf_ctx* ctx, int64_t n, const stf_item* items, DevBuf& dst) {
+    for (int64_t i = 0; i < n; i++) {
+        CHECK_LABEL(items[i].i1); CHECK_LABEL(items[i].i2);
+        if (items[i].l < 1 || items[i].l > ctx->L) FAIL(STF_E_ARG, "item level out of range");
+    }
+    CK(ctx->out32.ensure(sizeof(int32_t) * 5 * (size_t)std::max<int64_t>(1, n)));
+    CK(dst.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n)));
+    if (n == 0) return STF_OK;
+    CK(cudaMemcpyAsync(ctx->out32.p, items, sizeof(stf_item) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+    k_import_items<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->out32.as<int32_t>(), n, dst.as<Item16>());
+    KCHECK();
+    return STF_OK;
+}
+static int32_t zero_counts(stf_ctx* ctx) { CK(cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st)); return STF_OK; }
+
+extern "C" int32_t stf_collision_bfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out) {
+    NEED_OBJS();
+    if (n <= 0) return STF_OK;
+    for (int64_t i = 0; i < n; i++) if (items[i].l < 2) FAIL(STF_E_ARG, "_collision_randbfs needs a start level >= 2");
+    int32_t r = import_items(ctx, n, items, ctx->items); if (r) return r;
+    ctx->items_valid = false;
+    r = zero_counts(ctx); if (r) return r;
+    r = narrow_phase(ctx, n); if (r) return r;
+    k_export_results<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), n, ctx->out32.as<int32_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(stf_item) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    return sync_counts(ctx);
+}
+extern "C" int32_t stf_collision_dfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out) {
+    NEED_OBJS();
+    if (n <= 0) return STF_OK;
+    int32_t r = import_items(ctx, n, items, ctx->items); if (r) return r;
+    ctx->items_valid = false;
+    CK(ctx->res.ensure(sizeof(int4) * (size_t)n));
+    k_collision_dfs<<<nblk(n, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->items.as<Item16>(), n, ctx->res.as<int4>());
+    KCHECK();
+    k_export_results<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), n, ctx->out32.as<int32_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(stf_item) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_collision(stf_ctx* ctx, int32_t i1, int32_t i2, int32_t out[3]) {
+    NEED_OBJS(); CHECK_LABEL(i1); CHECK_LABEL(i2);
+    // inkernelbounds(Q, L, 1, 1) for both, else (-L, 1, 1)   qtree_functions.jl:46-50
+    int32_t a[5], b[5];
+    int32_t r = stf_get_level_info(ctx, i1, ctx->L, a); if (r) return r;
+    r = stf_get_level_info(ctx, i2, ctx->L, b); if (r) return r;
+    auto inb = [](const int32_t* m) { return 1 > m[2] && 1 > m[3] && 1 <= m[0] + m[2] && 1 <= m[1] + m[3]; };
+    if (!(inb(a) && inb(b))) { out[0] = -ctx->L; out[1] = 1; out[2] = 1; return STF_OK; }
+    stf_item it = { i1, i2, ctx->L, 1, 1 }, res;
+    r = stf_collision_bfs(ctx, 1, &it, &res); if (r) return r;
+    out[0] = res.l; out[1] = res.a; out[2] = res.b;
+    return STF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ result pipeline
+// ctx->hits[0..nh) → sorted by ((i1,i2),(l,a,b)) in ctx->hits2, optional unique, exported to ctx->out32; returns count
+static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_host_format, int64_t* nout) {
+    *nout = 0;
+    CK(ctx->hits2.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, nh)));
+    if (nh == 0) return STF_OK;
+    size_t kb = sizeof(uint64_t) * (size_t)nh, vb = sizeof(uint32_t) * (size_t)nh;
+    CK(ctx->hk.ensure(kb)); CK(ctx->hk2.ensure(kb)); CK(ctx->hv.ensure(vb)); CK(ctx->hv2.ensure(vb)); CK(ctx->keep.ensure(vb + 16));
+    CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(nh)));
+    k_hit_keys<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+    int f = radix_sort_pairs(ctx->st, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh, 0, ctx->label_bits, ctx->hist.as<uint32_t>());
+    uint64_t *k0 = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), *k1 = f ? ctx->hk.as<uint64_t>() : ctx->hk2.as<uint64_t>();
+    uint32_t *v0 = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), *v1 = f ? ctx->hv.as<uint32_t>() : ctx->hv2.as<uint32_t>();
+    int f2 = radix_sort_pairs(ctx->st, k0, v0, k1, v1, nh, 32, 32 + ctx->label_bits, ctx->hist.as<uint32_t>());
+    uint64_t* ks = f2 ? k1 : k0; uint32_t* vs = f2 ? v1 : v0;
+    k_gather_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), vs, nh, ctx->hits2.as<Item16>());
+    k_fix_ties<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ks, nh, unique, ctx->keep.as<uint32_t>());
+    KCHECK();
+    if (!export_host_format && !unique) { *nout = nh; return STF_OK; }
+    // positions = exclusive scan of keep (reuse the other value buffer)
+    uint32_t* pos = (vs == ctx->hv.as<uint32_t>()) ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
+    CK(cudaMemcpyAsync(pos, ctx->keep.p, vb, cudaMemcpyDeviceToDevice, ctx->st));
+    k_scan_u32<<<1, 1024, 0, ctx->st>>>(pos, nh, reinterpret_cast<uint32_t*>(ctx->counts.as<unsigned long long>() + C_KEPT));
+    CK(ctx->out32.ensure(sizeof(int32_t) * 5 * (size_t)nh));
+    k_export_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ctx->keep.as<uint32_t>(), pos, nh, ctx->out32.as<int32_t>());
+    KCHECK();
+    int32_t r = sync_counts(ctx); if (r) return r;
+    *nout = (int64_t)(uint32_t)ctx->h_counts[C_KEPT];
+    return STF_OK;
+}
+static int32_t deliver(stf_ctx* ctx, int64_t n, stf_item* out, int64_t cap, int64_t* count) {
+    ctx->last_result = n;
+    if (count) *count = n;
+    if (n > cap) FAIL(STF_E_CAPACITY, "output buffer too small");
+    if (n > 0) {
+        if (!out) FAIL(STF_E_ARG, "null output buffer");
+        CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(stf_item) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    return STF_OK;
+}
+extern "C" int32_t stf_fetch_result(stf_ctx* ctx, stf_item* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    return deliver(ctx, ctx->last_result, out, cap, count);
+}
+extern "C" int32_t stf_fetch_items(stf_ctx* ctx, stf_item* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (!ctx->items_valid) FAIL(STF_E_STATE, "no item list available");
+    int64_t n = ctx->last_items;
+    if (count) *count = n;
+    if (n > cap) FAIL(STF_E_CAPACITY, "output buffer too small");
+    if (n == 0) return STF_OK;
+    CK(ctx->bytes_tmp.ensure(sizeof(int32_t) * 5 * (size_t)n));
+    k_export_items<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), n, ctx->bytes_tmp.as<int32_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, sizeof(stf_item) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+
+// items in ctx->items (n known on host), `nd` direct hits already in ctx->hits[0..nd): BFS, append hits; *nh = total
+static int32_t collide_and_collect(stf_ctx* ctx, int64_t n, int64_t nd, int64_t* nh) {
+    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n + nd), true, ctx->st));
+    unsigned long long base = (unsigned long long)nd;
+    CK(cudaMemcpyAsync(ctx->counts.as<unsigned long long>() + C_NHITS, &base, sizeof(base), cudaMemcpyHostToDevice, ctx->st));
+    int32_t r = narrow_phase(ctx, n); if (r) return r;
+    if (n > 0) {
+        k_compact_hits<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), nullptr, n, ctx->hits.as<Item16>(), n + nd,
+                                                         ctx->counts.as<unsigned long long>() + C_NHITS);
+        KCHECK();
+    }
+    r = sync_counts(ctx); if (r) return r;
+    *nh = (int64_t)ctx->h_counts[C_NHITS];
+    ctx->ctr.items = n; ctx->ctr.direct = nd; ctx->ctr.hits = *nh;
+    ctx->ctr.overflow = (int64_t)ctx->h_counts[C_OVERFLOW]; ctx->ctr.visited = (int64_t)ctx->h_counts[C_VISITED];
+    ctx->last_items = n; ctx->items_valid = true;
+    return STF_OK;
+}
+
+extern "C" int32_t stf_collide_items(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (count) *count = 0;
+    if (n <= 0) { ctx->last_result = 0; return STF_OK; }
+    for (int64_t i = 0; i < n; i++) if (items[i].l < 2) FAIL(STF_E_ARG, "_collision_randbfs needs a start level >= 2");
+    int32_t r = import_items(ctx, n, items, ctx->items); if (r) return r;
+    r = zero_counts(ctx); if (r) return r;
+    int64_t nh = 0, nout = 0;
+    r = collide_and_collect(ctx, n, 0, &nh); if (r) return r;
+    r = finalize_hits(ctx, nh, 0, true, &nout); if (r) return r;
+    return deliver(ctx, nout, out, cap, count);
+}
+
+extern "C" int32_t stf_totalcollisions_native(stf_ctx* ctx, int32_t nl, const int32_t* labels, stf_item* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (count) *count = 0;
+    ctx->last_result = 0;
+    if (ctx->multi_scene) FAIL(STF_E_STATE, "totalcollisions_native is defined for one scene");
+    if (!labels) nl = ctx->n;
+    if (ctx->n <= 1 || nl <= 1) return STF_OK; // length(qtrees) > 1 || return colist  :127
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
+    r = zero_counts(ctx); if (r) return r;
+    int64_t npairs = (int64_t)nl * (nl - 1) / 2;
+    CK(ctx->nat_flt.ensure(sizeof(int32_t) * (size_t)nl)); CK(ctx->nat_m.ensure(sizeof(int)));
+    CK(ctx->items.ensure(sizeof(Item16) * (size_t)npairs));
+    k_native_filter<<<1, 1024, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, nl, dl, ctx->nat_flt.as<int32_t>(), ctx->nat_m.as<int>());
+    k_native_pairs<<<nblk((int64_t)nl * nl, 256), 256, 0, ctx->st>>>(ctx->nat_flt.as<int32_t>(), ctx->nat_m.as<int>(), nl, ctx->L, ctx->items.as<Item16>(), npairs,
+                                                                    ctx->counts.as<unsigned long long>());
+    KCHECK();
+    r = sync_counts(ctx); if (r) return r;
+    int64_t n = (int64_t)ctx->h_counts[C_ITEMS], nh = 0, nout = 0;
+    r = collide_and_collect(ctx, n, 0, &nh); if (r) return r;
+    r = finalize_hits(ctx, nh, 0, true, &nout); if (r) return r;
+    return deliver(ctx, nout, out, cap, count);
+}
+
+// ------------------------------------------------------------------------------------------------ broad phase
+// locate + sort; on return *keys/*vals point at nrec sorted records (INVALID keys last)
+static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int linked, int64_t* nrec_out, uint64_t** keys, uint32_t** vals) {
+    if (!ctx->sizelevel_ok) FAIL(STF_E_STATE, "locate!: an object is larger than the canvas (sizelevel == -1)");
+    int64_t nrec = 4ll * (linked ? ctx->n : nl);
+    *nrec_out = nrec;
+    size_t kb = sizeof(uint64_t) * (size_t)std::max<int64_t>(4, nrec), vb = sizeof(uint32_t) * (size_t)std::max<int64_t>(4, nrec);
+    CK(ctx->rk.ensure(kb)); CK(ctx->rk2.ensure(kb)); CK(ctx->rv.ensure(vb)); CK(ctx->rv2.ensure(vb));
+    CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
+    if (linked) {
+        if (nl > 0) k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
+                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>());
+        CK(cudaMemcpyAsync(ctx->rk.p, ctx->lkk.p, sizeof(uint64_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->rv.p, ctx->lkv.p, sizeof(uint32_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
+    } else if (nl > 0) {
+        k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
+                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->errflag.as<int>());
+    }
+    KCHECK();
+    int bits = 2 * STF_CELL_W + 5 + ctx->scene_bits;
+    int f = radix_sort_pairs(ctx->st, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nrec, 0, bits, ctx->hist.as<uint32_t>());
+    KCHECK();
+    *keys = f ? ctx->rk2.as<uint64_t>() : ctx->rk.as<uint64_t>();
+    *vals = f ? ctx->rv2.as<uint32_t>() : ctx->rv.as<uint32_t>();
+    ctx->ctr.records = nrec;
+    return STF_OK;
+}
+static int32_t export_cells(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, stf_cellrec* out, int64_t cap, int64_t* count) {
+    int32_t r = zero_counts(ctx); if (r) return r;
+    CK(ctx->out32.ensure(sizeof(int32_t) * 4 * (size_t)std::max<int64_t>(1, nrec)));
+    if (nrec > 0) k_export_cells<<<nblk(nrec, 256), 256, 0, ctx->st>>>(keys, vals, nrec, ctx->out32.as<int32_t>(), ctx->counts.as<unsigned long long>() + C_NVALID);
+    KCHECK();
+    r = sync_counts(ctx); if (r) return r;
+    int64_t nv = (int64_t)ctx->h_counts[C_NVALID];
+    if (count) *count = nv;
+    if (nv > cap) FAIL(STF_E_CAPACITY, "output buffer too small");
+    if (nv > 0) { CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(stf_cellrec) * (size_t)nv, cudaMemcpyDeviceToHost, ctx->st)); CK(cudaStreamSynchronize(ctx->st)); }
+    return STF_OK;
+}
+extern "C" int32_t stf_locate(stf_ctx* ctx, int32_t nl, const int32_t* labels, stf_cellrec* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (!labels) nl = ctx->n;
+    if (count) *count = 0;
+    if (nl <= 0) return STF_OK;
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
+    int64_t nrec; uint64_t* keys; uint32_t* vals;
+    r = locate_and_sort(ctx, nl, dl, 0, &nrec, &keys, &vals); if (r) return r;
+    return export_cells(ctx, nrec, keys, vals, out, cap, count);
+}
+extern "C" int32_t stf_linked_reset(stf_ctx* ctx) {
+    NEED_OBJS();
+    if (ctx->n) k_fill_invalid<<<nblk(4ll * ctx->n, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), 4ll * ctx->n);
+    KCHECK();
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* labels) {
+    NEED_OBJS();
+    if (!ctx->sizelevel_ok) FAIL(STF_E_STATE, "locate!: an object is larger than the canvas (sizelevel == -1)");
+    if (!labels) nl = ctx->n;
+    if (nl <= 0) return STF_OK;
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
+    k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
+                                                ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>());
+    KCHECK();
+    return sync_counts(ctx);
+}
+extern "C" int32_t stf_linked_clear(stf_ctx* ctx, int32_t nl, const int32_t* labels) {
+    NEED_OBJS();
+    if (nl <= 0 || !labels) return STF_OK;
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
+    k_clear_slots<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), nl, dl);
+    KCHECK();
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_linked_collect(stf_ctx* ctx, stf_cellrec* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (count) *count = 0;
+    if (ctx->n == 0) return STF_OK;
+    int64_t nrec; uint64_t* keys; uint32_t* vals;
+    int32_t r = locate_and_sort(ctx, 0, nullptr, 1, &nrec, &keys, &vals); if (r) return r;
+    return export_cells(ctx, nrec, keys, vals, out, cap, count);
+}
+
+// broad phase + narrow phase; leaves the raw hit list in ctx->hits, *nh hits
+static int32_t spacial_core(stf_ctx* ctx, int32_t nl, const int32_t* labels, int linked, int64_t* nh) {
+    *nh = 0;
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
+    const int32_t* moved_pos = nullptr;
+    if (linked) { // moved_pos[o] = position of o+1 in `labels`, -1 otherwise
+        std::vector<int32_t> mp((size_t)ctx->n, -1);
+        for (int i = 0; i < nl; i++) mp[(size_t)(labels ? labels[i] - 1 : i)] = i;
+        CK(cudaMemcpyAsync(ctx->moved_pos.p, mp.data(), sizeof(int32_t) * (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        moved_pos = ctx->moved_pos.as<int32_t>();
+    }
+    int64_t nrec; uint64_t* keys; uint32_t* vals;
+    r = locate_and_sort(ctx, nl, dl, linked, &nrec, &keys, &vals); if (r) return r;
+    int64_t n_items = 0, n_direct = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        r = zero_counts(ctx); if (r) return r;
+        if (ctx->items.cap < sizeof(Item16) * 1024) CK(ctx->items.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, 32 * nrec)));
+        if (ctx->direct.cap < sizeof(Item16) * 1024) CK(ctx->direct.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, nrec)));
+        EmitOut eo; eo.items = ctx->items.as<Item16>(); eo.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
+        eo.direct = ctx->direct.as<Item16>(); eo.direct_cap = (int64_t)(ctx->direct.cap / sizeof(Item16)); eo.counts = ctx->counts.as<unsigned long long>();
+        int64_t threads = nrec * (ctx->L - 1);
+        if (threads > 0) k_emit_items<<<nblk(threads, 256), 256, 0, ctx->st>>>(keys, vals, nrec, ctx->L, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), moved_pos, eo);
+        KCHECK();
+        r = sync_counts(ctx); if (r) return r;
+        n_items = (int64_t)ctx->h_counts[C_ITEMS]; n_direct = (int64_t)ctx->h_counts[C_DIRECT];
+        if (n_items <= eo.item_cap && n_direct <= eo.direct_cap) break;
+        if (attempt == 2) FAIL(STF_E_CUDA, "internal: item buffer did not converge");
+        CK(ctx->items.ensure(sizeof(Item16) * (size_t)(n_items + n_items / 4 + 1024)));
+        CK(ctx->direct.ensure(sizeof(Item16) * (size_t)(n_direct + n_direct / 4 + 1024)));
+    }
+    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n_items + n_direct)));
+    if (n_direct) CK(cudaMemcpyAsync(ctx->hits.p, ctx->direct.p, sizeof(Item16) * (size_t)n_direct, cudaMemcpyDeviceToDevice, ctx->st));
+    r = zero_counts(ctx); if (r) return r;
+    return collide_and_collect(ctx, n_items, n_direct, nh);
+}
+
+extern "C" int32_t stf_totalcollisions_spacial(stf_ctx* ctx, int32_t nl, const int32_t* labels, int32_t unique, stf_item* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (count) *count = 0;
+    ctx->last_result = 0;
+    if (!labels) nl = ctx->n;
+    if (ctx->n <= 1 || nl <= 0) return STF_OK; // length(qtrees) > 1 || return colist  :227
+    int64_t nh = 0, nout = 0;
+    int32_t r = spacial_core(ctx, nl, labels, 0, &nh); if (r) return r;
+    r = finalize_hits(ctx, nh, unique, true, &nout); if (r) return r;
+    return deliver(ctx, nout, out, cap, count);
+}
+extern "C" int32_t stf_partialcollisions(stf_ctx* ctx, int32_t nl, const int32_t* labels, int32_t unique, stf_item* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (count) *count = 0;
+    ctx->last_result = 0;
+    if (!labels) nl = ctx->n;
+    if (ctx->n == 0) return STF_OK;
+    int64_t nh = 0, nout = 0;
+    int32_t r = spacial_core(ctx, nl, labels, 1, &nh); if (r) return r;
+    r = finalize_hits(ctx, nh, unique, true, &nout); if (r) return r;
+    return deliver(ctx, nout, out, cap, count);
+}
+
+// ------------------------------------------------------------------------------------------------ fit step
+extern "C" int32_t stf_set_optimiser(stf_ctx* ctx, int32_t kind, double eta, double rho) {
+    if (!ctx || kind < 0 || kind > 2) return STF_E_ARG;
+    ctx->opt.kind = kind; ctx->opt.eta = eta; ctx->opt.rho = rho;
+    return STF_OK;
+}
+extern "C" int32_t stf_reset_velocity(stf_ctx* ctx, int32_t n, const int32_t* labels) {
+    NEED_OBJS();
+    if (!labels) { if (ctx->n) CK(cudaMemsetAsync(ctx->has_vel.p, 0, (size_t)ctx->n, ctx->st)); }
+    else for (int i = 0; i < n; i++) { CHECK_LABEL(labels[i]); CK(cudaMemsetAsync(ctx->has_vel.as<uint8_t>() + (labels[i] - 1), 0, 1, ctx->st)); }
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_get_velocity(stf_ctx* ctx, int32_t n, const int32_t* labels, double* v, uint8_t* has) {
+    NEED_OBJS();
+    std::vector<double> hv(2 * (size_t)std::max(1, ctx->n)); std::vector<uint8_t> hh((size_t)std::max(1, ctx->n));
+    if (ctx->n) {
+        CK(cudaMemcpyAsync(hv.data(), ctx->vel.p, sizeof(double) * 2 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(hh.data(), ctx->has_vel.p, (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int i = 0; i < n; i++) {
+        int lb = labels ? labels[i] : i + 1; CHECK_LABEL(lb);
+        has[i] = hh[lb - 1]; v[2 * i] = has[i] ? hv[2 * (size_t)(lb - 1)] : 0.0; v[2 * i + 1] = has[i] ? hv[2 * (size_t)(lb - 1) + 1] : 0.0;
+    }
+    return STF_OK;
+}
+// batchsteps! over hits[0..n) (device, list order)
+static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, uint64_t seed, uint64_t iter) {
+    if (n == 0) { ctx->ctr.moved = 0; return STF_OK; }
+    int64_t m = 2 * n;
+    CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)m)); CK(ctx->hk2.ensure(sizeof(uint64_t) * (size_t)m));
+    CK(ctx->hv.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->hv2.ensure(sizeof(uint32_t) * (size_t)m));
+    CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(m)));
+    CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)n));
+    k_step_endpoints<<<nblk(m, 256), 256, 0, ctx->st>>>(hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+    int f = radix_sort_pairs(ctx->st, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
+    k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), m, ctx->prev.as<uint32_t>());
+    CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
+    CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
+    CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_KEPT, 0, sizeof(unsigned long long), ctx->st)); // ticket lives in C_KEPT during the launch
+    StepArgs A;
+    A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.om = ctx->om.as<ObjMeta>(); A.L = ctx->L;
+    A.hits = hits; A.n = n; A.prev = ctx->prev.as<uint32_t>(); A.done = ctx->done.as<uint32_t>();
+    A.ticket = ctx->counts.as<unsigned long long>() + C_KEPT;
+    A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>();
+    A.opt = ctx->opt; A.seed = seed; A.iter = iter; A.counts = ctx->counts.as<unsigned long long>();
+    int blocks = (int)std::min<int64_t>((n + 3) / 4, 148 * 8);
+    k_batchsteps<<<blocks, 128, 0, ctx->st>>>(A);
+    KCHECK();
+    int32_t r = sync_counts(ctx); if (r) return r;
+    ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES];
+    return STF_OK;
+}
+extern "C" int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colist, uint64_t seed, uint64_t iteration) {
+    NEED_OBJS();
+    if (n <= 0) return STF_OK;
+    for (int64_t i = 0; i < n; i++) if (colist[i].l < 1) FAIL(STF_E_ARG, "collision point level must be >= 1");
+    int32_t r = import_items(ctx, n, colist, ctx->hits2); if (r) return r;
+    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), n, seed, iteration);
+}
+extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits) {
+    NEED_OBJS();
+    if (nhits) *nhits = 0;
+    if (!labels) nl = ctx->n;
+    if (ctx->n <= 1 || nl <= 0) return STF_OK;
+    int64_t nh = 0, nout = 0;
+    int32_t r = spacial_core(ctx, nl, labels, mode == 1, &nh); if (r) return r;
+    r = finalize_hits(ctx, nh, 0, false, &nout); if (r) return r; // canonical list order = sorted, stays on the device
+    if (nhits) *nhits = nh;
+    ctx->last_result = 0;
+    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
+}
+extern "C" int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out) {
+    if (!ctx || !out) return STF_E_ARG;
+    *out = ctx->ctr;
+    return STF_OK;
+}

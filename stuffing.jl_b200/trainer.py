@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference's Trainer module over the C ABI (/root/reference/src/fit.jl,
+fit_helper.jl).  grad2d, step!/move!, the optimiser update and the rebuild run on the GPU
+(stf_batchsteps / stf_fit_round); the trainers keep the reference's host control flow.
+
+Canonical mode replaces Julia's task-local RNG by the counter-based draws of
+include/stuffing_b200_rng.h, keyed (seed, iteration, k); `iteration` advances once per batchsteps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import i32, ptr
+from .qtrees import DeviceQTrees, DeviceTree, _dev, items_to_array, items_to_list, totalcollisions, DynamicColliders
+
+
+class Momentum:
+    """Momentum(η=1/4, ρ=0.5)  fit_helper.jl:13-27; the velocity lives on the device, per object"""
+    kind = 2
+
+    def __init__(self, eta=0.25, rho=0.5):
+        self.eta, self.rho = float(eta), float(rho)
+
+
+class SGD:
+    """SGD(η=1/4)  fit_helper.jl:29-38"""
+    kind = 1
+
+    def __init__(self, eta=0.25):
+        self.eta, self.rho = float(eta), 0.0
+
+
+class DefaultStep:
+    """(t, Δ) -> Δ ./ 6, the default optimiser argument of step!/batchsteps!  fit.jl:25,69"""
+    kind = 0
+    eta, rho = float("nan"), 0.0
+
+
+def eta(o):
+    return o.eta
+
+
+def set_eta(o, e):  # eta!(o, e)
+    o.eta = float(e)
+
+
+def reset(o, qts, labels):  # reset!.(optimiser, ts[repositioned])
+    d = _dev(qts)
+    lb = i32(list(labels))
+    d._ck(d.lib.stf_reset_velocity(d.h, len(lb), ptr(lb)))
+
+
+def grad2d(t: DeviceTree, l, a, b):
+    """grad2d(t, l, a, b) → (gh, gw)  fit_helper.jl:51-66"""
+    d = t.owner
+    out = np.zeros(2, np.int32)
+    d._ck(d.lib.stf_grad2d(d.h, 1, ptr(i32([t.label])), ptr(i32([l])), ptr(i32([a])), ptr(i32([b])), ptr(out)))
+    return int(out[0]), int(out[1])
+
+
+def intlog2(x: float) -> int:
+    """intlog2(x::Float64) = exponent bits - 1023  fit_helper.jl:74-78"""
+    return int((np.float64(x).view(np.int64) >> 52) - 1023)
+
+
+class StepClock:
+    """(seed, iteration) of the canonical-mode draws; one tick per batchsteps! call"""
+
+    def __init__(self, seed=0):
+        self.seed, self.iteration = int(seed), 0
+
+
+_default_clock = StepClock(0)
+
+
+def _set_opt(d: DeviceQTrees, optimiser):
+    optimiser = optimiser or DefaultStep()
+    d._ck(d.lib.stf_set_optimiser(d.h, optimiser.kind, optimiser.eta if optimiser.kind else 0.0, optimiser.rho))
+
+
+def batchsteps(qts, colist, optimiser=None, clock: StepClock | None = None):
+    """batchsteps!(qtrees, colist, optimiser)  fit.jl:69-75 (list order instead of shuffle!)"""
+    d = _dev(qts)
+    clock = clock or _default_clock
+    arr = items_to_array(colist)
+    _set_opt(d, optimiser)
+    d._ck(d.lib.stf_batchsteps(d.h, len(arr), ptr(arr), clock.seed, clock.iteration))
+    clock.iteration += 1
+
+
+def fit_round(qts, labels=None, optimiser=None, clock: StepClock | None = None, partial=False):
+    """one device-resident round: totalcollisions(qtrees[, labels]; unique=false) → batchsteps!; returns length(colist)"""
+    d = _dev(qts)
+    clock = clock or _default_clock
+    _set_opt(d, optimiser)
+    lb = None if labels is None else i32(list(labels))
+    nh = C.c_int64(0)
+    d._ck(d.lib.stf_fit_round(d.h, 1 if partial else 0, 0 if lb is None else len(lb), ptr(lb), clock.seed, clock.iteration, C.byref(nh)))
+    clock.iteration += 1
+    return nh.value
+
+
+def _labels_of(colist):
+    seen, out = set(), []
+    for r in colist:
+        for x in (int(r["i1"]), int(r["i2"])):
+            if x not in seen:
+                seen.add(x)
+                out.append(x)
+    return out
+
+
+def trainepoch_E(qts, optimiser=None, clock=None, **_kw):
+    """element-wise trainer  fit.jl:85-99"""
+    d = _dev(qts)
+    colist = totalcollisions(d, unique=False, raw=True)
+    nc = len(colist)
+    if nc == 0:
+        return nc
+    batchsteps(d, colist, optimiser, clock)
+    inds = _labels_of(colist)
+    for ni in range(1, len(d) // len(inds) + 1):
+        colist = totalcollisions(d, inds, unique=False, raw=True)
+        batchsteps(d, colist, optimiser, clock)
+        if ni > 8 * len(colist):
+            break
+    return nc
+
+
+class LRU:
+    """LRU{Int} over labels  fit_helper.jl:80-102: most recently pushed first"""
+
+    def __init__(self):
+        self.order = {}
+        self.tick = 0
+
+    def push(self, v):
+        self.tick += 1
+        self.order[v] = self.tick
+
+    def collect(self, firstn=None):
+        r = sorted(self.order, key=lambda k: -self.order[k])
+        return r if firstn is None else r[:firstn]
+
+
+def _em(qts, widen, optimiser, clock, memory: LRU):
+    """the shared shape of trainepoch_EM!/EM2!/EM3!  fit.jl:110-212: nested rounds on LRU-widened label sets"""
+    d = _dev(qts)
+    colist = totalcollisions(d, unique=False, raw=True)
+    nc = len(colist)
+    if nc == 0:
+        return nc
+    batchsteps(d, colist, optimiser, clock)
+
+    def level(depth, parent_len, inds_src):
+        inds = inds_src
+        if depth < len(widen):
+            for x in inds:  # push!.(memory, inds): the last pushed is the most recent
+                memory.push(x)
+            inds = memory.collect(len(inds) * widen[depth])
+        for ni in range(1, 2 * parent_len // max(1, len(inds)) + 1):
+            cl = totalcollisions(d, inds, unique=False, raw=True)
+            batchsteps(d, cl, optimiser, clock)
+            if ni > 2 * len(cl):
+                break
+            if depth + 1 <= len(widen):
+                sub = _labels_of(cl)
+                if sub:
+                    level(depth + 1, len(inds), sub)
+
+    level(0, len(d), _labels_of(colist))
+    return nc
+
+
+def trainepoch_EM(qts, optimiser=None, clock=None, memory=None, **_kw):
+    return _em(qts, [2], optimiser, clock, memory if memory is not None else LRU())
+
+
+def trainepoch_EM2(qts, optimiser=None, clock=None, memory=None, **_kw):
+    return _em(qts, [4, 2], optimiser, clock, memory if memory is not None else LRU())
+
+
+def trainepoch_EM3(qts, optimiser=None, clock=None, memory=None, **_kw):
+    return _em(qts, [8, 4, 2], optimiser, clock, memory if memory is not None else LRU())
+
+
+def trainepoch_D(qts, optimiser=None, clock=None, moved: DynamicColliders | None = None, loops=10, **_kw):
+    """dynamic trainer  fit.jl:224-233"""
+    d = _dev(qts)
+    moved = moved if moved is not None else DynamicColliders(d)
+    colist = []
+    for _ in range(loops):
+        colist = moved.dynamiccollisions(unique=False, raw=True)
+        if len(colist) == 0:
+            return 0
+        batchsteps(d, colist, optimiser, clock)
+    return len(colist)
+
+
+_DEFAULTS = {trainepoch_E: (20, 2000), trainepoch_EM: (10, 1000), trainepoch_EM2: (10, 1000), trainepoch_EM3: (10, 1000), trainepoch_D: (10, 2000)}
+
+
+def train(qts, epochs=-1, trainer=trainepoch_EM2, patience=None, optimiser=None, scheduler=lambda lr: lr * 0.5 ** 0.5,
+          callback=lambda ep: None, seed=0):
+    """train!/fit!  fit.jl:450-552 without the repositioning policy (place! is host-side and out of the
+    hot-path scope): epochs, the η scheduler on stagnation and the global early break."""
+    d = _dev(qts)
+    optimiser = optimiser if optimiser is not None else Momentum(0.25)
+    pat0, ep0 = _DEFAULTS.get(trainer, (10, 1000))
+    patience = pat0 if patience is None else patience
+    epochs = ep0 if epochs < 0 else epochs
+    clock = StepClock(seed)
+    res = {}
+    if trainer in (trainepoch_EM, trainepoch_EM2, trainepoch_EM3):
+        res["memory"] = LRU()
+    if trainer is trainepoch_D:
+        res["moved"] = DynamicColliders(d)
+    best_s, age_s, best_g, age_g = None, 0, None, 0
+    eta_list = []
+    ep = nc = 0
+    while ep < epochs:
+        nc = trainer(d, optimiser=optimiser, clock=clock, **res)
+        ep += 1
+        age_s += 1
+        age_g += 1
+        if best_s is None or nc < best_s:
+            best_s, age_s = nc, 0
+        if best_g is None or nc < best_g:
+            best_g, age_g = nc, 0
+        callback(ep)
+        if nc == 0:
+            break
+        if age_s > max(1, patience, epochs / 50):
+            if not eta_list or best_s < eta_list[-1][1]:
+                eta_list.append((optimiser.eta, best_s))
+                set_eta(optimiser, scheduler(optimiser.eta))
+            else:
+                last_eta, _ = eta_list.pop()
+                set_eta(optimiser, last_eta)
+            best_s, age_s = None, 0
+        if age_g > max(2, 2 * patience, epochs / 50 * max(1, len(d) / max(1, best_g))):
+            break
+    return ep, nc
+
+
+fit = train

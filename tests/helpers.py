@@ -1,0 +1,59 @@
+"""Shared helpers of the parity tests: build the same scene for the CPU oracle and for the device."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import _pkg  # noqa: E402
+import workloads  # noqa: E402
+
+
+def product():
+    return _pkg.load()
+
+
+def oracle():
+    from oracle import oracle as orc
+    orc.build()
+    return orc
+
+
+def device_from_oracle(S, qts_orc, **kw):
+    """a DeviceQTrees with the same level-1 payloads, defaults and level-1 shifts as the oracle trees.
+    Only valid while every oracle tree is in its freshly built state (shift chain from level 1)."""
+    hts = []
+    for t in qts_orc:
+        kh, kw_, rs, cs, canvas = t.info(1)
+        hts.append(S.HostTree(t.level(1), canvas, t.default, (rs, cs)))
+    return S.DeviceQTrees(hts, **kw)
+
+
+def assert_same_trees(d, qts_orc, labels=None):
+    """every level of every tree: same kernel size, same shift, same node codes"""
+    labels = range(1, len(qts_orc) + 1) if labels is None else labels
+    for lb in labels:
+        to, td = qts_orc[lb - 1], d[lb - 1]
+        assert len(to) == len(td)
+        for l in range(1, len(to) + 1):
+            io, idv = to.info(l), td.info(l)
+            assert io == idv, (lb, l, io, idv)
+            lo, ld = to.level(l), td.level(l)
+            assert np.array_equal(lo, ld), (lb, l)
+
+
+def rect_scene(orc, n, seed, sz=100, masksize=(1000, 1000), place=True):
+    """randqtrees(n; sz, masksize) of src/utils.jl:35-39 on the oracle"""
+    rng = np.random.default_rng(seed)
+    objs = workloads.rect_objects(n, sz, rng)
+    qts = orc.qtrees(objs, mask=np.ones(masksize, bool))
+    if place:
+        orc.place(qts, seed)
+    return qts
+
+
+def pairset(cl):
+    return {frozenset(p) for p, _ in cl}

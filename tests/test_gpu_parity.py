@@ -1,0 +1,407 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs — bit-exact for node codes, shifts, cells, items, hits and (l,a,b); velocities within 1e-12
+relative (they are FP64 on both sides and in practice identical).  Run with `-m gpu` on a B200."""
+import numpy as np
+import pytest
+
+from helpers import assert_same_trees, device_from_oracle, oracle, pairset, product, rect_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    return product()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return oracle()
+
+
+def box(n, r0, r1, c0, c1):
+    o = np.zeros((n, n))
+    o[r0 - 1:r1, c0 - 1:c1] = 1
+    return o
+
+
+# ---------------------------------------------------------------------------------------------- (1) build / rebuild
+def test_build_parity_random_masks(S, orc):
+    rng = np.random.default_rng(100)
+    shapes = [(0, 0), (1, 1), (1, 2), (2, 1), (3, 4), (5, 6), (15, 16), (16, 17), (17, 15), (31, 33), (32, 32), (33, 65),
+              (64, 1), (1, 64), (100, 100), (127, 129), (200, 77), (255, 257), (300, 300)]
+    qo = []
+    for k, (h, w) in enumerate(shapes):
+        vals = [(1, 2), (1, 1, 2), (1, 2, 3), (2,)][k % 4]
+        pic = rng.choice(np.array(vals, np.uint8), size=(h, w)).astype(np.uint8)
+        t = orc.OTree(pic, 512, orc.FULL if k % 5 == 0 else orc.EMPTY)
+        t.level_setshift(1, int(rng.integers(-700, 700)), int(rng.integers(-700, 700)))
+        qo.append(t.build())
+    d = device_from_oracle(S, qo, is_mask=np.zeros(len(qo), np.uint8))
+    assert_same_trees(d, qo)
+
+
+def test_build_parity_big_object(S, orc):
+    # a mask-sized object goes through the wide per-level kernels
+    i, j = np.mgrid[1:1501, 1:1301]
+    inside = ((i - 750) ** 2 / 750 ** 2 + (j - 650) ** 2 / 650 ** 2 < 1)
+    qo = [orc.maskqtree(inside), orc.qtree(np.ones((40, 30), bool), 2048)]
+    qo[1].setshift(1, 77, -13)
+    d = device_from_oracle(S, qo)
+    assert_same_trees(d, qo)
+    # move the big object by odd and negative amounts at several levels
+    for (l, s1, s2, mode) in [(1, -3, 5, "shift"), (3, 1, -1, "shift"), (1, -1001, 999, "set"), (5, 2, 3, "set")]:
+        if mode == "shift":
+            qo[0].shift(l, s1, s2); d[0].shift(l, s1, s2)
+        else:
+            qo[0].setshift(l, s1, s2); d[0].setshift(l, s1, s2)
+        assert_same_trees(d, qo)
+
+
+def test_shift_family_parity(S, orc):
+    rng = np.random.default_rng(101)
+    qo = []
+    for k in range(12):
+        h, w = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        pic = rng.choice(np.array([1, 1, 2], np.uint8), size=(h, w)).astype(np.uint8)
+        qo.append(orc.OTree(pic, 256, orc.EMPTY).build())
+    d = device_from_oracle(S, qo, is_mask=np.zeros(len(qo), np.uint8))
+    L = len(qo[0])
+    for step in range(40):
+        lb = int(rng.integers(1, len(qo) + 1))
+        l = int(rng.integers(1, L + 1))
+        s1, s2 = int(rng.integers(-5, 6)), int(rng.integers(-5, 6))
+        if rng.random() < 0.5:
+            qo[lb - 1].shift(l, s1, s2); d[lb - 1].shift(l, s1, s2)
+        else:
+            qo[lb - 1].setshift(l, s1 * 7, s2 * 7); d[lb - 1].setshift(l, s1 * 7, s2 * 7)
+    assert_same_trees(d, qo)
+    # test/test_qtrees.jl:16-19
+    qo[0].shift(3, 2, 5); d[0].shift(3, 2, 5)
+    qo[1].setshift(4, 1, 2); d[1].setshift(4, 1, 2)
+    assert_same_trees(d, qo, [1, 2])
+    # safe reads anywhere, inside and outside the kernels (test/test_qtrees.jl:11-13)
+    n = 2000
+    labels = rng.integers(1, len(qo) + 1, n); ls = rng.integers(1, L + 1, n)
+    a = rng.integers(-40, 300, n); b = rng.integers(-40, 300, n)
+    got = d.read_nodes(labels, ls, a, b)
+    want = [qo[labels[i] - 1].get(int(ls[i]), int(a[i]), int(b[i])) for i in range(n)]
+    assert list(got) == want
+    assert d[0].get(1, -10, -15) == S.EMPTY
+    with pytest.raises(IndexError):
+        d[0].set(1, -1000, -1500, S.EMPTY)
+
+
+# ---------------------------------------------------------------------------------------------- reference known answers
+def test_reference_known_answers(S):
+    # test/runtests.jl:36-46
+    qts = S.qtrees([box(100, 30, 50, 30, 50), box(100, 40, 80, 40, 80), box(100, 79, 90, 79, 90)], background=0.0)
+    assert len(S.totalcollisions(qts)) == 2
+    assert S.totalcollisions_spacial(qts) == [((1, 2), (5, 4, 4)), ((3, 2), (5, 5, 5))]
+    assert S.locate(qts).tree() == {(7, 1, 1): [1], (8, 1, 1): [2], (6, 3, 3): [3]}
+    qts[0].setshift((-1000, -1000))
+    assert S.collision(qts[0], qts[1]) == (-8, 1, 1)
+    # examples/collision.jl:2-20
+    q = S.qtrees([box(100, 35, 50, 30, 55), box(100, 45, 80, 50, 80), box(100, 60, 90, 67, 90)], background=0.0)
+    assert S.collision(q[0], q[1]) == (3, 13, 14)
+    assert S.collision(q[0], q[2]) == (-8, 1, 1)
+    assert S.collision_dfs(q[0], q[2]) == (-7, 1, 1)
+    assert S.collision(q[1], q[2]) == (5, 5, 5)
+
+
+def test_reference_edge_cases(S):
+    # test/test_qtrees.jl:116-169
+    assert S.totalcollisions_spacial([]) == []
+    assert S.totalcollisions_native([]) == []
+    qt1 = S.qtree(np.array([[1]]))
+    assert S.totalcollisions_spacial([qt1]) == []
+    assert S.totalcollisions_native([qt1]) == []
+    assert S.partialcollisions([qt1]) == []
+    for mk in (lambda: S.qtree(np.zeros((0, 0), np.int64), background=0), lambda: S.qtree(np.array([[1]]))):
+        qt1, qt2 = mk(), mk()
+        assert len(qt1) >= 2
+        assert S.collision_dfs(qt1, qt2)[0] < 0
+        assert S.collision(qt1, qt2)[0] < 0
+        assert S.totalcollisions_native([qt1, qt2]) == []
+        assert S.totalcollisions_spacial([qt1, qt2]) == []
+        assert S.partialcollisions([qt1, qt2]) == []
+    qt1 = S.qtree(np.array([[1]]), background=0)
+    qt2 = S.qtree(np.array([[1]]), background=0)
+    assert S.collision_dfs(qt1, qt2) == (1, 1, 1)
+    assert S.collision(qt1, qt2) == (1, 1, 1)
+    assert [c for _, c in S.totalcollisions_native([qt1, qt2])] == [(1, 1, 1)]
+    assert [c for _, c in S.totalcollisions_spacial([qt1, qt2])] == [(1, 1, 1)]
+    assert [c for _, c in S.partialcollisions([qt1, qt2])] == [(1, 1, 1)]
+    d = S.DeviceQTrees([qt1, qt2])
+    spt = S.locate(d, S.linked_spacial_qtree(d))
+    assert [c for _, c in S.partialcollisions(d, spt, [1])] == [(1, 1, 1)]
+    qt1.setshift((10, -10))
+    assert S.collision_dfs(qt1, qt2)[0] < 0
+    assert S.collision(qt1, qt2)[0] < 0
+    assert S.totalcollisions_native([qt1, qt2]) == []
+    assert S.totalcollisions_spacial([qt1, qt2]) == []
+    assert S.partialcollisions([qt1, qt2]) == []
+    t = [S.qtree(np.full((5, 6), c, np.uint8)) for c in (3, 3, 2, 1)]
+    assert S.collision(t[0], t[1]) == (-2, 1, 1)
+    assert S.collision(t[0], t[2]) == (3, 1, 1)
+    assert S.collision(t[0], t[3]) == (-4, 1, 1)
+    assert S.collision_dfs(t[0], t[1]) == (-1, 1, 1)
+    assert S.collision_dfs(t[0], t[2]) == (1, 5, 6)
+    assert S.collision_dfs(t[0], t[3]) == (-4, 1, 1)
+    assert S.totalcollisions_spacial([t[0], t[1]]) == []
+    with pytest.raises(S._lib.StuffingError):
+        S.DeviceQTrees([S.HostTree(np.zeros((2, 2), np.uint8), 4)])  # code 0 is not a node code
+
+
+def test_mask_default_full_branch(S, orc):
+    # test/test_fit.jl:27-51
+    i, j = np.mgrid[1:501, 1:801]
+    inside = ((i - 250) ** 2 / 250 ** 2 + (j - 400) ** 2 / 400 ** 2 < 1)
+    qo = orc.qtrees([np.ones((51, 40), bool)], mask=np.where(inside, 1, 0), maskbackground=0)
+    qo[1].setshift(1, 1000, 1000)
+    d = device_from_oracle(S, qo)
+    want = orc.totalcollisions_spacial(qo)
+    got = S.totalcollisions_spacial(d)
+    assert got == want and len(got) > 0
+    assert d.counters()["direct"] > 0
+
+
+# ---------------------------------------------------------------------------------------------- (2)+(3) collisions
+@pytest.fixture(scope="module")
+def scene200(S, orc):
+    qo = rect_scene(orc, 200, 21)
+    return qo, device_from_oracle(S, qo)
+
+
+def test_locate_parity(S, orc, scene200):
+    qo, d = scene200
+    assert S.locate(d).tree() == orc.locate_hash(qo)
+    labels = [5, 3, 9, 150, 1, 77]
+    assert S.locate(d, labels).tree() == orc.locate_hash(qo, labels)
+    lt_o = orc.LinkedTree(qo).locate(qo)
+    lt_d = S.locate(d, S.linked_spacial_qtree(d))
+    assert {k: set(v) for k, v in lt_d.collect_tree().items()} == {k: set(v) for k, v in lt_o.collect().items()}
+    lt_d.clear(1); lt_o.clear(1)
+    assert {k: set(v) for k, v in lt_d.collect_tree().items()} == {k: set(v) for k, v in lt_o.collect().items()}
+
+
+def test_bfs_every_item(S, orc, scene200):
+    qo, d = scene200
+    _, det = orc.totalcollisions_spacial(qo, details=True)
+    items = det["items"]
+    assert len(items) > 500
+    got = S.collision_bfs_items(d, items)
+    for k, ((i1, i2), at) in enumerate(items):
+        want = orc.collision_bfs(qo[i1 - 1], qo[i2 - 1], at)
+        assert (int(got[k]["l"]), int(got[k]["a"]), int(got[k]["b"])) == want, (k, (i1, i2), at)
+    # collision_dfs on the same pairs from the root
+    pairs = sorted({(i1, i2) for (i1, i2), _ in items})[:300]
+    for (i1, i2) in pairs:
+        assert S.collision_dfs(d[i1 - 1], d[i2 - 1]) == orc.collision_dfs(qo[i1 - 1], qo[i2 - 1])
+        assert S.collision(d[i1 - 1], d[i2 - 1]) == orc.collision(qo[i1 - 1], qo[i2 - 1])
+
+
+def test_spacial_native_partial_parity(S, orc, scene200):
+    qo, d = scene200
+    for unique in (True, False):
+        want, det = orc.totalcollisions_spacial(qo, unique=unique, details=True)
+        got = S.totalcollisions_spacial(d, unique=unique)
+        assert got == sorted(want)
+        c = d.counters()
+        assert c["items"] == len(det["items"]) and c["direct"] == det["n_direct"]
+        assert sorted(S.items_to_list(d.fetch_items())) == sorted(det["items"])
+    labels = [1, 3, 6, 99, 100, 150, 42]
+    assert S.totalcollisions_spacial(d, labels) == sorted(orc.totalcollisions_spacial(qo, labels))
+    assert S.totalcollisions_native(d) == sorted(orc.totalcollisions_native(qo))
+    assert S.totalcollisions_native(d, labels) == sorted(orc.totalcollisions_native(qo, labels))
+    # test/test_qtrees.jl:55-69
+    cls, cln = S.totalcollisions_spacial(d), S.totalcollisions_native(d)
+    spt = S.locate(d, S.linked_spacial_qtree(d))
+    clp = S.partialcollisions(d, spt, range(1, len(d) + 1))
+    assert pairset(cls) == pairset(cln) == pairset(clp) and len(cln) > 0
+    # partial against the oracle's linked tree, item by item
+    lo = orc.LinkedTree(qo).locate(qo)
+    for lbs in ([1, 3, 6, 99], [200, 5, 17, 18, 19, 1], list(range(1, 201))):
+        want, det = orc.partialcollisions(qo, lo, lbs, details=True)
+        got = S.partialcollisions(d, spt, lbs)
+        assert got == sorted(want)
+        assert sorted(S.items_to_list(d.fetch_items())) == sorted(det["items"])
+    c2 = {frozenset(p) for p, _ in S.totalcollisions(d) if set(p) & {1, 3, 6, 99}}
+    assert c2 == pairset(S.partialcollisions(d, spt, [1, 3, 6, 99]))
+
+
+def test_large_frontier_path(S, orc):
+    # dense noise: frontiers of thousands of MIX∧MIX nodes → the CTA-per-item path
+    rng = np.random.default_rng(7)
+    pics = [rng.choice(np.array([0, 0, 1]), size=(300, 280)), rng.choice(np.array([0, 0, 0, 1]), size=(290, 300)),
+            rng.choice(np.array([0, 1]), size=(64, 64)), np.ones((300, 300), np.int64)]
+    qo = orc.qtrees(pics, size=512, background=0)
+    qo[1].setshift(1, 13, 7); qo[2].setshift(1, 100, 120); qo[3].setshift(1, 30, 30)
+    d = device_from_oracle(S, qo, is_mask=np.zeros(4, np.uint8))
+    # thin diagonal lines never produce a FULL code above level 1: the BFS must carry wide frontiers
+    n = 400
+    diag1 = np.zeros((n, n), np.int64); diag2 = np.zeros((n, n), np.int64)
+    idx = np.arange(n)
+    diag1[idx, idx] = 1
+    diag2[idx, n - 1 - idx] = 1; diag2[idx, idx] = 1
+    qo2 = orc.qtrees([diag1, diag2, diag1.copy()], size=512, background=0)
+    qo2[2].setshift(1, 1, 0)
+    d2 = device_from_oracle(S, qo2, is_mask=np.zeros(3, np.uint8))
+    for (dd, oo) in ((d, qo), (d2, qo2)):
+        m = len(oo)
+        items = [((i, j), (len(oo[0]), 1, 1)) for i in range(1, m + 1) for j in range(1, m + 1) if i != j]
+        got = S.collision_bfs_items(dd, items)
+        for k, ((i1, i2), at) in enumerate(items):
+            assert (int(got[k]["l"]), int(got[k]["a"]), int(got[k]["b"])) == orc.collision_bfs(oo[i1 - 1], oo[i2 - 1], at)
+    assert d2.counters()["overflow"] > 0
+
+
+def test_out_of_canvas_objects(S, orc):
+    # objects pushed far outside the canvas: negative cell coordinates, hash vs linked visibility
+    qo = rect_scene(orc, 60, 33, sz=60, masksize=(500, 500))
+    rng = np.random.default_rng(5)
+    for lb in (3, 4, 5, 6, 7, 8):
+        qo[lb - 1].setshift(1, int(rng.integers(-1500, 1500)), int(rng.integers(-1500, 1500)))
+    qo[8].setshift(1, -900, -900); qo[9].setshift(1, -905, -895)
+    d = device_from_oracle(S, qo)
+    assert_same_trees(d, qo)
+    assert S.locate(d).tree() == orc.locate_hash(qo)
+    assert S.totalcollisions_spacial(d) == sorted(orc.totalcollisions_spacial(qo))
+    assert S.totalcollisions_spacial(d, unique=False) == sorted(orc.totalcollisions_spacial(qo, unique=False))
+    lo = orc.LinkedTree(qo); ld = S.linked_spacial_qtree(d)
+    assert S.partialcollisions(d, ld) == sorted(orc.partialcollisions(qo, lo))
+
+
+# ---------------------------------------------------------------------------------------------- (4) grad2d + step
+def test_grad2d_parity(S, orc, scene200):
+    qo, d = scene200
+    hits = orc.totalcollisions_spacial(qo, unique=False)
+    assert hits
+    for (i1, i2), (l, a, b) in hits[:200]:
+        for i in (i1, i2):
+            assert S.grad2d(d[i - 1], l, a, b) == orc.grad2d(qo[i - 1], l, a, b)
+    t = S.trainer
+    x = np.random.default_rng(3).random(1000) * 1000
+    assert sum(int(np.floor(np.log2(v))) for v in x) == sum(t.intlog2(v) for v in x)  # test/test_fit.jl:2-3
+
+
+@pytest.mark.parametrize("kind", ["momentum", "sgd", "default"])
+def test_batchsteps_parity(S, orc, kind):
+    """fixed iteration count, same hit lists, same draws: shifts, every level and velocities must agree"""
+    qo = rect_scene(orc, 150, 40, sz=80, masksize=(600, 600))
+    d = device_from_oracle(S, qo)
+    n = len(qo)
+    oo = orc.Opt(kind, 0.25, 0.5, n)
+    od = {"momentum": S.Momentum(0.25, 0.5), "sgd": S.SGD(0.25), "default": None}[kind]
+    clock = S.trainer.StepClock(seed=9)
+    for it in range(12):
+        hits = orc.totalcollisions(qo, unique=False)
+        hits_d = S.totalcollisions(d, unique=False)
+        assert hits_d == sorted(hits)
+        if not hits:
+            break
+        orc.batchsteps(qo, hits_d, oo, seed=9, iteration=it)
+        S.batchsteps(d, hits_d, od, clock)
+        rs, cs = d.getshifts()
+        assert [tuple(x) for x in zip(rs, cs)] == [t.getshift() for t in qo]
+    assert_same_trees(d, qo)
+    if kind == "momentum":
+        v = np.zeros(2 * n); has = np.zeros(n, np.uint8)
+        d._ck(d.lib.stf_get_velocity(d.h, n, None, v.ctypes.data, has.ctypes.data))
+        for lb in range(1, n + 1):
+            (vo, ho) = oo.velocity(lb)
+            assert bool(has[lb - 1]) == ho
+            if ho:
+                assert np.allclose(v[2 * lb - 2:2 * lb], vo, rtol=1e-12, atol=0)
+
+
+def test_fit_round_matches_host_loop(S, orc):
+    """stf_fit_round (device-resident collide → step) == totalcollisions + batchsteps on the oracle"""
+    qo = rect_scene(orc, 120, 41, sz=70, masksize=(500, 500))
+    d = device_from_oracle(S, qo)
+    oo = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    clock = S.trainer.StepClock(seed=4)
+    for it in range(10):
+        hits = sorted(orc.totalcollisions_spacial(qo, unique=False))
+        nh = S.fit_round(d, optimiser=S.Momentum(0.25, 0.5), clock=clock)
+        assert nh == len(hits)
+        orc.batchsteps(qo, hits, oo, seed=4, iteration=it)
+        rs, cs = d.getshifts()
+        assert [tuple(x) for x in zip(rs, cs)] == [t.getshift() for t in qo]
+    assert_same_trees(d, qo)
+
+
+def test_dynamic_loops(S, orc):
+    # test/test_qtrees.jl:71-113 on the device, checked against the oracle step by step
+    qo = rect_scene(orc, 200, 14)
+    d = device_from_oracle(S, qo)
+    n = len(qo)
+    moved = list(range(1, n + 1))
+    sp = S.linked_spacial_qtree(d)
+    lo = orc.LinkedTree(qo)
+    clock = S.trainer.StepClock(seed=7)
+    for it in range(10):
+        c1 = S.partialcollisions(d, sp, moved)
+        assert c1 == sorted(orc.partialcollisions(qo, lo, moved))
+        for p, _ in c1:
+            for x in p:
+                if x not in moved:
+                    moved.append(x)
+        c2 = S.totalcollisions_native(d)
+        assert len(c1) == len(c2) and pairset(c1) == pairset(c2)
+        S.batchsteps(d, c1, None, clock)
+        orc.batchsteps(qo, c1, None, seed=7, iteration=it)
+        d[2].shift(1, 1, 1); d[6].shift(1, -1, -1)
+        qo[2].shift(1, 1, 1); qo[6].shift(1, -1, -1)
+        for x in (3, 7):
+            if x not in moved:
+                moved.append(x)
+    assert_same_trees(d, qo)
+    colliders = S.DynamicColliders(d)
+    for it in range(10):
+        c1 = colliders.dynamiccollisions()
+        c2 = S.totalcollisions_native(d)
+        c3 = S.totalcollisions(d)
+        assert len(c1) in (len(c2), len(c3))
+        assert pairset(c1) in (pairset(c2), pairset(c3))
+        S.batchsteps(d, c1, None, clock)
+        d[2].shift(1, -1, -1); d[6].shift(1, 1, 1)
+        colliders.union([3, 7])
+
+
+def test_trainers_converge(S, orc):
+    # the statistical property of test/runtests.jl:48-68 and test/test_fit.jl:53-75: trainers reach 0 collisions
+    t = S.trainer
+    for trainer in (t.trainepoch_E, t.trainepoch_EM, t.trainepoch_EM2, t.trainepoch_EM3, t.trainepoch_D):
+        qo = rect_scene(orc, 40, 15, sz=60, masksize=(500, 800))
+        d = device_from_oracle(S, qo)
+        ep, nc = S.train(d, 300, trainer=trainer, optimiser=S.Momentum(0.25), seed=2)
+        assert nc == 0, (trainer.__name__, ep, nc)
+        assert S.totalcollisions(d) == []
+
+
+# ---------------------------------------------------------------------------------------------- multi-scene batches
+def test_scene_batch_equals_single_scenes(S, orc):
+    scenes = [rect_scene(orc, 30, 50 + s, sz=50, masksize=(230, 230)) for s in range(5)]
+    flat = [t for sc in scenes for t in sc]
+    scene_id = [s for s, sc in enumerate(scenes) for _ in sc]
+    is_mask = [int(k == 0) for sc in scenes for k in range(len(sc))]
+    d = device_from_oracle(S, flat, is_mask=is_mask, scene=scene_id)
+    want, off = [], 0
+    for sc in scenes:
+        for (i1, i2), c in orc.totalcollisions_spacial(sc, unique=False):
+            want.append(((i1 + off, i2 + off), c))
+        off += len(sc)
+    assert S.totalcollisions_spacial(d, unique=False) == sorted(want)
+    clock = S.trainer.StepClock(seed=11)
+    opt = orc.Opt("momentum", 0.25, 0.5, len(flat))
+    for it in range(6):
+        hits = S.totalcollisions_spacial(d, unique=False)
+        want, off = [], 0
+        for sc in scenes:
+            want += [((i1 + off, i2 + off), c) for (i1, i2), c in orc.totalcollisions_spacial(sc, unique=False)]
+            off += len(sc)
+        assert hits == sorted(want)
+        S.batchsteps(d, hits, S.Momentum(0.25, 0.5), clock)
+        orc.batchsteps(flat, hits, opt, seed=11, iteration=it, is_mask=is_mask)
+    assert_same_trees(d, flat)
