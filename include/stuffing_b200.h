@@ -102,7 +102,9 @@ int32_t stf_read_nodes(stf_ctx* ctx, int32_t n, const int32_t* labels, const int
                        const int32_t* a, const int32_t* b, uint8_t* out);
 int32_t stf_get_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level, int32_t* rs, int32_t* cs);
 /* mode 0: setshift!(t, level, rs, cs) (qtrees.jl:277-285); mode 1: shift!(t, level, rs, cs) (:267-275).
- * Levels <= level move, levels > level are rebuilt.  labels == NULL: objects 1..n */
+ * Levels <= level move, levels > level are rebuilt.  labels == NULL: objects 1..n.
+ * mode | STF_SHIFT_DEVICE_ARRAYS: rs/cs are device pointers (inputs already resident in HBM). */
+#define STF_SHIFT_DEVICE_ARRAYS 2
 int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level,
                        const int32_t* rs, const int32_t* cs, int32_t mode);
 /* setrshift!(t[l], v) / setcshift!(t[l], v) on one PaddedMat, no rebuild  qtrees.jl:134-135 */
@@ -165,6 +167,22 @@ int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* lab
                       uint64_t seed, uint64_t iteration, int64_t* nhits);
 
 int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out);
+/* number of kernels this context has launched since stf_create (bench.py's gpu_launches) */
+int64_t stf_launch_count(const stf_ctx* ctx);
+
+/* ---- per-stage device timers (CUDA events on the context's stream; for bench.py's roofline) ---- */
+#define STF_NSTAGES 8
+#define STF_STAGE_SHIFT 0     /* stf_set_shifts: shift update + pyramid rebuild (k_apply_shifts, k_build_objects) */
+#define STF_STAGE_LOCATE 1    /* k_locate */
+#define STF_STAGE_SORT 2      /* radix sort of the (cell,label) records */
+#define STF_STAGE_EMIT 3      /* k_emit_items: candidate generation */
+#define STF_STAGE_NARROW 4    /* k_collide_small + k_collide_big: frontier BFS */
+#define STF_STAGE_RESULT 5    /* hit compaction, sort!, unique!, export */
+#define STF_STAGE_STEP_PREP 6 /* endpoint sort + predecessor links of batchsteps */
+#define STF_STAGE_STEP 7      /* k_batchsteps: grad2d + step + rebuild */
+int32_t stf_profile_enable(stf_ctx* ctx, int32_t on);
+/* accumulated milliseconds and number of timed intervals per stage since the last reset */
+int32_t stf_profile_read(stf_ctx* ctx, double* ms, int64_t* calls, int32_t reset);
 
 #ifdef __cplusplus
 }

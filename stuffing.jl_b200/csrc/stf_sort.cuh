@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* _
 
 // Sorts (keys, vals) by bits [bit_lo, bit_hi) of the key.  Buffers ping-pong; returns 0 if the result
 // is in (keys, vals), 1 if it is in (keys_alt, vals_alt).  `hist` holds >= 256*nvw uint32.
-static inline int radix_sort_pairs(cudaStream_t st, uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
+static inline int radix_sort_pairs(cudaStream_t st, int64_t* launches, uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
                                    int64_t n, int bit_lo, int bit_hi, uint32_t* hist) {
     if (n <= 1) return 0;
     SortPlan p = sort_plan(n);
@@ -110,7 +110,7 @@ static inline int radix_sort_pairs(cudaStream_t st, uint64_t* keys, uint32_t* va
         k_sort_hist<<<p.blocks, SORT_THREADS, 0, st>>>(kin, n, shift, p.per_warp, p.nvw, hist);
         k_scan_u32<<<1, 1024, 0, st>>>(hist, (int64_t)256 * p.nvw, nullptr);
         k_sort_scatter<<<p.blocks, SORT_THREADS, 0, st>>>(kin, vin, n, shift, p.per_warp, p.nvw, hist, kout, vout);
-        flip ^= 1;
+        flip ^= 1; if (launches) *launches += 3;
     }
     return flip;
 }

@@ -46,7 +46,30 @@ struct stf_ctx {
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
     int64_t big_cap = 0; int big_ctas = 1;
     stf_counters_t ctr = {};
+    int64_t launches = 0; // kernels launched by this context (bench.py gpu_launches)
+    // per-stage device timers (stf_profile_*): pairs of events recorded on ctx->st
+    bool prof = false;
+    struct ProfRec { int stage; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending; std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[STF_NSTAGES] = {}; int64_t prof_calls[STF_NSTAGES] = {};
+    int prof_open = -1; cudaEvent_t prof_open_ev = nullptr;
 };
+static void stage_end(stf_ctx* ctx) {
+    if (!ctx->prof || ctx->prof_open < 0) return;
+    cudaEvent_t b;
+    if (ctx->prof_pool.empty()) cudaEventCreate(&b); else { b = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    cudaEventRecord(b, ctx->st);
+    ctx->prof_pending.push_back({ ctx->prof_open, ctx->prof_open_ev, b });
+    ctx->prof_open = -1;
+}
+static void stage_begin(stf_ctx* ctx, int stage) {
+    if (!ctx->prof) return;
+    stage_end(ctx);
+    cudaEvent_t a;
+    if (ctx->prof_pool.empty()) cudaEventCreate(&a); else { a = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    cudaEventRecord(a, ctx->st);
+    ctx->prof_open = stage; ctx->prof_open_ev = a;
+}
 
 #define CK(call)                                                                                         \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return STF_E_CUDA; } } while (0)
@@ -115,16 +138,16 @@ extern "C" int32_t stf_num_levels(const stf_ctx* ctx) { return ctx ? ctx->L : 0;
 // ------------------------------------------------------------------------------------------------ build helpers
 static int32_t build_worklist(stf_ctx* ctx, int nwork) { // ctx->work holds (object, from) pairs
     int blocks = std::min(nblk((int64_t)nwork * 32, 256), 148 * 8);
-    k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), nwork, ctx->om.as<ObjMeta>(), 0);
+    ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), nwork, ctx->om.as<ObjMeta>(), 0);
     KCHECK();
     return STF_OK;
 }
 static int32_t build_big(stf_ctx* ctx, int o, int from) { // levels from+1..L of one big object, many CTAs per level
     for (int l = from + 1; l <= ctx->L; l++) {
-        k_set_parent_shift<<<1, 1, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, o, l);
+        ctx->launches++, k_set_parent_shift<<<1, 1, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, o, l);
         int kh = ((ctx->h_om[o].kh1 - 2) >> (l - 1)) + 2, kw = ((ctx->h_om[o].kw1 - 2) >> (l - 1)) + 2;
         int64_t nw = (int64_t)wpc_of(kh) * kw;
-        k_build_level_wide<<<std::min(nblk(nw, 256), 148 * 16), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l);
+        ctx->launches++, k_build_level_wide<<<std::min(nblk(nw, 256), 148 * 16), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l);
     }
     KCHECK();
     return STF_OK;
@@ -202,7 +225,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     CK(cudaMemcpyAsync(ctx->om.p, ctx->h_om.data(), sizeof(ObjMeta) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->poff.p, poff.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->woff1.p, woff1.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->st));
-    k_fill_invalid<<<nblk(4ll * n, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), 4ll * n);
+    ctx->launches++, k_fill_invalid<<<nblk(4ll * n, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), 4ll * n);
 
     const uint8_t* d_payload = nullptr;
     std::vector<uint8_t> staging;
@@ -220,15 +243,15 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
         d_payload = ctx->payload.as<uint8_t>();
     }
     if (woff1[n]) {
-        k_pack_level1<<<nblk((int64_t)woff1[n], 256), 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), ctx->woff1.as<uint64_t>(), n, ctx->lm.as<LevelMeta>(), L,
+        ctx->launches++, k_pack_level1<<<nblk((int64_t)woff1[n], 256), 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), ctx->woff1.as<uint64_t>(), n, ctx->lm.as<LevelMeta>(), L,
                                                                       ctx->words.as<uint32_t>(), woff1[n], ctx->errflag.as<int>());
         KCHECK();
     }
     // buildqtree!(t) for every object: warp-per-object for small ones, level-by-level wide launches for big ones
-    k_fill_worklist<<<nblk(n, 256), 256, 0, ctx->st>>>(n, nullptr, 1, ctx->work.as<int2>());
+    ctx->launches++, k_fill_worklist<<<nblk(n, 256), 256, 0, ctx->st>>>(n, nullptr, 1, ctx->work.as<int2>());
     {
         int blocks = std::min(nblk((int64_t)n * 32, 256), 148 * 8);
-        k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), 1);
+        ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), 1);
         KCHECK();
     }
     for (int o : ctx->big_objs) { int32_t r = build_big(ctx, o, 1); if (r) return r; }
@@ -269,7 +292,7 @@ extern "C" int32_t stf_download_level(stf_ctx* ctx, int32_t label, int32_t l, ui
     size_t nb = (size_t)kh * kw;
     if (!nb) return STF_OK;
     CK(ctx->bytes_tmp.ensure(nb));
-    k_unpack_level<<<std::min(nblk((int64_t)nb, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l, ctx->bytes_tmp.as<uint8_t>());
+    ctx->launches++, k_unpack_level<<<std::min(nblk((int64_t)nb, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l, ctx->bytes_tmp.as<uint8_t>());
     KCHECK();
     CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, nb, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -290,7 +313,7 @@ extern "C" int32_t stf_read_nodes(stf_ctx* ctx, int32_t n, const int32_t* labels
     if (n <= 0) return STF_OK;
     int32_t r = upload_query(ctx, n, labels, l, a, b); if (r) return r;
     CK(ctx->bytes_tmp.ensure((size_t)n));
-    k_read_nodes<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, n, ctx->lab.as<int32_t>(), ctx->lab2.as<int32_t>(),
+    ctx->launches++, k_read_nodes<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, n, ctx->lab.as<int32_t>(), ctx->lab2.as<int32_t>(),
                                                     ctx->lab3.as<int32_t>(), ctx->lab4.as<int32_t>(), ctx->bytes_tmp.as<uint8_t>());
     KCHECK();
     CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
@@ -302,29 +325,37 @@ extern "C" int32_t stf_grad2d(stf_ctx* ctx, int32_t n, const int32_t* labels, co
     if (n <= 0) return STF_OK;
     int32_t r = upload_query(ctx, n, labels, l, a, b); if (r) return r;
     CK(ctx->out32.ensure(sizeof(int32_t) * 2 * (size_t)n));
-    k_grad2d<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, n, ctx->lab.as<int32_t>(), ctx->lab2.as<int32_t>(),
+    ctx->launches++, k_grad2d<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, n, ctx->lab.as<int32_t>(), ctx->lab2.as<int32_t>(),
                                                 ctx->lab3.as<int32_t>(), ctx->lab4.as<int32_t>(), ctx->out32.as<int32_t>());
     KCHECK();
     CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(int32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return STF_OK;
 }
+__global__ void k_get_shifts(const LevelMeta* __restrict__ lm, int L, int n, const int32_t* __restrict__ labels, int level, int32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int o = labels ? labels[i] - 1 : i;
+    LevelMeta m = lm[(size_t)o * L + (level - 1)];
+    out[i] = m.rs; out[n + i] = m.cs;
+}
 extern "C" int32_t stf_get_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level, int32_t* rs, int32_t* cs) {
     NEED_OBJS();
-    if (level < 1 || level > ctx->L) FAIL(STF_E_ARG, "level out of range");
-    std::vector<LevelMeta> all((size_t)ctx->n * ctx->L);
-    if (ctx->n) CK(cudaMemcpyAsync(all.data(), ctx->lm.p, sizeof(LevelMeta) * all.size(), cudaMemcpyDeviceToHost, ctx->st));
+    if (level < 1 || level > ctx->L || n < 0 || (!labels && n > ctx->n)) FAIL(STF_E_ARG, "bad level or count");
+    if (n == 0) return STF_OK;
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r;
+    CK(ctx->out32.ensure(sizeof(int32_t) * 2 * (size_t)n));
+    ctx->launches++, k_get_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, dl, level, ctx->out32.as<int32_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(rs, ctx->out32.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(cs, ctx->out32.as<int32_t>() + n, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    for (int i = 0; i < n; i++) {
-        int lb = labels ? labels[i] : i + 1; CHECK_LABEL(lb);
-        rs[i] = all[(size_t)(lb - 1) * ctx->L + level - 1].rs; cs[i] = all[(size_t)(lb - 1) * ctx->L + level - 1].cs;
-    }
     return STF_OK;
 }
 static int32_t rebuild_after(stf_ctx* ctx, int n, const int32_t* labels_host, int from) { // ctx->work filled with (o, from)
     if (from >= ctx->L) return STF_OK;
     int blocks = std::min(nblk((int64_t)n * 32, 256), 148 * 8);
-    k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0);
+    ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0);
     KCHECK();
     if (ctx->has_big)
         for (int i = 0; i < n; i++) { int o = labels_host ? labels_host[i] - 1 : i; if (ctx->h_om[o].big) { int32_t r = build_big(ctx, o, from); if (r) return r; } }
@@ -334,14 +365,20 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
     NEED_OBJS();
     if (level < 1 || level > ctx->L || n < 0 || (!labels && n > ctx->n)) FAIL(STF_E_ARG, "bad level or count");
     if (n == 0) return STF_OK;
+    stage_begin(ctx, STF_STAGE_SHIFT);
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r;
-    CK(ctx->lab2.ensure(sizeof(int32_t) * (size_t)n)); CK(ctx->lab3.ensure(sizeof(int32_t) * (size_t)n));
+    const int32_t *drs = rs, *dcs = cs;
+    if (!(mode & STF_SHIFT_DEVICE_ARRAYS)) {
+        CK(ctx->lab2.ensure(sizeof(int32_t) * (size_t)n)); CK(ctx->lab3.ensure(sizeof(int32_t) * (size_t)n));
+        CK(cudaMemcpyAsync(ctx->lab2.p, rs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->lab3.p, cs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+        drs = ctx->lab2.as<int32_t>(); dcs = ctx->lab3.as<int32_t>();
+    }
     CK(ctx->work.ensure(sizeof(int2) * (size_t)n));
-    CK(cudaMemcpyAsync(ctx->lab2.p, rs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->lab3.p, cs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
-    k_apply_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, dl, level, ctx->lab2.as<int32_t>(), ctx->lab3.as<int32_t>(), mode, ctx->work.as<int2>());
+    ctx->launches++, k_apply_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, dl, level, drs, dcs, mode & 1, ctx->work.as<int2>());
     KCHECK();
     r = rebuild_after(ctx, n, labels, level); if (r) return r;
+    stage_end(ctx);
     CK(cudaStreamSynchronize(ctx->st));
     return STF_OK;
 }
@@ -360,7 +397,7 @@ extern "C" int32_t stf_build(stf_ctx* ctx, int32_t n, const int32_t* labels, int
     if (n == 0 || layer > ctx->L) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r;
     CK(ctx->work.ensure(sizeof(int2) * (size_t)n));
-    k_fill_worklist<<<nblk(n, 256), 256, 0, ctx->st>>>(n, dl, layer - 1, ctx->work.as<int2>());
+    ctx->launches++, k_fill_worklist<<<nblk(n, 256), 256, 0, ctx->st>>>(n, dl, layer - 1, ctx->work.as<int2>());
     r = rebuild_after(ctx, n, labels, layer - 1); if (r) return r;
     CK(cudaStreamSynchronize(ctx->st));
     return STF_OK;
@@ -379,10 +416,10 @@ static int32_t narrow_phase(stf_ctx* ctx, int64_t n) {
     A.overflow = ctx->overflow.as<uint32_t>(); A.overflow_cap = n;
     int64_t groups = (n + 0) ; int per_block = NP_THREADS / NP_GROUP;
     int blocks = (int)std::min<int64_t>((groups + per_block - 1) / per_block, 148 * 32);
-    k_collide_small<<<blocks, NP_THREADS, 0, ctx->st>>>(A);
+    ctx->launches++, k_collide_small<<<blocks, NP_THREADS, 0, ctx->st>>>(A);
     KCHECK();
     CK(ctx->scratch.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->big_cap * ctx->big_ctas));
-    k_collide_big<<<ctx->big_ctas, NPB_THREADS, 0, ctx->st>>>(A, ctx->scratch.as<uint32_t>(), ctx->big_cap, ctx->errflag.as<int>());
+    ctx->launches++, k_collide_big<<<ctx->big_ctas, NPB_THREADS, 0, ctx->st>>>(A, ctx->scratch.as<uint32_t>(), ctx->big_cap, ctx->errflag.as<int>());
     KCHECK();
     return STF_OK;
 }
@@ -395,7 +432,7 @@ static int32_t import_items(stf_ctx* ctx, int64_t n, const stf_item* items, DevB
     CK(dst.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n)));
     if (n == 0) return STF_OK;
     CK(cudaMemcpyAsync(ctx->out32.p, items, sizeof(stf_item) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
-    k_import_items<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->out32.as<int32_t>(), n, dst.as<Item16>());
+    ctx->launches++, k_import_items<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->out32.as<int32_t>(), n, dst.as<Item16>());
     KCHECK();
     return STF_OK;
 }
@@ -409,10 +446,13 @@ extern "C" int32_t stf_collision_bfs(stf_ctx* ctx, int64_t n, const stf_item* it
     ctx->items_valid = false;
     r = zero_counts(ctx); if (r) return r;
     r = narrow_phase(ctx, n); if (r) return r;
-    k_export_results<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), n, ctx->out32.as<int32_t>());
+    ctx->launches++, k_export_results<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), n, ctx->out32.as<int32_t>());
     KCHECK();
     CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(stf_item) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
-    return sync_counts(ctx);
+    r = sync_counts(ctx); if (r) return r;
+    ctx->ctr.items = n; ctx->ctr.direct = 0; ctx->ctr.hits = 0;
+    ctx->ctr.overflow = (int64_t)ctx->h_counts[C_OVERFLOW]; ctx->ctr.visited = (int64_t)ctx->h_counts[C_VISITED];
+    return STF_OK;
 }
 extern "C" int32_t stf_collision_dfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out) {
     NEED_OBJS();
@@ -420,9 +460,9 @@ extern "C" int32_t stf_collision_dfs(stf_ctx* ctx, int64_t n, const stf_item* it
     int32_t r = import_items(ctx, n, items, ctx->items); if (r) return r;
     ctx->items_valid = false;
     CK(ctx->res.ensure(sizeof(int4) * (size_t)n));
-    k_collision_dfs<<<nblk(n, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->items.as<Item16>(), n, ctx->res.as<int4>());
+    ctx->launches++, k_collision_dfs<<<nblk(n, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->items.as<Item16>(), n, ctx->res.as<int4>());
     KCHECK();
-    k_export_results<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), n, ctx->out32.as<int32_t>());
+    ctx->launches++, k_export_results<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), n, ctx->out32.as<int32_t>());
     KCHECK();
     CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(stf_item) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -451,23 +491,25 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
     size_t kb = sizeof(uint64_t) * (size_t)nh, vb = sizeof(uint32_t) * (size_t)nh;
     CK(ctx->hk.ensure(kb)); CK(ctx->hk2.ensure(kb)); CK(ctx->hv.ensure(vb)); CK(ctx->hv2.ensure(vb)); CK(ctx->keep.ensure(vb + 16));
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(nh)));
-    k_hit_keys<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
-    int f = radix_sort_pairs(ctx->st, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh, 0, ctx->label_bits, ctx->hist.as<uint32_t>());
+    stage_begin(ctx, STF_STAGE_RESULT);
+    ctx->launches++, k_hit_keys<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+    int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh, 0, ctx->label_bits, ctx->hist.as<uint32_t>());
     uint64_t *k0 = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), *k1 = f ? ctx->hk.as<uint64_t>() : ctx->hk2.as<uint64_t>();
     uint32_t *v0 = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), *v1 = f ? ctx->hv.as<uint32_t>() : ctx->hv2.as<uint32_t>();
-    int f2 = radix_sort_pairs(ctx->st, k0, v0, k1, v1, nh, 32, 32 + ctx->label_bits, ctx->hist.as<uint32_t>());
+    int f2 = radix_sort_pairs(ctx->st, &ctx->launches, k0, v0, k1, v1, nh, 32, 32 + ctx->label_bits, ctx->hist.as<uint32_t>());
     uint64_t* ks = f2 ? k1 : k0; uint32_t* vs = f2 ? v1 : v0;
-    k_gather_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), vs, nh, ctx->hits2.as<Item16>());
-    k_fix_ties<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ks, nh, unique, ctx->keep.as<uint32_t>());
+    ctx->launches++, k_gather_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), vs, nh, ctx->hits2.as<Item16>());
+    ctx->launches++, k_fix_ties<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ks, nh, unique, ctx->keep.as<uint32_t>());
     KCHECK();
-    if (!export_host_format && !unique) { *nout = nh; return STF_OK; }
+    if (!export_host_format && !unique) { *nout = nh; stage_end(ctx); return STF_OK; }
     // positions = exclusive scan of keep (reuse the other value buffer)
     uint32_t* pos = (vs == ctx->hv.as<uint32_t>()) ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
     CK(cudaMemcpyAsync(pos, ctx->keep.p, vb, cudaMemcpyDeviceToDevice, ctx->st));
-    k_scan_u32<<<1, 1024, 0, ctx->st>>>(pos, nh, reinterpret_cast<uint32_t*>(ctx->counts.as<unsigned long long>() + C_KEPT));
+    ctx->launches++, k_scan_u32<<<1, 1024, 0, ctx->st>>>(pos, nh, reinterpret_cast<uint32_t*>(ctx->counts.as<unsigned long long>() + C_KEPT));
     CK(ctx->out32.ensure(sizeof(int32_t) * 5 * (size_t)nh));
-    k_export_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ctx->keep.as<uint32_t>(), pos, nh, ctx->out32.as<int32_t>());
+    ctx->launches++, k_export_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ctx->keep.as<uint32_t>(), pos, nh, ctx->out32.as<int32_t>());
     KCHECK();
+    stage_end(ctx);
     int32_t r = sync_counts(ctx); if (r) return r;
     *nout = (int64_t)(uint32_t)ctx->h_counts[C_KEPT];
     return STF_OK;
@@ -495,7 +537,7 @@ extern "C" int32_t stf_fetch_items(stf_ctx* ctx, stf_item* out, int64_t cap, int
     if (n > cap) FAIL(STF_E_CAPACITY, "output buffer too small");
     if (n == 0) return STF_OK;
     CK(ctx->bytes_tmp.ensure(sizeof(int32_t) * 5 * (size_t)n));
-    k_export_items<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), n, ctx->bytes_tmp.as<int32_t>());
+    ctx->launches++, k_export_items<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), n, ctx->bytes_tmp.as<int32_t>());
     KCHECK();
     CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, sizeof(stf_item) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -507,12 +549,15 @@ static int32_t collide_and_collect(stf_ctx* ctx, int64_t n, int64_t nd, int64_t*
     CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n + nd), true, ctx->st));
     unsigned long long base = (unsigned long long)nd;
     CK(cudaMemcpyAsync(ctx->counts.as<unsigned long long>() + C_NHITS, &base, sizeof(base), cudaMemcpyHostToDevice, ctx->st));
+    stage_begin(ctx, STF_STAGE_NARROW);
     int32_t r = narrow_phase(ctx, n); if (r) return r;
+    stage_begin(ctx, STF_STAGE_RESULT);
     if (n > 0) {
-        k_compact_hits<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), nullptr, n, ctx->hits.as<Item16>(), n + nd,
+        ctx->launches++, k_compact_hits<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), nullptr, n, ctx->hits.as<Item16>(), n + nd,
                                                          ctx->counts.as<unsigned long long>() + C_NHITS);
         KCHECK();
     }
+    stage_end(ctx);
     r = sync_counts(ctx); if (r) return r;
     *nh = (int64_t)ctx->h_counts[C_NHITS];
     ctx->ctr.items = n; ctx->ctr.direct = nd; ctx->ctr.hits = *nh;
@@ -546,8 +591,8 @@ extern "C" int32_t stf_totalcollisions_native(stf_ctx* ctx, int32_t nl, const in
     int64_t npairs = (int64_t)nl * (nl - 1) / 2;
     CK(ctx->nat_flt.ensure(sizeof(int32_t) * (size_t)nl)); CK(ctx->nat_m.ensure(sizeof(int)));
     CK(ctx->items.ensure(sizeof(Item16) * (size_t)npairs));
-    k_native_filter<<<1, 1024, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, nl, dl, ctx->nat_flt.as<int32_t>(), ctx->nat_m.as<int>());
-    k_native_pairs<<<nblk((int64_t)nl * nl, 256), 256, 0, ctx->st>>>(ctx->nat_flt.as<int32_t>(), ctx->nat_m.as<int>(), nl, ctx->L, ctx->items.as<Item16>(), npairs,
+    ctx->launches++, k_native_filter<<<1, 1024, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, nl, dl, ctx->nat_flt.as<int32_t>(), ctx->nat_m.as<int>());
+    ctx->launches++, k_native_pairs<<<nblk((int64_t)nl * nl, 256), 256, 0, ctx->st>>>(ctx->nat_flt.as<int32_t>(), ctx->nat_m.as<int>(), nl, ctx->L, ctx->items.as<Item16>(), npairs,
                                                                     ctx->counts.as<unsigned long long>());
     KCHECK();
     r = sync_counts(ctx); if (r) return r;
@@ -563,22 +608,25 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     if (!ctx->sizelevel_ok) FAIL(STF_E_STATE, "locate!: an object is larger than the canvas (sizelevel == -1)");
     int64_t nrec = 4ll * (linked ? ctx->n : nl);
     *nrec_out = nrec;
+    stage_begin(ctx, STF_STAGE_LOCATE);
     size_t kb = sizeof(uint64_t) * (size_t)std::max<int64_t>(4, nrec), vb = sizeof(uint32_t) * (size_t)std::max<int64_t>(4, nrec);
     CK(ctx->rk.ensure(kb)); CK(ctx->rk2.ensure(kb)); CK(ctx->rv.ensure(vb)); CK(ctx->rv2.ensure(vb));
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
     if (linked) {
-        if (nl > 0) k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
+        if (nl > 0) ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
                                                                ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>());
         CK(cudaMemcpyAsync(ctx->rk.p, ctx->lkk.p, sizeof(uint64_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->rv.p, ctx->lkv.p, sizeof(uint32_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
     } else if (nl > 0) {
-        k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
+        ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
                                                     ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->errflag.as<int>());
     }
     KCHECK();
+    stage_begin(ctx, STF_STAGE_SORT);
     int bits = 2 * STF_CELL_W + 5 + ctx->scene_bits;
-    int f = radix_sort_pairs(ctx->st, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nrec, 0, bits, ctx->hist.as<uint32_t>());
+    int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nrec, 0, bits, ctx->hist.as<uint32_t>());
     KCHECK();
+    stage_end(ctx);
     *keys = f ? ctx->rk2.as<uint64_t>() : ctx->rk.as<uint64_t>();
     *vals = f ? ctx->rv2.as<uint32_t>() : ctx->rv.as<uint32_t>();
     ctx->ctr.records = nrec;
@@ -587,7 +635,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
 static int32_t export_cells(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, stf_cellrec* out, int64_t cap, int64_t* count) {
     int32_t r = zero_counts(ctx); if (r) return r;
     CK(ctx->out32.ensure(sizeof(int32_t) * 4 * (size_t)std::max<int64_t>(1, nrec)));
-    if (nrec > 0) k_export_cells<<<nblk(nrec, 256), 256, 0, ctx->st>>>(keys, vals, nrec, ctx->out32.as<int32_t>(), ctx->counts.as<unsigned long long>() + C_NVALID);
+    if (nrec > 0) ctx->launches++, k_export_cells<<<nblk(nrec, 256), 256, 0, ctx->st>>>(keys, vals, nrec, ctx->out32.as<int32_t>(), ctx->counts.as<unsigned long long>() + C_NVALID);
     KCHECK();
     r = sync_counts(ctx); if (r) return r;
     int64_t nv = (int64_t)ctx->h_counts[C_NVALID];
@@ -608,7 +656,7 @@ extern "C" int32_t stf_locate(stf_ctx* ctx, int32_t nl, const int32_t* labels, s
 }
 extern "C" int32_t stf_linked_reset(stf_ctx* ctx) {
     NEED_OBJS();
-    if (ctx->n) k_fill_invalid<<<nblk(4ll * ctx->n, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), 4ll * ctx->n);
+    if (ctx->n) ctx->launches++, k_fill_invalid<<<nblk(4ll * ctx->n, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), 4ll * ctx->n);
     KCHECK();
     CK(cudaStreamSynchronize(ctx->st));
     return STF_OK;
@@ -619,7 +667,7 @@ extern "C" int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* la
     if (!labels) nl = ctx->n;
     if (nl <= 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
-    k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
+    ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
                                                 ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>());
     KCHECK();
     return sync_counts(ctx);
@@ -628,7 +676,7 @@ extern "C" int32_t stf_linked_clear(stf_ctx* ctx, int32_t nl, const int32_t* lab
     NEED_OBJS();
     if (nl <= 0 || !labels) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
-    k_clear_slots<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), nl, dl);
+    ctx->launches++, k_clear_slots<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), nl, dl);
     KCHECK();
     CK(cudaStreamSynchronize(ctx->st));
     return STF_OK;
@@ -664,8 +712,10 @@ static int32_t spacial_core(stf_ctx* ctx, int32_t nl, const int32_t* labels, int
         EmitOut eo; eo.items = ctx->items.as<Item16>(); eo.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
         eo.direct = ctx->direct.as<Item16>(); eo.direct_cap = (int64_t)(ctx->direct.cap / sizeof(Item16)); eo.counts = ctx->counts.as<unsigned long long>();
         int64_t threads = nrec * (ctx->L - 1);
-        if (threads > 0) k_emit_items<<<nblk(threads, 256), 256, 0, ctx->st>>>(keys, vals, nrec, ctx->L, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), moved_pos, eo);
+        stage_begin(ctx, STF_STAGE_EMIT);
+        if (threads > 0) ctx->launches++, k_emit_items<<<nblk(threads, 256), 256, 0, ctx->st>>>(keys, vals, nrec, ctx->L, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), moved_pos, eo);
         KCHECK();
+        stage_end(ctx);
         r = sync_counts(ctx); if (r) return r;
         n_items = (int64_t)ctx->h_counts[C_ITEMS]; n_direct = (int64_t)ctx->h_counts[C_DIRECT];
         if (n_items <= eo.item_cap && n_direct <= eo.direct_cap) break;
@@ -737,9 +787,10 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     CK(ctx->hv.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->hv2.ensure(sizeof(uint32_t) * (size_t)m));
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(m)));
     CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)n));
-    k_step_endpoints<<<nblk(m, 256), 256, 0, ctx->st>>>(hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
-    int f = radix_sort_pairs(ctx->st, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
-    k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), m, ctx->prev.as<uint32_t>());
+    stage_begin(ctx, STF_STAGE_STEP_PREP);
+    ctx->launches++, k_step_endpoints<<<nblk(m, 256), 256, 0, ctx->st>>>(hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+    int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
+    ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), m, ctx->prev.as<uint32_t>());
     CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
     CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
     CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_KEPT, 0, sizeof(unsigned long long), ctx->st)); // ticket lives in C_KEPT during the launch
@@ -750,8 +801,10 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>();
     A.opt = ctx->opt; A.seed = seed; A.iter = iter; A.counts = ctx->counts.as<unsigned long long>();
     int blocks = (int)std::min<int64_t>((n + 3) / 4, 148 * 8);
-    k_batchsteps<<<blocks, 128, 0, ctx->st>>>(A);
+    stage_begin(ctx, STF_STAGE_STEP);
+    ctx->launches++, k_batchsteps<<<blocks, 128, 0, ctx->st>>>(A);
     KCHECK();
+    stage_end(ctx);
     int32_t r = sync_counts(ctx); if (r) return r;
     ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES];
     return STF_OK;
@@ -780,3 +833,28 @@ extern "C" int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out) {
     *out = ctx->ctr;
     return STF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ per-stage device timers
+extern "C" int32_t stf_profile_enable(stf_ctx* ctx, int32_t on) {
+    if (!ctx) return STF_E_ARG;
+    stage_end(ctx);
+    ctx->prof = on != 0;
+    return STF_OK;
+}
+extern "C" int32_t stf_profile_read(stf_ctx* ctx, double* ms, int64_t* calls, int32_t reset) {
+    if (!ctx) return STF_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    stage_end(ctx);
+    CK(cudaStreamSynchronize(ctx->st));
+    for (auto& r : ctx->prof_pending) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ctx->prof_ms[r.stage] += t; ctx->prof_calls[r.stage]++; }
+        ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+    for (int i = 0; i < STF_NSTAGES; i++) { if (ms) ms[i] = ctx->prof_ms[i]; if (calls) calls[i] = ctx->prof_calls[i]; }
+    if (reset) for (int i = 0; i < STF_NSTAGES; i++) { ctx->prof_ms[i] = 0; ctx->prof_calls[i] = 0; }
+    return STF_OK;
+}
+
+extern "C" int64_t stf_launch_count(const stf_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -87,7 +87,7 @@ def test_shift_family_parity(S, orc):
     got = d.read_nodes(labels, ls, a, b)
     want = [qo[labels[i] - 1].get(int(ls[i]), int(a[i]), int(b[i])) for i in range(n)]
     assert list(got) == want
-    assert d[0].get(1, -10, -15) == S.EMPTY
+    assert d[0].get(1, -1000, -1500) == S.EMPTY
     with pytest.raises(IndexError):
         d[0].set(1, -1000, -1500, S.EMPTY)
 

@@ -42,9 +42,10 @@ def _rotate(img, deg):
 
 
 def word_object(rng):
-    height = max(4, int(round(6 * rng.exponential(1.0) + 8)))
+    fontsize = 6 * rng.exponential(1.0) + 8
+    height = max(4, int(round(0.75 * fontsize)))  # glyph (cap) height of a font of that size
     nchar = int(rng.integers(1, 9))
-    gw = max(3, int(round(height * 5 / 7)))
+    gw = max(3, int(round(0.6 * height)))
     cols = []
     for _ in range(nchar):
         g = rng.random((7, 5)) < 0.6
