@@ -79,56 +79,102 @@ __device__ __forceinline__ void emit_push(Item16* buf, int64_t cap, unsigned lon
     if ((int64_t)slot < cap) buf[slot] = it;
 }
 
-// candidate generation.  One thread per (sorted record r, k): k == 0 pairs r with the later records of its
-// own cell (qtree_functions.jl:233-239); k >= 1 looks the k-th ancestor cell up by binary search and runs
-// collisions_boundsfilter (:203-223) against every label stored there (:241-248).
+__device__ __forceinline__ int64_t upper_bound_u64(const uint64_t* __restrict__ keys, int64_t lo, int64_t hi, uint64_t key) {
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (keys[mid] <= key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// candidate generation, one WARP per sorted record r (low label in cell (l,a,b)).
+//  lane 0      : the later records of r's own cell            (same-cell pairs, qtree_functions.jl:233-239)
+//  lane k >= 1 : the records of the k-th ancestor cell, found by binary search (:241-248)
+// A warp scan turns the per-lane run lengths into one candidate range; the warp then walks that range 32
+// candidates at a time (balanced even when an ancestor holds hundreds of labels), applies
+// collisions_boundsfilter (:203-223) and reserves output slots with one atomic per 32 candidates.
 // moved_pos != NULL selects partialcollisions semantics (:285-326): a pair is generated iff at least one
 // side is in `labels` (moved_pos[o] >= 0); two moved labels of one cell are oriented (later, earlier).
-__global__ void k_emit_items(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t nrec, int L,
-                             const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const int32_t* __restrict__ moved_pos,
-                             EmitOut out) {
-    int K = L - 1;
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t r = t / K; int k = (int)(t - r * K);
-    if (r >= nrec) return;
-    uint64_t key = keys[r];
-    if (key == STF_KEY_INVALID) return;
-    int low = (int)vals[r];
-    int l, a, b; cell_unkey(key, &l, &a, &b);
-    int mp_low = moved_pos ? moved_pos[low - 1] : 0;
-    if (k == 0) {
-        for (int64_t h = r + 1; h < nrec && keys[h] == key; h++) {
-            int other = (int)vals[h];
-            int i1 = low, i2 = other;
-            if (moved_pos) {
-                int mp_o = moved_pos[other - 1];
-                if (mp_low < 0 && mp_o < 0) continue;
-                if (mp_low < 0 || (mp_o >= 0 && mp_o > mp_low)) { i1 = other; i2 = low; }
+#define EM_THREADS 256
+__global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                           const unsigned long long* __restrict__ nrec_dev, int64_t nrec_cap, int L,
+                                                           const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm,
+                                                           const int32_t* __restrict__ moved_pos, EmitOut out) {
+    __shared__ int s_start[EM_THREADS / 32][16];
+    __shared__ int s_pref[EM_THREADS / 32][17];
+    const unsigned FULLM = 0xffffffffu;
+    int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int64_t nrec = min((int64_t)*nrec_dev, nrec_cap); // valid records (sorted, compacted)
+    int64_t nwarps = (int64_t)gridDim.x * (EM_THREADS / 32);
+    for (int64_t r = (int64_t)blockIdx.x * (EM_THREADS / 32) + wib; r < nrec; r += nwarps) {
+        uint64_t key = keys[r];
+        int low = (int)vals[r];
+        int l, a, b; cell_unkey(key, &l, &a, &b);
+        int mp_low = moved_pos ? moved_pos[low - 1] : 0;
+        // ---- per-lane candidate run
+        int start = 0, cnt = 0;
+        if (lane == 0) {
+            start = (int)(r + 1);
+            cnt = (int)(upper_bound_u64(keys, r + 1, nrec, key) - (r + 1));
+        } else if (lane < L - 1 && l + lane <= L) {
+            int pa = a, pb = b;
+            for (int i = 0; i < lane; i++) { pa = (pa + 1) / 2; pb = (pb + 1) / 2; } // parent(): ÷ truncates toward zero
+            uint64_t scene_bits = key >> (5 + 2 * STF_CELL_W);
+            uint64_t akey = (scene_bits << (5 + 2 * STF_CELL_W)) | ((uint64_t)(uint32_t)(l + lane) << (2 * STF_CELL_W)) |
+                            ((uint64_t)(uint32_t)(pa + STF_CELL_BIAS) << STF_CELL_W) | (uint64_t)(uint32_t)(pb + STF_CELL_BIAS);
+            int64_t h = lower_bound_u64(keys, nrec, akey);
+            if (h < nrec && keys[h] == akey) { start = (int)h; cnt = (int)(upper_bound_u64(keys, h + 1, nrec, akey) - h); }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULLM, incl, o); if (lane >= o) incl += t; }
+        int total = __shfl_sync(FULLM, incl, 31);
+        if (total == 0) continue;
+        if (lane < 16) { s_start[wib][lane] = start; s_pref[wib][lane] = incl - cnt; }
+        if (lane == 16) s_pref[wib][16] = total;
+        __syncwarp();
+        LevelMeta lowm = lm[(size_t)(low - 1) * L + (l - 1)];
+        int lowcode = -1;
+        for (int c0 = 0; c0 < total; c0 += 32) {
+            int c = c0 + lane;
+            bool valid = c < total;
+            bool is_item = false, is_direct = false, want_code = false;
+            int i1 = low, i2 = 0;
+            if (valid) {
+                int k = 0;
+#pragma unroll
+                for (int j = 1; j < 16; j++) if (s_pref[wib][j] <= c) k = j; // runs are in lane order; empty runs share a prefix
+                // the LAST j with pref <= c and a non-empty run: pref[j] <= c < pref[j+1]
+                while (s_pref[wib][k + 1] <= c) k++; // (never taken: kept as a guard for empty trailing runs)
+                int other = (int)vals[s_start[wib][k] + (c - s_pref[wib][k])];
+                if (k == 0) {
+                    is_item = true; i2 = other;
+                    if (moved_pos) {
+                        int mp_o = moved_pos[other - 1];
+                        if (mp_low < 0 && mp_o < 0) is_item = false;
+                        else if (mp_low < 0 || (mp_o >= 0 && mp_o > mp_low)) { i1 = other; i2 = low; }
+                    }
+                } else if (!(moved_pos && mp_low < 0 && moved_pos[other - 1] < 0)) {
+                    LevelMeta hm = lm[(size_t)(other - 1) * L + (l - 1)];
+                    int rr = a - hm.rs - 1, cc = b - hm.cs - 1;
+                    i2 = other;
+                    if ((unsigned)rr < (unsigned)lm_kh(hm) && (unsigned)cc < (unsigned)lm_kw(hm)) is_item = true;
+                    else if (lm_dflt(hm) == CODE_FULL) want_code = true;
+                }
             }
-            emit_push(out.items, out.item_cap, out.counts, make_item(i1, i2, l, a, b));
+            if (__any_sync(FULLM, want_code)) {
+                if (lowcode < 0) lowcode = (int)node_code<false>(words, lowm, a, b);
+                is_direct = want_code && lowcode != (int)CODE_EMPTY;
+            }
+            unsigned im = __ballot_sync(FULLM, is_item), dm = __ballot_sync(FULLM, is_direct);
+            unsigned long long ibase = 0, dbase = 0;
+            if (lane == 0) {
+                if (im) ibase = atomicAdd(out.counts, (unsigned long long)__popc(im));
+                if (dm) dbase = atomicAdd(out.counts + 1, (unsigned long long)__popc(dm));
+            }
+            ibase = __shfl_sync(FULLM, ibase, 0); dbase = __shfl_sync(FULLM, dbase, 0);
+            unsigned lt = (1u << lane) - 1;
+            if (is_item) { int64_t slot = (int64_t)ibase + __popc(im & lt); if (slot < out.item_cap) out.items[slot] = make_item(i1, i2, l, a, b); }
+            if (is_direct) { int64_t slot = (int64_t)dbase + __popc(dm & lt); if (slot < out.direct_cap) out.direct[slot] = make_item(low, i2, l, a, b); }
         }
-        return;
-    }
-    if (l + k > L) return;
-    int pa = a, pb = b;
-    for (int i = 0; i < k; i++) { pa = (pa + 1) / 2; pb = (pb + 1) / 2; } // parent(): ÷ truncates toward zero
-    uint64_t scene_bits = key >> (5 + 2 * STF_CELL_W);
-    uint64_t akey = (scene_bits << (5 + 2 * STF_CELL_W)) | ((uint64_t)(uint32_t)(l + k) << (2 * STF_CELL_W)) |
-                    ((uint64_t)(uint32_t)(pa + STF_CELL_BIAS) << STF_CELL_W) | (uint64_t)(uint32_t)(pb + STF_CELL_BIAS);
-    int64_t h = lower_bound_u64(keys, nrec, akey);
-    LevelMeta lowm = lm[(size_t)(low - 1) * L + (l - 1)];
-    int lowcode = -1;
-    for (; h < nrec && keys[h] == akey; h++) {
-        int high = (int)vals[h];
-        if (moved_pos && mp_low < 0 && moved_pos[high - 1] < 0) continue;
-        LevelMeta hm = lm[(size_t)(high - 1) * L + (l - 1)];
-        int rr = a - hm.rs - 1, cc = b - hm.cs - 1;
-        if ((unsigned)rr < (unsigned)lm_kh(hm) && (unsigned)cc < (unsigned)lm_kw(hm)) {
-            emit_push(out.items, out.item_cap, out.counts, make_item(low, high, l, a, b));
-        } else if (lm_dflt(hm) == CODE_FULL) {
-            if (lowcode < 0) lowcode = (int)node_code<false>(words, lowm, a, b);
-            if (lowcode != (int)CODE_EMPTY) emit_push(out.direct, out.direct_cap, out.counts + 1, make_item(low, high, l, a, b));
-        }
+        __syncwarp();
     }
 }
 
@@ -446,13 +492,11 @@ __global__ void k_export_items(const Item16* __restrict__ items, int64_t n, int3
     int32_t* o = out + 5 * (size_t)i;
     o[0] = items[i].i1; o[1] = item_i2(items[i]); o[2] = item_l(items[i]); o[3] = items[i].a; o[4] = items[i].b;
 }
-__global__ void k_export_cells(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, int32_t* __restrict__ out, unsigned long long* __restrict__ nvalid) {
+__global__ void k_export_cells(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const unsigned long long* __restrict__ n_dev, int64_t cap, int32_t* __restrict__ out) {
+    int64_t n = min((int64_t)*n_dev, cap);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = keys[i];
-    if (k == STF_KEY_INVALID) return;
-    if (i + 1 == n || keys[i + 1] == STF_KEY_INVALID) *nvalid = (unsigned long long)(i + 1);
-    int l, a, b; cell_unkey(k, &l, &a, &b);
+    int l, a, b; cell_unkey(keys[i], &l, &a, &b);
     int32_t* o = out + 4 * (size_t)i;
     o[0] = l; o[1] = a; o[2] = b; o[3] = (int32_t)vals[i];
 }

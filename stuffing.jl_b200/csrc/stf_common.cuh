@@ -12,7 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define STF_MAX_LEVELS 17          // canvas <= 65536; kh,kw <= 32767 (15-bit fields)
+#define STF_MAX_LEVELS 16          // canvas <= 32768; kh,kw <= 32767 (15-bit fields); one half-warp of LevelMetas
 #define STF_CELL_W 22              // bits per cell coordinate in a sort key (biased by 2^21)
 #define STF_CELL_BIAS (1 << (STF_CELL_W - 1))
 #define STF_KEY_INVALID 0xFFFFFFFFFFFFFFFFull
@@ -60,12 +60,26 @@ template <bool CG> __device__ __forceinline__ uint32_t node_code(const uint32_t*
     return lm_dflt(m);
 }
 
-// 32 consecutive child fields of one child column, starting at 0-based row 32*pw - er
-template <bool CG> __device__ __forceinline__ uint64_t child_fields(const uint32_t* __restrict__ words, const LevelMeta& ch, int col, int pw, int er) {
+// OR of adjacent 2-bit field pairs, then keep the even fields: 16 fields (32 bits) -> 8 fields (16 bits).
+// Done on 32-bit halves so that every step is one shift + one LOP3 and the two halves overlap (ILP).
+__device__ __forceinline__ uint32_t compress_half(uint32_t h) {
+    uint32_t x = (h | (h >> 2)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+__device__ __forceinline__ uint32_t compress_pairs(uint64_t y) {
+    return compress_half((uint32_t)y) | (compress_half((uint32_t)(y >> 32)) << 16);
+}
+
+// 32 consecutive child fields of one child column, starting at 0-based row 32*pw - er.
+// `lvl` points at the first word of the child level (global memory, or a shared-memory copy of it)
+template <bool CG> __device__ __forceinline__ uint64_t child_fields(const uint32_t* __restrict__ lvl, const LevelMeta& ch, int col, int pw, int er) {
     uint32_t dw = dflt_word(lm_dflt(ch));
     int wpc = wpc_of(lm_kh(ch));
     if ((unsigned)col >= (unsigned)lm_kw(ch)) return ((uint64_t)dw << 32) | dw;
-    const uint32_t* base = words + ch.off + (size_t)col * wpc;
+    const uint32_t* base = lvl + (size_t)col * wpc;
     int k0 = 2 * pw;
     uint32_t w0 = k0 < wpc ? ldw<CG>(base + k0) : dw;
     uint32_t w1 = k0 + 1 < wpc ? ldw<CG>(base + k0 + 1) : dw;
@@ -82,41 +96,94 @@ template <bool CG> __device__ __forceinline__ uint64_t child_fields(const uint32
 
 // one word (16 nodes) of a parent level: qcode (qtrees.jl:50-53) on 2-bit fields.
 // er/ec = child shift - 2*parent shift in {-1,0,1} (÷2 truncates toward zero, qtrees.jl:225-226)
-template <bool CG> __device__ __forceinline__ uint32_t build_word(const uint32_t* __restrict__ words, const LevelMeta& ch, int er, int ec, int pc, int pw) {
+template <bool CG> __device__ __forceinline__ uint32_t build_word(const uint32_t* __restrict__ lvl, const LevelMeta& ch, int er, int ec, int pc, int pw) {
     int c0 = 2 * pc - ec;
-    uint64_t y = child_fields<CG>(words, ch, c0, pw, er) | child_fields<CG>(words, ch, c0 + 1, pw, er);
-    uint64_t z = y | (y >> 2);          // even fields hold the OR of each row pair
-    z &= 0x3333333333333333ull;         // compress the even 2-bit fields
-    z = (z | (z >> 2)) & 0x0F0F0F0F0F0F0F0Full;
-    z = (z | (z >> 4)) & 0x00FF00FF00FF00FFull;
-    z = (z | (z >> 8)) & 0x0000FFFF0000FFFFull;
-    z = (z | (z >> 16)) & 0x00000000FFFFFFFFull;
-    return (uint32_t)z;
+    uint64_t y = child_fields<CG>(lvl, ch, c0, pw, er) | child_fields<CG>(lvl, ch, c0 + 1, pw, er);
+    return compress_pairs(y);
+}
+
+__device__ __forceinline__ LevelMeta shfl_meta(const LevelMeta& m, int src) {
+    LevelMeta r;
+    r.off = __shfl_sync(0xffffffffu, m.off, src); r.rs = __shfl_sync(0xffffffffu, m.rs, src);
+    r.cs = __shfl_sync(0xffffffffu, m.cs, src); r.dims = __shfl_sync(0xffffffffu, m.dims, src);
+    return r;
+}
+template <bool CG> __device__ __forceinline__ void stmeta(LevelMeta* p, const LevelMeta& m) {
+    uint4 v = make_uint4(m.off, (uint32_t)m.rs, (uint32_t)m.cs, m.dims);
+    if (CG) __stcg(reinterpret_cast<uint4*>(p), v); else *reinterpret_cast<uint4*>(p) = v;
 }
 
 // buildqtree!(t, from+1) for one object by one warp (qtrees.jl:221-237): levels from+1..L are recomputed
 // from level `from`, each level's shift = child shift ÷ 2.
-template <bool CG> __device__ __forceinline__ void rebuild_levels_warp(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int o, int L, int from, int lane) {
-    LevelMeta ch = ldmeta<CG>(lm + (size_t)o * L + (from - 1));
+// Latency design: lane i holds the LevelMeta of level i+1 (`mine`, loaded by the caller in ONE round trip);
+// the first rebuilt level reads its children from global memory, every later level reads them from a
+// per-warp shared-memory copy of the level just produced (levels shrink 4x, so they fit after one step);
+// the global stores are fire-and-forget.  Returns the lane's meta with the new shifts (lanes >= from).
+#define RB_HALF 384   // words per shared-memory level buffer (two per warp)
+template <bool CG> __device__ __forceinline__ LevelMeta warp_rebuild(uint32_t* __restrict__ words, LevelMeta mine, int L, int from, int lane, uint32_t* __restrict__ sbuf) {
+    const unsigned FULLM = 0xffffffffu;
+    // shifts of the rebuilt levels in closed form: repeated `÷ 2` (toward zero) composes to `÷ 2^k`
+    int brs = __shfl_sync(FULLM, mine.rs, from - 1), bcs = __shfl_sync(FULLM, mine.cs, from - 1);
+    if (lane >= from && lane < L) { // x / 2^sh toward zero without an integer division
+        int sh = lane + 1 - from;
+        mine.rs = brs >= 0 ? (brs >> sh) : -((-brs) >> sh); mine.cs = bcs >= 0 ? (bcs >> sh) : -((-bcs) >> sh);
+    }
+    // constants of "my" level seen as a parent; its child level is held by lane-1
+    int crs = __shfl_up_sync(FULLM, mine.rs, 1), ccs = __shfl_up_sync(FULLM, mine.cs, 1);
+    uint32_t cdims = __shfl_up_sync(FULLM, mine.dims, 1), coff = __shfl_up_sync(FULLM, mine.off, 1);
+    int my_er = crs - 2 * mine.rs, my_ec = ccs - 2 * mine.cs;
+    bool in_smem = false; int cur = 0;
     for (int l = from + 1; l <= L; l++) {
-        LevelMeta* pp = lm + (size_t)o * L + (l - 1);
-        LevelMeta p = ldmeta<CG>(pp);
-        int rs = ch.rs / 2, cs = ch.cs / 2;
-        int er = ch.rs - 2 * rs, ec = ch.cs - 2 * cs;
-        p.rs = rs; p.cs = cs;
-        if (lane == 0) {
-            uint4 v = make_uint4(p.off, (uint32_t)rs, (uint32_t)cs, p.dims);
-            if (CG) __stcg(reinterpret_cast<uint4*>(pp), v); else *reinterpret_cast<uint4*>(pp) = v;
-        }
-        int wpc = wpc_of(lm_kh(p));
-        int nw = wpc * lm_kw(p);
-        for (int i = lane; i < nw; i += 32) {
-            int pc = i / wpc, pw = i - pc * wpc;
-            stw<CG>(words + p.off + i, build_word<CG>(words, ch, er, ec, pc, pw));
+        int s = l - 1;
+        uint32_t poff = __shfl_sync(FULLM, mine.off, s), pdims = __shfl_sync(FULLM, mine.dims, s);
+        LevelMeta ch; ch.off = __shfl_sync(FULLM, coff, s); ch.dims = __shfl_sync(FULLM, cdims, s); ch.rs = 0; ch.cs = 0;
+        int er = __shfl_sync(FULLM, my_er, s), ec = __shfl_sync(FULLM, my_ec, s);
+        int kwp = (int)((pdims >> 15) & 0x7fffu), wpc = wpc_of((int)(pdims & 0x7fffu));
+        int nw = wpc * kwp;
+        int wpcc = wpc_of(lm_kh(ch)), kwc = lm_kw(ch);
+        bool fits = nw <= RB_HALF;
+        uint32_t* dst = sbuf + (cur ^ 1) * RB_HALF;
+        const uint32_t* src = in_smem ? sbuf + cur * RB_HALF : words + ch.off;
+        if (wpcc <= 2 && wpc == 1 && kwp <= 32) {
+            // small level: one lane per parent column, both child columns are at most two words (kh <= 32)
+            if (lane < kwp) {
+                uint32_t d = lm_dflt(ch), dw = dflt_word(d);
+                uint64_t y = 0;
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    int cc = 2 * lane - ec + t;
+                    uint32_t w0 = dw, w1 = dw;
+                    if ((unsigned)cc < (unsigned)kwc) {
+                        const uint32_t* bp = src + cc * wpcc;
+                        w0 = in_smem ? bp[0] : ldw<CG>(bp);
+                        if (wpcc == 2) w1 = in_smem ? bp[1] : ldw<CG>(bp + 1);
+                    }
+                    y |= ((uint64_t)w1 << 32) | w0;
+                }
+                if (er > 0) y = (y << 2) | d; else if (er < 0) y = (y >> 2) | ((uint64_t)d << 62);
+                uint32_t wv = compress_pairs(y);
+                stw<CG>(words + poff + lane, wv);
+                dst[lane] = wv;
+            }
+        } else {
+            for (int i = lane; i < nw; i += 32) {
+                int pc = i / wpc, pw = i - pc * wpc;
+                uint32_t wv = in_smem ? build_word<false>(src, ch, er, ec, pc, pw) : build_word<CG>(src, ch, er, ec, pc, pw);
+                stw<CG>(words + poff + i, wv);
+                if (fits) dst[i] = wv;
+            }
         }
         __syncwarp();
-        ch = p;
+        in_smem = fits; cur ^= 1;
     }
+    return mine;
+}
+// convenience wrapper: loads and stores the metas itself
+template <bool CG> __device__ __forceinline__ void rebuild_levels_warp(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int o, int L, int from, int lane, uint32_t* __restrict__ sbuf) {
+    LevelMeta mine = {};
+    if (lane < L) mine = ldmeta<CG>(lm + (size_t)o * L + lane);
+    mine = warp_rebuild<CG>(words, mine, L, from, lane, sbuf);
+    if (lane >= from && lane < L) stmeta<CG>(lm + (size_t)o * L + lane, mine);
 }
 
 // ---- spatial cell keys: scene | level | a+bias | b+bias ----

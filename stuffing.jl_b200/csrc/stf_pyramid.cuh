@@ -49,12 +49,14 @@ __global__ void k_pack_level1(const uint8_t* __restrict__ payload, const uint64_
 // ---- warp-per-object build: worklist entry = (object, from_level): levels from+1..L ------------
 __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L,
                                 const int2* __restrict__ work, int nwork, const ObjMeta* __restrict__ om, int skip_big) {
+    __shared__ uint32_t sbuf[8][2 * RB_HALF]; // blockDim.x == 256
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int i = warp; i < nwork; i += nwarps) {
         int2 w = work[i];
         if (skip_big && om[w.x].big) continue;
-        if (w.y < L) rebuild_levels_warp<false>(words, lm, w.x, L, w.y, lane);
+        if (w.y < L) rebuild_levels_warp<false>(words, lm, w.x, L, w.y, lane, sbuf[threadIdx.x >> 5]);
+        __syncwarp();
     }
 }
 
@@ -68,7 +70,7 @@ __global__ void k_build_level_wide(uint32_t* __restrict__ words, LevelMeta* __re
     int64_t nw = (int64_t)wpc * lm_kw(p);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (int64_t)gridDim.x * blockDim.x) {
         int pc = (int)(i / wpc), pw = (int)(i - (int64_t)pc * wpc);
-        words[p.off + i] = build_word<false>(words, ch, er, ec, pc, pw);
+        words[p.off + i] = build_word<false>(words + ch.off, ch, er, ec, pc, pw);
     }
 }
 // the shift of level l must be set before the NEXT level reads it; done in its own tiny launch so

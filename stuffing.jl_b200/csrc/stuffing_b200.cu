@@ -9,6 +9,7 @@
 #include "stf_step.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -40,7 +41,7 @@ struct stf_ctx {
     DevBuf words, lm, om, payload, poff, woff1, work, lab, lab2, lab3, lab4, bytes_tmp;
     DevBuf rk, rv, rk2, rv2, hist, lkk, lkv;
     DevBuf items, direct, res, overflow, hits, hits2, hk, hv, hk2, hv2, keep, out32, scratch;
-    DevBuf counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m;
+    DevBuf dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m;
     unsigned long long* h_counts = nullptr; int* h_err = nullptr; // pinned
     OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
@@ -77,7 +78,7 @@ static void stage_begin(stf_ctx* ctx, int stage) {
 #define KCHECK() CK(cudaGetLastError())
 static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n + t - 1) / t); }
 
-enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_NVALID = 7, C_N = 8 };
+enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_N = 12 };
 
 static int32_t sync_counts(stf_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
@@ -158,7 +159,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
                              const uint8_t* is_mask, const int32_t* scene) {
     if (!ctx) return STF_E_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (n < 0 || canvas < 2 || (canvas & (canvas - 1)) || canvas > 65536) FAIL(STF_E_ARG, "canvas must be a power of two in [2, 65536]");
+    if (n < 0 || canvas < 2 || (canvas & (canvas - 1)) || canvas > 32768) FAIL(STF_E_ARG, "canvas must be a power of two in [2, 32768]");
     int L = 1; for (int s = canvas; s > 1; s >>= 1) L++;
     ctx->n = n; ctx->L = L; ctx->canvas = canvas; ctx->items_valid = false; ctx->last_result = 0;
     ctx->label_bits = 1; while ((1ll << ctx->label_bits) <= n) ctx->label_bits++;
@@ -436,7 +437,7 @@ static int32_t import_items(stf_ctx* ctx, int64_t n, const stf_item* items, DevB
     KCHECK();
     return STF_OK;
 }
-static int32_t zero_counts(stf_ctx* ctx) { CK(cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st)); return STF_OK; }
+static int32_t zero_counts(stf_ctx* ctx) { CK(cudaMemsetAsync(ctx->counts.p, 0, C_ZEROED * sizeof(unsigned long long), ctx->st)); return STF_OK; }
 
 extern "C" int32_t stf_collision_bfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out) {
     NEED_OBJS();
@@ -493,11 +494,17 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(nh)));
     stage_begin(ctx, STF_STAGE_RESULT);
     ctx->launches++, k_hit_keys<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
-    int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh, 0, ctx->label_bits, ctx->hist.as<uint32_t>());
-    uint64_t *k0 = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), *k1 = f ? ctx->hk.as<uint64_t>() : ctx->hk2.as<uint64_t>();
-    uint32_t *v0 = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), *v1 = f ? ctx->hv.as<uint32_t>() : ctx->hv2.as<uint32_t>();
-    int f2 = radix_sort_pairs(ctx->st, &ctx->launches, k0, v0, k1, v1, nh, 32, 32 + ctx->label_bits, ctx->hist.as<uint32_t>());
-    uint64_t* ks = f2 ? k1 : k0; uint32_t* vs = f2 ? v1 : v0;
+    uint64_t* ks; uint32_t* vs;
+    if (nh <= SORT_SMALL_MAX) { // (i1,i2) in one launch: the device picks the bit windows of i2 and i1 that vary
+        ctx->launches++, k_sort_small<<<1, SS_THREADS, 0, ctx->st>>>(ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nullptr, nh, 0, 64, nullptr);
+        ks = ctx->hk.as<uint64_t>(); vs = ctx->hv.as<uint32_t>();
+    } else {
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh, 0, ctx->label_bits, ctx->hist.as<uint32_t>());
+        uint64_t *k0 = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), *k1 = f ? ctx->hk.as<uint64_t>() : ctx->hk2.as<uint64_t>();
+        uint32_t *v0 = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), *v1 = f ? ctx->hv.as<uint32_t>() : ctx->hv2.as<uint32_t>();
+        int f2 = radix_sort_pairs(ctx->st, &ctx->launches, k0, v0, k1, v1, nh, 32, 32 + ctx->label_bits, ctx->hist.as<uint32_t>());
+        ks = f2 ? k1 : k0; vs = f2 ? v1 : v0;
+    }
     ctx->launches++, k_gather_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), vs, nh, ctx->hits2.as<Item16>());
     ctx->launches++, k_fix_ties<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ks, nh, unique, ctx->keep.as<uint32_t>());
     KCHECK();
@@ -624,21 +631,28 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     KCHECK();
     stage_begin(ctx, STF_STAGE_SORT);
     int bits = 2 * STF_CELL_W + 5 + ctx->scene_bits;
-    int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nrec, 0, bits, ctx->hist.as<uint32_t>());
+    unsigned long long* nvalid = ctx->counts.as<unsigned long long>() + C_NVALID;
+    if (nrec <= SORT_SMALL_MAX) { // one launch: compaction + only the digit windows in which keys differ
+        ctx->launches++, k_sort_small<<<1, SS_THREADS, 0, ctx->st>>>(ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(),
+                                                                    nullptr, nrec, 1, bits, nvalid);
+        *keys = ctx->rk.as<uint64_t>(); *vals = ctx->rv.as<uint32_t>();
+    } else {
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nrec, 0, bits, ctx->hist.as<uint32_t>());
+        *keys = f ? ctx->rk2.as<uint64_t>() : ctx->rk.as<uint64_t>();
+        *vals = f ? ctx->rv2.as<uint32_t>() : ctx->rv.as<uint32_t>();
+        ctx->launches++, k_count_valid<<<1, 1, 0, ctx->st>>>(*keys, nrec, nvalid);
+    }
     KCHECK();
     stage_end(ctx);
-    *keys = f ? ctx->rk2.as<uint64_t>() : ctx->rk.as<uint64_t>();
-    *vals = f ? ctx->rv2.as<uint32_t>() : ctx->rv.as<uint32_t>();
     ctx->ctr.records = nrec;
     return STF_OK;
 }
 static int32_t export_cells(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, stf_cellrec* out, int64_t cap, int64_t* count) {
-    int32_t r = zero_counts(ctx); if (r) return r;
     CK(ctx->out32.ensure(sizeof(int32_t) * 4 * (size_t)std::max<int64_t>(1, nrec)));
-    if (nrec > 0) ctx->launches++, k_export_cells<<<nblk(nrec, 256), 256, 0, ctx->st>>>(keys, vals, nrec, ctx->out32.as<int32_t>(), ctx->counts.as<unsigned long long>() + C_NVALID);
+    if (nrec > 0) ctx->launches++, k_export_cells<<<nblk(nrec, 256), 256, 0, ctx->st>>>(keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->out32.as<int32_t>());
     KCHECK();
-    r = sync_counts(ctx); if (r) return r;
-    int64_t nv = (int64_t)ctx->h_counts[C_NVALID];
+    int32_t r = sync_counts(ctx); if (r) return r;
+    int64_t nv = nrec > 0 ? (int64_t)ctx->h_counts[C_NVALID] : 0;
     if (count) *count = nv;
     if (nv > cap) FAIL(STF_E_CAPACITY, "output buffer too small");
     if (nv > 0) { CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(stf_cellrec) * (size_t)nv, cudaMemcpyDeviceToHost, ctx->st)); CK(cudaStreamSynchronize(ctx->st)); }
@@ -711,9 +725,12 @@ static int32_t spacial_core(stf_ctx* ctx, int32_t nl, const int32_t* labels, int
         if (ctx->direct.cap < sizeof(Item16) * 1024) CK(ctx->direct.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, nrec)));
         EmitOut eo; eo.items = ctx->items.as<Item16>(); eo.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
         eo.direct = ctx->direct.as<Item16>(); eo.direct_cap = (int64_t)(ctx->direct.cap / sizeof(Item16)); eo.counts = ctx->counts.as<unsigned long long>();
-        int64_t threads = nrec * (ctx->L - 1);
         stage_begin(ctx, STF_STAGE_EMIT);
-        if (threads > 0) ctx->launches++, k_emit_items<<<nblk(threads, 256), 256, 0, ctx->st>>>(keys, vals, nrec, ctx->L, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), moved_pos, eo);
+        if (nrec > 0) {
+            int blocks = (int)std::min<int64_t>((nrec + EM_THREADS / 32 - 1) / (EM_THREADS / 32), 148 * 8);
+            ctx->launches++, k_emit_items<<<blocks, EM_THREADS, 0, ctx->st>>>(keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
+                                                                            ctx->lm.as<LevelMeta>(), moved_pos, eo);
+        }
         KCHECK();
         stage_end(ctx);
         r = sync_counts(ctx); if (r) return r;
@@ -789,17 +806,27 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)n));
     stage_begin(ctx, STF_STAGE_STEP_PREP);
     ctx->launches++, k_step_endpoints<<<nblk(m, 256), 256, 0, ctx->st>>>(hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
-    int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
-    ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), m, ctx->prev.as<uint32_t>());
+    CK(cudaMemsetAsync(ctx->prev.p, 0, sizeof(uint32_t) * (size_t)m, ctx->st));
+    if (m <= SORT_SMALL_MAX) { // mask endpoints (INVALID) are compacted away; prev stays 0 for them
+        unsigned long long* nep = ctx->counts.as<unsigned long long>() + C_NEP;
+        ctx->launches++, k_sort_small<<<1, SS_THREADS, 0, ctx->st>>>(ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nullptr, m, 1, ctx->label_bits + 1, nep);
+        ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), nep, m, ctx->prev.as<uint32_t>());
+    } else {
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
+        ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
+    }
     CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
     CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
-    CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_KEPT, 0, sizeof(unsigned long long), ctx->st)); // ticket lives in C_KEPT during the launch
+    CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
     StepArgs A;
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.om = ctx->om.as<ObjMeta>(); A.L = ctx->L;
     A.hits = hits; A.n = n; A.prev = ctx->prev.as<uint32_t>(); A.done = ctx->done.as<uint32_t>();
-    A.ticket = ctx->counts.as<unsigned long long>() + C_KEPT;
+    A.ticket = ctx->counts.as<unsigned long long>() + C_TICKET;
     A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>();
     A.opt = ctx->opt; A.seed = seed; A.iter = iter; A.counts = ctx->counts.as<unsigned long long>();
+    { const char* e = getenv("STF_DEBUG_STEP"); A.dbg = e ? atoi(e) : 0; }
+    A.dbg_t = nullptr;
+    if (A.dbg & 16) { CK(ctx->dbg_t.ensure(sizeof(unsigned long long) * 4 * (size_t)n)); A.dbg_t = ctx->dbg_t.as<unsigned long long>(); }
     int blocks = (int)std::min<int64_t>((n + 3) / 4, 148 * 8);
     stage_begin(ctx, STF_STAGE_STEP);
     ctx->launches++, k_batchsteps<<<blocks, 128, 0, ctx->st>>>(A);
@@ -858,3 +885,10 @@ extern "C" int32_t stf_profile_read(stf_ctx* ctx, double* ms, int64_t* calls, in
 }
 
 extern "C" int64_t stf_launch_count(const stf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// debug: timeline of the last k_batchsteps launch (STF_DEBUG_STEP & 16): 4 x u64 nanosecond stamps per step
+extern "C" int32_t stf_debug_step_timeline(stf_ctx* ctx, int64_t n, unsigned long long* out) {
+    if (!ctx || !ctx->dbg_t.p) return STF_E_STATE;
+    CK(cudaMemcpy(out, ctx->dbg_t.p, sizeof(unsigned long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    return STF_OK;
+}
