@@ -120,11 +120,12 @@ template <bool CG> __device__ __forceinline__ void stmeta(LevelMeta* p, const Le
 // per-warp shared-memory copy of the level just produced (levels shrink 4x, so they fit after one step);
 // the global stores are fire-and-forget.  Returns the lane's meta with the new shifts (lanes >= from).
 #define RB_HALF 384   // words per shared-memory level buffer (two per warp)
-template <bool CG> __device__ __forceinline__ LevelMeta warp_rebuild(uint32_t* __restrict__ words, LevelMeta mine, int L, int from, int lane, uint32_t* __restrict__ sbuf) {
+// KEEP: the per-level shifts in `mine` are already final (lazy batchsteps tracks them); only the rasters are rebuilt.
+template <bool CG, bool KEEP = false> __device__ __forceinline__ LevelMeta warp_rebuild(uint32_t* __restrict__ words, LevelMeta mine, int L, int from, int lane, uint32_t* __restrict__ sbuf) {
     const unsigned FULLM = 0xffffffffu;
     // shifts of the rebuilt levels in closed form: repeated `÷ 2` (toward zero) composes to `÷ 2^k`
     int brs = __shfl_sync(FULLM, mine.rs, from - 1), bcs = __shfl_sync(FULLM, mine.cs, from - 1);
-    if (lane >= from && lane < L) { // x / 2^sh toward zero without an integer division
+    if (!KEEP && lane >= from && lane < L) { // x / 2^sh toward zero without an integer division
         int sh = lane + 1 - from;
         mine.rs = brs >= 0 ? (brs >> sh) : -((-brs) >> sh); mine.cs = bcs >= 0 ? (bcs >> sh) : -((-bcs) >> sh);
     }
@@ -133,19 +134,35 @@ template <bool CG> __device__ __forceinline__ LevelMeta warp_rebuild(uint32_t* _
     uint32_t cdims = __shfl_up_sync(FULLM, mine.dims, 1), coff = __shfl_up_sync(FULLM, mine.off, 1);
     int my_er = crs - 2 * mine.rs, my_ec = ccs - 2 * mine.cs;
     bool in_smem = false; int cur = 0;
+    bool in_reg = false; uint32_t regw = 0; // once a level is one word per column and <= 32 columns, lane j keeps column j
     for (int l = from + 1; l <= L; l++) {
         int s = l - 1;
         uint32_t poff = __shfl_sync(FULLM, mine.off, s), pdims = __shfl_sync(FULLM, mine.dims, s);
         LevelMeta ch; ch.off = __shfl_sync(FULLM, coff, s); ch.dims = __shfl_sync(FULLM, cdims, s); ch.rs = 0; ch.cs = 0;
         int er = __shfl_sync(FULLM, my_er, s), ec = __shfl_sync(FULLM, my_ec, s);
         int kwp = (int)((pdims >> 15) & 0x7fffu), wpc = wpc_of((int)(pdims & 0x7fffu));
-        int nw = wpc * kwp;
         int wpcc = wpc_of(lm_kh(ch)), kwc = lm_kw(ch);
+        if (in_reg) {
+            // register path: the child level lives in `regw` (wpcc == 1, kwc <= 32), so kh_p <= 9 and kw_p <= 17;
+            // two shuffles fetch the child columns, no memory on the dependent chain, the store is fire-and-forget
+            uint32_t d = lm_dflt(ch), dw = dflt_word(d);
+            int c0 = 2 * lane - ec;
+            uint32_t w0 = __shfl_sync(FULLM, regw, c0 & 31), w1 = __shfl_sync(FULLM, regw, (c0 + 1) & 31);
+            if ((unsigned)c0 >= (unsigned)kwc) w0 = dw;
+            if ((unsigned)(c0 + 1) >= (unsigned)kwc) w1 = dw;
+            uint64_t y = ((uint64_t)dw << 32) | (w0 | w1);
+            if (er > 0) y = (y << 2) | d; else if (er < 0) y = (y >> 2) | ((uint64_t)d << 62);
+            regw = compress_pairs(y);
+            if (lane < kwp) stw<CG>(words + poff + lane, regw);
+            continue;
+        }
+        int nw = wpc * kwp;
         bool fits = nw <= RB_HALF;
         uint32_t* dst = sbuf + (cur ^ 1) * RB_HALF;
         const uint32_t* src = in_smem ? sbuf + cur * RB_HALF : words + ch.off;
         if (wpcc <= 2 && wpc == 1 && kwp <= 32) {
             // small level: one lane per parent column, both child columns are at most two words (kh <= 32)
+            uint32_t wv = 0;
             if (lane < kwp) {
                 uint32_t d = lm_dflt(ch), dw = dflt_word(d);
                 uint64_t y = 0;
@@ -161,17 +178,17 @@ template <bool CG> __device__ __forceinline__ LevelMeta warp_rebuild(uint32_t* _
                     y |= ((uint64_t)w1 << 32) | w0;
                 }
                 if (er > 0) y = (y << 2) | d; else if (er < 0) y = (y >> 2) | ((uint64_t)d << 62);
-                uint32_t wv = compress_pairs(y);
+                wv = compress_pairs(y);
                 stw<CG>(words + poff + lane, wv);
-                dst[lane] = wv;
             }
-        } else {
-            for (int i = lane; i < nw; i += 32) {
-                int pc = i / wpc, pw = i - pc * wpc;
-                uint32_t wv = in_smem ? build_word<false>(src, ch, er, ec, pc, pw) : build_word<CG>(src, ch, er, ec, pc, pw);
-                stw<CG>(words + poff + i, wv);
-                if (fits) dst[i] = wv;
-            }
+            regw = wv; in_reg = true;
+            continue;
+        }
+        for (int i = lane; i < nw; i += 32) {
+            int pc = i / wpc, pw = i - pc * wpc;
+            uint32_t wv = in_smem ? build_word<false>(src, ch, er, ec, pc, pw) : build_word<CG>(src, ch, er, ec, pc, pw);
+            stw<CG>(words + poff + i, wv);
+            if (fits) dst[i] = wv;
         }
         __syncwarp();
         in_smem = fits; cur ^= 1;
@@ -184,6 +201,57 @@ template <bool CG> __device__ __forceinline__ void rebuild_levels_warp(uint32_t*
     if (lane < L) mine = ldmeta<CG>(lm + (size_t)o * L + lane);
     mine = warp_rebuild<CG>(words, mine, L, from, lane, sbuf);
     if (lane >= from && lane < L) stmeta<CG>(lm + (size_t)o * L + lane, mine);
+}
+
+
+// 32 consecutive 2-bit fields of kernel column c (0-based) from kernel row r0 on (0-based; r0 may be negative or run
+// past kh): PaddedMat safe-read semantics, everything outside the kernel is `default`.
+template <bool CG> __device__ __forceinline__ uint64_t fields64_at(const uint32_t* __restrict__ words, const LevelMeta& m, int c, int r0) {
+    uint32_t dw = dflt_word(lm_dflt(m));
+    int wpc = wpc_of(lm_kh(m));
+    if ((unsigned)c >= (unsigned)lm_kw(m)) return ((uint64_t)dw << 32) | dw;
+    const uint32_t* base = words + m.off + (size_t)c * wpc;
+    int w0 = r0 >> 4, off = (r0 & 15) * 2;
+    uint32_t x0 = (unsigned)w0 < (unsigned)wpc ? ldw<CG>(base + w0) : dw;
+    uint32_t x1 = (unsigned)(w0 + 1) < (unsigned)wpc ? ldw<CG>(base + w0 + 1) : dw;
+    uint32_t x2 = (unsigned)(w0 + 2) < (unsigned)wpc ? ldw<CG>(base + w0 + 2) : dw;
+    uint64_t lo = ((uint64_t)x1 << 32) | x0;
+    if (off) lo = (lo >> off) | ((uint64_t)x2 << (64 - off));
+    return lo;
+}
+__device__ __forceinline__ int decode2(uint32_t c) { return (int)((0x60u >> ((c & 3u) << 1)) & 3u); } // fit_helper.jl:42
+
+// grad2d (fit_helper.jl:51-66) at (l,a,b) of a tree whose levels > m are stale in memory (lazy batchsteps: moves only
+// update the per-level shifts, the rasters are materialised once per batch).  The 3x3 window of level l is derived
+// from level m through the build rule (qtrees.jl:221-237) with the CURRENT shifts: window origin lo_j = 2*lo_{j+1} - 1,
+// lane i = window column i, one 64-bit register = the rows of that column; each level is two shuffles, a pair-OR
+// compress and the clip against that level's kernel window (outside -> default).  Needs l - m <= 3 (24 columns).
+// `meta_at(j)` returns the LevelMeta of level j (warp-uniform).  Whole warp must call.
+template <bool CG, class MetaAt> __device__ __forceinline__ int2 grad_lazy(const uint32_t* __restrict__ words, MetaAt meta_at, int l, int a, int b, int m, int lane) {
+    const unsigned FULLM = 0xffffffffu;
+    int k = l - m;
+    int rlo = a - 1, clo = b - 1;
+    for (int i = 0; i < k; i++) { rlo = 2 * rlo - 1; clo = 2 * clo - 1; }
+    int n = 3 << k;
+    LevelMeta mm = meta_at(m);
+    uint64_t x = 0;
+    if (lane < n) x = fields64_at<CG>(words, mm, clo + lane - mm.cs - 1, rlo - mm.rs - 1);
+    for (int j = m + 1; j <= l; j++) {
+        rlo = (rlo + 1) >> 1; clo = (clo + 1) >> 1; n >>= 1; // exact: lo_{j-1} = 2*lo_j - 1
+        uint64_t y = __shfl_sync(FULLM, x, (2 * lane) & 31) | __shfl_sync(FULLM, x, (2 * lane + 1) & 31);
+        uint32_t p = compress_pairs(y);
+        LevelMeta pm = meta_at(j);
+        int lo = max(0, pm.rs + 1 - rlo), hi = min(n, pm.rs + lm_kh(pm) + 1 - rlo);
+        uint32_t mask = hi > lo ? (((1u << (2 * hi)) - 1u) & ~((1u << (2 * lo)) - 1u)) : 0u;
+        int col = clo + lane;
+        if (!(col > pm.cs && col <= pm.cs + lm_kw(pm))) mask = 0u;
+        x = (uint64_t)((p & mask) | (dflt_word(lm_dflt(pm)) & ~mask));
+    }
+    int f0 = decode2((uint32_t)x & 3u), f1 = decode2((uint32_t)(x >> 2) & 3u), f2 = decode2((uint32_t)(x >> 4) & 3u);
+    int rowdiff = f2 - f0, colsum = f0 + f1 + f2;
+    int gh = __shfl_sync(FULLM, rowdiff, 0) + __shfl_sync(FULLM, rowdiff, 1) + __shfl_sync(FULLM, rowdiff, 2);
+    int gw = __shfl_sync(FULLM, colsum, 2) - __shfl_sync(FULLM, colsum, 0);
+    return make_int2(gh, gw);
 }
 
 // ---- spatial cell keys: scene | level | a+bias | b+bias ----

@@ -120,8 +120,6 @@ __global__ void k_read_nodes(const uint32_t* __restrict__ words, const LevelMeta
     LevelMeta m = lm[(size_t)(labels[i] - 1) * L + (l[i] - 1)];
     out[i] = (uint8_t)node_code<false>(words, m, a[i], b[i]);
 }
-// decode2: EMPTY -> 0, FULL -> 2, MIX -> 1 (fit_helper.jl:42)
-__device__ __forceinline__ int decode2(uint32_t c) { return (int)((0x60u >> ((c & 3u) << 1)) & 3u); }
 template <bool CG> __device__ __forceinline__ int2 grad2d_dev(const uint32_t* __restrict__ words, const LevelMeta& m, int a, int b) {
 #define STF_D(r, c) decode2(node_code<CG>(words, m, (r), (c)))
     int diag = -STF_D(a - 1, b - 1) + STF_D(a + 1, b + 1);

@@ -42,25 +42,25 @@ struct StepArgs {
     uint32_t* words; LevelMeta* lm; const ObjMeta* om; int L;
     const Item16* hits; int64_t n;
     const uint32_t* prev; uint32_t* done; unsigned long long* ticket;
-    double* vel; uint8_t* has_vel; uint8_t* moved_flag;
+    double* vel; uint8_t* has_vel; uint8_t* moved_flag; int* dirty;
     OptState opt; uint64_t seed, iter;
     unsigned long long* counts; // [4] number of moves
     unsigned long long* dbg_t;  // optional timeline (4 x u64 per step) when dbg & 16
     int dbg;                    // STF_DEBUG_STEP experiments: 1 no wait, 2 no rebuild, 4 no fence (breaks parity)
 };
 
-// optimiser(t, Δ)  fit_helper.jl:19-35, fit.jl:25 — executed by one lane; (has, v0, v1) were prefetched
-__device__ __forceinline__ void opt_apply_dev(const StepArgs& A, int o, double& d0, double& d1, int has, double v0, double v1) {
+// optimiser(t, Δ)  fit_helper.jl:19-35, fit.jl:25 — every lane computes it, lane `st` stores; (has, v0, v1) were prefetched
+__device__ __forceinline__ void opt_apply_dev(const StepArgs& A, int o, double& d0, double& d1, int has, double v0, double v1, bool st) {
     if (A.opt.kind == 0) { d0 = d0 / 6.0; d1 = d1 / 6.0; return; }
     if (A.opt.kind == 1) { d0 = __dmul_rn(A.opt.eta, d0); d1 = __dmul_rn(A.opt.eta, d1); return; }
-    if (!has) { v0 = d0; v1 = d1; __stcg(A.has_vel + o, (uint8_t)1); } // v = get!(velocity, x, Δ)
+    if (!has) { v0 = d0; v1 = d1; if (st) __stcg(A.has_vel + o, (uint8_t)1); } // v = get!(velocity, x, Δ)
     double omr = __dsub_rn(1.0, A.opt.rho);
     v0 = __dadd_rn(__dmul_rn(A.opt.rho, v0), __dmul_rn(omr, d0)); // no FMA contraction: Julia does not fuse
     v1 = __dadd_rn(__dmul_rn(A.opt.rho, v1), __dmul_rn(omr, d1));
-    __stcg(A.vel + 2 * (size_t)o, v0); __stcg(A.vel + 2 * (size_t)o + 1, v1);
+    if (st) { __stcg(A.vel + 2 * (size_t)o, v0); __stcg(A.vel + 2 * (size_t)o + 1, v1); }
     d0 = __dmul_rn(A.opt.eta, v0); d1 = __dmul_rn(A.opt.eta, v1);
 }
-// move!  fit.jl:11-23 — decides (level, s1, s2); executed by one lane.  r_jit, r_d1, r_d2: the three draws of this
+// move!  fit.jl:11-23 — decides (level, s1, s2).  r_jit, r_d1, r_d2: the three draws of this
 // tree (jitter test, jitter diagonal, avoid-rest diagonal), computed in parallel by other lanes
 __device__ __forceinline__ double u64_to_unit(uint64_t r) { return (double)(r >> 11) * (1.0 / 9007199254740992.0); }
 __device__ __forceinline__ int3 move_decide(const StepArgs& A, double d0, double d1, uint64_t r_jit, uint64_t r_d1, uint64_t r_d2) {
@@ -79,116 +79,178 @@ __device__ __forceinline__ int3 move_decide(const StepArgs& A, double d0, double
     int s1 = d0 >= p ? 1 : (d0 <= -p ? -1 : 0), s2 = d1 >= p ? 1 : (d1 <= -p ? -1 : 0);
     return make_int3(min(A.L, 1 + u), s1, s2);
 }
-// shift!(t, lv, s1, s2)  qtrees.jl:267-275 by one warp.  `mine`: lane i holds the meta of level i+1 of object o.
-// Levels <= lv move by s*2^(lv-i); levels > lv are rebuilt; all changed metas are stored once.
-__device__ __forceinline__ void warp_shift_rebuild(const StepArgs& A, int o, LevelMeta mine, int3 mv, int lane, uint32_t* sbuf) {
-    int lv = mv.x;
-    if (lane < lv) { int f = 1 << (lv - 1 - lane); mine.rs += mv.y * f; mine.cs += mv.z * f; }
-    mine = warp_rebuild<true>(A.words, mine, A.L, lv, lane, sbuf);
-    if (lane < A.L) stmeta<true>(A.lm + (size_t)o * A.L + lane, mine);
-    if (lane == 0) { A.moved_flag[o] = 1; atomicAdd(A.counts + 4, 1ull); }
-}
-
-// Per step, dependent L2 round trips: (1) wait flags, (2) both objects' LevelMetas of every level (one per
-// lane: lanes 0-15 tree 1, 16-31 tree 2) + velocities, (3) the 2x8 gradient nodes (one per lane), (4) the
-// child words of the first rebuilt level; everything above is rebuilt through shared memory.
+// ---- lazy batchsteps -------------------------------------------------------------------------------------------
+// A move (shift!, qtrees.jl:267-275) translates levels <= lv and rebuilds levels > lv.  A pyramid that is consistent
+// (every level = buildqtree! of the level below) stays consistent under shift!, so it is a pure function of the level-1
+// raster and the per-level shifts.  Inside one batch a step therefore only updates the SHIFTS of the moved tree (all
+// levels, closed form) and records dirty[o] = lowest level whose raster is still valid in memory; the few gradient
+// nodes a later step of the same batch needs above that level are derived on the fly (grad_lazy), and every moved tree
+// is materialised ONCE after the batch (k_materialize).  No rebuild sits on the step-to-step dependency chain.
+// Per step, the dependent chain is: flag -> ONE round trip for everything that describes the two trees (each lane
+// loads the LevelMeta of "its" level — lanes 0-15 tree 1, 16-31 tree 2 — plus the meta of the hit level, the dirty
+// levels and both velocities, all as warp-broadcast loads) -> ONE round trip for the 2x8 gradient nodes -> two
+// ballots (the gradient sums are popcounts) -> the scalar arithmetic of step!/move!, done redundantly by every lane so
+// that nothing has to be broadcast -> stores, release fence, flag.  Everything that does not depend on tree state
+// (the hit, the draws, the mass-ratio tests) is computed before the wait.
 __global__ void __launch_bounds__(128) k_batchsteps(StepArgs A) {
-    __shared__ uint32_t sbuf[4][2 * RB_HALF];
+    __shared__ uint32_t sbuf[4][2 * RB_HALF]; // only the rare eager materialisation uses it
+    __shared__ uint64_t s_rnd[4][8];
+    __shared__ int2 s_shift[4][32];
+    const unsigned FULLM = 0xffffffffu;
     int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+    const uint64_t hbase = stf_mix64(stf_mix64(A.seed ^ 0x5354554646494E47ull) + A.iter); // stf_rand_u64 without the per-draw part
+    int k_round = 0;
     for (;;) {
         unsigned long long k = 0;
-        if (lane == 0) k = atomicAdd(A.ticket, 1ull);
-        k = __shfl_sync(0xffffffffu, k, 0);
+        if (A.dbg & 32) { if (k_round++) return; k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; } // timing experiment: no ticket
+        else {
+            if (lane == 0) k = atomicAdd(A.ticket, 1ull);
+            k = __shfl_sync(FULLM, k, 0);
+        }
         if ((int64_t)k >= A.n) return;
-        unsigned long long t_claim = 0, t_ready = 0, t_decided = 0;
-        if (A.dbg & 16) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_claim));
+        unsigned long long t_ready = 0, t_decided = 0;
         Item16 h = A.hits[k];
         int o1 = h.i1 - 1, o2 = item_i2(h) - 1;
         int l = item_l(h), a = h.a, b = h.b;
         ObjMeta om1 = A.om[o1], om2 = A.om[o2];
-        if (lane < 2 && !(A.dbg & 1)) { // wait for the previous step of each movable object
-            uint32_t pv = A.prev[2 * k + lane];
-            if (pv) { const volatile uint32_t* f = A.done + (pv - 1); if (A.dbg & 8) { while (*f == 0) __nanosleep(20); } else { while (*f == 0) { } } }
-        }
+        uint32_t pv = lane < 2 ? A.prev[2 * k + lane] : 0u;
+        // the 8 draws of this step (stuffing_b200_rng.h slots 0..7): lane j makes draw j, shared memory hands them round
+        if (lane < 8) s_rnd[wib][lane] = stf_mix64(hbase + (k << 3) + (uint64_t)lane);
         __syncwarp();
-        __threadfence();
-        if (A.dbg & 16) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ready));
-        // (2) metas of all levels of both trees + optimiser state
-        int oh = half ? o2 : o1;
-        LevelMeta mine = {};
-        if (hl < A.L) mine = ldmeta<true>(A.lm + (size_t)oh * A.L + hl);
-        int has = 0; double v0 = 0, v1 = 0;
-        if (hl == 0 && A.opt.kind == 2) {
-            has = __ldcg(A.has_vel + oh);
-            double2 vv = __ldcg(reinterpret_cast<const double2*>(A.vel + 2 * (size_t)oh));
-            v0 = vv.x; v1 = vv.y;
-        }
-        // (3) grad2d (fit_helper.jl:51-66): gh = sum dr*decode2, gw = sum dc*decode2 over the 8 neighbours
-        LevelMeta q = shfl_meta(mine, half * 16 + (l - 1));
-        int gh = 0, gw = 0;
-        if (hl < 8) {
-            int idx = hl < 4 ? hl : hl + 1; int dr = idx / 3 - 1, dc = idx % 3 - 1;
-            int v = decode2(node_code<true>(A.words, q, a + dr, b + dc));
-            gh = v * dr; gw = v * dc;
-        }
-#pragma unroll
-        for (int s = 1; s < 8; s <<= 1) { gh += __shfl_xor_sync(0xffffffffu, gh, s); gw += __shfl_xor_sync(0xffffffffu, gw, s); }
-        int g1x = __shfl_sync(0xffffffffu, gh, 0), g1y = __shfl_sync(0xffffffffu, gw, 0);
-        int g2x = __shfl_sync(0xffffffffu, gh, 16), g2y = __shfl_sync(0xffffffffu, gw, 16);
-        int has2 = __shfl_sync(0xffffffffu, has, 16); double v20 = __shfl_sync(0xffffffffu, v0, 16), v21 = __shfl_sync(0xffffffffu, v1, 16);
-        // the 8 draws of this step, one per lane (stuffing_b200_rng.h slots 0..7), gathered by lane 0
-        uint64_t rnd = stf_rand_u64(A.seed, A.iter, k, (uint32_t)(lane & 7));
         uint64_t R[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) R[j] = __shfl_sync(0xffffffffu, rnd, j);
+        for (int j = 0; j < 8; j++) R[j] = s_rnd[wib][j];
         bool m1 = om1.is_mask, m2 = om2.is_mask;
+        bool move1 = false, move2 = false;
+        if (!(m1 || m2)) { // step!  fit.jl:33-35
+            double s1 = (double)(om1.kh1 + om1.kw1), s2 = (double)(om2.kh1 + om2.kw1);
+            double ks1 = s1 * s1 * s1, ks2 = s2 * s2 * s2;
+            move1 = u64_to_unit(R[0]) < ks2 / ks1;
+            move2 = u64_to_unit(R[1]) < ks1 / ks2;
+        }
+        double ll = (double)(1ll << (l - 1));
+        int oh = half ? o2 : o1, oo = half ? o1 : o2;
+        if (pv && !(A.dbg & 1)) { // wait for the previous step of each movable object: relaxed polls (no L1 invalidation), then
+            const uint32_t* f = A.done + (pv - 1); uint32_t v; // one acquire; every later read of tree state is an L2 (.cg) read
+            do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v == 0);
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        }
+        __syncwarp();
+        long long s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+        if (A.dbg & 16) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ready)); asm volatile("mov.u64 %0, %%clock64;" : "=l"(s0)); }
+        // ---- round trip 1: tree state
+        LevelMeta mine = {};
+        if (hl < A.L) mine = ldmeta<true>(A.lm + (size_t)oh * A.L + hl);
+        LevelMeta q = ldmeta<true>(A.lm + (size_t)oh * A.L + (l - 1));
+        int dmh = __ldcg(A.dirty + oh), dmo = __ldcg(A.dirty + oo); // levels > dirty are stale in memory
+        int hasA = 0, hasB = 0; double2 vA = make_double2(0, 0), vB = make_double2(0, 0);
+        if (A.opt.kind == 2) {
+            hasA = __ldcg(A.has_vel + o1); hasB = __ldcg(A.has_vel + o2);
+            vA = __ldcg(reinterpret_cast<const double2*>(A.vel + 2 * (size_t)o1));
+            vB = __ldcg(reinterpret_cast<const double2*>(A.vel + 2 * (size_t)o2));
+        }
+        int dmA = half ? dmo : dmh, dmB = half ? dmh : dmo;
+        s_shift[wib][lane] = make_int2(mine.rs, mine.cs);
+        if (A.dbg & 16) asm volatile("mov.u64 %0, %%clock64;" : "=l"(s1) : "r"(mine.off), "r"(q.off), "r"(dmh), "r"(dmo), "d"(vB.y), "d"(vA.x), "r"(hasB));
+        // ---- round trip 2: grad2d (fit_helper.jl:51-66), 8 neighbours per tree, one per lane; sums by ballot + popc
+        uint32_t dv = 0;
+        if (hl < 8 && l <= dmh) {
+            int idx = hl < 4 ? hl : hl + 1; int dr = idx / 3 - 1, dc = idx % 3 - 1;
+            dv = (uint32_t)decode2(node_code<true>(A.words, q, a + dr, b + dc));
+        }
+        uint32_t b0 = __ballot_sync(FULLM, dv & 1u), b1 = __ballot_sync(FULLM, dv & 2u);
+        // lanes hl = 0..7 hold window cells (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
+#define STF_GSUM(B0, B1, P, M) ((__popc((B0) & (P)) + 2 * __popc((B1) & (P))) - (__popc((B0) & (M)) + 2 * __popc((B1) & (M))))
+        int g1x = STF_GSUM(b0, b1, 0xE0u, 0x07u), g1y = STF_GSUM(b0, b1, 0x94u, 0x29u);
+        int g2x = STF_GSUM(b0 >> 16, b1 >> 16, 0xE0u, 0x07u), g2y = STF_GSUM(b0 >> 16, b1 >> 16, 0x94u, 0x29u);
+#undef STF_GSUM
+        if (A.dbg & 16) asm volatile("mov.u64 %0, %%clock64;" : "=l"(s2) : "r"(g1x), "r"(g2y));
+        if (l > dmA || l > dmB) { // stale level (the tree moved earlier in this batch): derive the window from the lowest valid level
+#pragma unroll 1
+            for (int t = 0; t < 2; t++) {
+                int dmt = t ? dmB : dmA, ot = t ? o2 : o1;
+                if (l <= dmt) continue;
+                const LevelMeta* tl = A.lm + (size_t)ot * A.L;
+                if (l - dmt > 3) { // window too wide: materialise this tree now (rare), then read it
+                    LevelMeta tm = {};
+                    if (lane < A.L) tm = ldmeta<true>(tl + lane);
+                    warp_rebuild<true, true>(A.words, tm, A.L, dmt, lane, sbuf[wib]);
+                    __syncwarp();
+                    dmt = A.L; if (t) dmB = dmt; else dmA = dmt;
+                }
+                int2 g = grad_lazy<true>(A.words, [&](int j) { return ldmeta<true>(tl + (j - 1)); }, l, a, b, min(dmt, l), lane);
+                if (t) { g2x = g.x; g2y = g.y; } else { g1x = g.x; g1y = g.y; }
+            }
+        }
+        // ---- step!/step_mask! (fit.jl:25-56): every lane runs the same scalar arithmetic
         int3 mvA = make_int3(0, 0, 0), mvB = make_int3(0, 0, 0); int oA = -1, oB = -1;
-        if (lane == 0) { // the scalar arithmetic of step!/step_mask!
-            double ll = (double)(1ll << (l - 1));
+        bool st = lane == 0; // the lane that stores the optimiser state
+        {
             double d1x = ll * g1x, d1y = ll * g1y, d2x = ll * g2x, d2y = ll * g2y;
             if (m1 || m2) { // step_mask!  fit.jl:49-56 (i1 == 1 first, then i2 == 1: fit.jl:60-63)
                 int ot = m1 ? o2 : o1;
                 double dx = m1 ? (d2x - d1x) / 2 : (d1x - d2x) / 2, dy = m1 ? (d2y - d1y) / 2 : (d1y - d2y) / 2;
-                if (m1) opt_apply_dev(A, ot, dx, dy, has2, v20, v21); else opt_apply_dev(A, ot, dx, dy, has, v0, v1);
+                if (m1) opt_apply_dev(A, ot, dx, dy, hasB, vB.x, vB.y, st); else opt_apply_dev(A, ot, dx, dy, hasA, vA.x, vA.y, st);
                 mvA = move_decide(A, dx, dy, R[2], R[3], R[4]); oA = ot;
             } else { // step!  fit.jl:25-48
-                double s1 = (double)(om1.kh1 + om1.kw1), s2 = (double)(om2.kh1 + om2.kw1);
-                double ks1 = s1 * s1 * s1, ks2 = s2 * s2 * s2;
-                bool move1 = u64_to_unit(R[0]) < ks2 / ks1;
-                bool move2 = u64_to_unit(R[1]) < ks1 / ks2;
                 int slot = 2;
                 if (move1) {
                     double dx = d1x, dy = d1y;
                     if (!move2) { dx -= d2x; dy -= d2y; }
-                    opt_apply_dev(A, o1, dx, dy, has, v0, v1);
+                    opt_apply_dev(A, o1, dx, dy, hasA, vA.x, vA.y, st);
                     mvA = move_decide(A, dx, dy, R[2], R[3], R[4]); oA = o1; slot += 3;
                 }
                 if (move2) {
                     double dx = d2x, dy = d2y;
                     if (!move1) { dx -= d1x; dy -= d1y; }
-                    opt_apply_dev(A, o2, dx, dy, has2, v20, v21);
+                    opt_apply_dev(A, o2, dx, dy, hasB, vB.x, vB.y, st);
                     int3 mv = slot == 2 ? move_decide(A, dx, dy, R[2], R[3], R[4]) : move_decide(A, dx, dy, R[5], R[6], R[7]);
                     if (oA < 0) { mvA = mv; oA = o2; } else { mvB = mv; oB = o2; }
                 }
             }
         }
-        oA = __shfl_sync(0xffffffffu, oA, 0); oB = __shfl_sync(0xffffffffu, oB, 0);
-        mvA.x = __shfl_sync(0xffffffffu, mvA.x, 0); mvA.y = __shfl_sync(0xffffffffu, mvA.y, 0); mvA.z = __shfl_sync(0xffffffffu, mvA.z, 0);
-        mvB.x = __shfl_sync(0xffffffffu, mvB.x, 0); mvB.y = __shfl_sync(0xffffffffu, mvB.y, 0); mvB.z = __shfl_sync(0xffffffffu, mvB.z, 0);
-        long long c_decided = 0;
-        if (A.dbg & 16) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_decided)); c_decided = clock64(); }
-        // metas re-laid so that lane i holds level i+1 of the tree to rebuild
-        LevelMeta t1 = shfl_meta(mine, lane & 15), t2 = shfl_meta(mine, 16 + (lane & 15));
-        if (lane >= 16) { t1 = LevelMeta(); t2 = LevelMeta(); }
-        if (A.dbg & 2) { oA = -1; oB = -1; }
-        if (oA >= 0) { warp_shift_rebuild(A, oA, oA == o1 ? t1 : t2, mvA, lane, sbuf[wib]); __syncwarp(); }
-        if (oB >= 0) { warp_shift_rebuild(A, oB, oB == o1 ? t1 : t2, mvB, lane, sbuf[wib]); __syncwarp(); }
-        long long c_rebuilt = (A.dbg & 16) ? clock64() : 0;
-        if (!(A.dbg & 4)) __threadfence();
+        if (A.dbg & 16) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_decided)); asm volatile("mov.u64 %0, %%clock64;" : "=l"(s3) : "r"(mvA.x), "r"(mvB.x), "r"(oA), "r"(oB)); }
+        // ---- shift! on the metas only (qtrees.jl:267-275); both halves at once, half h holds tree (h ? o2 : o1)
+        bool isA = oA == oh, isB = oB == oh; // o1 != o2; a tree moves at most once per step
+        bool moves = isA || isB;
+        int3 mv = isA ? mvA : mvB;
+        int lv = moves ? mv.x : 1;
         __syncwarp();
-        if (lane == 0) {
-            if (A.dbg & 16) { unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end)); A.dbg_t[4 * k] = ((unsigned long long)(c_rebuilt - c_decided) << 32) | (unsigned long long)(clock64() - c_rebuilt); A.dbg_t[4 * k + 1] = t_ready; A.dbg_t[4 * k + 2] = t_decided; A.dbg_t[4 * k + 3] = t_end; }
-            *((volatile uint32_t*)(A.done + k)) = 1u;
+        int2 base = s_shift[wib][half * 16 + lv - 1];
+        if (moves && hl < A.L) {
+            if (hl < lv) { int f = 1 << (lv - 1 - hl); mine.rs += mv.y * f; mine.cs += mv.z * f; }
+            else { // levels above lv: (new shift of level lv) ÷ 2^sh toward zero (qtrees.jl:225-226 composed)
+                int sh = hl + 1 - lv, brs = base.x + mv.y, bcs = base.y + mv.z;
+                mine.rs = brs >= 0 ? (brs >> sh) : -((-brs) >> sh); mine.cs = bcs >= 0 ? (bcs >> sh) : -((-bcs) >> sh);
+            }
+            stmeta<true>(A.lm + (size_t)oh * A.L + hl, mine);
         }
+        int dcur = half ? dmB : dmA;
+        if (hl == 0) { int nd = moves ? min(dcur, lv) : dcur; if (nd != dmh) __stcg(A.dirty + oh, nd); }
+        if (A.dbg & 16) asm volatile("mov.u64 %0, %%clock64;" : "=l"(s4));
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        __syncwarp();
+        if (A.dbg & 16) asm volatile("mov.u64 %0, %%clock64;" : "=l"(s5));
+        if (lane == 0) {
+            *((volatile uint32_t*)(A.done + k)) = 1u;
+            if (A.dbg & 16) { unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end)); A.dbg_t[4 * k] = (unsigned long long)(((s1 - s0) >> 4) & 0xfff) | ((unsigned long long)(((s2 - s1) >> 4) & 0xfff) << 12) | ((unsigned long long)(((s3 - s2) >> 4) & 0xfff) << 24) | ((unsigned long long)(((s4 - s3) >> 4) & 0xfff) << 36) | ((unsigned long long)(((s5 - s4) >> 4) & 0xfff) << 48); A.dbg_t[4 * k + 1] = t_ready; A.dbg_t[4 * k + 2] = t_decided; A.dbg_t[4 * k + 3] = t_end; }
+        }
+        if (hl == 0 && moves) { A.moved_flag[oh] = 1; atomicAdd(A.counts + 4, 1ull); } // off the chain: only read after the kernel
+    }
+}
+
+// after the batch: one warp per object, rebuild the rasters of the levels above dirty[o] with the tracked shifts
+__global__ void __launch_bounds__(256) k_materialize(uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, int n, int* __restrict__ dirty) {
+    __shared__ uint32_t sbuf[8][2 * RB_HALF];
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int o = warp; o < n; o += nwarps) {
+        int m = dirty[o];
+        if (m >= L) continue;
+        LevelMeta mine = {};
+        if (lane < L) mine = ldmeta<false>(lm + (size_t)o * L + lane);
+        warp_rebuild<false, true>(words, mine, L, m, lane, sbuf[threadIdx.x >> 5]);
+        __syncwarp();
+        if (lane == 0) dirty[o] = L;
     }
 }

@@ -41,7 +41,7 @@ struct stf_ctx {
     DevBuf words, lm, om, payload, poff, woff1, work, lab, lab2, lab3, lab4, bytes_tmp;
     DevBuf rk, rv, rk2, rv2, hist, lkk, lkv;
     DevBuf items, direct, res, overflow, hits, hits2, hk, hv, hk2, hv2, keep, out32, scratch;
-    DevBuf dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m;
+    DevBuf dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
     unsigned long long* h_counts = nullptr; int* h_err = nullptr; // pinned
     OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
@@ -54,7 +54,30 @@ struct stf_ctx {
     std::vector<ProfRec> prof_pending; std::vector<cudaEvent_t> prof_pool;
     double prof_ms[STF_NSTAGES] = {}; int64_t prof_calls[STF_NSTAGES] = {};
     int prof_open = -1; cudaEvent_t prof_open_ev = nullptr;
+    // pinned staging for small host inputs (labels, shifts): the caller's buffer is only read during the call,
+    // the H2D copy is a true async DMA, and calls without outputs need no stream synchronisation
+    char* stg = nullptr; size_t stg_cap = 0, stg_off = 0; cudaEvent_t stg_ev = nullptr; bool stg_busy = false;
 };
+static cudaError_t stage_h2d(stf_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return cudaSuccess;
+    if (ctx->stg_busy && (ctx->stg_off + bytes > ctx->stg_cap || ctx->stg_off == 0)) { cudaEventSynchronize(ctx->stg_ev); ctx->stg_busy = false; ctx->stg_off = 0; }
+    if (ctx->stg_off + bytes > ctx->stg_cap) {
+        if (ctx->stg_busy) { cudaEventSynchronize(ctx->stg_ev); ctx->stg_busy = false; }
+        if (ctx->stg) cudaFreeHost(ctx->stg);
+        ctx->stg_cap = std::max(bytes * 2, (size_t)1 << 20); ctx->stg_off = 0;
+        cudaError_t e = cudaMallocHost(&ctx->stg, ctx->stg_cap); if (e != cudaSuccess) { ctx->stg = nullptr; ctx->stg_cap = 0; return e; }
+    }
+    if (!ctx->stg_ev) cudaEventCreateWithFlags(&ctx->stg_ev, cudaEventDisableTiming);
+    memcpy(ctx->stg + ctx->stg_off, src, bytes);
+    cudaError_t e = cudaMemcpyAsync(dst, ctx->stg + ctx->stg_off, bytes, cudaMemcpyHostToDevice, ctx->st);
+    ctx->stg_off += (bytes + 255) & ~(size_t)255;
+    cudaEventRecord(ctx->stg_ev, ctx->st); ctx->stg_busy = true;
+    return e;
+}
+static void stage_reset(stf_ctx* ctx) { // start of an API call: reuse the staging area once the previous copies are done
+    if (ctx->stg_busy && cudaEventQuery(ctx->stg_ev) == cudaSuccess) { ctx->stg_busy = false; }
+    if (!ctx->stg_busy) ctx->stg_off = 0;
+}
 static void stage_end(stf_ctx* ctx) {
     if (!ctx->prof || ctx->prof_open < 0) return;
     cudaEvent_t b;
@@ -94,7 +117,7 @@ static int32_t upload_labels(stf_ctx* ctx, DevBuf& buf, int32_t nl, const int32_
     if (!labels) return STF_OK;
     for (int i = 0; i < nl; i++) if (labels[i] < 1 || labels[i] > ctx->n) FAIL(STF_E_ARG, "label out of range");
     CK(buf.ensure(sizeof(int32_t) * (size_t)std::max(nl, 1)));
-    CK(cudaMemcpyAsync(buf.p, labels, sizeof(int32_t) * (size_t)nl, cudaMemcpyHostToDevice, ctx->st));
+    CK(stage_h2d(ctx, buf.p, labels, sizeof(int32_t) * (size_t)nl));
     *dev = buf.as<int32_t>();
     return STF_OK;
 }
@@ -124,10 +147,12 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->stg) cudaFreeHost(ctx->stg);
+    if (ctx->stg_ev) cudaEventDestroy(ctx->stg_ev);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -135,6 +160,8 @@ extern "C" const char* stf_last_error(const stf_ctx* ctx) { return ctx ? ctx->er
 extern "C" void* stf_stream(stf_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
 extern "C" int32_t stf_num_objects(const stf_ctx* ctx) { return ctx ? ctx->n : 0; }
 extern "C" int32_t stf_num_levels(const stf_ctx* ctx) { return ctx ? ctx->L : 0; }
+
+__global__ void k_fill_i32(int* __restrict__ p, int n, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 // ------------------------------------------------------------------------------------------------ build helpers
 static int32_t build_worklist(stf_ctx* ctx, int nwork) { // ctx->work holds (object, from) pairs
@@ -217,11 +244,13 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     CK(ctx->has_vel.ensure((size_t)std::max(1, n)));
     CK(ctx->moved_flag.ensure((size_t)std::max(1, n)));
     CK(ctx->moved_pos.ensure(sizeof(int32_t) * (size_t)std::max(1, n)));
+    CK(ctx->dirty.ensure(sizeof(int32_t) * (size_t)std::max(1, n)));
     CK(ctx->lkk.ensure(sizeof(uint64_t) * 4 * (size_t)std::max(1, n)));
     CK(ctx->lkv.ensure(sizeof(uint32_t) * 4 * (size_t)std::max(1, n)));
     CK(cudaMemsetAsync(ctx->has_vel.p, 0, (size_t)std::max(1, n), ctx->st));
     CK(cudaMemsetAsync(ctx->moved_flag.p, 0, (size_t)std::max(1, n), ctx->st));
     if (n == 0) { CK(cudaStreamSynchronize(ctx->st)); return STF_OK; }
+    ctx->launches++, k_fill_i32<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->dirty.as<int>(), n, L); // every raster valid
     CK(cudaMemcpyAsync(ctx->lm.p, h_lm.data(), sizeof(LevelMeta) * (size_t)n * L, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->om.p, ctx->h_om.data(), sizeof(ObjMeta) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->poff.p, poff.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->st));
@@ -272,7 +301,7 @@ extern "C" int32_t stf_upload_packed(stf_ctx* ctx, int32_t n, const uint8_t* pay
 }
 
 // ------------------------------------------------------------------------------------------------ tree state
-#define NEED_OBJS() do { if (!ctx) return STF_E_ARG; if (ctx->L == 0) FAIL(STF_E_STATE, "nothing uploaded"); CK(cudaSetDevice(ctx->device)); } while (0)
+#define NEED_OBJS() do { if (!ctx) return STF_E_ARG; if (ctx->L == 0) FAIL(STF_E_STATE, "nothing uploaded"); CK(cudaSetDevice(ctx->device)); stage_reset(ctx); } while (0)
 #define CHECK_LABEL(x) do { if ((x) < 1 || (x) > ctx->n) FAIL(STF_E_ARG, "label out of range"); } while (0)
 
 extern "C" int32_t stf_get_level_info(stf_ctx* ctx, int32_t label, int32_t l, int32_t out[5]) {
@@ -371,8 +400,8 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
     const int32_t *drs = rs, *dcs = cs;
     if (!(mode & STF_SHIFT_DEVICE_ARRAYS)) {
         CK(ctx->lab2.ensure(sizeof(int32_t) * (size_t)n)); CK(ctx->lab3.ensure(sizeof(int32_t) * (size_t)n));
-        CK(cudaMemcpyAsync(ctx->lab2.p, rs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaMemcpyAsync(ctx->lab3.p, cs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+        CK(stage_h2d(ctx, ctx->lab2.p, rs, sizeof(int32_t) * (size_t)n));
+        CK(stage_h2d(ctx, ctx->lab3.p, cs, sizeof(int32_t) * (size_t)n));
         drs = ctx->lab2.as<int32_t>(); dcs = ctx->lab3.as<int32_t>();
     }
     CK(ctx->work.ensure(sizeof(int2) * (size_t)n));
@@ -380,15 +409,13 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
     KCHECK();
     r = rebuild_after(ctx, n, labels, level); if (r) return r;
     stage_end(ctx);
-    CK(cudaStreamSynchronize(ctx->st));
-    return STF_OK;
+    return STF_OK; // stream-ordered: no output, inputs were staged
 }
 extern "C" int32_t stf_set_level_shift(stf_ctx* ctx, int32_t label, int32_t l, int32_t rs, int32_t cs) {
     NEED_OBJS(); CHECK_LABEL(label);
     if (l < 1 || l > ctx->L) FAIL(STF_E_ARG, "level out of range");
     int32_t v[2] = { rs, cs };
-    CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->lm.as<LevelMeta>() + (size_t)(label - 1) * ctx->L + (l - 1)) + 4, v, 8, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(stage_h2d(ctx, reinterpret_cast<char*>(ctx->lm.as<LevelMeta>() + (size_t)(label - 1) * ctx->L + (l - 1)) + 4, v, 8));
     return STF_OK;
 }
 extern "C" int32_t stf_build(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t layer) {
@@ -400,7 +427,6 @@ extern "C" int32_t stf_build(stf_ctx* ctx, int32_t n, const int32_t* labels, int
     CK(ctx->work.ensure(sizeof(int2) * (size_t)n));
     ctx->launches++, k_fill_worklist<<<nblk(n, 256), 256, 0, ctx->st>>>(n, dl, layer - 1, ctx->work.as<int2>());
     r = rebuild_after(ctx, n, labels, layer - 1); if (r) return r;
-    CK(cudaStreamSynchronize(ctx->st));
     return STF_OK;
 }
 
@@ -437,6 +463,17 @@ static int32_t import_items(stf_ctx* ctx, int64_t n, const stf_item* items, DevB
     KCHECK();
     return STF_OK;
 }
+// single-launch sort; `vbits` > 0 allows the packed shared-memory path when key < 2^(64 - vbits) and val < 2^vbits
+static int32_t sort_small(stf_ctx* ctx, uint64_t* k, uint32_t* v, uint64_t* k2, uint32_t* v2, const unsigned long long* n_dev, int64_t n_host,
+                          int compact, int max_bit, int vbits, unsigned long long* n_out) {
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_TINY_SMEM)); attr_set = true; }
+    bool tiny = vbits > 0 && max_bit + vbits <= 64;
+    ctx->launches++, k_sort_small<<<1, SS_THREADS, tiny ? SS_TINY_SMEM : 0, ctx->st>>>(k, v, k2, v2, n_dev, n_host, compact, max_bit, tiny ? vbits : 0, n_out);
+    KCHECK();
+    return STF_OK;
+}
+static inline int bits_for(int64_t x) { int b = 1; while ((1ll << b) <= x) b++; return b; }
 static int32_t zero_counts(stf_ctx* ctx) { CK(cudaMemsetAsync(ctx->counts.p, 0, C_ZEROED * sizeof(unsigned long long), ctx->st)); return STF_OK; }
 
 extern "C" int32_t stf_collision_bfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out) {
@@ -496,7 +533,7 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
     ctx->launches++, k_hit_keys<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
     uint64_t* ks; uint32_t* vs;
     if (nh <= SORT_SMALL_MAX) { // (i1,i2) in one launch: the device picks the bit windows of i2 and i1 that vary
-        ctx->launches++, k_sort_small<<<1, SS_THREADS, 0, ctx->st>>>(ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nullptr, nh, 0, 64, nullptr);
+        { int32_t rr = sort_small(ctx, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nullptr, nh, 0, 32 + ctx->label_bits, bits_for(nh), nullptr); if (rr) return rr; }
         ks = ctx->hk.as<uint64_t>(); vs = ctx->hv.as<uint32_t>();
     } else {
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh, 0, ctx->label_bits, ctx->hist.as<uint32_t>());
@@ -633,8 +670,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     int bits = 2 * STF_CELL_W + 5 + ctx->scene_bits;
     unsigned long long* nvalid = ctx->counts.as<unsigned long long>() + C_NVALID;
     if (nrec <= SORT_SMALL_MAX) { // one launch: compaction + only the digit windows in which keys differ
-        ctx->launches++, k_sort_small<<<1, SS_THREADS, 0, ctx->st>>>(ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(),
-                                                                    nullptr, nrec, 1, bits, nvalid);
+        { int32_t rr = sort_small(ctx, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nullptr, nrec, 1, bits, ctx->label_bits, nvalid); if (rr) return rr; }
         *keys = ctx->rk.as<uint64_t>(); *vals = ctx->rv.as<uint32_t>();
     } else {
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nrec, 0, bits, ctx->hist.as<uint32_t>());
@@ -779,7 +815,6 @@ extern "C" int32_t stf_reset_velocity(stf_ctx* ctx, int32_t n, const int32_t* la
     NEED_OBJS();
     if (!labels) { if (ctx->n) CK(cudaMemsetAsync(ctx->has_vel.p, 0, (size_t)ctx->n, ctx->st)); }
     else for (int i = 0; i < n; i++) { CHECK_LABEL(labels[i]); CK(cudaMemsetAsync(ctx->has_vel.as<uint8_t>() + (labels[i] - 1), 0, 1, ctx->st)); }
-    CK(cudaStreamSynchronize(ctx->st));
     return STF_OK;
 }
 extern "C" int32_t stf_get_velocity(stf_ctx* ctx, int32_t n, const int32_t* labels, double* v, uint8_t* has) {
@@ -809,7 +844,7 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     CK(cudaMemsetAsync(ctx->prev.p, 0, sizeof(uint32_t) * (size_t)m, ctx->st));
     if (m <= SORT_SMALL_MAX) { // mask endpoints (INVALID) are compacted away; prev stays 0 for them
         unsigned long long* nep = ctx->counts.as<unsigned long long>() + C_NEP;
-        ctx->launches++, k_sort_small<<<1, SS_THREADS, 0, ctx->st>>>(ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nullptr, m, 1, ctx->label_bits + 1, nep);
+        { int32_t rr = sort_small(ctx, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nullptr, m, 1, ctx->label_bits + 1, bits_for(m), nep); if (rr) return rr; }
         ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), nep, m, ctx->prev.as<uint32_t>());
     } else {
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
@@ -822,7 +857,7 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.om = ctx->om.as<ObjMeta>(); A.L = ctx->L;
     A.hits = hits; A.n = n; A.prev = ctx->prev.as<uint32_t>(); A.done = ctx->done.as<uint32_t>();
     A.ticket = ctx->counts.as<unsigned long long>() + C_TICKET;
-    A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>();
+    A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>(); A.dirty = ctx->dirty.as<int>();
     A.opt = ctx->opt; A.seed = seed; A.iter = iter; A.counts = ctx->counts.as<unsigned long long>();
     { const char* e = getenv("STF_DEBUG_STEP"); A.dbg = e ? atoi(e) : 0; }
     A.dbg_t = nullptr;
@@ -830,6 +865,8 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     int blocks = (int)std::min<int64_t>((n + 3) / 4, 148 * 8);
     stage_begin(ctx, STF_STAGE_STEP);
     ctx->launches++, k_batchsteps<<<blocks, 128, 0, ctx->st>>>(A);
+    // the steps only moved the shifts: materialise the rasters of every moved tree once
+    ctx->launches++, k_materialize<<<std::min(nblk((int64_t)ctx->n * 32, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->n, ctx->dirty.as<int>());
     KCHECK();
     stage_end(ctx);
     int32_t r = sync_counts(ctx); if (r) return r;
@@ -891,4 +928,8 @@ extern "C" int32_t stf_debug_step_timeline(stf_ctx* ctx, int64_t n, unsigned lon
     if (!ctx || !ctx->dbg_t.p) return STF_E_STATE;
     CK(cudaMemcpy(out, ctx->dbg_t.p, sizeof(unsigned long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
     return STF_OK;
+}
+
+extern "C" int32_t stf_debug_sort_cycles(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_sort_dbg, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
 }

@@ -14,7 +14,7 @@ rs, cs = W["rs"][1:].copy(), W["cs"][1:].copy()
 lib.stf_set_optimiser(h, 2, 0.25, 0.5)
 hits = S.totalcollisions_spacial(d, unique=False, raw=True)
 print("hits", len(hits))
-os.environ["STF_DEBUG_STEP"] = "16"
+os.environ["STF_DEBUG_STEP"] = sys.argv[1] if len(sys.argv) > 1 else "16"
 for it in range(3):
     d._ck(lib.stf_set_shifts(h, len(movable), movable.ctypes.data, 1, rs.ctypes.data, cs.ctypes.data, 0))
     d._ck(lib.stf_reset_velocity(h, 0, None))
@@ -23,8 +23,9 @@ n = len(hits)
 T = np.zeros((n, 4), np.uint64)
 lib.stf_debug_step_timeline.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
 print("rc", lib.stf_debug_step_timeline(h, n, T.ctypes.data))
-T = T.astype(np.int64); fence = T[:, 0] & 0xffffffff; cyc = T[:, 0] >> 32; print("fence cycles median", np.median(fence), "max", fence.max()); T[:, 0] = T[:, 1]; t0 = T[:, 1].min(); T -= t0
-print("rebuild cycles median", np.median(cyc), "ns median", np.median(T[:, 3] - T[:, 2]), "=> MHz", 1e3 * np.median(cyc) / np.median(T[:, 3] - T[:, 2]))
+seg = np.stack([((T[:, 0] >> np.uint64(12 * i)) & np.uint64(0xfff)).astype(np.int64) * 16 for i in range(5)], 1)
+print("cycles state-loads/grad/scalar/update-stores/fence: median", np.median(seg, 0).tolist(), "p90", np.percentile(seg, 90, 0).tolist(), "max", seg.max(0).tolist())
+T = T.astype(np.int64); T[:, 0] = T[:, 1]; t0 = T[:, 1].min(); T -= t0
 print("claim  min/median/max us", T[:, 0].min() / 1e3, np.median(T[:, 0]) / 1e3, T[:, 0].max() / 1e3)
 print("ready  min/median/max us", T[:, 1].min() / 1e3, np.median(T[:, 1]) / 1e3, T[:, 1].max() / 1e3)
 print("end    min/median/max us", T[:, 3].min() / 1e3, np.median(T[:, 3]) / 1e3, T[:, 3].max() / 1e3)
