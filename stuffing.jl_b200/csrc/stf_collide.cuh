@@ -12,42 +12,74 @@ namespace cg = cooperative_groups;
 // (2) broad phase
 // =============================================================================================
 
-// one thread per label: <= 4 cells, written to slots 4*slot..4*slot+3 (unused slots = INVALID key).
-// linked != 0: LinkedSpacialQTree semantics — slot = object, cells outside the root (L,1,1) dropped
-// (qtrees.jl:506).  linked == 0: HashSpacialQTree semantics — slot = position in `labels`.
+// one thread per label: <= 4 cells.
+// Slot mode (n_append == NULL): written to slots 4*slot..4*slot+3 (unused slots = INVALID key).
+//   linked != 0: LinkedSpacialQTree semantics — slot = object, cells outside the root (L,1,1) dropped (qtrees.jl:506).
+//   linked == 0: HashSpacialQTree semantics — slot = position in `labels`.
+// Append mode (n_append != NULL, hash semantics): the valid records are appended compactly (one atomic per warp) as
+//   (key, tie) with tie = position in `labels` (or the label itself when labels == NULL); a sort by (key, tie)
+//   reproduces the insertion order of the reference's Dict of Vectors (qtrees.jl:411-415) whatever the append order.
 __global__ void k_locate(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
                          int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                         int* __restrict__ err) {
+                         int* __restrict__ err, unsigned long long* __restrict__ n_append) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nl) return;
-    int o = labels ? labels[j] - 1 : j;
-    int slot = linked ? o : j;
-    const LevelMeta* olm = lm + (size_t)o * L;
-    LevelMeta top = olm[L - 1]; // sizelevel(qt) == length(qt)  qtrees.jl:191-193
-    int scene = om[o].scene;
-    int cnt = 0;
-    for (int k = 0; k < 4; k++) { // (1,1),(1,2),(2,1),(2,2)  qtree_functions.jl:167-170
-        int l = L, a = top.rs + 1 + (k >> 1), b = top.cs + 1 + (k & 1);
-        if (node_code<false>(words, top, a, b) == CODE_EMPTY) continue;
-        while (l > 2) { // positionlower  :141-158
-            LevelMeta cm = olm[l - 2];
-            int ca = a, cb = b, flag = 0, stop = 0;
-            for (int i = 0; i < 4; i++) {
-                int xa = 2 * a - (i & 1), xb = 2 * b - (i >> 1);
-                if (node_code<false>(words, cm, xa, xb) != CODE_EMPTY) {
-                    if (flag) { stop = 1; break; }
-                    flag = 1; ca = xa; cb = xb;
+    int cnt = 0; uint64_t ck[4]; int o = 0, slot = 0;
+    if (j < nl) {
+        o = labels ? labels[j] - 1 : j;
+        slot = linked ? o : j;
+        const LevelMeta* olm = lm + (size_t)o * L;
+        LevelMeta top = olm[L - 1]; // sizelevel(qt) == length(qt)  qtrees.jl:191-193
+        int scene = om[o].scene;
+        for (int k = 0; k < 4; k++) { // (1,1),(1,2),(2,1),(2,2)  qtree_functions.jl:167-170
+            int l = L, a = top.rs + 1 + (k >> 1), b = top.cs + 1 + (k & 1);
+            if (node_code<false>(words, top, a, b) == CODE_EMPTY) continue;
+            while (l > 2) { // positionlower  :141-158
+                LevelMeta cm = olm[l - 2];
+                int ca = a, cb = b, flag = 0, stop = 0;
+                for (int i = 0; i < 4; i++) {
+                    int xa = 2 * a - (i & 1), xb = 2 * b - (i >> 1);
+                    if (node_code<false>(words, cm, xa, xb) != CODE_EMPTY) {
+                        if (flag) { stop = 1; break; }
+                        flag = 1; ca = xa; cb = xb;
+                    }
                 }
+                if (stop || !flag) break; // !flag: inconsistent pyramid; the reference would not terminate (oracle: same stop)
+                l = l - 1; a = ca; b = cb;
             }
-            if (stop || !flag) break; // !flag: inconsistent pyramid; the reference would not terminate (oracle: same stop)
-            l = l - 1; a = ca; b = cb;
+            bool keep = true;
+            if (linked) { int r = 1 << (L - l); keep = (a >= 1 && a <= r && b >= 1 && b <= r); }
+            if (a <= -STF_CELL_BIAS || a >= STF_CELL_BIAS || b <= -STF_CELL_BIAS || b >= STF_CELL_BIAS) { atomicOr(err, 2); keep = false; }
+            if (keep) ck[cnt++] = cell_key(scene, l, a, b);
         }
-        bool keep = true;
-        if (linked) { int r = 1 << (L - l); keep = (a >= 1 && a <= r && b >= 1 && b <= r); }
-        if (a <= -STF_CELL_BIAS || a >= STF_CELL_BIAS || b <= -STF_CELL_BIAS || b >= STF_CELL_BIAS) { atomicOr(err, 2); keep = false; }
-        if (keep) { keys[4 * (size_t)slot + cnt] = cell_key(scene, l, a, b); vals[4 * (size_t)slot + cnt] = (uint32_t)(o + 1); cnt++; }
     }
-    for (int k = cnt; k < 4; k++) { keys[4 * (size_t)slot + k] = STF_KEY_INVALID; vals[4 * (size_t)slot + k] = (uint32_t)(o + 1); }
+    if (n_append) {
+        const unsigned FULLM = 0xffffffffu;
+        int lane = threadIdx.x & 31, incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULLM, incl, d); if (lane >= d) incl += t; }
+        int total = __shfl_sync(FULLM, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 31 && total) base = atomicAdd(n_append, (unsigned long long)total);
+        base = __shfl_sync(FULLM, base, 31) + (unsigned long long)(incl - cnt);
+        uint32_t tie = labels ? (uint32_t)j : (uint32_t)(o + 1);
+        for (int k = 0; k < cnt; k++) { keys[base + k] = ck[k]; vals[base + k] = tie; }
+        return;
+    }
+    if (j >= nl) return;
+    for (int k = 0; k < 4; k++) { keys[4 * (size_t)slot + k] = k < cnt ? ck[k] : STF_KEY_INVALID; vals[4 * (size_t)slot + k] = (uint32_t)(o + 1); }
+}
+// LinkedSpacialQTree table (4 slots per object) -> compact (key, label) records, unordered
+__global__ void k_compact_records(const uint64_t* __restrict__ tk, const uint32_t* __restrict__ tv, int64_t nslots,
+                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_append) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t k = i < nslots ? tk[i] : STF_KEY_INVALID;
+    bool v = k != STF_KEY_INVALID;
+    unsigned m = __ballot_sync(0xffffffffu, v);
+    int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0 && m) base = atomicAdd(n_append, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & ((1u << lane) - 1));
+    if (v) { keys[base] = k; vals[base] = tv[i]; }
 }
 
 __global__ void k_fill_invalid(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int64_t n) {
@@ -67,8 +99,9 @@ __device__ __forceinline__ int64_t lower_bound_u64(const uint64_t* __restrict__ 
 
 struct EmitOut {
     Item16* items; int64_t item_cap;
-    Item16* direct; int64_t direct_cap;
-    unsigned long long* counts; // [0] items, [1] direct hits
+    Item16* direct; int64_t direct_cap;   // direct hits go straight into the hit list ...
+    unsigned long long* counts;           // [0] items, [1] direct hits (statistics)
+    unsigned long long* nhits;            // ... whose fill counter this is
 };
 __device__ __forceinline__ void emit_push(Item16* buf, int64_t cap, unsigned long long* counter, const Item16& it) {
     cg::coalesced_group g = cg::coalesced_threads();
@@ -167,7 +200,7 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
             unsigned long long ibase = 0, dbase = 0;
             if (lane == 0) {
                 if (im) ibase = atomicAdd(out.counts, (unsigned long long)__popc(im));
-                if (dm) dbase = atomicAdd(out.counts + 1, (unsigned long long)__popc(dm));
+                if (dm) { dbase = atomicAdd(out.nhits, (unsigned long long)__popc(dm)); atomicAdd(out.counts + 1, (unsigned long long)__popc(dm)); }
             }
             ibase = __shfl_sync(FULLM, ibase, 0); dbase = __shfl_sync(FULLM, dbase, 0);
             unsigned lt = (1u << lane) - 1;
@@ -236,7 +269,8 @@ __global__ void k_native_pairs(const int32_t* __restrict__ flt, const int* __res
 struct NarrowArgs {
     const uint32_t* words; const LevelMeta* lm; int L;
     const Item16* items; const unsigned long long* n_items_dev; int64_t n_items_host; // device count if non-null
-    int4* res;                       // per item (l,a,b,0); l < 0 = miss
+    int4* res;                       // per item (l,a,b,0); l < 0 = miss (NULL: not wanted)
+    Item16* hits; int64_t hits_cap; unsigned long long* nhits; // hits (l >= 0) appended here (NULL: not wanted)
     unsigned long long* counts;      // [2] overflow count, [3] visited
     uint32_t* overflow;              // item indices that need the big path
     int64_t overflow_cap;
@@ -305,7 +339,11 @@ __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
                 if ((int64_t)s < A.overflow_cap) A.overflow[s] = (uint32_t)it;
                 result = make_int4(-1, 0, 0, -1);
             }
-            A.res[it] = result;
+            if (A.res) A.res[it] = result;
+            if (A.hits && result.x >= 0) { // cp[1] >= 0  qtree_functions.jl:104-106
+                unsigned long long s = atomicAdd(A.nhits, 1ull);
+                if ((int64_t)s < A.hits_cap) A.hits[s] = make_item(item.i1, item_i2(item), result.x, result.y, result.z);
+            }
         }
         g.sync();
     }
@@ -320,7 +358,6 @@ __global__ void __launch_bounds__(NPB_THREADS) k_collide_big(NarrowArgs A, uint3
     __shared__ int w_push[NPB_THREADS / 32];
     __shared__ int w_hit[NPB_THREADS / 32];
     __shared__ int4 s_result;
-    __shared__ int s_flag;
     int64_t nov = (int64_t)A.counts[2];
     if (nov > A.overflow_cap) nov = A.overflow_cap;
     uint32_t* f0 = scratch + (size_t)blockIdx.x * 2 * cap_per_cta;
@@ -385,24 +422,17 @@ __global__ void __launch_bounds__(NPB_THREADS) k_collide_big(NarrowArgs A, uint3
             __syncthreads();
             cur ^= 1; cnt = ncnt; lev -= 1; depth += 1;
         }
-        if (threadIdx.x == 0) { A.res[it] = result; s_flag = 0; }
+        if (threadIdx.x == 0) {
+            if (A.res) A.res[it] = result;
+            if (A.hits && result.x >= 0) {
+                unsigned long long s = atomicAdd(A.nhits, 1ull);
+                if ((int64_t)s < A.hits_cap) A.hits[s] = make_item(item.i1, item_i2(item), result.x, result.y, result.z);
+            }
+        }
         __syncthreads();
     }
     for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, o);
     if (lane == 0 && visited) atomicAdd(A.counts + 3, visited);
-}
-
-// hits = results with l >= 0 (cp[1] >= 0, qtree_functions.jl:104-106), appended after `base` entries
-__global__ void k_compact_hits(const Item16* __restrict__ items, const int4* __restrict__ res, const unsigned long long* __restrict__ n_dev, int64_t n_host,
-                               Item16* __restrict__ hits, int64_t cap, unsigned long long* __restrict__ nhits) {
-    int64_t n = n_dev ? min((int64_t)*n_dev, n_host) : n_host;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int4 r = res[i];
-    if (r.x >= 0) {
-        Item16 it = items[i];
-        emit_push(hits, cap, nhits, make_item(it.i1, item_i2(it), r.x, r.y, r.z));
-    }
 }
 
 // collision_dfs (qtree_functions.jl:2-20): one thread per pair, explicit stack

@@ -116,189 +116,6 @@ static inline int radix_sort_pairs(cudaStream_t st, int64_t* launches, uint64_t*
 }
 static inline size_t radix_sort_hist_words(int64_t n) { return (size_t)256 * sort_plan(n).nvw; }
 
-// =============================================================================================
-// single-launch sort for latency-bound sizes (n <= SORT_SMALL_MAX): ONE CTA runs
-//   phase 0  ordered compaction of the valid records (key != INVALID), and the OR of all key
-//            differences, from which the digit windows are chosen on the device — bit ranges in which no
-//            two keys differ are never sorted;
-//   phase 1+ stable 8-bit LSD passes (warp-private histograms, block scan over (digit, warp),
-//            __match_any_sync ranks);
-// and leaves the result in (keys, vals) whatever the number of passes.  n may live on the device.
-// If the valid records fit (n <= SS_TINY_CAP and key < 2^(64-vbits)), (key,val) are packed into one
-// 64-bit word and ALL passes run in shared memory: one global read and one global write in total.
-// =============================================================================================
-#define SS_THREADS 1024
-#define SS_WARPS 32
-#define SS_UNROLL 4
-#define SORT_SMALL_MAX (1 << 18)
-#define SS_TINY_CAP 11264
-#define SS_TINY_SMEM (2 * 8 * SS_TINY_CAP)
-
-__device__ __forceinline__ uint32_t ss_block_exclusive(uint32_t v, uint32_t* wsum, uint32_t* total) {
-    // exclusive scan of one value per thread over the block; all threads must call
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) wsum[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        uint32_t x = wsum[lane], xi = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
-        wsum[lane] = xi - x;
-        if (lane == 31) *total = xi;
-    }
-    __syncthreads();
-    uint32_t r = wsum[w] + incl - v;
-    return r;
-}
-
-// one stable 8-bit pass over n elements.  PACKED: one u64 array (key<<vbits | val); else split (key, val) arrays
-__device__ long long g_sort_dbg[16];
-#define SS_STAMP(i) do { if (threadIdx.x == 0) g_sort_dbg[i] = clock64() - t_start; } while (0)
-template <bool PACKED>
-__device__ __forceinline__ void ss_pass(const uint64_t* __restrict__ ksrc, const uint32_t* __restrict__ vsrc, uint64_t* __restrict__ kdst, uint32_t* __restrict__ vdst,
-                                        int64_t n, int shift, uint32_t (*cnt)[256], uint32_t* wsum, uint32_t* s_total) {
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int64_t per = ((n + SS_WARPS - 1) / SS_WARPS + 31) / 32 * 32;
-    int64_t beg = (int64_t)w * per, end = min(n, beg + per);
-    long long tp0 = clock64();
-    for (int d = lane; d < 256; d += 32) cnt[w][d] = 0;
-    __syncwarp();
-    for (int64_t i0 = beg; i0 < end; i0 += 32 * SS_UNROLL) {
-        uint64_t k[SS_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SS_UNROLL; u++) { int64_t i = i0 + 32 * u + lane; k[u] = i < end ? ksrc[i] : 0; }
-#pragma unroll
-        for (int u = 0; u < SS_UNROLL; u++) { int64_t i = i0 + 32 * u + lane; if (i < end) atomicAdd(&cnt[w][(k[u] >> shift) & 255], 1u); }
-    }
-    __syncthreads();
-    long long tp1 = clock64();
-    { // exclusive scan over (digit, warp): thread t owns digit t>>2, warps (t&3)*8 .. +8
-        int d = threadIdx.x >> 2, w0 = (threadIdx.x & 3) * 8;
-        uint32_t loc[8], sum = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { loc[j] = cnt[w0 + j][d]; sum += loc[j]; }
-        uint32_t run = ss_block_exclusive(sum, wsum, s_total);
-#pragma unroll
-        for (int j = 0; j < 8; j++) { cnt[w0 + j][d] = run; run += loc[j]; }
-    }
-    __syncthreads();
-    long long tp2 = clock64();
-    for (int64_t i0 = beg; i0 < end; i0 += 32 * SS_UNROLL) {
-        uint64_t k[SS_UNROLL]; uint32_t v[SS_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SS_UNROLL; u++) {
-            int64_t i = i0 + 32 * u + lane; bool in = i < end;
-            k[u] = in ? ksrc[i] : 0; v[u] = (!PACKED && in) ? vsrc[i] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < SS_UNROLL; u++) {
-            int64_t i = i0 + 32 * u + lane;
-            bool valid = i < end;
-            uint32_t d = valid ? (uint32_t)((k[u] >> shift) & 255) : 256u + lane;
-            uint32_t peers = __match_any_sync(0xffffffffu, d);
-            uint32_t rank = __popc(peers & ((1u << lane) - 1));
-            uint32_t dst = valid ? cnt[w][d] + rank : 0;
-            __syncwarp();
-            if (valid && rank == 0) cnt[w][d] += __popc(peers);
-            __syncwarp();
-            if (valid) { kdst[dst] = k[u]; if (!PACKED) vdst[dst] = v[u]; }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { long long tp3 = clock64(); g_sort_dbg[4] = tp1 - tp0; g_sort_dbg[5] = tp2 - tp1; g_sort_dbg[6] = tp3 - tp2; }
-}
-
-__global__ void __launch_bounds__(SS_THREADS) k_sort_small(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint64_t* __restrict__ keys_alt,
-                                                           uint32_t* __restrict__ vals_alt, const unsigned long long* __restrict__ n_dev, int64_t n_host,
-                                                           int compact_invalid, int max_bit, int vbits, unsigned long long* __restrict__ n_out) {
-    extern __shared__ uint64_t tiny[]; // 2 x SS_TINY_CAP packed words (only when launched with SS_TINY_SMEM)
-    __shared__ uint32_t cnt[SS_WARPS][256];
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t s_total;
-    __shared__ unsigned long long s_or[SS_WARPS];
-    __shared__ int s_shift[9], s_npass;
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    long long t_start = clock64();
-    int64_t n = n_dev ? (int64_t)*n_dev : n_host;
-    if (n > n_host) n = n_host;
-    bool can_pack = vbits > 0 && max_bit + vbits <= 64;
-    uint64_t* ksrc = keys; uint32_t* vsrc = vals; uint64_t* kdst = keys_alt; uint32_t* vdst = vals_alt;
-
-    // ---- phase 0: stable compaction → alt buffers (and, packed, into shared memory while it fits)
-    uint32_t base = 0;
-    for (int64_t c0 = 0; c0 < n; c0 += SS_THREADS * SS_UNROLL) {
-        uint64_t k[SS_UNROLL]; uint32_t v[SS_UNROLL]; uint32_t nv = 0;
-        int64_t i0 = c0 + (int64_t)threadIdx.x * SS_UNROLL; // contiguous per thread keeps the order
-#pragma unroll
-        for (int u = 0; u < SS_UNROLL; u++) {
-            bool in = i0 + u < n;
-            k[u] = in ? ksrc[i0 + u] : STF_KEY_INVALID; v[u] = in ? vsrc[i0 + u] : 0;
-            nv += (in && !(compact_invalid && k[u] == STF_KEY_INVALID));
-        }
-        uint32_t off = ss_block_exclusive(nv, wsum, &s_total) + base;
-#pragma unroll
-        for (int u = 0; u < SS_UNROLL; u++) {
-            bool in = i0 + u < n;
-            if (in && !(compact_invalid && k[u] == STF_KEY_INVALID)) {
-                kdst[off] = k[u]; vdst[off] = v[u];
-                if (can_pack && off < SS_TINY_CAP) tiny[off] = (k[u] << vbits) | v[u];
-                off++;
-            }
-        }
-        base += s_total;
-        __syncthreads();
-    }
-    SS_STAMP(0);
-    n = base;
-    { uint64_t* tk = ksrc; ksrc = kdst; kdst = tk; uint32_t* tv = vsrc; vsrc = vdst; vdst = tv; }
-    bool packed = can_pack && n <= SS_TINY_CAP;
-    __syncthreads();
-
-    // ---- digit windows: only bit ranges in which keys differ
-    unsigned long long vary = 0;
-    if (packed) { uint64_t p0 = n > 0 ? tiny[0] : 0; for (int64_t i = threadIdx.x; i < n; i += SS_THREADS) vary |= tiny[i] ^ p0; vary >>= vbits; }
-    else { uint64_t key0 = n > 0 ? ksrc[0] : 0; for (int64_t i = threadIdx.x; i < n; i += SS_THREADS) vary |= ksrc[i] ^ key0; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vary |= __shfl_xor_sync(0xffffffffu, vary, o);
-    if (lane == 0) s_or[w] = vary;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long V = 0;
-        for (int i = 0; i < SS_WARPS; i++) V |= s_or[i];
-        if (max_bit < 64) V &= (1ull << max_bit) - 1;
-        int np = 0;
-        while (V) { int p = __ffsll((long long)V) - 1; s_shift[np++] = p; V &= (p + 8 >= 64) ? 0ull : ~((1ull << (p + 8)) - 1); }
-        s_npass = np;
-        if (n_out) *n_out = (unsigned long long)n;
-    }
-    __syncthreads();
-    int npass = s_npass;
-    SS_STAMP(1);
-    if (threadIdx.x == 0) { g_sort_dbg[8] = n; g_sort_dbg[9] = npass; g_sort_dbg[10] = packed; }
-
-    if (packed) {
-        uint64_t* a = tiny; uint64_t* b = tiny + SS_TINY_CAP;
-        for (int pass = 0; pass < npass; pass++) {
-            ss_pass<true>(a, nullptr, b, nullptr, n, s_shift[pass] + vbits, cnt, wsum, &s_total);
-            uint64_t* t = a; a = b; b = t;
-        }
-        SS_STAMP(2);
-        uint64_t vmask = (1ull << vbits) - 1;
-        for (int64_t i = threadIdx.x; i < n; i += SS_THREADS) { uint64_t p = a[i]; keys[i] = p >> vbits; vals[i] = (uint32_t)(p & vmask); }
-        SS_STAMP(3);
-        return;
-    }
-    for (int pass = 0; pass < npass; pass++) {
-        ss_pass<false>(ksrc, vsrc, kdst, vdst, n, s_shift[pass], cnt, wsum, &s_total);
-        uint64_t* tk = ksrc; ksrc = kdst; kdst = tk; uint32_t* tv = vsrc; vsrc = vdst; vdst = tv;
-    }
-    if (ksrc != keys) { // an odd number of hops: bring the result home
-        for (int64_t i = threadIdx.x; i < n; i += SS_THREADS) { keys[i] = ksrc[i]; vals[i] = vsrc[i]; }
-    }
-}
 // first INVALID key of a sorted array (multi-launch path), so that both sort paths publish the valid count
 __global__ void k_count_valid(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* __restrict__ n_out) {
     int64_t lo = 0, hi = n;

@@ -40,7 +40,7 @@ __device__ __forceinline__ int intlog2_dev(double x) { return (int)((__double_as
 
 struct StepArgs {
     uint32_t* words; LevelMeta* lm; const ObjMeta* om; int L;
-    const Item16* hits; int64_t n;
+    const Item16* hits; int64_t n; const unsigned long long* n_dev; // n_dev != NULL: the step count lives on the device
     const uint32_t* prev; uint32_t* done; unsigned long long* ticket;
     double* vel; uint8_t* has_vel; uint8_t* moved_flag; int* dirty;
     OptState opt; uint64_t seed, iter;
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(128) k_batchsteps(StepArgs A) {
     const unsigned FULLM = 0xffffffffu;
     int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
     const uint64_t hbase = stf_mix64(stf_mix64(A.seed ^ 0x5354554646494E47ull) + A.iter); // stf_rand_u64 without the per-draw part
+    const int64_t nsteps = A.n_dev ? (int64_t)*A.n_dev : A.n;
     int k_round = 0;
     for (;;) {
         unsigned long long k = 0;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(128) k_batchsteps(StepArgs A) {
             if (lane == 0) k = atomicAdd(A.ticket, 1ull);
             k = __shfl_sync(FULLM, k, 0);
         }
-        if ((int64_t)k >= A.n) return;
+        if ((int64_t)k >= nsteps) return;
         unsigned long long t_ready = 0, t_decided = 0;
         Item16 h = A.hits[k];
         int o1 = h.i1 - 1, o2 = item_i2(h) - 1;

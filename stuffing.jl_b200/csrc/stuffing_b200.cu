@@ -5,6 +5,7 @@
 #include "stf_common.cuh"
 #include "stf_pyramid.cuh"
 #include "stf_sort.cuh"
+#include "stf_finalize.cuh"
 #include "stf_collide.cuh"
 #include "stf_step.cuh"
 
@@ -46,6 +47,8 @@ struct stf_ctx {
     OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
     int64_t big_cap = 0; int big_ctas = 1;
+    bool force_big = false; // the single-CTA latency path overflowed once: stay on the multi-launch path
+    int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
     stf_counters_t ctr = {};
     int64_t launches = 0; // kernels launched by this context (bench.py gpu_launches)
     // per-stage device timers (stf_profile_*): pairs of events recorded on ctx->st
@@ -101,11 +104,11 @@ static void stage_begin(stf_ctx* ctx, int stage) {
 #define KCHECK() CK(cudaGetLastError())
 static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n + t - 1) / t); }
 
-enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_N = 12 };
+enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_N = 12 };
 
 static int32_t sync_counts(stf_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(ctx->h_err, ctx->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->errflag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st)); // [0] error bits, [1] path status
     CK(cudaStreamSynchronize(ctx->st));
     if (*ctx->h_err & 1) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st); FAIL(STF_E_BADCODE, "node code outside 1..3 in uploaded payload"); }
     if (*ctx->h_err & 2) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st); FAIL(STF_E_RANGE, "spatial cell coordinate outside +-2^21"); }
@@ -131,12 +134,12 @@ extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
     stf_ctx* ctx = new stf_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || cudaMallocHost(&ctx->h_err, sizeof(int)) != cudaSuccess ||
-        ctx->counts.ensure(C_N * sizeof(unsigned long long)) != cudaSuccess || ctx->errflag.ensure(sizeof(int)) != cudaSuccess) {
+        cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || cudaMallocHost(&ctx->h_err, 2 * sizeof(int)) != cudaSuccess ||
+        ctx->counts.ensure(C_N * sizeof(unsigned long long)) != cudaSuccess || ctx->errflag.ensure(2 * sizeof(int)) != cudaSuccess) {
         delete ctx; return STF_E_CUDA;
     }
     cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st);
-    cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st);
+    cudaMemsetAsync(ctx->errflag.p, 0, 2 * sizeof(int), ctx->st);
     *out = ctx;
     return STF_OK;
 }
@@ -164,12 +167,6 @@ extern "C" int32_t stf_num_levels(const stf_ctx* ctx) { return ctx ? ctx->L : 0;
 __global__ void k_fill_i32(int* __restrict__ p, int n, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 // ------------------------------------------------------------------------------------------------ build helpers
-static int32_t build_worklist(stf_ctx* ctx, int nwork) { // ctx->work holds (object, from) pairs
-    int blocks = std::min(nblk((int64_t)nwork * 32, 256), 148 * 8);
-    ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), nwork, ctx->om.as<ObjMeta>(), 0);
-    KCHECK();
-    return STF_OK;
-}
 static int32_t build_big(stf_ctx* ctx, int o, int from) { // levels from+1..L of one big object, many CTAs per level
     for (int l = from + 1; l <= ctx->L; l++) {
         ctx->launches++, k_set_parent_shift<<<1, 1, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, o, l);
@@ -431,18 +428,32 @@ extern "C" int32_t stf_build(stf_ctx* ctx, int32_t n, const int32_t* labels, int
 }
 
 // ------------------------------------------------------------------------------------------------ narrow phase
-// runs the BFS over ctx->items[0..n) into ctx->res; n is host-known
-static int32_t narrow_phase(stf_ctx* ctx, int64_t n) {
-    CK(ctx->res.ensure(sizeof(int4) * (size_t)std::max<int64_t>(1, n)));
-    CK(ctx->overflow.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, n)));
-    if (n == 0) return STF_OK;
+static void set_smem_attrs() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(k_sort_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
+    cudaFuncSetAttribute(k_finalize_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
+    cudaFuncSetAttribute(k_step_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
+    done = true;
+}
+// runs the BFS over ctx->items.  n_host >= 0: host-known item count; n_host < 0: the count is on the device
+// (counts[C_ITEMS], clamped to `cap`).  want_res: per-item results into ctx->res; want_hits: hits (l >= 0) appended to
+// ctx->hits through counts[C_NHITS].
+static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want_res, bool want_hits) {
+    int64_t nmax = n_host >= 0 ? n_host : cap;
+    if (want_res) CK(ctx->res.ensure(sizeof(int4) * (size_t)std::max<int64_t>(1, nmax)));
+    CK(ctx->overflow.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nmax)));
+    if (nmax == 0) return STF_OK;
     NarrowArgs A;
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.L = ctx->L;
-    A.items = ctx->items.as<Item16>(); A.n_items_dev = nullptr; A.n_items_host = n;
-    A.res = ctx->res.as<int4>(); A.counts = ctx->counts.as<unsigned long long>();
-    A.overflow = ctx->overflow.as<uint32_t>(); A.overflow_cap = n;
-    int64_t groups = (n + 0) ; int per_block = NP_THREADS / NP_GROUP;
-    int blocks = (int)std::min<int64_t>((groups + per_block - 1) / per_block, 148 * 32);
+    A.items = ctx->items.as<Item16>();
+    A.n_items_dev = n_host >= 0 ? nullptr : ctx->counts.as<unsigned long long>() + C_ITEMS; A.n_items_host = nmax;
+    A.res = want_res ? ctx->res.as<int4>() : nullptr; A.counts = ctx->counts.as<unsigned long long>();
+    A.hits = want_hits ? ctx->hits.as<Item16>() : nullptr; A.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16)); A.nhits = ctx->counts.as<unsigned long long>() + C_NHITS;
+    A.overflow = ctx->overflow.as<uint32_t>(); A.overflow_cap = nmax;
+    int per_block = NP_THREADS / NP_GROUP;
+    int64_t want = n_host >= 0 ? n_host : std::max<int64_t>(ctx->hint_items, 4096);
+    int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want + per_block - 1) / per_block), 148 * 32);
     ctx->launches++, k_collide_small<<<blocks, NP_THREADS, 0, ctx->st>>>(A);
     KCHECK();
     CK(ctx->scratch.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->big_cap * ctx->big_ctas));
@@ -463,17 +474,6 @@ static int32_t import_items(stf_ctx* ctx, int64_t n, const stf_item* items, DevB
     KCHECK();
     return STF_OK;
 }
-// single-launch sort; `vbits` > 0 allows the packed shared-memory path when key < 2^(64 - vbits) and val < 2^vbits
-static int32_t sort_small(stf_ctx* ctx, uint64_t* k, uint32_t* v, uint64_t* k2, uint32_t* v2, const unsigned long long* n_dev, int64_t n_host,
-                          int compact, int max_bit, int vbits, unsigned long long* n_out) {
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_TINY_SMEM)); attr_set = true; }
-    bool tiny = vbits > 0 && max_bit + vbits <= 64;
-    ctx->launches++, k_sort_small<<<1, SS_THREADS, tiny ? SS_TINY_SMEM : 0, ctx->st>>>(k, v, k2, v2, n_dev, n_host, compact, max_bit, tiny ? vbits : 0, n_out);
-    KCHECK();
-    return STF_OK;
-}
-static inline int bits_for(int64_t x) { int b = 1; while ((1ll << b) <= x) b++; return b; }
 static int32_t zero_counts(stf_ctx* ctx) { CK(cudaMemsetAsync(ctx->counts.p, 0, C_ZEROED * sizeof(unsigned long long), ctx->st)); return STF_OK; }
 
 extern "C" int32_t stf_collision_bfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out) {
@@ -483,7 +483,7 @@ extern "C" int32_t stf_collision_bfs(stf_ctx* ctx, int64_t n, const stf_item* it
     int32_t r = import_items(ctx, n, items, ctx->items); if (r) return r;
     ctx->items_valid = false;
     r = zero_counts(ctx); if (r) return r;
-    r = narrow_phase(ctx, n); if (r) return r;
+    r = narrow_phase(ctx, n, n, true, false); if (r) return r;
     ctx->launches++, k_export_results<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), n, ctx->out32.as<int32_t>());
     KCHECK();
     CK(cudaMemcpyAsync(out, ctx->out32.p, sizeof(stf_item) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
@@ -521,21 +521,36 @@ extern "C" int32_t stf_collision(stf_ctx* ctx, int32_t i1, int32_t i2, int32_t o
 }
 
 // ------------------------------------------------------------------------------------------------ result pipeline
-// ctx->hits[0..nh) → sorted by ((i1,i2),(l,a,b)) in ctx->hits2, optional unique, exported to ctx->out32; returns count
+// ctx->hits[0..nh) (host-known count) → sorted by ((i1,i2),(l,a,b)) in ctx->hits2, optional unique, exported to ctx->out32
 static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_host_format, int64_t* nout) {
     *nout = 0;
     CK(ctx->hits2.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, nh)));
     if (nh == 0) return STF_OK;
+    stage_begin(ctx, STF_STAGE_RESULT);
+    if (nh <= BS_CAP && 2 * ctx->label_bits + FIN_IDX_BITS <= 64) { // one CTA: sort, tie order, unique, export
+        set_smem_attrs();
+        if (export_host_format) CK(ctx->out32.ensure(sizeof(int32_t) * 5 * (size_t)nh));
+        unsigned long long v = (unsigned long long)nh;
+        CK(stage_h2d(ctx, ctx->counts.as<unsigned long long>() + C_NHITS, &v, sizeof(v)));
+        FinalizeArgs F = {};
+        F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = nh;
+        F.n_items_dev = nullptr; F.item_cap = 0; F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = unique;
+        F.out5 = export_host_format ? ctx->out32.as<int32_t>() : nullptr; F.kept = ctx->counts.as<unsigned long long>() + C_KEPT;
+        F.do_prep = 0; F.status = ctx->errflag.as<int>() + 1;
+        ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
+        KCHECK();
+        stage_end(ctx);
+        if (!export_host_format) { *nout = nh; return STF_OK; }
+        int32_t r = sync_counts(ctx); if (r) return r;
+        *nout = (int64_t)ctx->h_counts[C_KEPT];
+        return STF_OK;
+    }
     size_t kb = sizeof(uint64_t) * (size_t)nh, vb = sizeof(uint32_t) * (size_t)nh;
     CK(ctx->hk.ensure(kb)); CK(ctx->hk2.ensure(kb)); CK(ctx->hv.ensure(vb)); CK(ctx->hv2.ensure(vb)); CK(ctx->keep.ensure(vb + 16));
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(nh)));
-    stage_begin(ctx, STF_STAGE_RESULT);
     ctx->launches++, k_hit_keys<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
     uint64_t* ks; uint32_t* vs;
-    if (nh <= SORT_SMALL_MAX) { // (i1,i2) in one launch: the device picks the bit windows of i2 and i1 that vary
-        { int32_t rr = sort_small(ctx, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nullptr, nh, 0, 32 + ctx->label_bits, bits_for(nh), nullptr); if (rr) return rr; }
-        ks = ctx->hk.as<uint64_t>(); vs = ctx->hv.as<uint32_t>();
-    } else {
+    {
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh, 0, ctx->label_bits, ctx->hist.as<uint32_t>());
         uint64_t *k0 = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), *k1 = f ? ctx->hk.as<uint64_t>() : ctx->hk2.as<uint64_t>();
         uint32_t *v0 = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), *v1 = f ? ctx->hv.as<uint32_t>() : ctx->hv2.as<uint32_t>();
@@ -588,25 +603,19 @@ extern "C" int32_t stf_fetch_items(stf_ctx* ctx, stf_item* out, int64_t cap, int
     return STF_OK;
 }
 
-// items in ctx->items (n known on host), `nd` direct hits already in ctx->hits[0..nd): BFS, append hits; *nh = total
+// items in ctx->items (n known on host), `nd` direct hits already in ctx->hits[0..nd): BFS, hits appended; *nh = total
 static int32_t collide_and_collect(stf_ctx* ctx, int64_t n, int64_t nd, int64_t* nh) {
     CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n + nd), true, ctx->st));
     unsigned long long base = (unsigned long long)nd;
-    CK(cudaMemcpyAsync(ctx->counts.as<unsigned long long>() + C_NHITS, &base, sizeof(base), cudaMemcpyHostToDevice, ctx->st));
+    CK(stage_h2d(ctx, ctx->counts.as<unsigned long long>() + C_NHITS, &base, sizeof(base)));
     stage_begin(ctx, STF_STAGE_NARROW);
-    int32_t r = narrow_phase(ctx, n); if (r) return r;
-    stage_begin(ctx, STF_STAGE_RESULT);
-    if (n > 0) {
-        ctx->launches++, k_compact_hits<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), nullptr, n, ctx->hits.as<Item16>(), n + nd,
-                                                         ctx->counts.as<unsigned long long>() + C_NHITS);
-        KCHECK();
-    }
+    int32_t r = narrow_phase(ctx, n, n, false, true); if (r) return r;
     stage_end(ctx);
     r = sync_counts(ctx); if (r) return r;
     *nh = (int64_t)ctx->h_counts[C_NHITS];
     ctx->ctr.items = n; ctx->ctr.direct = nd; ctx->ctr.hits = *nh;
     ctx->ctr.overflow = (int64_t)ctx->h_counts[C_OVERFLOW]; ctx->ctr.visited = (int64_t)ctx->h_counts[C_VISITED];
-    ctx->last_items = n; ctx->items_valid = true;
+    ctx->last_items = n; ctx->items_valid = true; ctx->hint_items = n;
     return STF_OK;
 }
 
@@ -647,32 +656,58 @@ extern "C" int32_t stf_totalcollisions_native(stf_ctx* ctx, int32_t nl, const in
 }
 
 // ------------------------------------------------------------------------------------------------ broad phase
-// locate + sort; on return *keys/*vals point at nrec sorted records (INVALID keys last)
-static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int linked, int64_t* nrec_out, uint64_t** keys, uint32_t** vals) {
+static bool fast_path_ok(const stf_ctx* ctx, int64_t nl) {
+    int key_bits = 2 * STF_CELL_W + 5 + ctx->scene_bits;
+    return !ctx->force_big && nl <= BS_CAP && key_bits + ctx->label_bits <= 64 && 2 * ctx->label_bits + FIN_IDX_BITS <= 64 && !getenv("STF_FORCE_BIG");
+}
+// locate + sort; on return *keys/*vals point at the sorted records, their number is in counts[C_NVALID] (device);
+// *nrec_out = capacity bound (4 slots per located object).  `labels_dev` = the device copy of `labels` (or NULL).
+// fast: records appended compactly and sorted by ONE CTA (status bit STF_ST_RETRY_BIG if they do not fit);
+// else: 4 fixed slots per object, multi-launch LSD radix sort, INVALID keys last.
+static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int linked, bool fast, int64_t* nrec_out, uint64_t** keys, uint32_t** vals) {
     if (!ctx->sizelevel_ok) FAIL(STF_E_STATE, "locate!: an object is larger than the canvas (sizelevel == -1)");
     int64_t nrec = 4ll * (linked ? ctx->n : nl);
     *nrec_out = nrec;
     stage_begin(ctx, STF_STAGE_LOCATE);
     size_t kb = sizeof(uint64_t) * (size_t)std::max<int64_t>(4, nrec), vb = sizeof(uint32_t) * (size_t)std::max<int64_t>(4, nrec);
     CK(ctx->rk.ensure(kb)); CK(ctx->rk2.ensure(kb)); CK(ctx->rv.ensure(vb)); CK(ctx->rv2.ensure(vb));
+    int bits = 2 * STF_CELL_W + 5 + ctx->scene_bits;
+    unsigned long long* nvalid = ctx->counts.as<unsigned long long>() + C_NVALID;
+    unsigned long long* nappend = ctx->counts.as<unsigned long long>() + C_NREC;
+    if (fast) {
+        set_smem_attrs();
+        CK(cudaMemsetAsync(nappend, 0, sizeof(unsigned long long), ctx->st));
+        if (linked) {
+            if (nl > 0) ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
+                                                                   ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>(), nullptr);
+            ctx->launches++, k_compact_records<<<nblk(nrec, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), nrec, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend);
+        } else if (nl > 0) {
+            ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
+                                                        ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ctx->errflag.as<int>(), nappend);
+        }
+        KCHECK();
+        stage_begin(ctx, STF_STAGE_SORT);
+        ctx->launches++, k_sort_records<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
+                                                                                  linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, ctx->errflag.as<int>() + 1);
+        KCHECK();
+        *keys = ctx->rk.as<uint64_t>(); *vals = ctx->rv.as<uint32_t>();
+        stage_end(ctx);
+        ctx->ctr.records = nrec;
+        return STF_OK;
+    }
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
     if (linked) {
         if (nl > 0) ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
-                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>());
+                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>(), nullptr);
         CK(cudaMemcpyAsync(ctx->rk.p, ctx->lkk.p, sizeof(uint64_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->rv.p, ctx->lkv.p, sizeof(uint32_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
     } else if (nl > 0) {
         ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
-                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->errflag.as<int>());
+                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->errflag.as<int>(), nullptr);
     }
     KCHECK();
     stage_begin(ctx, STF_STAGE_SORT);
-    int bits = 2 * STF_CELL_W + 5 + ctx->scene_bits;
-    unsigned long long* nvalid = ctx->counts.as<unsigned long long>() + C_NVALID;
-    if (nrec <= SORT_SMALL_MAX) { // one launch: compaction + only the digit windows in which keys differ
-        { int32_t rr = sort_small(ctx, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nullptr, nrec, 1, bits, ctx->label_bits, nvalid); if (rr) return rr; }
-        *keys = ctx->rk.as<uint64_t>(); *vals = ctx->rv.as<uint32_t>();
-    } else {
+    {
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nrec, 0, bits, ctx->hist.as<uint32_t>());
         *keys = f ? ctx->rk2.as<uint64_t>() : ctx->rk.as<uint64_t>();
         *vals = f ? ctx->rv2.as<uint32_t>() : ctx->rv.as<uint32_t>();
@@ -701,7 +736,7 @@ extern "C" int32_t stf_locate(stf_ctx* ctx, int32_t nl, const int32_t* labels, s
     if (nl <= 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
     int64_t nrec; uint64_t* keys; uint32_t* vals;
-    r = locate_and_sort(ctx, nl, dl, 0, &nrec, &keys, &vals); if (r) return r;
+    r = locate_and_sort(ctx, nl, dl, 0, false, &nrec, &keys, &vals); if (r) return r;
     return export_cells(ctx, nrec, keys, vals, out, cap, count);
 }
 extern "C" int32_t stf_linked_reset(stf_ctx* ctx) {
@@ -718,7 +753,7 @@ extern "C" int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* la
     if (nl <= 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
     ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
-                                                ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>());
+                                                ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>(), nullptr);
     KCHECK();
     return sync_counts(ctx);
 }
@@ -736,50 +771,126 @@ extern "C" int32_t stf_linked_collect(stf_ctx* ctx, stf_cellrec* out, int64_t ca
     if (count) *count = 0;
     if (ctx->n == 0) return STF_OK;
     int64_t nrec; uint64_t* keys; uint32_t* vals;
-    int32_t r = locate_and_sort(ctx, 0, nullptr, 1, &nrec, &keys, &vals); if (r) return r;
+    int32_t r = locate_and_sort(ctx, 0, nullptr, 1, false, &nrec, &keys, &vals); if (r) return r;
     return export_cells(ctx, nrec, keys, vals, out, cap, count);
 }
 
-// broad phase + narrow phase; leaves the raw hit list in ctx->hits, *nh hits
+static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, const int32_t* moved_pos) {
+    EmitOut eo; eo.items = ctx->items.as<Item16>(); eo.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
+    eo.direct = ctx->hits.as<Item16>(); eo.direct_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
+    eo.counts = ctx->counts.as<unsigned long long>(); eo.nhits = ctx->counts.as<unsigned long long>() + C_NHITS;
+    stage_begin(ctx, STF_STAGE_EMIT);
+    if (nrec > 0) {
+        int blocks = (int)std::min<int64_t>((nrec / 4 + EM_THREADS / 32 - 1) / (EM_THREADS / 32) + 1, 148 * 8); // ~1 record per located object
+        ctx->launches++, k_emit_items<<<blocks, EM_THREADS, 0, ctx->st>>>(keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
+                                                                        ctx->lm.as<LevelMeta>(), moved_pos, eo);
+    }
+    KCHECK();
+    stage_end(ctx);
+    return STF_OK;
+}
+static int32_t upload_moved_pos(stf_ctx* ctx, int32_t nl, const int32_t* labels, const int32_t** moved_pos) {
+    // moved_pos[o] = position of o+1 in `labels`, -1 otherwise
+    std::vector<int32_t> mp((size_t)ctx->n, -1);
+    for (int i = 0; i < nl; i++) mp[(size_t)(labels ? labels[i] - 1 : i)] = i;
+    CK(stage_h2d(ctx, ctx->moved_pos.p, mp.data(), sizeof(int32_t) * (size_t)ctx->n));
+    *moved_pos = ctx->moved_pos.as<int32_t>();
+    return STF_OK;
+}
+static void read_round_counters(stf_ctx* ctx) {
+    ctx->ctr.items = (int64_t)ctx->h_counts[C_ITEMS]; ctx->ctr.direct = (int64_t)ctx->h_counts[C_DIRECT]; ctx->ctr.hits = (int64_t)ctx->h_counts[C_NHITS];
+    ctx->ctr.overflow = (int64_t)ctx->h_counts[C_OVERFLOW]; ctx->ctr.visited = (int64_t)ctx->h_counts[C_VISITED];
+    ctx->last_items = ctx->ctr.items; ctx->items_valid = true; ctx->hint_items = ctx->ctr.items;
+}
+
+// Latency path of one many-body round: every count stays on the device, the host only enqueues.  Broad phase
+// (append-locate, one-CTA sort, candidates) + narrow phase; the unordered hit list is left in ctx->hits with its count
+// in counts[C_NHITS].  Buffer sizes come from the previous round; the finalize kernel raises RETRY bits if one was too
+// small or the scene is too large for the single-CTA kernels, and the caller re-runs.
+static int32_t spacial_core_fast(stf_ctx* ctx, int32_t nl, const int32_t* labels, int linked) {
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
+    const int32_t* moved_pos = nullptr;
+    if (linked) { r = upload_moved_pos(ctx, nl, labels, &moved_pos); if (r) return r; }
+    int64_t nrec; uint64_t* keys; uint32_t* vals;
+    CK(cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st));
+    CK(cudaMemsetAsync(ctx->errflag.as<int>() + 1, 0, sizeof(int), ctx->st));
+    r = locate_and_sort(ctx, nl, dl, linked, true, &nrec, &keys, &vals); if (r) return r;
+    int64_t want_items = std::max<int64_t>(std::max<int64_t>(1024, 32 * nrec / 4), ctx->hint_items + ctx->hint_items / 4 + 1024);
+    if ((int64_t)(ctx->items.cap / sizeof(Item16)) < want_items) CK(ctx->items.ensure(sizeof(Item16) * (size_t)want_items));
+    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)(BS_CAP + 1024))); // more hits than BS_CAP leave the fast path anyway
+    r = launch_emit(ctx, nrec, keys, vals, moved_pos); if (r) return r;
+    stage_begin(ctx, STF_STAGE_NARROW);
+    r = narrow_phase(ctx, -1, (int64_t)(ctx->items.cap / sizeof(Item16)), false, true); if (r) return r;
+    stage_end(ctx);
+    return STF_OK;
+}
+// after the final sync of a fast round: 0 = done, 1 = re-run (buffers grown / path switched)
+static int fast_round_verdict(stf_ctx* ctx) {
+    int st = ctx->h_err[1];
+    if (!st) return 0;
+    cudaMemsetAsync(ctx->errflag.as<int>() + 1, 0, sizeof(int), ctx->st);
+    if (st & STF_ST_RETRY_BIG) ctx->force_big = true;
+    if (st & STF_ST_RETRY_GROW) ctx->hint_items = (int64_t)ctx->h_counts[C_ITEMS]; // sizes the candidate list of the re-run
+    return 1;
+}
+
+// throughput path: broad phase + narrow phase with host-known counts; leaves the raw hit list in ctx->hits, *nh hits
 static int32_t spacial_core(stf_ctx* ctx, int32_t nl, const int32_t* labels, int linked, int64_t* nh) {
     *nh = 0;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
     const int32_t* moved_pos = nullptr;
-    if (linked) { // moved_pos[o] = position of o+1 in `labels`, -1 otherwise
-        std::vector<int32_t> mp((size_t)ctx->n, -1);
-        for (int i = 0; i < nl; i++) mp[(size_t)(labels ? labels[i] - 1 : i)] = i;
-        CK(cudaMemcpyAsync(ctx->moved_pos.p, mp.data(), sizeof(int32_t) * (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaStreamSynchronize(ctx->st));
-        moved_pos = ctx->moved_pos.as<int32_t>();
-    }
+    if (linked) { r = upload_moved_pos(ctx, nl, labels, &moved_pos); if (r) return r; }
     int64_t nrec; uint64_t* keys; uint32_t* vals;
-    r = locate_and_sort(ctx, nl, dl, linked, &nrec, &keys, &vals); if (r) return r;
+    r = locate_and_sort(ctx, nl, dl, linked, false, &nrec, &keys, &vals); if (r) return r;
     int64_t n_items = 0, n_direct = 0;
     for (int attempt = 0; attempt < 3; attempt++) {
         r = zero_counts(ctx); if (r) return r;
         if (ctx->items.cap < sizeof(Item16) * 1024) CK(ctx->items.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, 32 * nrec)));
-        if (ctx->direct.cap < sizeof(Item16) * 1024) CK(ctx->direct.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, nrec)));
-        EmitOut eo; eo.items = ctx->items.as<Item16>(); eo.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
-        eo.direct = ctx->direct.as<Item16>(); eo.direct_cap = (int64_t)(ctx->direct.cap / sizeof(Item16)); eo.counts = ctx->counts.as<unsigned long long>();
-        stage_begin(ctx, STF_STAGE_EMIT);
-        if (nrec > 0) {
-            int blocks = (int)std::min<int64_t>((nrec + EM_THREADS / 32 - 1) / (EM_THREADS / 32), 148 * 8);
-            ctx->launches++, k_emit_items<<<blocks, EM_THREADS, 0, ctx->st>>>(keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
-                                                                            ctx->lm.as<LevelMeta>(), moved_pos, eo);
-        }
+        if (ctx->hits.cap < sizeof(Item16) * 1024) CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, nrec)));
+        int64_t item_cap = (int64_t)(ctx->items.cap / sizeof(Item16)), direct_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
+        r = launch_emit(ctx, nrec, keys, vals, moved_pos); if (r) return r;
+        r = sync_counts(ctx); if (r) return r;
+        n_items = (int64_t)ctx->h_counts[C_ITEMS]; n_direct = (int64_t)ctx->h_counts[C_DIRECT];
+        if (n_items <= item_cap && n_direct <= direct_cap) break;
+        if (attempt == 2) FAIL(STF_E_CUDA, "internal: item buffer did not converge");
+        CK(ctx->items.ensure(sizeof(Item16) * (size_t)(n_items + n_items / 4 + 1024)));
+        CK(ctx->hits.ensure(sizeof(Item16) * (size_t)(n_direct + n_direct / 4 + 1024)));
+    }
+    // direct hits are already at the front of ctx->hits (counts[C_NHITS] == n_direct); keep them while growing
+    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n_items + n_direct), true, ctx->st));
+    stage_begin(ctx, STF_STAGE_NARROW);
+    r = narrow_phase(ctx, n_items, n_items, false, true); if (r) return r;
+    stage_end(ctx);
+    r = sync_counts(ctx); if (r) return r;
+    read_round_counters(ctx);
+    ctx->ctr.items = n_items; ctx->ctr.direct = n_direct; ctx->last_items = n_items;
+    *nh = (int64_t)ctx->h_counts[C_NHITS];
+    return STF_OK;
+}
+
+// many-body call with export: fast path when the scene fits, else the throughput path
+static int32_t manybody_export(stf_ctx* ctx, int32_t nl, const int32_t* labels, int linked, int32_t unique, stf_item* out, int64_t cap, int64_t* count) {
+    for (int attempt = 0; attempt < 4 && fast_path_ok(ctx, linked ? ctx->n : nl); attempt++) {
+        int32_t r = spacial_core_fast(ctx, nl, labels, linked); if (r) return r;
+        CK(ctx->hits2.ensure(sizeof(Item16) * (size_t)(BS_CAP + 1024))); CK(ctx->out32.ensure(sizeof(int32_t) * 5 * (size_t)(BS_CAP + 1024)));
+        stage_begin(ctx, STF_STAGE_RESULT);
+        FinalizeArgs F = {};
+        F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
+        F.n_items_dev = ctx->counts.as<unsigned long long>() + C_ITEMS; F.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
+        F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = unique;
+        F.out5 = ctx->out32.as<int32_t>(); F.kept = ctx->counts.as<unsigned long long>() + C_KEPT; F.do_prep = 0; F.status = ctx->errflag.as<int>() + 1;
+        ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
         KCHECK();
         stage_end(ctx);
         r = sync_counts(ctx); if (r) return r;
-        n_items = (int64_t)ctx->h_counts[C_ITEMS]; n_direct = (int64_t)ctx->h_counts[C_DIRECT];
-        if (n_items <= eo.item_cap && n_direct <= eo.direct_cap) break;
-        if (attempt == 2) FAIL(STF_E_CUDA, "internal: item buffer did not converge");
-        CK(ctx->items.ensure(sizeof(Item16) * (size_t)(n_items + n_items / 4 + 1024)));
-        CK(ctx->direct.ensure(sizeof(Item16) * (size_t)(n_direct + n_direct / 4 + 1024)));
+        if (fast_round_verdict(ctx)) continue;
+        read_round_counters(ctx);
+        return deliver(ctx, (int64_t)ctx->h_counts[C_KEPT], out, cap, count);
     }
-    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n_items + n_direct)));
-    if (n_direct) CK(cudaMemcpyAsync(ctx->hits.p, ctx->direct.p, sizeof(Item16) * (size_t)n_direct, cudaMemcpyDeviceToDevice, ctx->st));
-    r = zero_counts(ctx); if (r) return r;
-    return collide_and_collect(ctx, n_items, n_direct, nh);
+    int64_t nh = 0, nout = 0;
+    int32_t r = spacial_core(ctx, nl, labels, linked, &nh); if (r) return r;
+    r = finalize_hits(ctx, nh, unique, true, &nout); if (r) return r;
+    return deliver(ctx, nout, out, cap, count);
 }
 
 extern "C" int32_t stf_totalcollisions_spacial(stf_ctx* ctx, int32_t nl, const int32_t* labels, int32_t unique, stf_item* out, int64_t cap, int64_t* count) {
@@ -788,10 +899,7 @@ extern "C" int32_t stf_totalcollisions_spacial(stf_ctx* ctx, int32_t nl, const i
     ctx->last_result = 0;
     if (!labels) nl = ctx->n;
     if (ctx->n <= 1 || nl <= 0) return STF_OK; // length(qtrees) > 1 || return colist  :227
-    int64_t nh = 0, nout = 0;
-    int32_t r = spacial_core(ctx, nl, labels, 0, &nh); if (r) return r;
-    r = finalize_hits(ctx, nh, unique, true, &nout); if (r) return r;
-    return deliver(ctx, nout, out, cap, count);
+    return manybody_export(ctx, nl, labels, 0, unique, out, cap, count);
 }
 extern "C" int32_t stf_partialcollisions(stf_ctx* ctx, int32_t nl, const int32_t* labels, int32_t unique, stf_item* out, int64_t cap, int64_t* count) {
     NEED_OBJS();
@@ -799,10 +907,7 @@ extern "C" int32_t stf_partialcollisions(stf_ctx* ctx, int32_t nl, const int32_t
     ctx->last_result = 0;
     if (!labels) nl = ctx->n;
     if (ctx->n == 0) return STF_OK;
-    int64_t nh = 0, nout = 0;
-    int32_t r = spacial_core(ctx, nl, labels, 1, &nh); if (r) return r;
-    r = finalize_hits(ctx, nh, unique, true, &nout); if (r) return r;
-    return deliver(ctx, nout, out, cap, count);
+    return manybody_export(ctx, nl, labels, 1, unique, out, cap, count);
 }
 
 // ------------------------------------------------------------------------------------------------ fit step
@@ -831,45 +936,51 @@ extern "C" int32_t stf_get_velocity(stf_ctx* ctx, int32_t n, const int32_t* labe
     }
     return STF_OK;
 }
-// batchsteps! over hits[0..n) (device, list order)
-static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, uint64_t seed, uint64_t iter) {
-    if (n == 0) { ctx->ctr.moved = 0; return STF_OK; }
-    int64_t m = 2 * n;
-    CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)m)); CK(ctx->hk2.ensure(sizeof(uint64_t) * (size_t)m));
-    CK(ctx->hv.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->hv2.ensure(sizeof(uint32_t) * (size_t)m));
-    CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(m)));
-    CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)n));
-    stage_begin(ctx, STF_STAGE_STEP_PREP);
-    ctx->launches++, k_step_endpoints<<<nblk(m, 256), 256, 0, ctx->st>>>(hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
-    CK(cudaMemsetAsync(ctx->prev.p, 0, sizeof(uint32_t) * (size_t)m, ctx->st));
-    if (m <= SORT_SMALL_MAX) { // mask endpoints (INVALID) are compacted away; prev stays 0 for them
-        unsigned long long* nep = ctx->counts.as<unsigned long long>() + C_NEP;
-        { int32_t rr = sort_small(ctx, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nullptr, m, 1, ctx->label_bits + 1, bits_for(m), nep); if (rr) return rr; }
-        ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), nep, m, ctx->prev.as<uint32_t>());
-    } else {
-        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
-        ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
-    }
-    CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
-    CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
-    CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
+// k_batchsteps + k_materialize over `hits`; the step count is host-known (n_dev == NULL) or lives on the device
+static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, const unsigned long long* n_dev, uint64_t seed, uint64_t iter) {
     StepArgs A;
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.om = ctx->om.as<ObjMeta>(); A.L = ctx->L;
-    A.hits = hits; A.n = n; A.prev = ctx->prev.as<uint32_t>(); A.done = ctx->done.as<uint32_t>();
+    A.hits = hits; A.n = n_host; A.n_dev = n_dev; A.prev = ctx->prev.as<uint32_t>(); A.done = ctx->done.as<uint32_t>();
     A.ticket = ctx->counts.as<unsigned long long>() + C_TICKET;
     A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>(); A.dirty = ctx->dirty.as<int>();
     A.opt = ctx->opt; A.seed = seed; A.iter = iter; A.counts = ctx->counts.as<unsigned long long>();
     { const char* e = getenv("STF_DEBUG_STEP"); A.dbg = e ? atoi(e) : 0; }
     A.dbg_t = nullptr;
-    if (A.dbg & 16) { CK(ctx->dbg_t.ensure(sizeof(unsigned long long) * 4 * (size_t)n)); A.dbg_t = ctx->dbg_t.as<unsigned long long>(); }
-    int blocks = (int)std::min<int64_t>((n + 3) / 4, 148 * 8);
+    if (A.dbg & 16) { CK(ctx->dbg_t.ensure(sizeof(unsigned long long) * 4 * (size_t)std::max<int64_t>(n_host, BS_CAP))); A.dbg_t = ctx->dbg_t.as<unsigned long long>(); }
+    int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (n_host + 3) / 4), 148 * 8);
     stage_begin(ctx, STF_STAGE_STEP);
     ctx->launches++, k_batchsteps<<<blocks, 128, 0, ctx->st>>>(A);
     // the steps only moved the shifts: materialise the rasters of every moved tree once
     ctx->launches++, k_materialize<<<std::min(nblk((int64_t)ctx->n * 32, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->n, ctx->dirty.as<int>());
     KCHECK();
     stage_end(ctx);
-    int32_t r = sync_counts(ctx); if (r) return r;
+    return STF_OK;
+}
+// batchsteps! over hits[0..n) (device, list order, host-known n)
+static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, uint64_t seed, uint64_t iter) {
+    if (n == 0) { ctx->ctr.moved = 0; return STF_OK; }
+    int64_t m = 2 * n;
+    CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)n));
+    stage_begin(ctx, STF_STAGE_STEP_PREP);
+    CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
+    if (m <= BS_CAP && ctx->label_bits + 1 + FIN_IDX_BITS <= 64) { // one CTA: endpoints, sort, links
+        set_smem_attrs();
+        ctx->launches++, k_step_links<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(hits, (int)n, ctx->label_bits, ctx->om.as<ObjMeta>(), ctx->prev.as<uint32_t>(), ctx->done.as<uint32_t>(),
+                                                                                 ctx->counts.as<unsigned long long>() + C_TICKET);
+    } else {
+        CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)m)); CK(ctx->hk2.ensure(sizeof(uint64_t) * (size_t)m));
+        CK(ctx->hv.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->hv2.ensure(sizeof(uint32_t) * (size_t)m));
+        CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(m)));
+        ctx->launches++, k_step_endpoints<<<nblk(m, 256), 256, 0, ctx->st>>>(hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+        CK(cudaMemsetAsync(ctx->prev.p, 0, sizeof(uint32_t) * (size_t)m, ctx->st));
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
+        ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
+        CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
+        CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
+    }
+    KCHECK();
+    int32_t r = launch_steps(ctx, hits, n, nullptr, seed, iter); if (r) return r;
+    r = sync_counts(ctx); if (r) return r;
     ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES];
     return STF_OK;
 }
@@ -880,16 +991,41 @@ extern "C" int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colis
     int32_t r = import_items(ctx, n, colist, ctx->hits2); if (r) return r;
     return batchsteps_device(ctx, ctx->hits2.as<Item16>(), n, seed, iteration);
 }
+// One fit iteration on the device: many-body collision detection over the active labels, then batchsteps! on the result
+// (canonical list order = sorted by ((i1,i2),(l,a,b))).  Latency path: ~10 launches, ONE host synchronisation.
 extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits) {
     NEED_OBJS();
     if (nhits) *nhits = 0;
     if (!labels) nl = ctx->n;
     if (ctx->n <= 1 || nl <= 0) return STF_OK;
+    ctx->last_result = 0;
+    int linked = mode == 1;
+    for (int attempt = 0; attempt < 4 && fast_path_ok(ctx, linked ? ctx->n : nl); attempt++) {
+        int32_t r = spacial_core_fast(ctx, nl, labels, linked); if (r) return r;
+        CK(ctx->hits2.ensure(sizeof(Item16) * (size_t)(BS_CAP + 1024)));
+        CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)(BS_CAP + 1024))); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)(BS_CAP + 1024)));
+        stage_begin(ctx, STF_STAGE_RESULT);
+        FinalizeArgs F = {};
+        F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
+        F.n_items_dev = ctx->counts.as<unsigned long long>() + C_ITEMS; F.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
+        F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = 0; F.out5 = nullptr; F.kept = nullptr;
+        F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
+        F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
+        F.status = ctx->errflag.as<int>() + 1;
+        ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
+        KCHECK();
+        r = launch_steps(ctx, ctx->hits2.as<Item16>(), std::max<int64_t>(ctx->ctr.hits, 2048), ctx->counts.as<unsigned long long>() + C_NSTEPS, seed, iteration); if (r) return r;
+        r = sync_counts(ctx); if (r) return r;
+        if (fast_round_verdict(ctx)) continue; // no step ran (n_steps == 0): nothing to undo
+        read_round_counters(ctx);
+        ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES];
+        if (nhits) *nhits = ctx->ctr.hits;
+        return STF_OK;
+    }
     int64_t nh = 0, nout = 0;
-    int32_t r = spacial_core(ctx, nl, labels, mode == 1, &nh); if (r) return r;
+    int32_t r = spacial_core(ctx, nl, labels, linked, &nh); if (r) return r;
     r = finalize_hits(ctx, nh, 0, false, &nout); if (r) return r; // canonical list order = sorted, stays on the device
     if (nhits) *nhits = nh;
-    ctx->last_result = 0;
     return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
 }
 extern "C" int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out) {
@@ -930,6 +1066,6 @@ extern "C" int32_t stf_debug_step_timeline(stf_ctx* ctx, int64_t n, unsigned lon
     return STF_OK;
 }
 
-extern "C" int32_t stf_debug_sort_cycles(long long* out16) {
-    return cudaMemcpyFromSymbol(out16, g_sort_dbg, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
-}
+#ifdef STF_BS_DEBUG
+extern "C" int32_t stf_debug_sort_cycles(long long* out64) { return cudaMemcpyFromSymbol(out64, g_bs_dbg, sizeof(long long) * 64) == cudaSuccess ? 0 : -1; }
+#endif
