@@ -24,15 +24,15 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_records(const uint64_t* __r
         return;
     }
     int n = (int)n64;
-    int ipt = bs_ipt(n), e0 = threadIdx.x * ipt;
+    int ch = bs_chunks(n);
     uint64_t x[BS_ITEMS];
 #pragma unroll
     for (int c = 0; c < BS_ITEMS; c++) {
-        int e = e0 + c;
+        int e = bs_index(n, c);
         x[c] = 0;
-        if (c < ipt && e < n) x[c] = (keys_in[e] << vbits) | (uint64_t)tie_in[e];
+        if (c < ch && e < n) x[c] = (keys_in[e] << vbits) | (uint64_t)tie_in[e];
     }
-    bs_sort(S, x, n); // key major, tie-break (label or position in `labels`) minor: a total order,
+    bs_sort(S, x, n, 0, key_bits + vbits); // key major, tie-break (label or position in `labels`) minor: a total order,
     uint64_t vmask = (1ull << vbits) - 1;  // so the unordered (atomic-append) input gives a deterministic result
     for (int e = threadIdx.x; e < n; e += BS_THREADS) {
         uint64_t p = S.buf[e];
@@ -68,12 +68,12 @@ __device__ __forceinline__ void fin_step_links(BlockSortSmem& S, const Item16* _
     int n2 = 2 * n;
     uint64_t x[BS_ITEMS];
     {
-        int ipt = bs_ipt(n2), e0 = threadIdx.x * ipt;
+        int ch = bs_chunks(n2);
 #pragma unroll
         for (int c = 0; c < BS_ITEMS; c++) {
-            int e = e0 + c;
+            int e = bs_index(n2, c);
             x[c] = 0;
-            if (c < ipt && e < n2) {
+            if (c < ch && e < n2) {
                 Item16 h = list[e >> 1];
                 uint32_t o = (uint32_t)((e & 1) ? item_i2(h) : h.i1) - 1u;
                 uint64_t ok = om[o].is_mask ? (1ull << lb) : (uint64_t)o;
@@ -82,7 +82,7 @@ __device__ __forceinline__ void fin_step_links(BlockSortSmem& S, const Item16* _
         }
     }
     __syncthreads();
-    bs_sort(S, x, n2);
+    bs_sort(S, x, n2, FIN_IDX_BITS, FIN_IDX_BITS + lb + 1);
     for (int j = threadIdx.x; j < n2; j += BS_THREADS) {
         uint64_t cur = S.buf[j];
         uint64_t ok = cur >> FIN_IDX_BITS; uint32_t e = (uint32_t)(cur & ((1u << FIN_IDX_BITS) - 1));
@@ -114,18 +114,18 @@ __global__ void __launch_bounds__(BS_THREADS) k_finalize_hits(FinalizeArgs A) {
     // ---- sort by (i1, i2); payload = position in the unordered list
     uint64_t x[BS_ITEMS];
     {
-        int ipt = bs_ipt(n), e0 = threadIdx.x * ipt;
+        int ch = bs_chunks(n);
 #pragma unroll
         for (int c = 0; c < BS_ITEMS; c++) {
-            int e = e0 + c;
+            int e = bs_index(n, c);
             x[c] = 0;
-            if (c < ipt && e < n) {
+            if (c < ch && e < n) {
                 Item16 h = A.hits[e];
                 x[c] = ((uint64_t)(uint32_t)h.i1 << (lb + FIN_IDX_BITS)) | ((uint64_t)(uint32_t)item_i2(h) << FIN_IDX_BITS) | (uint64_t)e;
             }
         }
     }
-    bs_sort(S, x, n);
+    bs_sort(S, x, n, FIN_IDX_BITS, FIN_IDX_BITS + 2 * lb);
     // ---- gather into canonical order
     for (int p = threadIdx.x; p < n; p += BS_THREADS) A.sorted[p] = A.hits[(uint32_t)(S.buf[p] & ((1u << FIN_IDX_BITS) - 1))];
     __syncthreads();

@@ -13,7 +13,7 @@ out = np.zeros(64, np.int64)
 lib.stf_debug_sort_cycles.argtypes = [C.c_void_p]
 def show(tag):
     lib.stf_debug_sort_cycles(out.ctypes.data)
-    print(tag, "n", out[4], "thread sort + store", out[1] - out[0], "merge levels", out[2] - out[1], "cycles")
+    print(tag, "n", out[4], "npass", out[3], "plan", out[1] - out[0], "passes", out[2] - out[1], "last pass: zero+rank", out[9] - out[8], "scan", out[10] - out[9], "scatter", out[11] - out[10], "reload", out[12] - out[11])
 hits = S.totalcollisions_spacial(d, unique=False, raw=True)
 show("last sort of totalcollisions (hits):")
 lib.stf_set_optimiser(h, 2, 0.25, 0.5)
