@@ -198,7 +198,7 @@ def run_ours(args, W):
     ms_res = timed(True, args.steps)
     bracket()
     launches = lib.stf_launch_count(h) - l0
-    stage_ms = np.zeros(8); stage_calls = np.zeros(8, np.int64)
+    stage_ms = np.zeros(9); stage_calls = np.zeros(9, np.int64)
     lib.stf_profile_read(h, stage_ms.ctypes.data, stage_calls.ctypes.data, 1)
     lib.stf_profile_enable(h, 0)
     bracket()

@@ -171,7 +171,7 @@ int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out);
 int64_t stf_launch_count(const stf_ctx* ctx);
 
 /* ---- per-stage device timers (CUDA events on the context's stream; for bench.py's roofline) ---- */
-#define STF_NSTAGES 8
+#define STF_NSTAGES 9
 #define STF_STAGE_SHIFT 0     /* stf_set_shifts: shift update + pyramid rebuild (k_apply_shifts, k_build_objects) */
 #define STF_STAGE_LOCATE 1    /* k_locate */
 #define STF_STAGE_SORT 2      /* radix sort of the (cell,label) records */
@@ -179,7 +179,8 @@ int64_t stf_launch_count(const stf_ctx* ctx);
 #define STF_STAGE_NARROW 4    /* k_collide_small + k_collide_big: frontier BFS */
 #define STF_STAGE_RESULT 5    /* hit compaction, sort!, unique!, export */
 #define STF_STAGE_STEP_PREP 6 /* endpoint sort + predecessor links of batchsteps */
-#define STF_STAGE_STEP 7      /* k_batchsteps: grad2d + step + rebuild */
+#define STF_STAGE_STEP 7      /* k_batchsteps (grad2d + step on the shifts) + k_materialize (one rebuild per moved tree) */
+#define STF_STAGE_BUILD 8     /* upload: level-1 pack + full pyramid build from the u8 payload resident in HBM */
 int32_t stf_profile_enable(stf_ctx* ctx, int32_t on);
 /* accumulated milliseconds and number of timed intervals per stage since the last reset */
 int32_t stf_profile_read(stf_ctx* ctx, double* ms, int64_t* calls, int32_t reset);

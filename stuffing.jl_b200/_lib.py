@@ -60,7 +60,7 @@ EXPORTS = {
     "stf_profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),
     "stf_profile_read": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
 }
-STAGES = ("shift_rebuild", "locate", "sort", "emit", "narrow", "result", "step_prep", "step")
+STAGES = ("shift_rebuild", "locate", "sort", "emit", "narrow", "result", "step_prep", "step", "build")
 
 COUNTER_FIELDS = ("records", "items", "direct", "hits", "overflow", "moved", "visited", "reserved")
 

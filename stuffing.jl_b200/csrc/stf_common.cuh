@@ -121,7 +121,9 @@ template <bool CG> __device__ __forceinline__ void stmeta(LevelMeta* p, const Le
 // the global stores are fire-and-forget.  Returns the lane's meta with the new shifts (lanes >= from).
 #define RB_HALF 384   // words per shared-memory level buffer (two per warp)
 // KEEP: the per-level shifts in `mine` are already final (lazy batchsteps tracks them); only the rasters are rebuilt.
-template <bool CG, bool KEEP = false> __device__ __forceinline__ LevelMeta warp_rebuild(uint32_t* __restrict__ words, LevelMeta mine, int L, int from, int lane, uint32_t* __restrict__ sbuf) {
+// FIRST_SMEM: level `from` has already been staged in sbuf[0 .. ) by the caller (fused pack + build).
+// upto: last level whose raster is built (shifts are still computed for every level).
+template <bool CG, bool KEEP = false, bool FIRST_SMEM = false> __device__ __forceinline__ LevelMeta warp_rebuild(uint32_t* __restrict__ words, LevelMeta mine, int L, int from, int lane, uint32_t* __restrict__ sbuf, int upto = STF_MAX_LEVELS) {
     const unsigned FULLM = 0xffffffffu;
     // shifts of the rebuilt levels in closed form: repeated `÷ 2` (toward zero) composes to `÷ 2^k`
     int brs = __shfl_sync(FULLM, mine.rs, from - 1), bcs = __shfl_sync(FULLM, mine.cs, from - 1);
@@ -133,9 +135,10 @@ template <bool CG, bool KEEP = false> __device__ __forceinline__ LevelMeta warp_
     int crs = __shfl_up_sync(FULLM, mine.rs, 1), ccs = __shfl_up_sync(FULLM, mine.cs, 1);
     uint32_t cdims = __shfl_up_sync(FULLM, mine.dims, 1), coff = __shfl_up_sync(FULLM, mine.off, 1);
     int my_er = crs - 2 * mine.rs, my_ec = ccs - 2 * mine.cs;
-    bool in_smem = false; int cur = 0;
+    bool in_smem = FIRST_SMEM; int cur = 0;
     bool in_reg = false; uint32_t regw = 0; // once a level is one word per column and <= 32 columns, lane j keeps column j
-    for (int l = from + 1; l <= L; l++) {
+    const int last = min(L, upto);
+    for (int l = from + 1; l <= last; l++) {
         int s = l - 1;
         uint32_t poff = __shfl_sync(FULLM, mine.off, s), pdims = __shfl_sync(FULLM, mine.dims, s);
         LevelMeta ch; ch.off = __shfl_sync(FULLM, coff, s); ch.dims = __shfl_sync(FULLM, cdims, s); ch.rs = 0; ch.cs = 0;

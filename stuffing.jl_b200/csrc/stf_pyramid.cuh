@@ -5,46 +5,184 @@
 #include "stf_common.cuh"
 
 // ---- level-1 pack: u8 codes (column-major payload, pitch kh) -> 2-bit words -------------------
-// one thread per output word; `woff1[o]` = first level-1 word of object o in a dense numbering
-// (prefix sum over objects), `poff[o]` = byte offset of its payload in `payload`.
-__global__ void k_pack_level1(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ poff,
-                              const uint64_t* __restrict__ woff1, int n, const LevelMeta* __restrict__ lm, int L,
+// word w of a column: 16 payload bytes at any alignment are fetched as 5 aligned words + funnel shifts (the buffer has
+// slack); the tail word of a column takes `default` in the fields past kh.  Validates the codes (1..3).
+__device__ __forceinline__ uint32_t pack_word(const uint8_t* __restrict__ col, int kh, int w, uint32_t d, int& bad) {
+    // One branch-free path for full and tail words (a warp mixes both): always fetch 16 bytes — a tail word over-reads
+    // into the next column / next object / the zeroed slack, all of which have clear high bits — and replace the fields
+    // past kh by `default` afterwards.  4 bytes -> 8 bits with one multiply: (x & 0x03030303) * (2^24+2^18+2^12+2^6)
+    // moves byte k's code to bits 24+2k (the cross terms land below bit 24 or overflow, none carries).
+    const uint8_t* src = col + 16 * w;
+    int nv = min(16, kh - 16 * w);
+    const uint32_t* ap = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    int sh = (int)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+    uint32_t t[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) t[k] = __ldg(ap + k);
+    uint32_t out = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t x = __funnelshift_r(t[k], t[k + 1], sh);
+        hi |= x;
+        out |= (((x & 0x03030303u) * 0x01041040u) >> 24) << (8 * k);
+    }
+    uint32_t fm = nv >= 16 ? 0xFFFFFFFFu : ((1u << (2 * nv)) - 1u);
+    // codes are 1..3: no bit above the low two in the 16 fetched bytes, no zero field among the first nv
+    bad |= ((hi & 0xFCFCFCFCu) != 0) | ((~(out | (out >> 1)) & 0x55555555u & fm) != 0);
+    return (out & fm) | (dflt_word(d) & ~fm);
+}
+// one thread per output word of the listed (big) objects; `woff1[i]` = first level-1 word of list entry i in a dense
+// numbering (prefix sum), `poff[o]` = byte offset of object o's payload.
+__global__ void k_pack_level1(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ poff, const int32_t* __restrict__ list,
+                              const uint64_t* __restrict__ woff1, int nlist, const LevelMeta* __restrict__ lm, int L,
                               uint32_t* __restrict__ words, uint64_t total_words, int* __restrict__ err) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_words) return;
-    int lo = 0, hi = n; // largest o with woff1[o] <= i
+    int lo = 0, hi = nlist; // largest entry with woff1[entry] <= i
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (woff1[mid] <= i) lo = mid; else hi = mid; }
-    int o = lo;
+    int o = list[lo];
     LevelMeta m = lm[(size_t)o * L];
     int kh = lm_kh(m), wpc = wpc_of(kh);
-    uint32_t local = (uint32_t)(i - woff1[o]);
+    uint32_t local = (uint32_t)(i - woff1[lo]);
     int c = local / wpc, w = local - c * wpc;
-    const uint8_t* src = payload + poff[o] + (size_t)c * kh + 16 * w;
-    int nv = min(16, kh - 16 * w);
-    uint32_t d = lm_dflt(m), out = 0; int bad = 0;
-    if (nv == 16) { // 16 payload bytes at any alignment: 5 aligned words + funnel shifts (buffer has slack)
-        const uint32_t* ap = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
-        int sh = (int)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
-        uint32_t t[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) t[k] = ap[k];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t x = __funnelshift_r(t[k], t[k + 1], sh);
-            bad |= ((x & 0xFCFCFCFCu) != 0) | (((x | (x >> 1)) & 0x01010101u) != 0x01010101u);
-            uint32_t y = (x & 3u) | ((x >> 6) & 0xCu) | ((x >> 12) & 0x30u) | ((x >> 18) & 0xC0u);
-            out |= y << (8 * k);
-        }
-    } else {
-        for (int j = 0; j < 16; j++) {
-            uint32_t code = j < nv ? src[j] : d;
-            bad |= (code < 1u || code > 3u);
-            out |= (code & 3u) << (2 * j);
-        }
-    }
+    int bad = 0;
+    uint32_t out = pack_word(payload + poff[o] + (size_t)c * kh, kh, w, lm_dflt(m), bad);
     if (bad) atomicOr(err, 1);
     words[m.off + local] = out;
 }
+
+// ---- fused pack + build, small objects (level 1 <= RB_HALF words).  Instruction issue, not bandwidth, limits this
+// kernel (a ~1 KB object has as many levels as a mask), so the work is split by shape:
+//   phase A, one WARP per object: read the payload once (contiguous, all loads in flight together), pack level 1 into
+//            global AND shared memory, build the levels that still have real width out of shared memory / registers;
+//   phase B, one THREAD per object (32 objects of the warp at once): from the first level with kh <= 16 and kw <= 8 up
+//            to the root the whole level lives in 8 registers; a level is 5 x (two selects per child column, pair-OR,
+//            2-bit compress) — ~1 warp instruction per object and level instead of ~100.
+// HBM traffic = the payload once + the packed pyramid once.
+__device__ __forceinline__ uint32_t sel3(int e, uint32_t a, uint32_t b, uint32_t c) { return e > 0 ? a : (e == 0 ? b : c); }
+__device__ __forceinline__ int tail_level(int kh, int kw, int L) { // first level that fits 8 registers (or L)
+    int t = 1;
+    while ((kh > 16 || kw > 8) && t < L) { kh = kh / 2 + 1; kw = kw / 2 + 1; t++; }
+    return t;
+}
+__global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ poff, const int32_t* __restrict__ list, int nlist,
+                                                          uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L, int* __restrict__ err) {
+    __shared__ uint32_t sbuf[8][2 * RB_HALF];
+    const unsigned FULLM = 0xffffffffu;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    int bad = 0;
+    for (int g = warp; g * 32 < nlist; g += nwarps) {
+        int my_i = g * 32 + lane;
+        int my_o = my_i < nlist ? list[my_i] : -1;
+        // ---- phase A
+        for (int k = 0; k < 32; k++) {
+            int o = __shfl_sync(FULLM, my_o, k);
+            if (o < 0) break;
+            LevelMeta mine = {};
+            if (lane < L) mine = lm[(size_t)o * L + lane];
+            LevelMeta m1 = shfl_meta(mine, 0);
+            int kh = lm_kh(m1), wpc = wpc_of(kh), nw = wpc * lm_kw(m1);
+            const uint8_t* base = payload + poff[o];
+            uint32_t d = lm_dflt(m1);
+            const uint32_t inv = 0xFFFFFFFFu / (uint32_t)wpc + 1u; // j / wpc == umulhi(j, inv) while j * wpc < 2^32
+            for (int j = lane; j < nw; j += 32) {
+                int c = wpc > 1 ? (int)__umulhi((uint32_t)j, inv) : j, w = j - c * wpc; // (inv overflows for wpc == 1)
+                uint32_t out = pack_word(base + c * kh, kh, w, d, bad);
+                words[m1.off + j] = out;
+                sbuf[wib][j] = out;
+            }
+            __syncwarp();
+            mine = warp_rebuild<false, false, true>(words, mine, L, 1, lane, sbuf[wib], tail_level(kh, lm_kw(m1), L));
+            if (lane >= 1 && lane < L) lm[(size_t)o * L + lane] = mine;
+            __syncwarp();
+        }
+        // ---- phase B: lane k finishes object k
+        if (my_o >= 0) {
+            LevelMeta m1 = lm[(size_t)my_o * L];
+            int kh = lm_kh(m1), kw = lm_kw(m1), rs = m1.rs, cs = m1.cs, t = 1;
+            uint32_t off = m1.off; const uint32_t d = lm_dflt(m1), dw = dflt_word(d);
+            while ((kh > 16 || kw > 8) && t < L) { off += (uint32_t)(wpc_of(kh) * kw); kh = kh / 2 + 1; kw = kw / 2 + 1; rs /= 2; cs /= 2; t++; }
+            if (t < L && kh <= 16 && kw <= 8) {
+                uint32_t cur[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) cur[i] = i < kw ? words[off + i] : dw;
+                for (int l = t + 1; l <= L; l++) {
+                    int prs = rs / 2, pcs = cs / 2; // qtrees.jl:225-226 (÷ truncates toward zero)
+                    int er = rs - 2 * prs, ec = cs - 2 * pcs, kwp = kw / 2 + 1;
+                    uint32_t poff_ = off + (uint32_t)kw; // one word per column at these sizes
+                    uint32_t nxt[5];
+#pragma unroll
+                    for (int pc = 0; pc < 5; pc++) {
+#define STF_COL(i) (((i) >= 0 && (i) < 8 && (i) < kw) ? cur[((i) >= 0 && (i) < 8) ? (i) : 0] : dw)
+                        uint32_t w0 = sel3(ec, STF_COL(2 * pc - 1), STF_COL(2 * pc), STF_COL(2 * pc + 1));
+                        uint32_t w1 = sel3(ec, STF_COL(2 * pc), STF_COL(2 * pc + 1), STF_COL(2 * pc + 2));
+#undef STF_COL
+                        uint64_t y = ((uint64_t)dw << 32) | (w0 | w1);
+                        if (er > 0) y = (y << 2) | d; else if (er < 0) y = (y >> 2) | ((uint64_t)d << 62);
+                        nxt[pc] = compress_pairs(y);
+                        if (pc < kwp) words[poff_ + pc] = nxt[pc];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) cur[i] = i < 5 ? nxt[i < 5 ? i : 0] : dw;
+                    off = poff_; kh = kh / 2 + 1; kw = kwp; rs = prs; cs = pcs;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (bad) atomicOr(err, 1);
+}
+
+// ---- fused pack + build, mid-size objects: one CTA per object (THREADS = 128 for a few KB, 512 for mask-sized ones).
+// Level 1 is packed straight from global memory into global memory (4 words per thread in flight; it is re-read once,
+// L2-hot, to form level 2); level 2 and everything above are staged in shared memory, sized by the host to the largest
+// listed object (a_words for levels 2,4,.., b_words for levels 3,5,..) so that several CTAs share an SM.
+// (A persistent variant that streamed the payload through shared memory with TMA bulk copies — cp.async.bulk + mbarrier,
+// 3 x 32 KB in flight per SM — measured 1.5x SLOWER on B200: one 512-thread CTA per SM cannot issue the pack arithmetic
+// fast enough; the kernel is bound by instruction issue, not by the load path.)
+template <int THREADS> __global__ void __launch_bounds__(THREADS) k_pack_build_mid(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ poff, const int32_t* __restrict__ list,
+                                                                                   uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L, int a_words, int* __restrict__ err) {
+    extern __shared__ uint32_t pbm[]; // A: a_words, B: the rest
+    __shared__ LevelMeta sm[STF_MAX_LEVELS];
+    uint32_t* A = pbm; uint32_t* B = pbm + a_words;
+    const int o = list[blockIdx.x], tid = threadIdx.x;
+    if (tid < L) sm[tid] = lm[(size_t)o * L + tid];
+    __syncthreads();
+    if (tid == 0) for (int l = 1; l < L; l++) { sm[l].rs = sm[l - 1].rs / 2; sm[l].cs = sm[l - 1].cs / 2; } // qtrees.jl:225-226
+    LevelMeta m1 = sm[0];
+    const int kh = lm_kh(m1), wpc = wpc_of(kh), nw = wpc * lm_kw(m1);
+    const uint8_t* base = payload + poff[o];
+    const uint32_t d = lm_dflt(m1);
+    int bad = 0;
+    uint32_t* out = words + m1.off;
+    const uint32_t inv = 0xFFFFFFFFu / (uint32_t)wpc + 1u; // j / wpc == umulhi(j, inv): nw * wpc < 2^32 for every listed object
+#pragma unroll 4
+    for (int j = tid; j < nw; j += THREADS) {
+        int c = wpc > 1 ? (int)__umulhi((uint32_t)j, inv) : j, w = j - c * wpc; // (inv overflows for wpc == 1)
+        out[j] = pack_word(base + (size_t)c * kh, kh, w, d, bad);
+    }
+    if (bad) atomicOr(err, 1);
+    __syncthreads();
+    if (tid >= 1 && tid < L) lm[(size_t)o * L + tid] = sm[tid];
+    const uint32_t* src = out; // level 1: global (written by this CTA, visible after the barrier)
+    uint32_t* dst = A;
+    for (int l = 2; l <= L; l++) {
+        LevelMeta ch = sm[l - 2], p = sm[l - 1];
+        int er = ch.rs - 2 * p.rs, ec = ch.cs - 2 * p.cs;
+        int pw_ = wpc_of(lm_kh(p)), pn = pw_ * lm_kw(p);
+        for (int j = tid; j < pn; j += THREADS) {
+            int pc = j / pw_, pw = j - pc * pw_;
+            uint32_t v = build_word<false>(src, ch, er, ec, pc, pw);
+            words[p.off + j] = v;
+            dst[j] = v;
+        }
+        __syncthreads();
+        src = dst; dst = (dst == A) ? B : A;
+    }
+}
+#define PBM_A 16384   // largest level 2 (words) a CTA stages; beyond that the object is built by wide launches
+#define PBM_B 4608
 
 // ---- warp-per-object build: worklist entry = (object, from_level): levels from+1..L ------------
 __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L,

@@ -195,6 +195,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     uint64_t words = 0; int max_scene = 0;
     ctx->big_objs.clear(); ctx->sizelevel_ok = true;
     std::vector<int64_t> n2(n, 0);
+    std::vector<int32_t> l_small, l_mid, l_mid2, l_big; std::vector<uint64_t> big_woff(1, 0); uint64_t midA[2] = { 0, 0 }, midB[2] = { 0, 0 }; // upload classes (fused pack+build kernels)
     for (int o = 0; o < n; o++) {
         if (kh[o] < 0 || kw[o] < 0 || kh[o] > 32767 || kw[o] > 32767) FAIL(STF_E_ARG, "kernel size must be in [0, 32767]");
         if (dflt[o] != STF_EMPTY && dflt[o] != STF_FULL) FAIL(STF_E_ARG, "default must be EMPTY or FULL");
@@ -204,6 +205,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
         if (m.scene < 0) FAIL(STF_E_ARG, "negative scene id");
         max_scene = std::max(max_scene, m.scene);
         int a = kh[o], b = kw[o];
+        uint64_t lw[3] = { 0, 0, 0 };
         for (int l = 1; l <= L; l++) {
             LevelMeta& v = h_lm[(size_t)o * L + l - 1];
             if (words > 0xFFFFFFF0ull) FAIL(STF_E_ARG, "pyramids exceed 2^32 words per context");
@@ -213,11 +215,15 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
             uint64_t nw = (uint64_t)wpc_of(a) * b;
             if (l == 1) { woff1[o + 1] = woff1[o] + nw; poff[o + 1] = poff[o] + (uint64_t)a * b; }
             if (l == 2) { n2[o] = (int64_t)a * b; m.big = nw > 4096; }
+            if (l <= 3) lw[l - 1] = nw;
             if (l == L && (a > 2 || b > 2)) ctx->sizelevel_ok = false; // sizelevel == -1  qtrees.jl:182-193
             words += nw;
             a = a / 2 + 1; b = b / 2 + 1; // qtrees.jl:185
         }
         if (m.big) ctx->big_objs.push_back(o);
+        if (lw[0] <= RB_HALF) l_small.push_back(o);
+        else if (L >= 3 && lw[1] <= PBM_A && lw[2] <= PBM_B && !m.big) { int k = lw[0] <= 4096 ? 0 : 1; (k ? l_mid2 : l_mid).push_back(o); midA[k] = std::max(midA[k], lw[1]); midB[k] = std::max(midB[k], lw[2]); }
+        else { l_big.push_back(o); big_woff.push_back(big_woff.back() + lw[0]); }
     }
     ctx->has_big = !ctx->big_objs.empty();
     ctx->total_words = words;
@@ -251,14 +257,14 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     CK(cudaMemcpyAsync(ctx->lm.p, h_lm.data(), sizeof(LevelMeta) * (size_t)n * L, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->om.p, ctx->h_om.data(), sizeof(ObjMeta) * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->poff.p, poff.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->woff1.p, woff1.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->st));
     ctx->launches++, k_fill_invalid<<<nblk(4ll * n, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), 4ll * n);
 
     const uint8_t* d_payload = nullptr;
     std::vector<uint8_t> staging;
-    if (packed && packed_on_device) d_payload = packed; // needs >= 8 readable bytes of slack after the payload
+    if (packed && packed_on_device) d_payload = packed; // needs >= 32 readable bytes of slack after the payload (zero or valid codes)
     else {
         CK(ctx->payload.ensure((size_t)poff[n] + 64));
+        CK(cudaMemsetAsync(ctx->payload.as<uint8_t>() + poff[n], 0, 64, ctx->st)); // pack_word over-reads up to 19 bytes
         const uint8_t* src = packed;
         if (!packed) {
             staging.resize((size_t)poff[n] + 1);
@@ -269,19 +275,48 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
         if (poff[n]) CK(cudaMemcpyAsync(ctx->payload.p, src, (size_t)poff[n], cudaMemcpyHostToDevice, ctx->st));
         d_payload = ctx->payload.as<uint8_t>();
     }
-    if (woff1[n]) {
-        ctx->launches++, k_pack_level1<<<nblk((int64_t)woff1[n], 256), 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), ctx->woff1.as<uint64_t>(), n, ctx->lm.as<LevelMeta>(), L,
-                                                                      ctx->words.as<uint32_t>(), woff1[n], ctx->errflag.as<int>());
-        KCHECK();
+    // upload lists of the three build classes
+    size_t n_mid1 = l_mid.size(); l_mid.insert(l_mid.end(), l_mid2.begin(), l_mid2.end());
+    size_t nlist = l_small.size() + l_mid.size() + l_big.size();
+    CK(ctx->work.ensure(sizeof(int2) * (size_t)std::max<size_t>(1, std::max<size_t>(n, nlist))));
+    CK(ctx->lab4.ensure(sizeof(int32_t) * std::max<size_t>(1, nlist)));
+    int32_t* d_list = ctx->lab4.as<int32_t>();
+    if (!l_small.empty()) CK(cudaMemcpyAsync(d_list, l_small.data(), sizeof(int32_t) * l_small.size(), cudaMemcpyHostToDevice, ctx->st));
+    if (!l_mid.empty()) CK(cudaMemcpyAsync(d_list + l_small.size(), l_mid.data(), sizeof(int32_t) * l_mid.size(), cudaMemcpyHostToDevice, ctx->st));
+    if (!l_big.empty()) {
+        CK(cudaMemcpyAsync(d_list + l_small.size() + l_mid.size(), l_big.data(), sizeof(int32_t) * l_big.size(), cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->woff1.p, big_woff.data(), sizeof(uint64_t) * big_woff.size(), cudaMemcpyHostToDevice, ctx->st));
     }
-    // buildqtree!(t) for every object: warp-per-object for small ones, level-by-level wide launches for big ones
-    ctx->launches++, k_fill_worklist<<<nblk(n, 256), 256, 0, ctx->st>>>(n, nullptr, 1, ctx->work.as<int2>());
-    {
-        int blocks = std::min(nblk((int64_t)n * 32, 256), 148 * 8);
-        ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), 1);
-        KCHECK();
+    stage_begin(ctx, STF_STAGE_BUILD);
+    // buildqtree!(t) for every object, fused with the level-1 pack: a warp per small object, a CTA per mid-size object;
+    // big objects (mask-sized) are packed by a wide launch and built level by level with wide launches
+    if (!l_small.empty()) {
+        int blocks = std::min(nblk((int64_t)l_small.size() * 32, 256), 148 * 8);
+        ctx->launches++, k_pack_build_small<<<blocks, 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list, (int)l_small.size(), ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->errflag.as<int>());
     }
+    for (int k = 0; k < 2; k++) { // a CTA per mid-size object: 128 threads for a few KB, 512 for mask-sized ones
+        size_t cnt = k ? l_mid.size() - n_mid1 : n_mid1;
+        if (!cnt) continue;
+        static bool attr = false;
+        if (!attr) {
+            CK(cudaFuncSetAttribute(k_pack_build_mid<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * (PBM_A + PBM_B))));
+            CK(cudaFuncSetAttribute(k_pack_build_mid<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * (PBM_A + PBM_B))));
+            attr = true;
+        }
+        int aw = (int)((midA[k] + 31) & ~31ull), bw = (int)((midB[k] + 31) & ~31ull);
+        const int32_t* lst = d_list + l_small.size() + (k ? n_mid1 : 0);
+        size_t smem = sizeof(uint32_t) * (size_t)(aw + bw);
+        if (k == 0) ctx->launches++, k_pack_build_mid<128><<<(int)cnt, 128, smem, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), lst, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, aw, ctx->errflag.as<int>());
+        else ctx->launches++, k_pack_build_mid<512><<<(int)cnt, 512, smem, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), lst, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, aw, ctx->errflag.as<int>());
+    }
+    if (!l_big.empty()) {
+        uint64_t tw = big_woff.back();
+        ctx->launches++, k_pack_level1<<<nblk((int64_t)tw, 256), 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list + l_small.size() + l_mid.size(), ctx->woff1.as<uint64_t>(), (int)l_big.size(),
+                                                                      ctx->lm.as<LevelMeta>(), L, ctx->words.as<uint32_t>(), tw, ctx->errflag.as<int>());
+    }
+    KCHECK();
     for (int o : ctx->big_objs) { int32_t r = build_big(ctx, o, 1); if (r) return r; }
+    stage_end(ctx);
     int32_t r = sync_counts(ctx); // staging must outlive the copy; also surfaces bad codes
     return r;
 }
