@@ -134,6 +134,26 @@ __global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restr
     if (bad) atomicOr(err, 1);
 }
 
+// levels from+1..L of one object by one CTA: level `from` is read from global memory (L2-hot), every later level from
+// the shared-memory copy of the level just produced (A holds levels from+1, from+3, .., B the others)
+template <int THREADS> __device__ __forceinline__ void cta_build_levels(uint32_t* __restrict__ words, const LevelMeta* sm, int L, int from, uint32_t* A, uint32_t* B) {
+    const int tid = threadIdx.x;
+    const uint32_t* src = words + sm[from - 1].off;
+    uint32_t* dst = A;
+    for (int l = from + 1; l <= L; l++) {
+        LevelMeta ch = sm[l - 2], p = sm[l - 1];
+        int er = ch.rs - 2 * p.rs, ec = ch.cs - 2 * p.cs;
+        int pw_ = wpc_of(lm_kh(p)), pn = pw_ * lm_kw(p);
+        for (int j = tid; j < pn; j += THREADS) {
+            int pc = j / pw_, pw = j - pc * pw_;
+            uint32_t v = build_word<false>(src, ch, er, ec, pc, pw);
+            words[p.off + j] = v;
+            dst[j] = v;
+        }
+        __syncthreads();
+        src = dst; dst = (dst == A) ? B : A;
+    }
+}
 // ---- fused pack + build, mid-size objects: one CTA per object (THREADS = 128 for a few KB, 512 for mask-sized ones).
 // Level 1 is packed straight from global memory into global memory (4 words per thread in flight; it is re-read once,
 // L2-hot, to form level 2); level 2 and everything above are staged in shared memory, sized by the host to the largest
@@ -165,21 +185,7 @@ template <int THREADS> __global__ void __launch_bounds__(THREADS) k_pack_build_m
     if (bad) atomicOr(err, 1);
     __syncthreads();
     if (tid >= 1 && tid < L) lm[(size_t)o * L + tid] = sm[tid];
-    const uint32_t* src = out; // level 1: global (written by this CTA, visible after the barrier)
-    uint32_t* dst = A;
-    for (int l = 2; l <= L; l++) {
-        LevelMeta ch = sm[l - 2], p = sm[l - 1];
-        int er = ch.rs - 2 * p.rs, ec = ch.cs - 2 * p.cs;
-        int pw_ = wpc_of(lm_kh(p)), pn = pw_ * lm_kw(p);
-        for (int j = tid; j < pn; j += THREADS) {
-            int pc = j / pw_, pw = j - pc * pw_;
-            uint32_t v = build_word<false>(src, ch, er, ec, pc, pw);
-            words[p.off + j] = v;
-            dst[j] = v;
-        }
-        __syncthreads();
-        src = dst; dst = (dst == A) ? B : A;
-    }
+    cta_build_levels<THREADS>(words, sm, L, 1, A, B);
 }
 #define PBM_A 16384   // largest level 2 (words) a CTA stages; beyond that the object is built by wide launches
 #define PBM_B 4608
@@ -198,7 +204,9 @@ __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restr
     }
 }
 
-// ---- wide build of ONE level of ONE (big) object: grid-stride over parent words ----------------
+// ---- wide build of ONE level of ONE (big) object: grid-stride over parent words.  The level's shift (child ÷ 2,
+// qtrees.jl:225-226) is derived by every thread from the child meta and stored by one thread: nobody in this launch
+// reads it, the next level's launch does.
 __global__ void k_build_level_wide(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L, int o, int l) {
     LevelMeta ch = lm[(size_t)o * L + (l - 2)];
     LevelMeta p = lm[(size_t)o * L + (l - 1)];
@@ -210,15 +218,20 @@ __global__ void k_build_level_wide(uint32_t* __restrict__ words, LevelMeta* __re
         int pc = (int)(i / wpc), pw = (int)(i - (int64_t)pc * wpc);
         words[p.off + i] = build_word<false>(words + ch.off, ch, er, ec, pc, pw);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { lm[(size_t)o * L + (l - 1)].rs = rs; lm[(size_t)o * L + (l - 1)].cs = cs; }
 }
-// the shift of level l must be set before the NEXT level reads it; done in its own tiny launch so
-// that no block of k_build_level_wide races with it
-__global__ void k_set_parent_shift(LevelMeta* __restrict__ lm, int L, int o, int l) {
-    LevelMeta ch = lm[(size_t)o * L + (l - 2)];
-    lm[(size_t)o * L + (l - 1)].rs = ch.rs / 2;
-    lm[(size_t)o * L + (l - 1)].cs = ch.cs / 2;
+// once a level of a big object fits a CTA's shared memory, ONE launch finishes the pyramid: levels from+1..L
+__global__ void __launch_bounds__(512) k_build_tail_cta(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L, int o, int from, int a_words) {
+    extern __shared__ uint32_t pbm[];
+    __shared__ LevelMeta sm[STF_MAX_LEVELS];
+    const int tid = threadIdx.x;
+    if (tid < L) sm[tid] = lm[(size_t)o * L + tid];
+    __syncthreads();
+    if (tid == 0) for (int l = from; l < L; l++) { sm[l].rs = sm[l - 1].rs / 2; sm[l].cs = sm[l - 1].cs / 2; }
+    __syncthreads();
+    if (tid >= from && tid < L) lm[(size_t)o * L + tid] = sm[tid];
+    cta_build_levels<512>(words, sm, L, from, pbm, pbm + a_words);
 }
-
 // ---- shift!/setshift! (qtrees.jl:267-287): levels <= level move by s*2^(level-i); build list -----
 __global__ void k_apply_shifts(LevelMeta* __restrict__ lm, int L, int n, const int32_t* __restrict__ labels, int level,
                                const int32_t* __restrict__ rs, const int32_t* __restrict__ cs, int add, int2* __restrict__ work) {

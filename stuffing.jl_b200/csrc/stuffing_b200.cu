@@ -167,11 +167,16 @@ extern "C" int32_t stf_num_levels(const stf_ctx* ctx) { return ctx ? ctx->L : 0;
 __global__ void k_fill_i32(int* __restrict__ p, int n, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 // ------------------------------------------------------------------------------------------------ build helpers
-static int32_t build_big(stf_ctx* ctx, int o, int from) { // levels from+1..L of one big object, many CTAs per level
+static int32_t build_big(stf_ctx* ctx, int o, int from) { // levels from+1..L of one big object: wide launches while a level is large, then one CTA
+    static bool attr = false;
+    if (!attr) { CK(cudaFuncSetAttribute(k_build_tail_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * (PBM_A + PBM_B)))); attr = true; }
+    auto words_of = [&](int l) { int kh = ((ctx->h_om[o].kh1 - 2) >> (l - 1)) + 2, kw = ((ctx->h_om[o].kw1 - 2) >> (l - 1)) + 2; if (l == 1) { kh = ctx->h_om[o].kh1; kw = ctx->h_om[o].kw1; } return (int64_t)wpc_of(kh) * kw; };
     for (int l = from + 1; l <= ctx->L; l++) {
-        ctx->launches++, k_set_parent_shift<<<1, 1, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, o, l);
-        int kh = ((ctx->h_om[o].kh1 - 2) >> (l - 1)) + 2, kw = ((ctx->h_om[o].kw1 - 2) >> (l - 1)) + 2;
-        int64_t nw = (int64_t)wpc_of(kh) * kw;
+        int64_t nw = words_of(l);
+        if (nw <= PBM_A && (l + 1 > ctx->L || words_of(l + 1) <= PBM_B)) { // level l and everything above by one CTA
+            ctx->launches++, k_build_tail_cta<<<1, 512, sizeof(uint32_t) * (PBM_A + PBM_B), ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l - 1, PBM_A);
+            break;
+        }
         ctx->launches++, k_build_level_wide<<<std::min(nblk(nw, 256), 148 * 16), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l);
     }
     KCHECK();
