@@ -166,6 +166,20 @@ int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colist, uint64_t
 int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels,
                       uint64_t seed, uint64_t iteration, int64_t* nhits);
 
+/* ---- item-parallel sharding of ONE scene over the GPUs of a box (the reference has no counterpart:
+ * its narrow phase is threaded with Threads.@spawn over index chunks, qtree_functions.jl:52-110).
+ * Every rank holds an identical replica.  Per fit iteration:
+ *   stf_shard_collide : broad phase + narrow phase over the candidate pairs of the sorted records rank, rank+nranks, ...;
+ *                       *nlocal = local hit count (the hits stay on the device)
+ *   (caller)          : stride = 1 + max over ranks of nlocal (one scalar all-reduce)
+ *   stf_shard_pack    : writes [header | nlocal hit records] into send_dev (stride 16-byte records; stream-synchronised)
+ *   (caller)          : ONE all-gather of the stride-sized buffers over NVLink (ncclAllGather) into recv_dev
+ *   stf_shard_step    : union of the gathered lists -> canonical order -> batchsteps!; every rank computes the same
+ *                       moves, so the replicas stay bit-identical without exchanging pyramids.  *nhits = length(colist). */
+int32_t stf_shard_collide(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, int32_t rank, int32_t nranks, int64_t* nlocal);
+int32_t stf_shard_pack(stf_ctx* ctx, void* send_dev, int64_t stride);
+int32_t stf_shard_step(stf_ctx* ctx, const void* recv_dev, int32_t nranks, int64_t stride, uint64_t seed, uint64_t iteration, int64_t* nhits);
+
 int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out);
 /* number of kernels this context has launched since stf_create (bench.py's gpu_launches) */
 int64_t stf_launch_count(const stf_ctx* ctx);

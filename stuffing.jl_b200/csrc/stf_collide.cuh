@@ -129,14 +129,15 @@ __device__ __forceinline__ int64_t upper_bound_u64(const uint64_t* __restrict__ 
 __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                            const unsigned long long* __restrict__ nrec_dev, int64_t nrec_cap, int L,
                                                            const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm,
-                                                           const int32_t* __restrict__ moved_pos, EmitOut out) {
+                                                           const int32_t* __restrict__ moved_pos, EmitOut out, int shard_rank, int shard_n) {
     __shared__ int s_start[EM_THREADS / 32][16];
     __shared__ int s_pref[EM_THREADS / 32][17];
     const unsigned FULLM = 0xffffffffu;
     int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int64_t nrec = min((int64_t)*nrec_dev, nrec_cap); // valid records (sorted, compacted)
     int64_t nwarps = (int64_t)gridDim.x * (EM_THREADS / 32);
-    for (int64_t r = (int64_t)blockIdx.x * (EM_THREADS / 32) + wib; r < nrec; r += nwarps) {
+    // item-parallel sharding: rank k of shard_n generates the candidates of the records k, k+shard_n, ...
+    for (int64_t r = ((int64_t)blockIdx.x * (EM_THREADS / 32) + wib) * shard_n + shard_rank; r < nrec; r += nwarps * shard_n) {
         uint64_t key = keys[r];
         int low = (int)vals[r];
         int l, a, b; cell_unkey(key, &l, &a, &b);
@@ -529,4 +530,20 @@ __global__ void k_export_cells(const uint64_t* __restrict__ keys, const uint32_t
     int l, a, b; cell_unkey(keys[i], &l, &a, &b);
     int32_t* o = out + 4 * (size_t)i;
     o[0] = l; o[1] = a; o[2] = b; o[3] = (int32_t)vals[i];
+}
+
+// ---- item-parallel sharding: the exchange buffer of one rank = [header: count][count hit records] padded to `stride`
+__global__ void k_shard_pack(const Item16* __restrict__ hits, int64_t n, Item16* __restrict__ send, int64_t stride) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { Item16 h; h.i1 = (int32_t)(n & 0x7fffffff); h.i2l = (int32_t)(n >> 31); h.a = 0; h.b = 0; send[0] = h; }
+    if (i < n && i + 1 < stride) send[i + 1] = hits[i];
+}
+// gathered segments of all ranks -> one compact hit list (rank order; the canonical order comes from the sort after)
+__global__ void k_shard_unpack(const Item16* __restrict__ recv, int nranks, int64_t stride, Item16* __restrict__ hits, int64_t cap, unsigned long long* __restrict__ nhits) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int s = (int)(i / stride); int64_t k = i - (int64_t)s * stride;
+    if (s >= nranks || k == 0) { if (i == 0) { unsigned long long t = 0; for (int q = 0; q < nranks; q++) { Item16 h = recv[(int64_t)q * stride]; t += (unsigned long long)(uint32_t)h.i1 | ((unsigned long long)(uint32_t)h.i2l << 31); } *nhits = t; } return; }
+    int64_t base = 0, mine = 0;
+    for (int q = 0; q <= s; q++) { Item16 h = recv[(int64_t)q * stride]; int64_t c = (int64_t)(uint32_t)h.i1 | ((int64_t)(uint32_t)h.i2l << 31); if (q < s) base += c; else mine = c; }
+    if (k - 1 < mine && base + k - 1 < cap) hits[base + k - 1] = recv[i];
 }

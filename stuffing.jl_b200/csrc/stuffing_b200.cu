@@ -47,6 +47,7 @@ struct stf_ctx {
     OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
     int64_t big_cap = 0; int big_ctas = 1;
+    int shard_rank = 0, shard_n = 1; // item-parallel sharding of the candidate generation (stf_shard_*)
     bool force_big = false; // the single-CTA latency path overflowed once: stay on the multi-launch path
     int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
     stf_counters_t ctr = {};
@@ -823,7 +824,7 @@ static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, con
     if (nrec > 0) {
         int blocks = (int)std::min<int64_t>((nrec / 4 + EM_THREADS / 32 - 1) / (EM_THREADS / 32) + 1, 148 * 8); // ~1 record per located object
         ctx->launches++, k_emit_items<<<blocks, EM_THREADS, 0, ctx->st>>>(keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
-                                                                        ctx->lm.as<LevelMeta>(), moved_pos, eo);
+                                                                        ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n);
     }
     KCHECK();
     stage_end(ctx);
@@ -1066,6 +1067,62 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
     int32_t r = spacial_core(ctx, nl, labels, linked, &nh); if (r) return r;
     r = finalize_hits(ctx, nh, 0, false, &nout); if (r) return r; // canonical list order = sorted, stays on the device
     if (nhits) *nhits = nh;
+    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
+}
+// ---- item-parallel sharding of one scene over several GPUs.  Every rank holds an identical replica;
+// rank r of `nranks` generates and tests the candidate pairs of the sorted records r, r+nranks, ...; the local hit
+// lists are exchanged by the caller (one all-gather of fixed-stride buffers per fit iteration, NCCL over NVLink), and
+// every rank then runs the same canonical batchsteps on the union, which keeps the replicas bit-identical.
+extern "C" int32_t stf_shard_collide(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, int32_t rank, int32_t nranks, int64_t* nlocal) {
+    NEED_OBJS();
+    if (nlocal) *nlocal = 0;
+    if (nranks < 1 || rank < 0 || rank >= nranks) FAIL(STF_E_ARG, "bad rank");
+    if (!labels) nl = ctx->n;
+    ctx->last_result = 0;
+    if (ctx->n <= 1 || nl <= 0) { ctx->ctr.hits = 0; return STF_OK; }
+    int linked = mode == 1;
+    ctx->shard_rank = rank; ctx->shard_n = nranks;
+    int32_t r = STF_OK; int64_t nh = 0; bool done = false;
+    for (int attempt = 0; attempt < 4 && !done && fast_path_ok(ctx, linked ? ctx->n : nl); attempt++) {
+        r = spacial_core_fast(ctx, nl, labels, linked); if (r) break;
+        r = sync_counts(ctx); if (r) break;
+        int64_t items = (int64_t)ctx->h_counts[C_ITEMS], hits = (int64_t)ctx->h_counts[C_NHITS];
+        if (ctx->h_err[1] & STF_ST_RETRY_BIG) { cudaMemsetAsync(ctx->errflag.as<int>() + 1, 0, sizeof(int), ctx->st); ctx->force_big = true; break; }
+        if (items > (int64_t)(ctx->items.cap / sizeof(Item16))) { ctx->hint_items = items; continue; }
+        if (hits > (int64_t)(ctx->hits.cap / sizeof(Item16))) { ctx->force_big = true; break; }
+        read_round_counters(ctx); nh = hits; done = true;
+    }
+    if (!r && !done) r = spacial_core(ctx, nl, labels, linked, &nh);
+    ctx->shard_rank = 0; ctx->shard_n = 1;
+    if (r) return r;
+    ctx->ctr.hits = nh;
+    if (nlocal) *nlocal = nh;
+    return STF_OK;
+}
+extern "C" int32_t stf_shard_pack(stf_ctx* ctx, void* send_dev, int64_t stride) {
+    NEED_OBJS();
+    int64_t n = ctx->ctr.hits;
+    if (!send_dev || stride < n + 1) FAIL(STF_E_CAPACITY, "exchange stride too small for the local hit list");
+    ctx->launches++, k_shard_pack<<<nblk(std::max<int64_t>(1, n), 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), n, reinterpret_cast<Item16*>(send_dev), stride);
+    KCHECK();
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_shard_step(stf_ctx* ctx, const void* recv_dev, int32_t nranks, int64_t stride, uint64_t seed, uint64_t iteration, int64_t* nhits) {
+    NEED_OBJS();
+    if (nhits) *nhits = 0;
+    if (!recv_dev || nranks < 1 || stride < 1) FAIL(STF_E_ARG, "bad exchange buffer");
+    int64_t cap = (int64_t)nranks * (stride - 1);
+    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, cap)));
+    ctx->launches++, k_shard_unpack<<<nblk((int64_t)nranks * stride, 256), 256, 0, ctx->st>>>(reinterpret_cast<const Item16*>(recv_dev), nranks, stride, ctx->hits.as<Item16>(), cap,
+                                                                                          ctx->counts.as<unsigned long long>() + C_NHITS);
+    KCHECK();
+    int32_t r = sync_counts(ctx); if (r) return r;
+    int64_t nh = (int64_t)ctx->h_counts[C_NHITS], nout = 0;
+    if (nh > cap) FAIL(STF_E_ARG, "corrupt exchange headers");
+    r = finalize_hits(ctx, nh, 0, false, &nout); if (r) return r; // canonical list order = sorted: identical on every rank
+    if (nhits) *nhits = nh;
+    ctx->ctr.hits = nh;
     return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
 }
 extern "C" int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out) {

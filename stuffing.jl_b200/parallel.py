@@ -1,7 +1,20 @@
-"""Multi-GPU plumbing of the hot path: the path shards by SCENE (independent scenes never interact), so
-ranks own disjoint scene ranges and no data-path collective exists.  torch.distributed is used only for the
-barrier and the max-over-ranks time / sum-over-ranks unit reductions of a measurement."""
+"""Multi-GPU plumbing of the hot path (one process per GPU, torch.distributed over NCCL/NVLink).
+
+The path shards two ways:
+  * by SCENE — independent scenes never interact: ranks own disjoint scene ranges, no data-path collective;
+  * by ITEM inside one scene (`ShardedFit`) — every rank holds an identical replica, generates and tests only the
+    candidate pairs of the sorted records rank, rank+world, ...; per fit iteration ONE all-gather of the local hit
+    lists (16 B per hit, fixed stride) is exchanged, then every rank runs the same canonical batchsteps, which keeps
+    the replicas bit-identical without shipping pyramids.
+torch.distributed is plumbing: the exchange buffers are torch tensors, everything else happens behind the C ABI
+(stf_shard_collide / stf_shard_pack / stf_shard_step)."""
 from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+HIT_WORDS = 4  # one exchanged record = 16 bytes = 4 x int32: (i1, i2 | l << 26, a, b); record 0 of a segment = header
 
 
 def shard_range(n_units: int, rank: int, world: int) -> range:
@@ -21,3 +34,73 @@ def reduce_job(ms_local: float, units_local: float, dist=None, device=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), float(u.item())
+
+
+# ---- the exchange format, restated on the host (tests drive it over gloo; the device twins are k_shard_pack/unpack)
+def exchange_stride(nlocal_max: int, quantum: int = 256) -> int:
+    """records per rank segment: header + the longest local list, rounded up so that buffers are reused across rounds"""
+    return ((nlocal_max + 1 + quantum - 1) // quantum) * quantum
+
+
+def pack_segment(hits: np.ndarray, stride: int) -> np.ndarray:
+    """hits: (n, 4) int32 records → one (stride, 4) segment: [count | records | padding]"""
+    n = len(hits)
+    if n + 1 > stride:
+        raise ValueError("exchange stride too small for the local hit list")
+    seg = np.zeros((stride, HIT_WORDS), np.int32)
+    seg[0, 0] = n & 0x7FFFFFFF
+    seg[0, 1] = n >> 31
+    seg[1:n + 1] = hits
+    return seg
+
+
+def unpack_segments(recv: np.ndarray, world: int, stride: int) -> np.ndarray:
+    """(world*stride, 4) gathered buffer → the union of the local lists in rank order"""
+    recv = recv.reshape(world, stride, HIT_WORDS)
+    parts = []
+    for r in range(world):
+        n = int(recv[r, 0, 0]) | (int(recv[r, 0, 1]) << 31)
+        parts.append(recv[r, 1:n + 1])
+    return np.concatenate(parts) if parts else np.zeros((0, HIT_WORDS), np.int32)
+
+
+class ShardedFit:
+    """item-parallel fit iterations of ONE scene replicated on every rank.  `d` is this rank's DeviceQTrees."""
+
+    def __init__(self, d, rank: int = 0, world: int = 1, dist=None):
+        import torch
+        self.torch, self.d, self.rank, self.world, self.dist = torch, d, rank, world, dist
+        self.dev = torch.device("cuda", d.device)
+        self.send = self.recv = None
+        self.bytes_exchanged = 0
+
+    def _buffers(self, stride):
+        t = self.torch
+        if self.send is None or self.send.shape[0] < stride:
+            self.send = t.zeros((stride, HIT_WORDS), dtype=t.int32, device=self.dev)
+            self.recv = t.zeros((self.world * stride, HIT_WORDS), dtype=t.int32, device=self.dev) if self.world > 1 else self.send
+        return self.send, self.recv
+
+    def round(self, seed: int, iteration: int, labels=None, mode: int = 0) -> int:
+        """one fit iteration; returns length(colist).  Collectives: one scalar all-reduce (stride) + ONE all-gather."""
+        d, t = self.d, self.torch
+        lb = None if labels is None else np.ascontiguousarray(labels, np.int32)
+        nloc = C.c_int64(0)
+        d._ck(d.lib.stf_shard_collide(d.h, mode, 0 if lb is None else len(lb), None if lb is None else lb.ctypes.data, self.rank, self.world, C.byref(nloc)))
+        nmax = nloc.value
+        if self.world > 1:
+            m = t.tensor([nmax], dtype=t.int64, device=self.dev)
+            self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX)
+            nmax = int(m.item())
+        stride = exchange_stride(nmax)
+        if self.send is not None and self.send.shape[0] >= stride:
+            stride = self.send.shape[0]
+        send, recv = self._buffers(stride)
+        d._ck(d.lib.stf_shard_pack(d.h, send.data_ptr(), stride))
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(recv, send)
+            t.cuda.current_stream(self.dev).synchronize()
+            self.bytes_exchanged += self.world * stride * 16
+        nh = C.c_int64(0)
+        d._ck(d.lib.stf_shard_step(d.h, recv.data_ptr(), self.world, stride, seed, iteration, C.byref(nh)))
+        return nh.value

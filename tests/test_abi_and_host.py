@@ -104,3 +104,52 @@ def test_two_rank_gloo_reduction(tmp_path):
                           "--master-port", "29541", str(script)], env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK 11.0 4096.0" in out.stdout
+
+
+_SHARD_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["STF_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+import _pkg
+S = _pkg.load()
+from stuffing_b200 import parallel
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# every rank "finds" the hits of its share of the records: a deterministic global list, dealt round-robin
+rng = np.random.default_rng(7)
+allhits = rng.integers(1, 1000, size=(1237, 4)).astype(np.int32)
+local = allhits[rank::world]
+# the protocol of ShardedFit.round: scalar all-reduce(max) -> stride, fixed-stride all-gather, union in rank order
+m = torch.tensor([len(local)], dtype=torch.int64); dist.all_reduce(m, op=dist.ReduceOp.MAX)
+stride = parallel.exchange_stride(int(m.item()))
+send = torch.from_numpy(parallel.pack_segment(local, stride))
+recv = torch.zeros((world * stride, 4), dtype=torch.int32)
+dist.all_gather_into_tensor(recv, send)
+union = parallel.unpack_segments(recv.numpy(), world, stride)
+want = np.concatenate([allhits[r::world] for r in range(world)])
+assert np.array_equal(union, want), "union differs"
+# every rank must hold the same union (the canonical sort + batchsteps then keep the replicas identical)
+digest = torch.tensor([int(union.astype(np.int64).sum()), len(union)], dtype=torch.int64)
+lo, hi = digest.clone(), digest.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+assert torch.equal(lo, hi)
+try:
+    parallel.pack_segment(local, len(local))      # stride must leave room for the header
+    raise SystemExit("pack_segment accepted a short stride")
+except ValueError:
+    pass
+if rank == 0:
+    print("SHARD-OK", len(union), stride)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_shard_exchange(tmp_path):
+    """host side of the item-parallel path (SURVEY §8e-2): stride agreement, fixed-stride all-gather, union order"""
+    script = tmp_path / "shard_worker.py"
+    script.write_text(_SHARD_WORKER)
+    env = dict(os.environ, STF_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29543", str(script)], env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "SHARD-OK 1237 768" in out.stdout

@@ -405,3 +405,46 @@ def test_scene_batch_equals_single_scenes(S, orc):
         S.batchsteps(d, hits, S.Momentum(0.25, 0.5), clock)
         orc.batchsteps(flat, hits, opt, seed=11, iteration=it, is_mask=is_mask)
     assert_same_trees(d, flat)
+
+
+def test_item_parallel_shards_match_single_context(S, orc):
+    """SURVEY §8e-2 on one GPU: two replicas play rank 0 and rank 1 of the item-parallel path (the all-gather is a
+    device copy here; NCCL itself is covered by tools/check_shard.py under torchrun); both must stay bit-identical to
+    a single context running stf_fit_round, and to the oracle."""
+    import ctypes as C
+    import torch
+    from stuffing_b200 import parallel
+    qo = rect_scene(orc, 300, 11, sz=70, masksize=(600, 600))
+    ref = device_from_oracle(S, qo)
+    reps = [device_from_oracle(S, qo) for _ in range(2)]
+    opt = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    for d in [ref] + reps:
+        d.lib.stf_set_optimiser(d.h, 2, 0.25, 0.5)
+    for it in range(4):
+        nh = C.c_int64(0)
+        ref._ck(ref.lib.stf_fit_round(ref.h, 0, 0, None, 5, it, C.byref(nh)))
+        nloc = []
+        for r, d in enumerate(reps):
+            n = C.c_int64(0)
+            d._ck(d.lib.stf_shard_collide(d.h, 0, 0, None, r, 2, C.byref(n)))
+            nloc.append(n.value)
+        assert sum(nloc) == nh.value and min(nloc) > 0
+        stride = parallel.exchange_stride(max(nloc))
+        recv = torch.zeros((2 * stride, 4), dtype=torch.int32, device="cuda")
+        for r, d in enumerate(reps):
+            d._ck(d.lib.stf_shard_pack(d.h, recv[r * stride:].data_ptr(), stride))
+        host = recv.cpu().numpy()
+        assert len(parallel.unpack_segments(host, 2, stride)) == nh.value      # host twin of k_shard_unpack
+        for d in reps:
+            n = C.c_int64(0)
+            d._ck(d.lib.stf_shard_step(d.h, recv.data_ptr(), 2, stride, 5, it, C.byref(n)))
+            assert n.value == nh.value
+        hits = sorted(orc.totalcollisions_spacial(qo, unique=False))
+        assert len(hits) == nh.value
+        orc.batchsteps(qo, hits, opt, seed=5, iteration=it)
+        want = np.array([t.getshift() for t in qo])
+        for d in [ref] + reps:
+            rs, cs = d.getshifts()
+            assert np.array_equal(rs, want[:, 0]) and np.array_equal(cs, want[:, 1])
+    for d in reps:
+        assert_same_trees(d, qo, labels=range(1, 60))
