@@ -187,6 +187,33 @@ class DeviceQTrees:
         self._cap = 1 << 14
         self._buf = np.zeros(self._cap, ITEM_DT)
 
+    @classmethod
+    def from_packed(cls, payload, kh, kw, rs, cs, dflt, canvas, is_mask=None, scene=None, device: int = 0, payload_dev_ptr=None):
+        """many trees from ONE concatenated column-major payload (stf_upload_packed): the bulk-upload route for
+        batches of scenes.  `payload_dev_ptr`: the payload already lives in HBM (needs 32 bytes of zeroed slack)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        rc = self.lib.stf_create(device, C.byref(self.h))
+        if rc != 0:
+            raise StuffingError(rc, "stf_create failed: no CUDA device (there is no CPU fallback)")
+        kh, kw, rs, cs = i32(kh), i32(kw), i32(rs), i32(cs)
+        dflt = np.ascontiguousarray(dflt, np.uint8)
+        self.n, self.device, self.canvas, self.defaults = len(kh), device, int(canvas), [int(x) for x in dflt]
+        im = None if is_mask is None else np.ascontiguousarray(is_mask, np.uint8)
+        sc = None if scene is None else i32(scene)
+        if payload_dev_ptr is not None:
+            src, on_dev = C.c_void_p(payload_dev_ptr), 1
+        else:
+            payload = np.ascontiguousarray(payload, np.uint8)
+            src, on_dev = C.c_void_p(payload.ctypes.data), 0
+        self._ck(self.lib.stf_upload_packed(self.h, self.n, src, on_dev, ptr(kh), ptr(kw), ptr(rs), ptr(cs), ptr(dflt), self.canvas, ptr(im), ptr(sc)))
+        self._keep = None
+        self.nlevels = self.lib.stf_num_levels(self.h)
+        self._cap = 1 << 14
+        self._buf = np.zeros(self._cap, ITEM_DT)
+        return self
+
     def __del__(self):
         try:
             if self.h:
