@@ -1,11 +1,16 @@
-// stf_sort.cuh — device radix sort (stable, LSD, 8-bit digits) and exclusive scan.
-// Replaces the Dict / linked-list bucketing of HashSpacialQTree and LinkedSpacialQTree
-// (qtrees.jl:411-415, 501-538) and the final sort! of the many-body calls (qtree_functions.jl:252).
+// stf_sort.cuh — throughput path: multi-launch LSD radix sort (stable, 8-bit digits), order-preserving compaction,
+// exclusive scan.  Replaces the Dict / linked-list bucketing of HashSpacialQTree and LinkedSpacialQTree
+// (qtrees.jl:411-415, 501-538) and the final sort! of the many-body calls (qtree_functions.jl:252) when a scene or a
+// batch of scenes is too large for the single-CTA kernels of stf_finalize.cuh.
 //
-// Granularity: one WARP owns a contiguous slice of the input and a private 256-bin histogram in
-// shared memory.  Ranks inside a 32-key chunk come from __match_any_sync, so equal digits keep
-// their input order (stable).  Three launches per pass: histogram, scan over (digit, warp), scatter.
+// * Digits are assembled only from key bits that actually vary (a host-built DigitPass per pass: up to 8 bit runs
+//   gathered into one 8-bit digit), so a 49..61-bit cell key costs ceil(varying bits / 8) passes, not 7.
+// * Granularity: one WARP owns a contiguous slice of the input and a private 256-bin histogram in shared memory.
+//   Ranks inside a 32-key chunk come from __match_any_sync, so equal digits keep their input order (stable).
+// * Three launches per pass: histogram, scan (one CTA per DIGIT scans that digit's per-warp counts; the 256 digit
+//   totals are scanned again by every scatter CTA), scatter.
 #pragma once
+#include <vector>
 #include "stf_common.cuh"
 
 #define SORT_WARPS_PER_BLOCK 8
@@ -24,19 +29,125 @@ static inline SortPlan sort_plan(int64_t n) {
     return p;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, int per_warp, int nvw, uint32_t* __restrict__ hist) {
+// one 8-bit digit = up to 8 runs of key bits: digit = sum ((key >> shift) & mask) << out
+struct DigitPass { int nseg; int shift[8]; uint32_t mask[8]; int out[8]; };
+__host__ __device__ __forceinline__ uint32_t digit_of(uint64_t key, const DigitPass& P) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (i < P.nseg) d |= ((uint32_t)(key >> P.shift[i]) & P.mask[i]) << P.out[i];
+    return d;
+}
+// passes that sort by exactly the bits set in `bits` (LSB-first): the order equals the order by the full key whenever
+// all other bits are equal across the keys
+static inline std::vector<DigitPass> plan_digits(uint64_t bits) {
+    std::vector<DigitPass> passes;
+    DigitPass cur = {}; int fill = 0;
+    int b = 0;
+    while (b < 64) {
+        if (!((bits >> b) & 1)) { b++; continue; }
+        int e = b; while (e < 64 && ((bits >> e) & 1)) e++; // run [b, e)
+        while (b < e) {
+            int take = std::min(e - b, 8 - fill);
+            cur.shift[cur.nseg] = b; cur.mask[cur.nseg] = (1u << take) - 1; cur.out[cur.nseg] = fill; cur.nseg++;
+            fill += take; b += take;
+            if (fill == 8) { passes.push_back(cur); cur = DigitPass(); fill = 0; }
+        }
+    }
+    if (fill) passes.push_back(cur);
+    return passes;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint64_t* __restrict__ keys, int64_t n, DigitPass P, int per_warp, int nvw, uint32_t* __restrict__ hist) {
     __shared__ uint32_t cnt[SORT_WARPS_PER_BLOCK][256];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int vw = blockIdx.x * SORT_WARPS_PER_BLOCK + w;
     for (int d = lane; d < 256; d += 32) cnt[w][d] = 0;
     __syncwarp();
     int64_t beg = (int64_t)vw * per_warp, end = min(n, beg + per_warp);
-    for (int64_t i = beg + lane; i < end; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & 255], 1u);
+    for (int64_t i = beg + lane; i < end; i += 32) atomicAdd(&cnt[w][digit_of(keys[i], P)], 1u);
     __syncwarp();
     for (int d = lane; d < 256; d += 32) hist[(size_t)d * nvw + vw] = cnt[w][d];
 }
+// CTA d: exclusive scan of digit d's per-warp counts (in place), digit total -> dtot[d]
+__global__ void __launch_bounds__(256) k_sort_scan_digit(uint32_t* __restrict__ hist, int nvw, uint32_t* __restrict__ dtot) {
+    __shared__ uint32_t wsum[8];
+    uint32_t* row = hist + (size_t)blockIdx.x * nvw;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int per = (nvw + 255) / 256, beg = threadIdx.x * per, end = min(nvw, beg + per);
+    uint32_t s = 0;
+    for (int i = beg; i < end; i++) s += row[i];
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+    for (int i = 0; i < 8; i++) { if (i < w) off += wsum[i]; tot += wsum[i]; }
+    uint32_t run = off + incl - s;
+    for (int i = beg; i < end; i++) { uint32_t v = row[i]; row[i] = run; run += v; }
+    if (threadIdx.x == 0) dtot[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, DigitPass P,
+                                                               int per_warp, int nvw, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ dtot,
+                                                               uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    __shared__ uint32_t base[SORT_WARPS_PER_BLOCK][256];
+    __shared__ uint32_t dbase[256];
+    __shared__ uint32_t wsum[8];
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    { // exclusive scan of the 256 digit totals (SORT_THREADS == 256: one digit per thread)
+        uint32_t v = dtot[threadIdx.x], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        uint32_t off = 0;
+        for (int i = 0; i < w; i++) off += wsum[i];
+        dbase[threadIdx.x] = off + incl - v;
+        __syncthreads();
+    }
+    int vw = blockIdx.x * SORT_WARPS_PER_BLOCK + w;
+    for (int d = lane; d < 256; d += 32) base[w][d] = hist[(size_t)d * nvw + vw] + dbase[d];
+    __syncwarp();
+    int64_t beg = (int64_t)vw * per_warp, end = min(n, beg + per_warp);
+    for (int64_t i0 = beg; i0 < end; i0 += 32) {
+        int64_t i = i0 + lane;
+        bool valid = i < end;
+        uint64_t k = valid ? keys[i] : 0;
+        uint32_t v = valid ? vals[i] : 0;
+        uint32_t d = valid ? digit_of(k, P) : 256u + lane; // invalid lanes never match
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t dst = 0;
+        if (valid) dst = base[w][d] + rank;
+        __syncwarp();
+        if (valid && rank == 0) base[w][d] += __popc(peers);
+        __syncwarp();
+        if (valid) { keys_out[dst] = k; vals_out[dst] = v; }
+    }
+}
 
-// exclusive scan of `m` uint32 by ONE block (m = 256*nvw <= ~600k; a few microseconds)
+// Sorts (keys, vals) by the key bits set in `bits`.  Buffers ping-pong; returns 0 if the result is in (keys, vals),
+// 1 if it is in (keys_alt, vals_alt).  `hist` holds >= 256*nvw + 256 uint32 (the last 256: digit totals).
+static inline int radix_sort_pairs(cudaStream_t st, int64_t* launches, uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
+                                   int64_t n, uint64_t bits, uint32_t* hist) {
+    if (n <= 1) return 0;
+    SortPlan p = sort_plan(n);
+    uint32_t* dtot = hist + (size_t)256 * p.nvw;
+    int flip = 0;
+    for (const DigitPass& P : plan_digits(bits)) {
+        uint64_t* kin = flip ? keys_alt : keys; uint32_t* vin = flip ? vals_alt : vals;
+        uint64_t* kout = flip ? keys : keys_alt; uint32_t* vout = flip ? vals : vals_alt;
+        k_sort_hist<<<p.blocks, SORT_THREADS, 0, st>>>(kin, n, P, p.per_warp, p.nvw, hist);
+        k_sort_scan_digit<<<256, 256, 0, st>>>(hist, p.nvw, dtot);
+        k_sort_scatter<<<p.blocks, SORT_THREADS, 0, st>>>(kin, vin, n, P, p.per_warp, p.nvw, hist, dtot, kout, vout);
+        flip ^= 1; if (launches) *launches += 3;
+    }
+    return flip;
+}
+static inline uint64_t bit_range(int lo, int hi) { return (hi >= 64 ? ~0ull : ((1ull << hi) - 1)) & ~((1ull << lo) - 1); }
+static inline size_t radix_sort_hist_words(int64_t n) { return (size_t)256 * sort_plan(n).nvw + 256; }
+
+// exclusive scan of `m` uint32 by ONE block (small m only: per-block counts of a compaction)
 __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, int64_t m, uint32_t* __restrict__ total) {
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry, btot;
@@ -71,54 +182,39 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, 
     if (threadIdx.x == 0 && total) *total = carry;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, int shift,
-                                                               int per_warp, int nvw, const uint32_t* __restrict__ hist,
-                                                               uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-    __shared__ uint32_t base[SORT_WARPS_PER_BLOCK][256];
-    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int vw = blockIdx.x * SORT_WARPS_PER_BLOCK + w;
-    for (int d = lane; d < 256; d += 32) base[w][d] = hist[(size_t)d * nvw + vw];
-    __syncwarp();
-    int64_t beg = (int64_t)vw * per_warp, end = min(n, beg + per_warp);
-    for (int64_t i0 = beg; i0 < end; i0 += 32) {
-        int64_t i = i0 + lane;
-        bool valid = i < end;
-        uint64_t k = valid ? keys[i] : 0;
-        uint32_t v = valid ? vals[i] : 0;
-        uint32_t d = valid ? (uint32_t)((k >> shift) & 255) : 256u + lane; // invalid lanes never match
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t rank = __popc(peers & ((1u << lane) - 1));
-        uint32_t dst = 0;
-        if (valid) dst = base[w][d] + rank;
-        __syncwarp();
-        if (valid && rank == 0) base[w][d] += __popc(peers);
-        __syncwarp();
-        if (valid) { keys_out[dst] = k; vals_out[dst] = v; }
-    }
+// ---- order-preserving compaction of the 4-slot record table (INVALID keys dropped) + the OR of all key differences
+#define CMP_BLOCK 1024
+__global__ void __launch_bounds__(CMP_BLOCK) k_compact_count(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ blockcnt) {
+    int64_t i = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
+    int c = __syncthreads_count(i < n && keys[i] != STF_KEY_INVALID);
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = (uint32_t)c;
 }
-
-// Sorts (keys, vals) by bits [bit_lo, bit_hi) of the key.  Buffers ping-pong; returns 0 if the result
-// is in (keys, vals), 1 if it is in (keys_alt, vals_alt).  `hist` holds >= 256*nvw uint32.
-static inline int radix_sort_pairs(cudaStream_t st, int64_t* launches, uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
-                                   int64_t n, int bit_lo, int bit_hi, uint32_t* hist) {
-    if (n <= 1) return 0;
-    SortPlan p = sort_plan(n);
-    int flip = 0;
-    for (int shift = bit_lo; shift < bit_hi; shift += 8) {
-        uint64_t* kin = flip ? keys_alt : keys; uint32_t* vin = flip ? vals_alt : vals;
-        uint64_t* kout = flip ? keys : keys_alt; uint32_t* vout = flip ? vals : vals_alt;
-        k_sort_hist<<<p.blocks, SORT_THREADS, 0, st>>>(kin, n, shift, p.per_warp, p.nvw, hist);
-        k_scan_u32<<<1, 1024, 0, st>>>(hist, (int64_t)256 * p.nvw, nullptr);
-        k_sort_scatter<<<p.blocks, SORT_THREADS, 0, st>>>(kin, vin, n, shift, p.per_warp, p.nvw, hist, kout, vout);
-        flip ^= 1; if (launches) *launches += 3;
-    }
-    return flip;
+__global__ void __launch_bounds__(CMP_BLOCK) k_compact_write(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, const uint32_t* __restrict__ blockoff,
+                                                             uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    __shared__ uint32_t wsum[32];
+    int64_t i = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t k = i < n ? keys[i] : STF_KEY_INVALID;
+    bool v = k != STF_KEY_INVALID;
+    unsigned m = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    uint32_t off = blockoff[blockIdx.x];
+    for (int j = 0; j < w; j++) off += wsum[j];
+    if (v) { uint32_t dst = off + __popc(m & ((1u << lane) - 1)); keys_out[dst] = k; vals_out[dst] = vals[i]; }
 }
-static inline size_t radix_sort_hist_words(int64_t n) { return (size_t)256 * sort_plan(n).nvw; }
-
-// first INVALID key of a sorted array (multi-launch path), so that both sort paths publish the valid count
-__global__ void k_count_valid(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* __restrict__ n_out) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (keys[mid] != STF_KEY_INVALID) lo = mid + 1; else hi = mid; }
-    *n_out = (unsigned long long)lo;
+// vary |= OR over i < n of keys[i] ^ keys[0]  (n on the device): the bits the sort has to look at
+__global__ void __launch_bounds__(256) k_vary_or(const uint64_t* __restrict__ keys, const unsigned long long* __restrict__ n_dev, int64_t cap, unsigned long long* __restrict__ vary) {
+    __shared__ unsigned long long wor[8];
+    int64_t n = min((int64_t)*n_dev, cap);
+    unsigned long long x = 0;
+    if (n > 0) {
+        uint64_t ref = keys[0];
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x |= keys[i] ^ ref;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x |= __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) wor[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long t = 0; for (int j = 0; j < 8; j++) t |= wor[j]; if (t) atomicOr(vary, t); }
 }

@@ -105,7 +105,7 @@ static void stage_begin(stf_ctx* ctx, int stage) {
 #define KCHECK() CK(cudaGetLastError())
 static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n + t - 1) / t); }
 
-enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_N = 12 };
+enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_N = 16 };
 
 static int32_t sync_counts(stf_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
@@ -591,12 +591,10 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(nh)));
     ctx->launches++, k_hit_keys<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
     uint64_t* ks; uint32_t* vs;
-    {
-        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh, 0, ctx->label_bits, ctx->hist.as<uint32_t>());
-        uint64_t *k0 = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), *k1 = f ? ctx->hk.as<uint64_t>() : ctx->hk2.as<uint64_t>();
-        uint32_t *v0 = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), *v1 = f ? ctx->hv.as<uint32_t>() : ctx->hv2.as<uint32_t>();
-        int f2 = radix_sort_pairs(ctx->st, &ctx->launches, k0, v0, k1, v1, nh, 32, 32 + ctx->label_bits, ctx->hist.as<uint32_t>());
-        ks = f2 ? k1 : k0; vs = f2 ? v1 : v0;
+    { // (i1, i2) = bits [32, 32+lb) and [0, lb): one LSD sort over exactly those bits
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh,
+                                 bit_range(0, ctx->label_bits) | bit_range(32, 32 + ctx->label_bits), ctx->hist.as<uint32_t>());
+        ks = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(); vs = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
     }
     ctx->launches++, k_gather_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), vs, nh, ctx->hits2.as<Item16>());
     ctx->launches++, k_fix_ties<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ks, nh, unique, ctx->keep.as<uint32_t>());
@@ -748,11 +746,22 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     }
     KCHECK();
     stage_begin(ctx, STF_STAGE_SORT);
-    {
-        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nrec, 0, bits, ctx->hist.as<uint32_t>());
-        *keys = f ? ctx->rk2.as<uint64_t>() : ctx->rk.as<uint64_t>();
-        *vals = f ? ctx->rv2.as<uint32_t>() : ctx->rv.as<uint32_t>();
-        ctx->launches++, k_count_valid<<<1, 1, 0, ctx->st>>>(*keys, nrec, nvalid);
+    { // order-preserving compaction of the slot table (rk,rv) -> (rk2,rv2), then a stable sort over the varying key bits
+        int nb = nblk(nrec, CMP_BLOCK);
+        CK(ctx->keep.ensure(sizeof(uint32_t) * (size_t)(nb + 16)));
+        unsigned long long* vary = ctx->counts.as<unsigned long long>() + C_VARY;
+        CK(cudaMemsetAsync(nvalid, 0, sizeof(unsigned long long), ctx->st)); CK(cudaMemsetAsync(vary, 0, sizeof(unsigned long long), ctx->st));
+        ctx->launches++, k_compact_count<<<nb, CMP_BLOCK, 0, ctx->st>>>(ctx->rk.as<uint64_t>(), nrec, ctx->keep.as<uint32_t>());
+        ctx->launches++, k_scan_u32<<<1, 1024, 0, ctx->st>>>(ctx->keep.as<uint32_t>(), nb, reinterpret_cast<uint32_t*>(nvalid));
+        ctx->launches++, k_compact_write<<<nb, CMP_BLOCK, 0, ctx->st>>>(ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nrec, ctx->keep.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>());
+        ctx->launches++, k_vary_or<<<std::min(nblk(nrec / 4 + 1, 256), 148 * 4), 256, 0, ctx->st>>>(ctx->rk2.as<uint64_t>(), nvalid, nrec, vary);
+        KCHECK();
+        int32_t r = sync_counts(ctx); if (r) return r;
+        int64_t nv = (int64_t)ctx->h_counts[C_NVALID];
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nv,
+                                 (uint64_t)ctx->h_counts[C_VARY] & bit_range(0, bits), ctx->hist.as<uint32_t>());
+        *keys = f ? ctx->rk.as<uint64_t>() : ctx->rk2.as<uint64_t>();
+        *vals = f ? ctx->rv.as<uint32_t>() : ctx->rv2.as<uint32_t>();
     }
     KCHECK();
     stage_end(ctx);
@@ -1014,7 +1023,7 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
         CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(m)));
         ctx->launches++, k_step_endpoints<<<nblk(m, 256), 256, 0, ctx->st>>>(hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->prev.p, 0, sizeof(uint32_t) * (size_t)m, ctx->st));
-        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, 0, ctx->label_bits + 1, ctx->hist.as<uint32_t>());
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, bit_range(0, ctx->label_bits + 1), ctx->hist.as<uint32_t>());
         ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
         CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
