@@ -36,12 +36,30 @@ __global__ void k_step_prev(const uint64_t* __restrict__ keys, const uint32_t* _
     prev[e] = pv;
 }
 
+// Dependency depth of every step by Jacobi relaxation: after i sweeps lvl[k] = min(depth[k], i), so ANY number of sweeps
+// yields lvl[pred] <= lvl[k], and (lvl, k) is a topological order (a predecessor always has the smaller k).  Claiming
+// tickets in that order puts all steps without a pending predecessor first: independent chains (e.g. the scenes of a
+// batch) overlap instead of being walked one after the other.
+__global__ void k_step_level(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ lin, uint32_t* __restrict__ lout, int64_t n) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t p0 = prev[2 * k], p1 = prev[2 * k + 1], l = 0;
+    if (p0) l = lin[p0 - 1] + 1;
+    if (p1) l = max(l, lin[p1 - 1] + 1);
+    lout[k] = l;
+}
+__global__ void k_step_level_keys(const uint32_t* __restrict__ lvl, int64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { keys[k] = lvl[k]; vals[k] = (uint32_t)k; }
+}
+
 __device__ __forceinline__ int intlog2_dev(double x) { return (int)((__double_as_longlong(x) >> 52) - 1023); } // fit_helper.jl:74-78
 
 struct StepArgs {
     uint32_t* words; LevelMeta* lm; const ObjMeta* om; int L;
     const Item16* hits; int64_t n; const unsigned long long* n_dev; // n_dev != NULL: the step count lives on the device
     const uint32_t* prev; uint32_t* done; unsigned long long* ticket;
+    const uint32_t* order; // optional: ticket t runs step order[t] (a topological order that interleaves independent chains)
     double* vel; uint8_t* has_vel; uint8_t* moved_flag; int* dirty;
     OptState opt; uint64_t seed, iter;
     unsigned long long* counts; // [4] number of moves
@@ -109,6 +127,7 @@ __global__ void __launch_bounds__(128) k_batchsteps(StepArgs A) {
             k = __shfl_sync(FULLM, k, 0);
         }
         if ((int64_t)k >= nsteps) return;
+        if (A.order) k = A.order[k];
         unsigned long long t_ready = 0, t_decided = 0;
         Item16 h = A.hits[k];
         int o1 = h.i1 - 1, o2 = item_i2(h) - 1;

@@ -987,11 +987,11 @@ extern "C" int32_t stf_get_velocity(stf_ctx* ctx, int32_t n, const int32_t* labe
     return STF_OK;
 }
 // k_batchsteps + k_materialize over `hits`; the step count is host-known (n_dev == NULL) or lives on the device
-static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, const unsigned long long* n_dev, uint64_t seed, uint64_t iter) {
+static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, const unsigned long long* n_dev, uint64_t seed, uint64_t iter, const uint32_t* order = nullptr) {
     StepArgs A;
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.om = ctx->om.as<ObjMeta>(); A.L = ctx->L;
     A.hits = hits; A.n = n_host; A.n_dev = n_dev; A.prev = ctx->prev.as<uint32_t>(); A.done = ctx->done.as<uint32_t>();
-    A.ticket = ctx->counts.as<unsigned long long>() + C_TICKET;
+    A.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; A.order = order;
     A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>(); A.dirty = ctx->dirty.as<int>();
     A.opt = ctx->opt; A.seed = seed; A.iter = iter; A.counts = ctx->counts.as<unsigned long long>();
     { const char* e = getenv("STF_DEBUG_STEP"); A.dbg = e ? atoi(e) : 0; }
@@ -1011,6 +1011,7 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     if (n == 0) { ctx->ctr.moved = 0; return STF_OK; }
     int64_t m = 2 * n;
     CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)n));
+    const uint32_t* order = nullptr;
     stage_begin(ctx, STF_STAGE_STEP_PREP);
     CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
     if (m <= BS_CAP && ctx->label_bits + 1 + FIN_IDX_BITS <= 64) { // one CTA: endpoints, sort, links
@@ -1027,9 +1028,18 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
         ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
         CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
+        if (n >= 16384) { // many chains (a batch of scenes): claim the steps level by level
+            CK(ctx->keep.ensure(sizeof(uint32_t) * 2 * (size_t)n));
+            uint32_t* la = ctx->keep.as<uint32_t>(); uint32_t* lb = la + n;
+            CK(cudaMemsetAsync(la, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
+            for (int sweep = 0; sweep < 16; sweep++) { ctx->launches++, k_step_level<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->prev.as<uint32_t>(), la, lb, n); std::swap(la, lb); }
+            ctx->launches++, k_step_level_keys<<<nblk(n, 256), 256, 0, ctx->st>>>(la, n, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+            int f2 = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), n, bit_range(0, 5), ctx->hist.as<uint32_t>());
+            order = f2 ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
+        }
     }
     KCHECK();
-    int32_t r = launch_steps(ctx, hits, n, nullptr, seed, iter); if (r) return r;
+    int32_t r = launch_steps(ctx, hits, n, nullptr, seed, iter, order); if (r) return r;
     r = sync_counts(ctx); if (r) return r;
     ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES];
     return STF_OK;
