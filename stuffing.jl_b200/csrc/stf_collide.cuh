@@ -275,18 +275,57 @@ struct NarrowArgs {
     unsigned long long* counts;      // [2] overflow count, [3] visited
     uint32_t* overflow;              // item indices that need the big path
     int64_t overflow_cap;
+    uint32_t* surv; unsigned long long* nsurv; // stage 1 -> stage 2: indices of the items that go below the first level
 };
+
+// Stage 1, one THREAD per item: the four children of the start node.  Most candidate pairs end here (a FULL code =
+// the hit the sequential BFS returns first; no MIX child = miss at the start node, qtree_functions.jl:27-41), with every
+// lane busy; only the pairs with a MIX-in-both child go on to the group-per-item frontier kernel below.
+__global__ void __launch_bounds__(256) k_collide_first(NarrowArgs A) {
+    int64_t n = A.n_items_dev ? (int64_t)*A.n_items_dev : A.n_items_host;
+    if (A.n_items_dev && n > A.n_items_host) n = A.n_items_host; // clamp to buffer capacity
+    unsigned long long visited = 0;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (int64_t)gridDim.x * blockDim.x) {
+        Item16 item = A.items[it];
+        int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
+        int lev = item_l(item), a = item.a, b = item.b;
+        LevelMeta m1 = A.lm[(size_t)o1 * A.L + (lev - 2)], m2 = A.lm[(size_t)o2 * A.L + (lev - 2)];
+        uint32_t code[4];
+#pragma unroll
+        for (int cn = 0; cn < 4; cn++) {
+            int ca = 2 * a - (cn & 1), cb = 2 * b - (cn >> 1);
+            code[cn] = node_code<false>(A.words, m1, ca, cb) & node_code<false>(A.words, m2, ca, cb);
+        }
+        int hit = -1; bool mix = false;
+#pragma unroll
+        for (int cn = 3; cn >= 0; cn--) { if (code[cn] == CODE_FULL) hit = cn; mix |= (code[cn] == CODE_MIX); }
+        if (hit < 0 && mix && lev - 1 > 1) { // undecided: the frontier kernel restarts it from the start node
+            unsigned long long s_ = atomicAdd(A.nsurv, 1ull);
+            A.surv[s_] = (uint32_t)it;
+            continue;
+        }
+        visited += 4;
+        int4 result = hit >= 0 ? make_int4(lev - 1, 2 * a - (hit & 1), 2 * b - (hit >> 1), 0) : make_int4(-lev, a, b, 0);
+        if (A.res) A.res[it] = result;
+        if (A.hits && result.x >= 0) {
+            unsigned long long s_ = atomicAdd(A.nhits, 1ull);
+            if ((int64_t)s_ < A.hits_cap) A.hits[s_] = make_item(item.i1, item_i2(item), result.x, result.y, result.z);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, o);
+    if ((threadIdx.x & 31) == 0 && visited) atomicAdd(A.counts + 3, visited);
+}
 
 __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
     __shared__ uint32_t fr[NP_THREADS / NP_GROUP][2][NP_FCAP];
     cg::thread_block_tile<NP_GROUP> g = cg::tiled_partition<NP_GROUP>(cg::this_thread_block());
     int gl = g.thread_rank();
     int gib = threadIdx.x / NP_GROUP;
-    int64_t n = A.n_items_dev ? (int64_t)*A.n_items_dev : A.n_items_host;
-    if (n > A.n_items_host && A.n_items_host >= 0 && A.n_items_dev) n = A.n_items_host; // clamp to buffer capacity
+    int64_t n = (int64_t)*A.nsurv; // stage 2: only the items k_collide_first could not decide
     int64_t ngroups = (int64_t)gridDim.x * (NP_THREADS / NP_GROUP);
     unsigned long long visited = 0;
-    for (int64_t it = (int64_t)blockIdx.x * (NP_THREADS / NP_GROUP) + gib; it < n; it += ngroups) {
+    for (int64_t j = (int64_t)blockIdx.x * (NP_THREADS / NP_GROUP) + gib; j < n; j += ngroups) {
+        int64_t it = A.surv[j];
         Item16 item = A.items[it];
         int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
         int lev = item_l(item), ata = item.a, atb = item.b;

@@ -42,7 +42,7 @@ struct stf_ctx {
     DevBuf words, lm, om, payload, poff, woff1, work, lab, lab2, lab3, lab4, bytes_tmp;
     DevBuf rk, rv, rk2, rv2, hist, lkk, lkv;
     DevBuf items, direct, res, overflow, hits, hits2, hk, hv, hk2, hv2, keep, out32, scratch;
-    DevBuf dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
+    DevBuf surv, dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
     unsigned long long* h_counts = nullptr; int* h_err = nullptr; // pinned
     OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
@@ -105,7 +105,7 @@ static void stage_begin(stf_ctx* ctx, int stage) {
 #define KCHECK() CK(cudaGetLastError())
 static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n + t - 1) / t); }
 
-enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_N = 16 };
+enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_SURV = 13, C_N = 16 };
 
 static int32_t sync_counts(stf_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
@@ -151,7 +151,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
@@ -492,9 +492,13 @@ static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want
     A.res = want_res ? ctx->res.as<int4>() : nullptr; A.counts = ctx->counts.as<unsigned long long>();
     A.hits = want_hits ? ctx->hits.as<Item16>() : nullptr; A.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16)); A.nhits = ctx->counts.as<unsigned long long>() + C_NHITS;
     A.overflow = ctx->overflow.as<uint32_t>(); A.overflow_cap = nmax;
+    CK(ctx->surv.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nmax)));
+    A.surv = ctx->surv.as<uint32_t>(); A.nsurv = ctx->counts.as<unsigned long long>() + C_SURV;
+    CK(cudaMemsetAsync(A.nsurv, 0, sizeof(unsigned long long), ctx->st));
     int per_block = NP_THREADS / NP_GROUP;
     int64_t want = n_host >= 0 ? n_host : std::max<int64_t>(ctx->hint_items, 4096);
-    int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want + per_block - 1) / per_block), 148 * 32);
+    ctx->launches++, k_collide_first<<<(int)std::min<int64_t>(std::max<int64_t>(1, (want + 255) / 256), 148 * 16), 256, 0, ctx->st>>>(A);
+    int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want / 2 + per_block - 1) / per_block), 148 * 32); // typically < half the items survive
     ctx->launches++, k_collide_small<<<blocks, NP_THREADS, 0, ctx->st>>>(A);
     KCHECK();
     CK(ctx->scratch.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->big_cap * ctx->big_ctas));
