@@ -199,7 +199,114 @@ def trainepoch_D(qts, optimiser=None, clock=None, moved: DynamicColliders | None
     return len(colist)
 
 
-_DEFAULTS = {trainepoch_E: (20, 2000), trainepoch_EM: (10, 1000), trainepoch_EM2: (10, 1000), trainepoch_EM3: (10, 1000), trainepoch_D: (10, 2000)}
+# ------------------------------------------------------------------------------------------------ pairwise trainers
+def filttrain(qts, inpool, outpool, nearlevel2, optimiser=None, clock=None):
+    """filttrain!(qtrees, inpool, outpool, nearlevel2; optimiser)  fit.jl:235-266: every pair of `inpool` is tested from
+    the root ((L,1,1), no bounds pre-check); pairs whose result level cp[1] >= nearlevel2 go to `outpool` (misses report
+    -level of the deepest node still MIX in both trees: the nearness score), hits (cp[1] > 0) are stepped.  Canonical
+    mode: pool order instead of shuffle!(inpool), colist in pool order.  One stf_collision_bfs call for the whole pool."""
+    d = _dev(qts)
+    if len(inpool) == 0:
+        return 0
+    L = d.nlevels
+    arr = np.zeros(len(inpool), _lib.ITEM_DT)
+    pool = np.asarray(inpool, np.int32).reshape(-1, 2)
+    arr["i1"], arr["i2"], arr["l"], arr["a"], arr["b"] = pool[:, 0], pool[:, 1], L, 1, 1
+    out = np.zeros(len(arr), _lib.ITEM_DT)
+    d._ck(d.lib.stf_collision_bfs(d.h, len(arr), ptr(arr), ptr(out)))
+    near = out["l"] >= nearlevel2
+    if outpool is not None:
+        outpool.extend((int(a), int(b)) for a, b in pool[near])
+    colist = out[near & (out["l"] > 0)]
+    batchsteps(d, colist, optimiser, clock)
+    return len(colist)
+
+
+def _allpairs(n):
+    return [(i, j) for i in range(1, n + 1) for j in range(i + 1, n + 1)]
+
+
+def trainepoch_P(qts, optimiser=None, clock=None, nearlevel=None, **_kw):
+    """pairwise trainer  fit.jl:268-296"""
+    d = _dev(qts)
+    nearlevel = min(-1, -d.nlevels / 2 if nearlevel is None else nearlevel)
+    indpairs, nearlist, colist = _allpairs(len(d)), [], []
+    nc = filttrain(d, indpairs, nearlist, nearlevel, optimiser, clock)
+    if nc == 0:
+        return 0
+    for ni in range(1, len(indpairs) // len(nearlist) + 1):
+        colist.clear()
+        nc1 = filttrain(d, nearlist, colist, 0, optimiser, clock)
+        if ni > 8 * nc1:
+            break
+        for ci in range(1, len(nearlist) // max(1, len(colist)) + 1 if colist else 1):
+            nc2 = filttrain(d, colist, None, 0, optimiser, clock)
+            if ci > 4 * nc2:
+                break
+    return nc
+
+
+def trainepoch_P2(qts, optimiser=None, clock=None, nearlevel1=None, nearlevel2=None, **_kw):
+    """pairwise trainer (more levels)  fit.jl:298-341"""
+    d = _dev(qts)
+    nearlevel1 = min(-1, -d.nlevels * 0.75 if nearlevel1 is None else nearlevel1)
+    nearlevel2 = min(-1, -d.nlevels * 0.5 if nearlevel2 is None else nearlevel2)
+    indpairs, nearlist1, nearlist2, colist = _allpairs(len(d)), [], [], []
+    nc = filttrain(d, indpairs, nearlist1, nearlevel1, optimiser, clock)
+    if nc == 0:
+        return 0
+    for ni1 in range(1, len(indpairs) // len(nearlist1) + 1):
+        nearlist2.clear()
+        nc1 = filttrain(d, nearlist1, nearlist2, nearlevel2, optimiser, clock)
+        if ni1 > nc1:
+            break
+        for ni2 in range(1, len(nearlist1) // max(1, len(nearlist2)) + 1 if nearlist2 else 1):
+            colist.clear()
+            nc2 = filttrain(d, nearlist2, colist, 0, optimiser, clock)
+            if nc2 == 0 or ni2 > 4 + nc2:
+                break
+            for ci in range(1, len(nearlist2) // max(1, len(colist)) + 1 if colist else 1):
+                nc3 = filttrain(d, colist, None, 0, optimiser, clock)
+                if ci > 4 * nc3:
+                    break
+    return nc
+
+
+def levelpools(qts, levels=None):
+    """levelpools(qtrees, levels=[-length(qtrees[1]):4:-3..., -1])  fit.jl:343-352: the first pool holds every pair"""
+    d = _dev(qts)
+    levels = list(range(-d.nlevels, -2, 4)) + [-1] if levels is None else list(levels)
+    pools = [[lv, []] for lv in levels]
+    pools[0][1] = _allpairs(len(d))
+    return pools
+
+
+def trainepoch_Px(qts, optimiser=None, clock=None, levelpools_=None, **_kw):
+    """pairwise trainer (general levels)  fit.jl:354-376: a cascade of pools, each fed by the pairs that came at least as
+    near as the next pool's level"""
+    d = _dev(qts)
+    pools = levelpools(d) if levelpools_ is None else levelpools_
+    nc = 0
+    if not pools:
+        return nc
+    outpool = pools[1][1] if len(pools) >= 2 else None
+    outlevel = pools[1][0] if len(pools) >= 2 else 0
+    inpool = pools[0][1]
+    if not inpool:
+        return nc
+    for niter in range(1, max(1, len(d) // len(inpool)) + 1):
+        if outpool is not None:
+            outpool.clear()
+        nc = filttrain(d, inpool, outpool, outlevel, optimiser, clock)
+        if nc == 0 or niter > 8 * nc:
+            break
+        if len(pools) >= 2:
+            trainepoch_Px(d, optimiser=optimiser, clock=clock, levelpools_=pools[1:])
+    return nc
+
+
+_DEFAULTS = {trainepoch_E: (20, 2000), trainepoch_EM: (10, 1000), trainepoch_EM2: (10, 1000), trainepoch_EM3: (10, 1000), trainepoch_D: (10, 2000),
+             trainepoch_P: (10, 100), trainepoch_P2: (2, 100), trainepoch_Px: (10, 1000)}
 
 
 def train(qts, epochs=-1, trainer=trainepoch_EM2, patience=None, optimiser=None, scheduler=lambda lr: lr * 0.5 ** 0.5,

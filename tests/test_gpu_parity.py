@@ -448,3 +448,37 @@ def test_item_parallel_shards_match_single_context(S, orc):
             assert np.array_equal(rs, want[:, 0]) and np.array_equal(cs, want[:, 1])
     for d in reps:
         assert_same_trees(d, qo, labels=range(1, 60))
+
+
+def test_pairwise_trainers_filttrain_parity_and_convergence(S, orc):
+    """filttrain!/trainepoch_P!/P2!/Px! (fit.jl:235-376).  filttrain is checked pair by pair against the
+    oracle (root BFS results incl. the miss levels used as nearness score, then batchsteps on the hits); the trainers
+    must converge like the reference's (test/test_fit.jl:53-75)."""
+    t = S.trainer
+    qo = rect_scene(orc, 30, 23, sz=70, masksize=(400, 400))
+    d = device_from_oracle(S, qo)
+    L = len(qo[0])
+    pairs = [(i, j) for i in range(1, len(qo) + 1) for j in range(i + 1, len(qo) + 1)]
+    opt = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    clock = t.StepClock(seed=3)
+    pool = pairs
+    for rnd, nearlevel in enumerate((-L / 2, 0, 0)):
+        out_dev = []
+        nc = t.filttrain(d, pool, out_dev, nearlevel, S.Momentum(0.25, 0.5), clock)
+        res = [orc.collision_bfs(qo[i1 - 1], qo[i2 - 1], at=(L, 1, 1)) for i1, i2 in pool]
+        out_orc = [p for p, r in zip(pool, res) if r[0] >= nearlevel]
+        hits = [(p, r) for p, r in zip(pool, res) if r[0] >= nearlevel and r[0] > 0]
+        assert out_dev == out_orc and nc == len(hits) and (rnd > 0 or nc > 0)
+        orc.batchsteps(qo, hits, opt, seed=3, iteration=rnd)
+        rs, cs = d.getshifts()
+        want = np.array([x.getshift() for x in qo])
+        assert np.array_equal(rs, want[:, 0]) and np.array_equal(cs, want[:, 1])
+        pool = out_dev
+        if not pool:
+            break
+    for trainer in (t.trainepoch_P, t.trainepoch_P2, t.trainepoch_Px):
+        qo = rect_scene(orc, 24, 15, sz=60, masksize=(400, 600))
+        d = device_from_oracle(S, qo)
+        ep, nc = S.train(d, 300, trainer=trainer, optimiser=S.Momentum(0.25), seed=2)
+        assert nc == 0, (trainer.__name__, ep, nc)
+        assert S.totalcollisions(d) == []
