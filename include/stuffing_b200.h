@@ -166,6 +166,14 @@ int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colist, uint64_t
 int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels,
                       uint64_t seed, uint64_t iteration, int64_t* nhits);
 
+/* ---- ground composition for place! / reposition! (qtree_functions.jl:452-518, fit.jl:420-436).
+ * ground = deepcopy(qtrees[mask_label]) with every other tree overlap!-ed except the `excl_labels` (the trees about to be
+ * re-placed).  The room search itself (findroom_uniform: a sequential BFS driven by one RNG stream) stays on the host
+ * and reads the levels it visits with stf_ground_level (u8 codes, column-major kh x kw; info = kh, kw, rshift, cshift,
+ * canvas size of the level). */
+int32_t stf_ground_compose(stf_ctx* ctx, int32_t mask_label, int32_t n_excl, const int32_t* excl_labels);
+int32_t stf_ground_level(stf_ctx* ctx, int32_t l, uint8_t* out, int32_t info[5]);
+
 /* ---- item-parallel sharding of ONE scene over the GPUs of a box (the reference has no counterpart:
  * its narrow phase is threaded with Threads.@spawn over index chunks, qtree_functions.jl:52-110).
  * Every rank holds an identical replica.  Per fit iteration:

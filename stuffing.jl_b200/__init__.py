@@ -13,3 +13,5 @@ from .qtrees import (DeviceQTrees, DeviceTree, HostTree, DynamicColliders, EMPTY
                      setpositions, totalcollisions, totalcollisions_native, totalcollisions_native_items, totalcollisions_spacial)
 from . import trainer  # noqa: F401
 from .trainer import Momentum, SGD, batchsteps, fit, fit_round, grad2d, train  # noqa: F401
+from . import place as placement  # noqa: F401
+from .place import place, overlap_ground  # noqa: F401

@@ -232,6 +232,41 @@ __global__ void __launch_bounds__(512) k_build_tail_cta(uint32_t* __restrict__ w
     if (tid >= from && tid < L) lm[(size_t)o * L + tid] = sm[tid];
     cta_build_levels<512>(words, sm, L, from, pbm, pbm + a_words);
 }
+// ---- overlap!(ground, trees) at level 1 (qtree_functions.jl:452-497), all trees at once.  Elementwise rule
+// overlap(p1, p2) = ((p1 ⊻ EMPTY) | (p2 ⊻ EMPTY)) ⊻ EMPTY on the 2-bit codes = OR of the "contains full" bits, AND of
+// the "contains empty" bits: two commutative atomics per touched ground word, so the result does not depend on the
+// order of the trees.  One warp per listed tree; writes are clipped to the ground kernel (outside it the ground reads
+// `default` = FULL for a mask and _overlap! never descends).  The upper ground levels are rebuilt afterwards.
+__global__ void __launch_bounds__(256) k_overlap_level1(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, const int32_t* __restrict__ list, int nlist,
+                                                        uint32_t* __restrict__ gwords, LevelMeta g) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int gkh = lm_kh(g), gkw = lm_kw(g), gwpc = wpc_of(gkh);
+    for (int i = warp; i < nlist; i += nwarps) {
+        int o = list[i];
+        LevelMeta m = lm[(size_t)o * L];
+        int kh = lm_kh(m), kw = lm_kw(m), wpc = wpc_of(kh), nw = wpc * kw;
+        int dr = m.rs - g.rs, dc = m.cs - g.cs;
+        for (int j = lane; j < nw; j += 32) {
+            int c = j / wpc, w = j - c * wpc;
+            int gc = dc + c;
+            if ((unsigned)gc >= (unsigned)gkw) continue;
+            int gr0 = dr + 16 * w;
+            int lo = max(0, -gr0), hi = min(min(16, kh - 16 * w), gkh - gr0);
+            if (hi <= lo) continue;
+            uint32_t vm = (hi >= 16 ? 0xFFFFFFFFu : ((1u << (2 * hi)) - 1u)) & ~((1u << (2 * lo)) - 1u);
+            uint32_t x = words[m.off + j];
+            uint64_t H = (uint64_t)(x & 0xAAAAAAAAu & vm), Z = (uint64_t)(~x & 0x55555555u & vm);
+            int gw0 = gr0 >> 4, sh = (gr0 & 15) * 2;
+            H <<= sh; Z <<= sh;
+            uint32_t* gp = gwords + g.off + (size_t)gc * gwpc;
+            uint32_t h0 = (uint32_t)H, h1 = (uint32_t)(H >> 32), z0 = (uint32_t)Z, z1 = (uint32_t)(Z >> 32);
+            if (gw0 >= 0 && gw0 < gwpc) { if (h0) atomicOr(gp + gw0, h0); if (z0) atomicAnd(gp + gw0, ~z0); }
+            if (gw0 + 1 >= 0 && gw0 + 1 < gwpc) { if (h1) atomicOr(gp + gw0 + 1, h1); if (z1) atomicAnd(gp + gw0 + 1, ~z1); }
+        }
+    }
+}
+
 // ---- shift!/setshift! (qtrees.jl:267-287): levels <= level move by s*2^(level-i); build list -----
 __global__ void k_apply_shifts(LevelMeta* __restrict__ lm, int L, int n, const int32_t* __restrict__ labels, int level,
                                const int32_t* __restrict__ rs, const int32_t* __restrict__ cs, int add, int2* __restrict__ work) {

@@ -42,11 +42,12 @@ struct stf_ctx {
     DevBuf words, lm, om, payload, poff, woff1, work, lab, lab2, lab3, lab4, bytes_tmp;
     DevBuf rk, rv, rk2, rv2, hist, lkk, lkv;
     DevBuf items, direct, res, overflow, hits, hits2, hk, hv, hk2, hv2, keep, out32, scratch;
-    DevBuf surv, dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
+    DevBuf gwords, glm, surv, dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
     unsigned long long* h_counts = nullptr; int* h_err = nullptr; // pinned
     OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
     int64_t big_cap = 0; int big_ctas = 1;
+    int ground_of = -1; // object whose copy the ground pyramid currently is (stf_ground_compose)
     int shard_rank = 0, shard_n = 1; // item-parallel sharding of the candidate generation (stf_shard_*)
     bool force_big = false; // the single-CTA latency path overflowed once: stay on the multi-launch path
     int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
@@ -151,7 +152,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
@@ -168,20 +169,24 @@ extern "C" int32_t stf_num_levels(const stf_ctx* ctx) { return ctx ? ctx->L : 0;
 __global__ void k_fill_i32(int* __restrict__ p, int n, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 // ------------------------------------------------------------------------------------------------ build helpers
-static int32_t build_big(stf_ctx* ctx, int o, int from) { // levels from+1..L of one big object: wide launches while a level is large, then one CTA
+// levels from+1..L of one big object living in (words, lm) at meta index `mi`: wide launches while a level is large, then one CTA
+static int32_t build_big_on(stf_ctx* ctx, uint32_t* words, LevelMeta* lm, int mi, int kh1, int kw1, int from) {
     static bool attr = false;
     if (!attr) { CK(cudaFuncSetAttribute(k_build_tail_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * (PBM_A + PBM_B)))); attr = true; }
-    auto words_of = [&](int l) { int kh = ((ctx->h_om[o].kh1 - 2) >> (l - 1)) + 2, kw = ((ctx->h_om[o].kw1 - 2) >> (l - 1)) + 2; if (l == 1) { kh = ctx->h_om[o].kh1; kw = ctx->h_om[o].kw1; } return (int64_t)wpc_of(kh) * kw; };
+    auto words_of = [&](int l) { int kh = ((kh1 - 2) >> (l - 1)) + 2, kw = ((kw1 - 2) >> (l - 1)) + 2; if (l == 1) { kh = kh1; kw = kw1; } return (int64_t)wpc_of(kh) * kw; };
     for (int l = from + 1; l <= ctx->L; l++) {
         int64_t nw = words_of(l);
         if (nw <= PBM_A && (l + 1 > ctx->L || words_of(l + 1) <= PBM_B)) { // level l and everything above by one CTA
-            ctx->launches++, k_build_tail_cta<<<1, 512, sizeof(uint32_t) * (PBM_A + PBM_B), ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l - 1, PBM_A);
+            ctx->launches++, k_build_tail_cta<<<1, 512, sizeof(uint32_t) * (PBM_A + PBM_B), ctx->st>>>(words, lm, ctx->L, mi, l - 1, PBM_A);
             break;
         }
-        ctx->launches++, k_build_level_wide<<<std::min(nblk(nw, 256), 148 * 16), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l);
+        ctx->launches++, k_build_level_wide<<<std::min(nblk(nw, 256), 148 * 16), 256, 0, ctx->st>>>(words, lm, ctx->L, mi, l);
     }
     KCHECK();
     return STF_OK;
+}
+static int32_t build_big(stf_ctx* ctx, int o, int from) {
+    return build_big_on(ctx, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), o, ctx->h_om[o].kh1, ctx->h_om[o].kw1, from);
 }
 
 static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics, const int32_t* pitch, const uint8_t* packed, int packed_on_device,
@@ -1092,6 +1097,63 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
     if (nhits) *nhits = nh;
     return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
 }
+// ---- ground composition for place!/reposition!: deepcopy(mask) with every other tree overlapped
+// (qtree_functions.jl:505-518 `for i in 1:length(sortedtrees) if i in indexes continue end; overlap!(ground, sortedtrees[i])`).
+// The parallel part of place! runs on the device; the sequential, RNG-driven room search reads the result on the host.
+extern "C" int32_t stf_ground_compose(stf_ctx* ctx, int32_t mask_label, int32_t n_excl, const int32_t* excl_labels) {
+    NEED_OBJS(); CHECK_LABEL(mask_label);
+    if (ctx->multi_scene) FAIL(STF_E_STATE, "ground composition is defined for one scene");
+    int mo = mask_label - 1, L = ctx->L;
+    std::vector<char> skip((size_t)ctx->n, 0);
+    skip[mo] = 1;
+    for (int i = 0; i < n_excl; i++) { CHECK_LABEL(excl_labels[i]); skip[excl_labels[i] - 1] = 1; }
+    std::vector<int32_t> list; list.reserve(ctx->n);
+    for (int o = 0; o < ctx->n; o++) if (!skip[o]) list.push_back(o);
+    // the ground = a copy of the mask's pyramid (levels are contiguous per object) with its own metas
+    uint32_t base = ctx->h_off[(size_t)mo * L];
+    uint64_t total = 0; { int a = ctx->h_om[mo].kh1, b = ctx->h_om[mo].kw1; for (int l = 1; l <= L; l++) { total += (uint64_t)wpc_of(a) * b; a = a / 2 + 1; b = b / 2 + 1; } }
+    CK(ctx->gwords.ensure(sizeof(uint32_t) * (size_t)(total + 16))); CK(ctx->glm.ensure(sizeof(LevelMeta) * (size_t)L));
+    CK(cudaMemcpyAsync(ctx->gwords.p, ctx->words.as<uint32_t>() + base, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToDevice, ctx->st));
+    std::vector<LevelMeta> hm((size_t)L);
+    CK(cudaMemcpyAsync(hm.data(), ctx->lm.as<LevelMeta>() + (size_t)mo * L, sizeof(LevelMeta) * (size_t)L, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int l = 0; l < L; l++) hm[l].off -= base;
+    CK(stage_h2d(ctx, ctx->glm.p, hm.data(), sizeof(LevelMeta) * (size_t)L));
+    if (!list.empty()) {
+        CK(ctx->lab4.ensure(sizeof(int32_t) * list.size()));
+        CK(stage_h2d(ctx, ctx->lab4.p, list.data(), sizeof(int32_t) * list.size()));
+        int blocks = std::min(nblk((int64_t)list.size() * 32, 256), 148 * 8);
+        ctx->launches++, k_overlap_level1<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->lab4.as<int32_t>(), (int)list.size(),
+                                                                  ctx->gwords.as<uint32_t>(), hm[0]);
+        KCHECK();
+    }
+    // buildqtree!(ground): every upper level from the composed level 1 (shifts unchanged: same chain as the mask's)
+    int32_t r = build_big_on(ctx, ctx->gwords.as<uint32_t>(), ctx->glm.as<LevelMeta>(), 0, ctx->h_om[mo].kh1, ctx->h_om[mo].kw1, 1); if (r) return r;
+    ctx->ground_of = mo;
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_ground_level(stf_ctx* ctx, int32_t l, uint8_t* out, int32_t info[5]) {
+    NEED_OBJS();
+    if (ctx->ground_of < 0) FAIL(STF_E_STATE, "no ground composed");
+    if (l < 1 || l > ctx->L) FAIL(STF_E_ARG, "level out of range");
+    int mo = ctx->ground_of;
+    int kh = ((ctx->h_om[mo].kh1 - 2) >> (l - 1)) + 2, kw = ((ctx->h_om[mo].kw1 - 2) >> (l - 1)) + 2;
+    if (l == 1) { kh = ctx->h_om[mo].kh1; kw = ctx->h_om[mo].kw1; }
+    LevelMeta m;
+    CK(cudaMemcpyAsync(&m, ctx->glm.as<LevelMeta>() + (l - 1), sizeof(m), cudaMemcpyDeviceToHost, ctx->st));
+    size_t nb = (size_t)kh * kw;
+    if (nb && out) {
+        CK(ctx->bytes_tmp.ensure(nb));
+        ctx->launches++, k_unpack_level<<<std::min(nblk((int64_t)nb, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->gwords.as<uint32_t>(), ctx->glm.as<LevelMeta>(), ctx->L, 0, l, ctx->bytes_tmp.as<uint8_t>());
+        KCHECK();
+        CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, nb, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    if (info) { info[0] = kh; info[1] = kw; info[2] = m.rs; info[3] = m.cs; info[4] = ctx->canvas >> (l - 1); }
+    return STF_OK;
+}
+
 // ---- item-parallel sharding of one scene over several GPUs.  Every rank holds an identical replica;
 // rank r of `nranks` generates and tests the candidate pairs of the sorted records r, r+nranks, ...; the local hit
 // lists are exchanged by the caller (one all-gather of fixed-stride buffers per fit iteration, NCCL over NVLink), and

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from helpers import assert_same_trees, device_from_oracle, oracle, pairset, product, rect_scene
+import workloads  # noqa: E402  (helpers puts the repo root on sys.path)
 
 pytestmark = pytest.mark.gpu
 
@@ -482,3 +483,38 @@ def test_pairwise_trainers_filttrain_parity_and_convergence(S, orc):
         ep, nc = S.train(d, 300, trainer=trainer, optimiser=S.Momentum(0.25), seed=2)
         assert nc == 0, (trainer.__name__, ep, nc)
         assert S.totalcollisions(d) == []
+
+
+def test_place_ground_composition_and_room_search(S, orc):
+    """SURVEY §8 f-1.  (a) the device ground (deepcopy(mask) + overlap! of every tree) equals the oracle's sequential
+    overlap!, level by level; (b) place!(qtrees) — device ground, host room search — assigns exactly the shifts of the
+    oracle's place! with the same seed; (c) place!(qtrees, inds) re-places a subset on the ground of all the others."""
+    rng = np.random.default_rng(77)
+    objs = workloads.rect_objects(60, 50, rng)
+    qo = orc.qtrees(objs, mask=np.ones((300, 420), bool))
+    d = device_from_oracle(S, qo)
+    # (b) full placement
+    S.place(d, seed=5)
+    orc.place(qo, 5)
+    rs, cs = d.getshifts()
+    want = np.array([t.getshift() for t in qo])
+    assert np.array_equal(rs, want[:, 0]) and np.array_equal(cs, want[:, 1])
+    assert_same_trees(d, qo, labels=range(1, 12))
+    # (a) ground of everything, against the oracle's overlap! chain
+    g = S.overlap_ground(d)
+    go = qo[0].copy()
+    for t in qo[1:]:
+        orc.overlap(go, t)
+    for l in range(1, len(go) + 1):
+        kh, kw, grs, gcs, _ = go.info(l)
+        codes, hrs, hcs = g.levels[l - 1]
+        assert (codes.shape[0], codes.shape[1], hrs, hcs) == (kh, kw, grs, gcs)
+        assert np.array_equal(codes, go.level(l)), l
+    # (c) re-place three trees on the ground of the others: they land on EMPTY ground cells
+    moved = [7, 21, 40]
+    g_before = S.overlap_ground(d, exclude=moved)
+    S.place(d, moved, seed=9)
+    for lb in moved:
+        t = d[lb - 1]
+        ca, cb = t.getcenter()
+        assert g_before.get(1, ca, cb) == S.EMPTY
