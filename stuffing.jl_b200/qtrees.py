@@ -175,6 +175,7 @@ class DeviceQTrees:
         pics = (C.c_void_p * max(1, self.n))(*[t.codes.ctypes.data for t in trees])
         self._keep = trees
         kh, kw = i32([t.codes.shape[0] for t in trees]), i32([t.codes.shape[1] for t in trees])
+        self.kh1, self.kw1 = kh, kw
         pitch = i32([max(1, t.codes.shape[0]) for t in trees])
         rs, cs = i32([t.shift1[0] for t in trees]), i32([t.shift1[1] for t in trees])
         dflt = np.asarray(self.defaults, np.uint8)
@@ -200,6 +201,7 @@ class DeviceQTrees:
         kh, kw, rs, cs = i32(kh), i32(kw), i32(rs), i32(cs)
         dflt = np.ascontiguousarray(dflt, np.uint8)
         self.n, self.device, self.canvas, self.defaults = len(kh), device, int(canvas), [int(x) for x in dflt]
+        self.kh1, self.kw1 = kh, kw
         im = None if is_mask is None else np.ascontiguousarray(is_mask, np.uint8)
         sc = None if scene is None else i32(scene)
         if payload_dev_ptr is not None:

@@ -112,17 +112,24 @@ def _labels_of(colist):
     return out
 
 
-def trainepoch_E(qts, optimiser=None, clock=None, **_kw):
+def _note(last, colist):
+    """the reference's trainers share one `colist` vector (resource[:colist]); train! reads the LAST list of the epoch"""
+    if last is not None:
+        last["colist"] = colist
+    return colist
+
+
+def trainepoch_E(qts, optimiser=None, clock=None, last=None, **_kw):
     """element-wise trainer  fit.jl:85-99"""
     d = _dev(qts)
-    colist = totalcollisions(d, unique=False, raw=True)
+    colist = _note(last, totalcollisions(d, unique=False, raw=True))
     nc = len(colist)
     if nc == 0:
         return nc
     batchsteps(d, colist, optimiser, clock)
     inds = _labels_of(colist)
     for ni in range(1, len(d) // len(inds) + 1):
-        colist = totalcollisions(d, inds, unique=False, raw=True)
+        colist = _note(last, totalcollisions(d, inds, unique=False, raw=True))
         batchsteps(d, colist, optimiser, clock)
         if ni > 8 * len(colist):
             break
@@ -145,10 +152,10 @@ class LRU:
         return r if firstn is None else r[:firstn]
 
 
-def _em(qts, widen, optimiser, clock, memory: LRU):
+def _em(qts, widen, optimiser, clock, memory: LRU, last=None):
     """the shared shape of trainepoch_EM!/EM2!/EM3!  fit.jl:110-212: nested rounds on LRU-widened label sets"""
     d = _dev(qts)
-    colist = totalcollisions(d, unique=False, raw=True)
+    colist = _note(last, totalcollisions(d, unique=False, raw=True))
     nc = len(colist)
     if nc == 0:
         return nc
@@ -161,7 +168,7 @@ def _em(qts, widen, optimiser, clock, memory: LRU):
                 memory.push(x)
             inds = memory.collect(len(inds) * widen[depth])
         for ni in range(1, 2 * parent_len // max(1, len(inds)) + 1):
-            cl = totalcollisions(d, inds, unique=False, raw=True)
+            cl = _note(last, totalcollisions(d, inds, unique=False, raw=True))
             batchsteps(d, cl, optimiser, clock)
             if ni > 2 * len(cl):
                 break
@@ -174,25 +181,25 @@ def _em(qts, widen, optimiser, clock, memory: LRU):
     return nc
 
 
-def trainepoch_EM(qts, optimiser=None, clock=None, memory=None, **_kw):
-    return _em(qts, [2], optimiser, clock, memory if memory is not None else LRU())
+def trainepoch_EM(qts, optimiser=None, clock=None, memory=None, last=None, **_kw):
+    return _em(qts, [2], optimiser, clock, memory if memory is not None else LRU(), last)
 
 
-def trainepoch_EM2(qts, optimiser=None, clock=None, memory=None, **_kw):
-    return _em(qts, [4, 2], optimiser, clock, memory if memory is not None else LRU())
+def trainepoch_EM2(qts, optimiser=None, clock=None, memory=None, last=None, **_kw):
+    return _em(qts, [4, 2], optimiser, clock, memory if memory is not None else LRU(), last)
 
 
-def trainepoch_EM3(qts, optimiser=None, clock=None, memory=None, **_kw):
-    return _em(qts, [8, 4, 2], optimiser, clock, memory if memory is not None else LRU())
+def trainepoch_EM3(qts, optimiser=None, clock=None, memory=None, last=None, **_kw):
+    return _em(qts, [8, 4, 2], optimiser, clock, memory if memory is not None else LRU(), last)
 
 
-def trainepoch_D(qts, optimiser=None, clock=None, moved: DynamicColliders | None = None, loops=10, **_kw):
+def trainepoch_D(qts, optimiser=None, clock=None, moved: DynamicColliders | None = None, loops=10, last=None, **_kw):
     """dynamic trainer  fit.jl:224-233"""
     d = _dev(qts)
     moved = moved if moved is not None else DynamicColliders(d)
     colist = []
     for _ in range(loops):
-        colist = moved.dynamiccollisions(unique=False, raw=True)
+        colist = _note(last, moved.dynamiccollisions(unique=False, raw=True))
         if len(colist) == 0:
             return 0
         batchsteps(d, colist, optimiser, clock)
@@ -226,11 +233,12 @@ def _allpairs(n):
     return [(i, j) for i in range(1, n + 1) for j in range(i + 1, n + 1)]
 
 
-def trainepoch_P(qts, optimiser=None, clock=None, nearlevel=None, **_kw):
+def trainepoch_P(qts, optimiser=None, clock=None, nearlevel=None, last=None, **_kw):
     """pairwise trainer  fit.jl:268-296"""
     d = _dev(qts)
     nearlevel = min(-1, -d.nlevels / 2 if nearlevel is None else nearlevel)
     indpairs, nearlist, colist = _allpairs(len(d)), [], []
+    _note(last, colist)
     nc = filttrain(d, indpairs, nearlist, nearlevel, optimiser, clock)
     if nc == 0:
         return 0
@@ -252,6 +260,7 @@ def trainepoch_P2(qts, optimiser=None, clock=None, nearlevel1=None, nearlevel2=N
     nearlevel1 = min(-1, -d.nlevels * 0.75 if nearlevel1 is None else nearlevel1)
     nearlevel2 = min(-1, -d.nlevels * 0.5 if nearlevel2 is None else nearlevel2)
     indpairs, nearlist1, nearlist2, colist = _allpairs(len(d)), [], [], []
+    _note(_kw.get("last"), colist)
     nc = filttrain(d, indpairs, nearlist1, nearlevel1, optimiser, clock)
     if nc == 0:
         return 0
@@ -286,6 +295,7 @@ def trainepoch_Px(qts, optimiser=None, clock=None, levelpools_=None, **_kw):
     near as the next pool's level"""
     d = _dev(qts)
     pools = levelpools(d) if levelpools_ is None else levelpools_
+    _note(_kw.get("last"), pools[-1][1] if pools else [])
     nc = 0
     if not pools:
         return nc
@@ -309,45 +319,193 @@ _DEFAULTS = {trainepoch_E: (20, 2000), trainepoch_EM: (10, 1000), trainepoch_EM2
              trainepoch_P: (10, 100), trainepoch_P2: (2, 100), trainepoch_Px: (10, 1000)}
 
 
+class MonotoneIndicator:
+    """MonotoneIndicator{Int}  fit_helper.jl:102-118"""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.min, self.age = None, 0
+
+    def update(self, v):
+        self.age += 1
+        if self.min is None or v < self.min:
+            self.age, self.min = 0, v
+
+
+def _pairs_of(colist):
+    """first.(colist): a trainer's list holds CoItems (structured rows) or bare pairs"""
+    if isinstance(colist, np.ndarray):
+        return [(int(r["i1"]), int(r["i2"])) for r in colist]
+    return [(int(p[0][0]), int(p[0][1])) if isinstance(p[0], (tuple, list)) else (int(p[0]), int(p[1])) for p in colist]
+
+
+def outofkernelbounds(qts, mask_label=1):
+    """outofkernelbounds(mask, qtrees[2:end]) .+ 1  qtrees.jl:298-306: labels whose CENTRE lies outside the mask kernel"""
+    d = _dev(qts)
+    rs, cs = d.getshifts()
+    ca, cb = rs + np.asarray(d.kh1) // 2, cs + np.asarray(d.kw1) // 2
+    m = mask_label - 1
+    inside = (ca > rs[m]) & (ca <= rs[m] + d.kh1[m]) & (cb > cs[m]) & (cb <= cs[m] + d.kw1[m])
+    return [int(i) + 1 for i in np.flatnonzero(~inside) if i != m]
+
+
+def select_coinds(qts, colist, rng, from_=lambda i: True, force=False):
+    """select_coinds  fit.jl:378-418: about 1/8 of the colliding pairs (those with the largest labels first) nominate
+    their larger label for re-placement if a deterministic DFS still finds them colliding.  Canonical mode: randexp from
+    the sequential generator of place!."""
+    d = _dev(qts)
+    pairs = _pairs_of(colist)
+    n = len(pairs)
+    if n == 0:
+        return []
+    import math
+    keep = [(n / 8.0 * -math.log(1.0 - rng.f64())) > k for k in range(1, n + 1)]
+    order = sorted(range(n), key=lambda k: -max(pairs[k]))  # sort!(colist, by=maximum, rev=true): stable
+    pairs = [pairs[k] for k in order]
+    L = d.nlevels
+    arr = np.zeros(n, _lib.ITEM_DT)
+    arr["i1"], arr["i2"], arr["l"], arr["a"], arr["b"] = [p[0] for p in pairs], [p[1] for p in pairs], L, 1, 1
+    out = np.zeros(n, _lib.ITEM_DT)
+    d._ck(d.lib.stf_collision_dfs(d.h, n, ptr(arr), ptr(out)))
+    hit = out["l"] >= 0
+    selected = []
+    for k in range(n):
+        if keep[k]:
+            mij = max(pairs[k])
+            if mij in selected or not from_(mij - 1):
+                continue
+            if hit[k]:
+                selected.append(mij)
+    if not selected:
+        for k in range(n):
+            if not keep[k]:
+                mij = max(pairs[k])
+                if not from_(mij - 1):
+                    continue
+                if force or hit[k]:
+                    selected.append(mij)
+                    break
+    return selected
+
+
+def reposition(qts, colist=None, rng=None, from_=lambda i: True, force=False):
+    """reposition!  fit.jl:420-436: trees whose centre left the mask kernel are re-placed first; otherwise the trees
+    select_coinds nominates.  place! = ground composition on the device + room search on the host (place.py)."""
+    from .place import Rng, place
+    d = _dev(qts)
+    rng = rng if rng is not None else Rng(0)
+    out = outofkernelbounds(d)
+    if out:
+        place(d, out, seed=rng.u64())
+        return out
+    if colist is not None:
+        sel = select_coinds(d, colist, rng, from_=from_, force=force)
+        if sel:
+            place(d, sel, seed=rng.u64())
+        return sel
+    return out
+
+
+def randommove(qts, colist, rng):
+    """randommove!  fit.jl:437-448: a random diagonal shift of the larger tree of the last (≤ 3) pairs in label order"""
+    d = _dev(qts)
+    rows = list(colist) if not isinstance(colist, np.ndarray) else [r for r in colist]
+    pairs = _pairs_of(colist)
+    order = sorted(range(len(pairs)), key=lambda k: -max(pairs[k]))
+    sel = order[max(0, len(order) - 3):]
+    moved = []
+    for k in sel:
+        lb = max(pairs[k])
+        lvl = 1
+        if isinstance(colist, np.ndarray):
+            lvl = max(1, int(rows[k]["l"]) - 1)
+        s1 = 1 if rng.u64() & 1 else -1
+        s2 = 1 if rng.u64() & 1 else -1
+        d.shift([lb], lvl, [s1], [s2])
+        moved.append(lb)
+    return moved
+
+
 def train(qts, epochs=-1, trainer=trainepoch_EM2, patience=None, optimiser=None, scheduler=lambda lr: lr * 0.5 ** 0.5,
-          callback=lambda ep: None, seed=0):
-    """train!/fit!  fit.jl:450-552 without the repositioning policy (place! is host-side and out of the
-    hot-path scope): epochs, the η scheduler on stagnation and the global early break."""
+          callback=lambda ep: None, callback_pre=lambda ep: None, reposition_=True, seed=0, **kargs):
+    """train!/fit!  fit.jl:450-552, policy included: epochs, the repositioning of stuck trees (reposition!, forced after
+    repeats, randommove!), out-of-bounds recovery, the η scheduler on stagnation and the global early break.
+    `reposition_`: bool | float in [0,1] | int | collection of indices | predicate, as the reference's `reposition`."""
+    from .place import Rng
     d = _dev(qts)
     optimiser = optimiser if optimiser is not None else Momentum(0.25)
     pat0, ep0 = _DEFAULTS.get(trainer, (10, 1000))
     patience = pat0 if patience is None else patience
     epochs = ep0 if epochs < 0 else epochs
-    clock = StepClock(seed)
-    res = {}
+    flag = True
+    if callable(reposition_):
+        from_ = reposition_
+    elif isinstance(reposition_, bool):
+        from_, flag = (lambda i: reposition_), reposition_
+    elif isinstance(reposition_, float):
+        assert 0 <= reposition_ <= 1
+        th = (len(d) - 1) * (1 - reposition_)
+        from_ = lambda i: i >= th  # noqa: E731
+    elif isinstance(reposition_, int):
+        from_ = lambda i: i >= reposition_  # noqa: E731
+    else:
+        rset = set(reposition_)
+        from_ = lambda i: i in rset  # noqa: E731
+    clock, rng = StepClock(seed), Rng(seed ^ 0x5EED)
+    res, last = {}, {"colist": []}
     if trainer in (trainepoch_EM, trainepoch_EM2, trainepoch_EM3):
         res["memory"] = LRU()
     if trainer is trainepoch_D:
         res["moved"] = DynamicColliders(d)
-    best_s, age_s, best_g, age_g = None, 0, None, 0
+    if trainer is trainepoch_Px:
+        res["levelpools_"] = levelpools(d)
+    moved = res.get("moved")
+    indi_r, indi_g, indi_s = MonotoneIndicator(), MonotoneIndicator(), MonotoneIndicator()
     eta_list = []
+    reposition_count, last_repositioned = 0, None
     ep = nc = 0
     while ep < epochs:
-        nc = trainer(d, optimiser=optimiser, clock=clock, **res)
+        callback_pre(ep)
+        nc = trainer(d, optimiser=optimiser, clock=clock, last=last, **res, **kargs)
+        colist = last["colist"] if last["colist"] is not None else []
         ep += 1
-        age_s += 1
-        age_g += 1
-        if best_s is None or nc < best_s:
-            best_s, age_s = nc, 0
-        if best_g is None or nc < best_g:
-            best_g, age_g = nc, 0
+        indi_r.update(nc); indi_g.update(nc); indi_s.update(nc)
+        if nc != 0 and flag and len(d) / 20 > len(colist) > 0 and patience > 0 and (indi_r.age >= patience or indi_r.age > len(colist)):
+            force = reposition_count >= 2
+            repositioned = reposition(d, colist, rng, from_=from_, force=force)
+            if repositioned:
+                indi_r.reset()
+                reset(optimiser, d, repositioned)
+                if moved is not None:
+                    moved.union(repositioned)
+            rset_now = set(repositioned)
+            reposition_count = reposition_count + 1 if last_repositioned == rset_now else 0
+            last_repositioned = rset_now
+            if reposition_count >= 1:
+                if reposition_count >= 10:
+                    break  # the repositioning strategy failed
+                rm = randommove(d, colist, rng)
+                if moved is not None:
+                    moved.union(rm)
         callback(ep)
         if nc == 0:
-            break
-        if age_s > max(1, patience, epochs / 50):
-            if not eta_list or best_s < eta_list[-1][1]:
-                eta_list.append((optimiser.eta, best_s))
+            outlabels = reposition(d, None, rng)
+            if not outlabels:
+                break
+            nc += len(outlabels)
+            if moved is not None:
+                moved.union(outlabels)
+        if indi_s.age > max(1, patience, epochs / 50):
+            if not eta_list or indi_s.min < eta_list[-1][1] or (indi_s.min == eta_list[-1][1] and rng.f64() > 0.5):
+                eta_list.append((optimiser.eta, indi_s.min))
                 set_eta(optimiser, scheduler(optimiser.eta))
             else:
                 last_eta, _ = eta_list.pop()
                 set_eta(optimiser, last_eta)
-            best_s, age_s = None, 0
-        if age_g > max(2, 2 * patience, epochs / 50 * max(1, len(d) / max(1, best_g))):
+            indi_s.reset()
+        if indi_g.age > max(2, 2 * patience, epochs / 50 * max(1, len(d) / max(1, indi_g.min))):
             break
     return ep, nc
 

@@ -518,3 +518,34 @@ def test_place_ground_composition_and_room_search(S, orc):
         t = d[lb - 1]
         ca, cb = t.getcenter()
         assert g_before.get(1, ca, cb) == S.EMPTY
+
+
+def test_train_policy_reposition(S, orc):
+    """the policy layer of train! (fit.jl:378-552) over the device path: out-of-bounds recovery through
+    place!, select_coinds nominations, randommove!, and convergence of a crowded scene with repositioning switched on."""
+    t = S.trainer
+    from stuffing_b200.place import Rng
+    qo = rect_scene(orc, 50, 31, sz=60, masksize=(420, 420))
+    d = device_from_oracle(S, qo)
+    assert t.outofkernelbounds(d) == []
+    d.setshift([5, 9], 1, [-500, 3000], [-500, 40])           # centres far outside the mask kernel
+    assert t.outofkernelbounds(d) == [5, 9]
+    assert t.reposition(d, None, Rng(3)) == [5, 9] and t.outofkernelbounds(d) == []
+    # nominations: labels of colliding pairs only, the larger label of a pair, each at most once; `force` always names one
+    d.setshift(list(range(2, 12)), 1, [200] * 10, [200] * 10)  # pile ten trees up
+    colist = S.totalcollisions(d, unique=False, raw=True)
+    assert len(colist) > 10
+    sel = t.select_coinds(d, colist, Rng(1))
+    big = {max(int(r["i1"]), int(r["i2"])) for r in colist}
+    assert len(sel) == len(set(sel)) and set(sel) <= big
+    assert len(t.select_coinds(d, colist[:1], Rng(2), force=True)) == 1
+    before = d.getshifts()
+    moved = t.randommove(d, colist, Rng(4))
+    after = d.getshifts()
+    assert 1 <= len(moved) <= 3 and any(before[0][m - 1] != after[0][m - 1] for m in moved)
+    # a crowded scene (more area than a plain fit resolves quickly): the full policy reaches 0 collisions, everything inside
+    qo = rect_scene(orc, 45, 32, sz=70, masksize=(360, 360))
+    d = device_from_oracle(S, qo)
+    d.setshift(list(range(2, 47)), 1, [180] * 45, [180] * 45)
+    ep, nc = S.train(d, 600, trainer=t.trainepoch_EM2, optimiser=S.Momentum(0.25), patience=5, seed=6)
+    assert nc == 0 and S.totalcollisions(d) == [] and t.outofkernelbounds(d) == [], (ep, nc)
