@@ -7,6 +7,7 @@
 #pragma once
 #include "stf_common.cuh"
 #include "stf_blocksort.cuh"
+#include "stf_clustersort.cuh"
 
 #define STF_ST_RETRY_GROW 1   // an output buffer was too small: grow and re-run the round
 #define STF_ST_RETRY_BIG 2    // too many records / hits for the single-CTA kernels: use the multi-launch path
@@ -41,6 +42,38 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_records(const uint64_t* __r
         vals_out[e] = val_map ? (uint32_t)val_map[v] : v;
     }
     if (threadIdx.x == 0) *n_out = (unsigned long long)n;
+}
+
+// the same on a thread-block cluster (8 CTAs): CTA c sorts and writes the records [c*P, (c+1)*P)
+__global__ void __cluster_dims__(CS_CTAS, 1, 1) __launch_bounds__(CS_THREADS) k_sort_records_cl(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ tie_in,
+                                                             const unsigned long long* __restrict__ n_dev, int64_t cap, int key_bits, int vbits,
+                                                             const int32_t* __restrict__ val_map, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                             unsigned long long* __restrict__ n_out, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ClusterSortSmem& S = *reinterpret_cast<ClusterSortSmem*>(smem_raw);
+    const int c = (int)cg::this_cluster().block_rank();
+    int64_t n64 = (int64_t)*n_dev;
+    if (n64 > cap || n64 > CS_CAP) {
+        if (c == 0 && threadIdx.x == 0) { atomicOr(status, STF_ST_RETRY_BIG); *n_out = 0; }
+        return;
+    }
+    const int n = (int)n64, P = cs_slice(n), nl = min(max(n - c * P, 0), P);
+    uint64_t x[CS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; j++) {
+        int e = cs_local(j);
+        x[j] = 0;
+        if (e < nl) x[j] = (keys_in[c * P + e] << vbits) | (uint64_t)tie_in[c * P + e];
+    }
+    cs_sort(S, x, n, 0, key_bits + vbits);
+    const uint64_t vmask = (1ull << vbits) - 1;
+    for (int e = threadIdx.x; e < nl; e += CS_THREADS) {
+        uint64_t p = S.buf[e];
+        uint32_t v = (uint32_t)(p & vmask);
+        keys_out[c * P + e] = p >> vbits;
+        vals_out[c * P + e] = val_map ? (uint32_t)val_map[v] : v;
+    }
+    if (c == 0 && threadIdx.x == 0) *n_out = (unsigned long long)n;
 }
 
 struct FinalizeArgs {

@@ -478,6 +478,7 @@ static void set_smem_attrs() {
     static bool done = false;
     if (done) return;
     cudaFuncSetAttribute(k_sort_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
+    cudaFuncSetAttribute(k_sort_records_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BYTES);
     cudaFuncSetAttribute(k_finalize_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
     cudaFuncSetAttribute(k_step_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
     done = true;
@@ -735,8 +736,12 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
         }
         KCHECK();
         stage_begin(ctx, STF_STAGE_SORT);
-        ctx->launches++, k_sort_records<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
-                                                                                  linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, ctx->errflag.as<int>() + 1);
+        if (getenv("STF_NO_CLUSTER")) // single-CTA variant (kept for comparison)
+            ctx->launches++, k_sort_records<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
+                                                                                      linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, ctx->errflag.as<int>() + 1);
+        else // one cluster of 8 CTAs
+            ctx->launches++, k_sort_records_cl<<<CS_CTAS, CS_THREADS, CS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
+                                                                                               linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, ctx->errflag.as<int>() + 1);
         KCHECK();
         *keys = ctx->rk.as<uint64_t>(); *vals = ctx->rv.as<uint32_t>();
         stage_end(ctx);
