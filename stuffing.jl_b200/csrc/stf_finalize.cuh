@@ -218,3 +218,80 @@ __global__ void __launch_bounds__(BS_THREADS) k_step_links(const Item16* __restr
     fin_step_links(S, list, n, lb, om, prev, done);
     if (threadIdx.x == 0) *ticket = 0;
 }
+
+// ---- the fit-round finalize on a thread-block cluster (no export): sort!(hits) -> canonical order -> tie order ->
+// step-dependency links.  CTA c owns slice c of every sorted sequence; neighbours across a slice boundary are read from
+// global memory (sorted keys) or from the previous CTA's shared memory (endpoint records).
+__global__ void __cluster_dims__(CS_CTAS, 1, 1) __launch_bounds__(CS_THREADS) k_finalize_prep_cl(FinalizeArgs A, uint64_t* __restrict__ skey) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ClusterSortSmem& S = *reinterpret_cast<ClusterSortSmem*>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    int64_t nh64 = (int64_t)*A.nh_dev;
+    bool grow = nh64 > A.hits_cap || (A.n_items_dev && (int64_t)*A.n_items_dev > A.item_cap);
+    bool big = nh64 > CS_CAP / 2;
+    if (grow || big) {
+        if (c == 0 && threadIdx.x == 0) { atomicOr(A.status, grow ? STF_ST_RETRY_GROW : STF_ST_RETRY_BIG); *A.n_steps = 0; *A.ticket = 0; }
+        return;
+    }
+    const int n = (int)nh64, lb = A.label_bits;
+    uint64_t x[CS_ITEMS];
+    { // ---- sort by (i1, i2); payload = position in the unordered list
+        const int P = cs_slice(n), nl = min(max(n - c * P, 0), P);
+#pragma unroll
+        for (int j = 0; j < CS_ITEMS; j++) {
+            int e = cs_local(j);
+            x[j] = 0;
+            if (e < nl) { Item16 h = A.hits[c * P + e]; x[j] = ((uint64_t)(uint32_t)h.i1 << (lb + FIN_IDX_BITS)) | ((uint64_t)(uint32_t)item_i2(h) << FIN_IDX_BITS) | (uint64_t)(c * P + e); }
+        }
+        cs_sort(S, x, n, FIN_IDX_BITS, FIN_IDX_BITS + 2 * lb);
+        for (int e = threadIdx.x; e < nl; e += CS_THREADS) { // gather into canonical order; keys to global for the neighbours
+            uint64_t p = S.buf[e];
+            A.sorted[c * P + e] = A.hits[(uint32_t)(p & ((1u << FIN_IDX_BITS) - 1))];
+            skey[c * P + e] = p >> FIN_IDX_BITS;
+        }
+        cluster.sync();
+        for (int e = threadIdx.x; e < nl; e += CS_THREADS) { // order each run of one ordered pair by (l,a,b)
+            int p = c * P + e;
+            uint64_t key = skey[p];
+            if (p > 0 && skey[p - 1] == key) continue;
+            int q = p + 1;
+            while (q < n && skey[q] == key) q++;
+            for (int i = p + 1; i < q; i++) {
+                Item16 v = A.sorted[i]; int y = i - 1;
+                while (y >= p && fin_lab_less(v, A.sorted[y])) { A.sorted[y + 1] = A.sorted[y]; y--; }
+                A.sorted[y + 1] = v;
+            }
+        }
+        cluster.sync();
+    }
+    { // ---- endpoints (step p, side s) sorted by object, stable in list order -> prev links
+        const int n2 = 2 * n, P = cs_slice(n2), nl = min(max(n2 - c * P, 0), P);
+#pragma unroll
+        for (int j = 0; j < CS_ITEMS; j++) {
+            int e = cs_local(j);
+            x[j] = 0;
+            if (e < nl) {
+                int g = c * P + e;
+                Item16 h = A.sorted[g >> 1];
+                uint32_t o = (uint32_t)((g & 1) ? item_i2(h) : h.i1) - 1u;
+                uint64_t ok = A.om[o].is_mask ? (1ull << lb) : (uint64_t)o;
+                x[j] = (ok << FIN_IDX_BITS) | (uint64_t)g;
+            }
+        }
+        cs_sort(S, x, n2, FIN_IDX_BITS, FIN_IDX_BITS + lb + 1);
+        for (int e = threadIdx.x; e < nl; e += CS_THREADS) {
+            uint64_t cur = S.buf[e];
+            uint64_t ok = cur >> FIN_IDX_BITS; uint32_t g = (uint32_t)(cur & ((1u << FIN_IDX_BITS) - 1));
+            uint32_t pv = 0;
+            if (ok != (1ull << lb) && (e > 0 || c > 0)) {
+                uint64_t pr = e > 0 ? S.buf[e - 1] : cluster.map_shared_rank(&S, c - 1)->buf[P - 1]; // the slice before is full
+                if ((pr >> FIN_IDX_BITS) == ok) pv = ((uint32_t)(pr & ((1u << FIN_IDX_BITS) - 1)) >> 1) + 1;
+            }
+            A.prev[g] = pv;
+        }
+        for (int p = c * CS_THREADS + threadIdx.x; p < n; p += CS_CTAS * CS_THREADS) A.done[p] = 0;
+        if (c == 0 && threadIdx.x == 0) { *A.ticket = 0; *A.n_steps = (unsigned long long)n; }
+        cluster.sync(); // nobody leaves while a neighbour may still read its shared memory
+    }
+}

@@ -479,6 +479,7 @@ static void set_smem_attrs() {
     if (done) return;
     cudaFuncSetAttribute(k_sort_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
     cudaFuncSetAttribute(k_sort_records_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BYTES);
+    cudaFuncSetAttribute(k_finalize_prep_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BYTES);
     cudaFuncSetAttribute(k_finalize_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
     cudaFuncSetAttribute(k_step_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
     done = true;
@@ -1086,7 +1087,11 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
         F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
         F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
         F.status = ctx->errflag.as<int>() + 1;
-        ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
+        if (getenv("STF_NO_CLUSTER")) ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
+        else {
+            CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)(CS_CAP + 1024)));
+            ctx->launches++, k_finalize_prep_cl<<<CS_CTAS, CS_THREADS, CS_SMEM_BYTES, ctx->st>>>(F, ctx->hk.as<uint64_t>());
+        }
         KCHECK();
         r = launch_steps(ctx, ctx->hits2.as<Item16>(), std::max<int64_t>(ctx->ctr.hits, 2048), ctx->counts.as<unsigned long long>() + C_NSTEPS, seed, iteration); if (r) return r;
         r = sync_counts(ctx); if (r) return r;
