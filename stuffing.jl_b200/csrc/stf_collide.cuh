@@ -263,7 +263,7 @@ __global__ void k_native_pairs(const int32_t* __restrict__ flt, const int* __res
 // order; a ballot finds the first FULL code (= the node the sequential BFS returns) and an ordered
 // ballot/popc compaction appends the MIX children to the next frontier.
 // Frontier entries are (alpha,beta) offsets below the start node: a = at.a*2^d - alpha.
-#define NP_GROUP 8
+#define NP_GROUP 4
 #define NP_FCAP 64
 #define NP_THREADS 128
 
