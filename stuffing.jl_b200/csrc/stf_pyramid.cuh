@@ -65,6 +65,50 @@ __device__ __forceinline__ int tail_level(int kh, int kw, int L) { // first leve
     while ((kh > 16 || kw > 8) && t < L) { kh = kh / 2 + 1; kw = kw / 2 + 1; t++; }
     return t;
 }
+// Thread-per-object tail of a (re)build: starting from level `from` (whose raster and every raster up to the first
+// level T with kh <= 16 and kw <= 8 are valid in memory) one THREAD builds the levels T+1..L of its object: the whole
+// level lives in 8 registers, a level is 5 x (two selects per child column, pair-OR, 2-bit compress).
+// KEEP: the per-level shifts are state and are read from the metas (lazy batchsteps); otherwise shift_l = shift_{l-1} / 2.
+template <bool KEEP> __device__ __forceinline__ void thread_tail_build(uint32_t* __restrict__ words, const LevelMeta* __restrict__ olm, int L, int from) {
+    LevelMeta m = olm[from - 1];
+    int kh = lm_kh(m), kw = lm_kw(m), rs = m.rs, cs = m.cs, t = from;
+    uint32_t off = m.off; const uint32_t d = lm_dflt(m), dw = dflt_word(d);
+    while ((kh > 16 || kw > 8) && t < L) {
+        off += (uint32_t)(wpc_of(kh) * kw); kh = kh / 2 + 1; kw = kw / 2 + 1; t++;
+        if (KEEP) { LevelMeta x = olm[t - 1]; rs = x.rs; cs = x.cs; } else { rs /= 2; cs /= 2; }
+    }
+    if (!(t < L && kh <= 16 && kw <= 8)) return;
+    uint32_t cur[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cur[i] = i < kw ? words[off + i] : dw;
+    for (int l = t + 1; l <= L; l++) {
+        int prs = rs / 2, pcs = cs / 2; // qtrees.jl:225-226 (÷ truncates toward zero)
+        if (KEEP) { LevelMeta x = olm[l - 1]; prs = x.rs; pcs = x.cs; }
+        int er = rs - 2 * prs, ec = cs - 2 * pcs, kwp = kw / 2 + 1;
+        uint32_t poff_ = off + (uint32_t)kw; // one word per column at these sizes
+        uint32_t nxt[5];
+#pragma unroll
+        for (int pc = 0; pc < 5; pc++) {
+#define STF_COL(i) (((i) >= 0 && (i) < 8 && (i) < kw) ? cur[((i) >= 0 && (i) < 8) ? (i) : 0] : dw)
+            uint32_t w0 = sel3(ec, STF_COL(2 * pc - 1), STF_COL(2 * pc), STF_COL(2 * pc + 1));
+            uint32_t w1 = sel3(ec, STF_COL(2 * pc), STF_COL(2 * pc + 1), STF_COL(2 * pc + 2));
+#undef STF_COL
+            uint64_t y = ((uint64_t)dw << 32) | (w0 | w1);
+            if (er > 0) y = (y << 2) | d; else if (er < 0) y = (y >> 2) | ((uint64_t)d << 62);
+            nxt[pc] = compress_pairs(y);
+            if (pc < kwp) words[poff_ + pc] = nxt[pc];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) cur[i] = i < 5 ? nxt[i < 5 ? i : 0] : dw;
+        off = poff_; kh = kh / 2 + 1; kw = kwp; rs = prs; cs = pcs;
+    }
+}
+// first level >= from that the thread tail can take over (or L)
+__device__ __forceinline__ int tail_level_from(int kh, int kw, int L, int from) { // (kh, kw) = dims of level `from`
+    int t = from;
+    while ((kh > 16 || kw > 8) && t < L) { kh = kh / 2 + 1; kw = kw / 2 + 1; t++; }
+    return t;
+}
 __global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ poff, const int32_t* __restrict__ list, int nlist,
                                                           uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L, int* __restrict__ err) {
     __shared__ uint32_t sbuf[8][2 * RB_HALF];
@@ -98,37 +142,7 @@ __global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restr
             __syncwarp();
         }
         // ---- phase B: lane k finishes object k
-        if (my_o >= 0) {
-            LevelMeta m1 = lm[(size_t)my_o * L];
-            int kh = lm_kh(m1), kw = lm_kw(m1), rs = m1.rs, cs = m1.cs, t = 1;
-            uint32_t off = m1.off; const uint32_t d = lm_dflt(m1), dw = dflt_word(d);
-            while ((kh > 16 || kw > 8) && t < L) { off += (uint32_t)(wpc_of(kh) * kw); kh = kh / 2 + 1; kw = kw / 2 + 1; rs /= 2; cs /= 2; t++; }
-            if (t < L && kh <= 16 && kw <= 8) {
-                uint32_t cur[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) cur[i] = i < kw ? words[off + i] : dw;
-                for (int l = t + 1; l <= L; l++) {
-                    int prs = rs / 2, pcs = cs / 2; // qtrees.jl:225-226 (÷ truncates toward zero)
-                    int er = rs - 2 * prs, ec = cs - 2 * pcs, kwp = kw / 2 + 1;
-                    uint32_t poff_ = off + (uint32_t)kw; // one word per column at these sizes
-                    uint32_t nxt[5];
-#pragma unroll
-                    for (int pc = 0; pc < 5; pc++) {
-#define STF_COL(i) (((i) >= 0 && (i) < 8 && (i) < kw) ? cur[((i) >= 0 && (i) < 8) ? (i) : 0] : dw)
-                        uint32_t w0 = sel3(ec, STF_COL(2 * pc - 1), STF_COL(2 * pc), STF_COL(2 * pc + 1));
-                        uint32_t w1 = sel3(ec, STF_COL(2 * pc), STF_COL(2 * pc + 1), STF_COL(2 * pc + 2));
-#undef STF_COL
-                        uint64_t y = ((uint64_t)dw << 32) | (w0 | w1);
-                        if (er > 0) y = (y << 2) | d; else if (er < 0) y = (y >> 2) | ((uint64_t)d << 62);
-                        nxt[pc] = compress_pairs(y);
-                        if (pc < kwp) words[poff_ + pc] = nxt[pc];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) cur[i] = i < 5 ? nxt[i < 5 ? i : 0] : dw;
-                    off = poff_; kh = kh / 2 + 1; kw = kwp; rs = prs; cs = pcs;
-                }
-            }
-        }
+        if (my_o >= 0) thread_tail_build<false>(words, lm + (size_t)my_o * L, L, 1);
         __syncwarp();
     }
     if (bad) atomicOr(err, 1);
@@ -190,16 +204,30 @@ template <int THREADS> __global__ void __launch_bounds__(THREADS) k_pack_build_m
 #define PBM_A 16384   // largest level 2 (words) a CTA stages; beyond that the object is built by wide launches
 #define PBM_B 4608
 
-// ---- warp-per-object build: worklist entry = (object, from_level): levels from+1..L ------------
+// ---- warp-per-object build: worklist entry = (object, from_level): levels from+1..L.  32 entries per warp: the levels
+// with real width by the whole warp (warp_rebuild), the tail levels by one thread per entry (thread_tail_build) ----------
 __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L,
-                                const int2* __restrict__ work, int nwork, const ObjMeta* __restrict__ om, int skip_big) {
+                                const int2* __restrict__ work, int nwork, const ObjMeta* __restrict__ om, int skip_big, int grp) {
     __shared__ uint32_t sbuf[8][2 * RB_HALF]; // blockDim.x == 256
+    const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = warp; i < nwork; i += nwarps) {
-        int2 w = work[i];
-        if (skip_big && om[w.x].big) continue;
-        if (w.y < L) rebuild_levels_warp<false>(words, lm, w.x, L, w.y, lane, sbuf[threadIdx.x >> 5]);
+    for (int g = warp; g * grp < nwork; g += nwarps) { // grp (1..32) entries per warp: few entries -> more warps, shorter chains
+        int my_i = g * grp + lane;
+        int2 mine_w = (lane < grp && my_i < nwork) ? work[my_i] : make_int2(-1, 0);
+        if (mine_w.x >= 0 && ((skip_big && om[mine_w.x].big) || mine_w.y >= L)) mine_w.x = -1;
+        for (int k = 0; k < grp; k++) {
+            int o = __shfl_sync(FULLM, mine_w.x, k), from = __shfl_sync(FULLM, mine_w.y, k);
+            if (o < 0) continue;
+            LevelMeta mine = {};
+            if (lane < L) mine = lm[(size_t)o * L + lane];
+            LevelMeta mf = shfl_meta(mine, from - 1);
+            int T = grp >= 4 ? tail_level_from(lm_kh(mf), lm_kw(mf), L, from) : L; // a thread tail pays off from ~4 objects per warp
+            mine = warp_rebuild<false>(words, mine, L, from, lane, sbuf[threadIdx.x >> 5], T);
+            if (lane >= from && lane < L) lm[(size_t)o * L + lane] = mine;
+            __syncwarp();
+        }
+        if (grp >= 4 && mine_w.x >= 0) thread_tail_build<false>(words, lm + (size_t)mine_w.x * L, L, mine_w.y);
         __syncwarp();
     }
 }

@@ -259,18 +259,28 @@ __global__ void __launch_bounds__(128) k_batchsteps(StepArgs A) {
     }
 }
 
-// after the batch: one warp per object, rebuild the rasters of the levels above dirty[o] with the tracked shifts
-__global__ void __launch_bounds__(256) k_materialize(uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, int n, int* __restrict__ dirty) {
+// after the batch: rebuild the rasters of the levels above dirty[o] with the tracked shifts.  32 objects per warp: the
+// levels with real width by the whole warp, the tail levels by one thread per object.
+__global__ void __launch_bounds__(256) k_materialize(uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, int n, int* __restrict__ dirty, int grp) {
     __shared__ uint32_t sbuf[8][2 * RB_HALF];
+    const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int o = warp; o < n; o += nwarps) {
-        int m = dirty[o];
-        if (m >= L) continue;
-        LevelMeta mine = {};
-        if (lane < L) mine = ldmeta<false>(lm + (size_t)o * L + lane);
-        warp_rebuild<false, true>(words, mine, L, m, lane, sbuf[threadIdx.x >> 5]);
+    for (int g = warp; g * grp < n; g += nwarps) { // grp (1..32) objects per warp
+        int o_mine = g * grp + lane;
+        int m_mine = (lane < grp && o_mine < n) ? dirty[o_mine] : L;
+        unsigned todo = __ballot_sync(FULLM, m_mine < L);
+        while (todo) {
+            int k = __ffs(todo) - 1; todo &= todo - 1;
+            int o = g * grp + k, m = __shfl_sync(FULLM, m_mine, k);
+            LevelMeta mine = {};
+            if (lane < L) mine = ldmeta<false>(lm + (size_t)o * L + lane);
+            LevelMeta mf = shfl_meta(mine, m - 1);
+            int T = grp >= 4 ? tail_level_from(lm_kh(mf), lm_kw(mf), L, m) : L; // a thread tail pays off from ~4 objects per warp
+            warp_rebuild<false, true>(words, mine, L, m, lane, sbuf[threadIdx.x >> 5], T);
+            __syncwarp();
+        }
+        if (m_mine < L) { if (grp >= 4) thread_tail_build<true>(words, lm + (size_t)o_mine * L, L, m_mine); dirty[o_mine] = L; }
         __syncwarp();
-        if (lane == 0) dirty[o] = L;
     }
 }

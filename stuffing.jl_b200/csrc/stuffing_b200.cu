@@ -105,6 +105,8 @@ static void stage_begin(stf_ctx* ctx, int stage) {
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 #define KCHECK() CK(cudaGetLastError())
 static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n + t - 1) / t); }
+// entries per warp of the grouped rebuild kernels: one per warp while the GPU has warps to spare, up to 32 beyond that
+static inline int rebuild_group(int64_t n) { int64_t g = n / (148 * 64); return g < 4 ? 1 : (int)std::min<int64_t>(32, g); }
 
 enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_SURV = 13, C_N = 16 };
 
@@ -427,8 +429,9 @@ extern "C" int32_t stf_get_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
 }
 static int32_t rebuild_after(stf_ctx* ctx, int n, const int32_t* labels_host, int from) { // ctx->work filled with (o, from)
     if (from >= ctx->L) return STF_OK;
-    int blocks = std::min(nblk((int64_t)n * 32, 256), 148 * 8);
-    ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0);
+    int grp = rebuild_group(n);
+    int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
+    ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp);
     KCHECK();
     if (ctx->has_big)
         for (int i = 0; i < n; i++) { int o = labels_host ? labels_host[i] - 1 : i; if (ctx->h_om[o].big) { int32_t r = build_big(ctx, o, from); if (r) return r; } }
@@ -1016,7 +1019,8 @@ static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, co
     stage_begin(ctx, STF_STAGE_STEP);
     ctx->launches++, k_batchsteps<<<blocks, 128, 0, ctx->st>>>(A);
     // the steps only moved the shifts: materialise the rasters of every moved tree once
-    ctx->launches++, k_materialize<<<std::min(nblk((int64_t)ctx->n * 32, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->n, ctx->dirty.as<int>());
+    { int grp = rebuild_group(ctx->n);
+      ctx->launches++, k_materialize<<<std::min(nblk(((int64_t)ctx->n + grp - 1) / grp * 32, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->n, ctx->dirty.as<int>(), grp); }
     KCHECK();
     stage_end(ctx);
     return STF_OK;
