@@ -7,29 +7,35 @@
 // ---- level-1 pack: u8 codes (column-major payload, pitch kh) -> 2-bit words -------------------
 // word w of a column: 16 payload bytes at any alignment are fetched as 5 aligned words + funnel shifts (the buffer has
 // slack); the tail word of a column takes `default` in the fields past kh.  Validates the codes (1..3).
-__device__ __forceinline__ uint32_t pack_word(const uint8_t* __restrict__ col, int kh, int w, uint32_t d, int& bad) {
-    // One branch-free path for full and tail words (a warp mixes both): always fetch 16 bytes — a tail word over-reads
-    // into the next column / next object / the zeroed slack, all of which have clear high bits — and replace the fields
-    // past kh by `default` afterwards.  4 bytes -> 8 bits with one multiply: (x & 0x03030303) * (2^24+2^18+2^12+2^6)
-    // moves byte k's code to bits 24+2k (the cross terms land below bit 24 or overflow, none carries).
-    const uint8_t* src = col + 16 * w;
-    int nv = min(16, kh - 16 * w);
+__device__ __forceinline__ uint32_t pack16(const uint8_t* __restrict__ src, uint32_t fm, uint32_t dw, uint32_t& hi_acc, uint32_t& zero_acc) {
+    // 16 u8 codes at any byte alignment -> one 2-bit word.  One branch-free path for full and tail words (a warp mixes
+    // both): always fetch 16 bytes as 5 aligned words + funnel shifts — a tail word over-reads into the next column / next
+    // object / the zeroed slack, all of which have clear high bits — and replace the fields outside `fm` by `default`.
+    // 4 bytes -> 8 bits with one multiply: (x & 0x03030303) * (2^24+2^18+2^12+2^6) moves byte k's code to bits 24+2k
+    // (the cross terms land below bit 24 or overflow, none carries); three byte-permutes gather the four top bytes.
     const uint32_t* ap = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
     int sh = (int)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
     uint32_t t[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) t[k] = __ldg(ap + k);
-    uint32_t out = 0, hi = 0;
+    uint32_t p[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         uint32_t x = __funnelshift_r(t[k], t[k + 1], sh);
-        hi |= x;
-        out |= (((x & 0x03030303u) * 0x01041040u) >> 24) << (8 * k);
+        hi_acc |= x;
+        p[k] = (x & 0x03030303u) * 0x01041040u;
     }
-    uint32_t fm = nv >= 16 ? 0xFFFFFFFFu : ((1u << (2 * nv)) - 1u);
-    // codes are 1..3: no bit above the low two in the 16 fetched bytes, no zero field among the first nv
-    bad |= ((hi & 0xFCFCFCFCu) != 0) | ((~(out | (out >> 1)) & 0x55555555u & fm) != 0);
-    return (out & fm) | (dflt_word(d) & ~fm);
+    uint32_t out = __byte_perm(__byte_perm(p[0], p[1], 0x0073), __byte_perm(p[2], p[3], 0x0073), 0x5410);
+    zero_acc |= ~(out | (out >> 1)) & 0x55555555u & fm; // codes are 1..3: a zero field among the valid ones is an error
+    return (out & fm) | (dw & ~fm);
+}
+// field mask of word w of a column of kh nodes (all 16 fields, or the first kh - 16w of the last word)
+__device__ __forceinline__ uint32_t tail_mask(int kh) { int nv = kh - 16 * (wpc_of(kh) - 1); return nv >= 16 ? 0xFFFFFFFFu : ((1u << (2 * nv)) - 1u); }
+__device__ __forceinline__ uint32_t pack_word(const uint8_t* __restrict__ col, int kh, int w, uint32_t d, int& bad) {
+    uint32_t hi = 0, z = 0;
+    uint32_t r = pack16(col + 16 * w, w == wpc_of(kh) - 1 ? tail_mask(kh) : 0xFFFFFFFFu, dflt_word(d), hi, z);
+    bad |= ((hi & 0xFCFCFCFCu) != 0) | (z != 0);
+    return r;
 }
 // one thread per output word of the listed (big) objects; `woff1[i]` = first level-1 word of list entry i in a dense
 // numbering (prefix sum), `poff[o]` = byte offset of object o's payload.
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restr
     const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
-    int bad = 0;
+    uint32_t hi_acc = 0, zero_acc = 0;
     for (int g = warp; g * 32 < nlist; g += nwarps) {
         int my_i = g * 32 + lane;
         int my_o = my_i < nlist ? list[my_i] : -1;
@@ -130,9 +136,10 @@ __global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restr
             const uint8_t* base = payload + poff[o];
             uint32_t d = lm_dflt(m1);
             const uint32_t inv = 0xFFFFFFFFu / (uint32_t)wpc + 1u; // j / wpc == umulhi(j, inv) while j * wpc < 2^32
+            const uint32_t tm = tail_mask(kh), dwd = dflt_word(d);
             for (int j = lane; j < nw; j += 32) {
-                int c = wpc > 1 ? (int)__umulhi((uint32_t)j, inv) : j, w = j - c * wpc; // (inv overflows for wpc == 1)
-                uint32_t out = pack_word(base + c * kh, kh, w, d, bad);
+                uint32_t c = wpc > 1 ? __umulhi((uint32_t)j, inv) : (uint32_t)j, w = (uint32_t)j - c * (uint32_t)wpc; // (inv overflows for wpc == 1)
+                uint32_t out = pack16(base + (c * (uint32_t)kh + 16u * w), (int)w == wpc - 1 ? tm : 0xFFFFFFFFu, dwd, hi_acc, zero_acc);
                 words[m1.off + j] = out;
                 sbuf[wib][j] = out;
             }
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restr
         if (my_o >= 0) thread_tail_build<false>(words, lm + (size_t)my_o * L, L, 1);
         __syncwarp();
     }
-    if (bad) atomicOr(err, 1);
+    if ((hi_acc & 0xFCFCFCFCu) | zero_acc) atomicOr(err, 1);
 }
 
 // levels from+1..L of one object by one CTA: level `from` is read from global memory (L2-hot), every later level from
@@ -188,15 +195,22 @@ template <int THREADS> __global__ void __launch_bounds__(THREADS) k_pack_build_m
     const int kh = lm_kh(m1), wpc = wpc_of(kh), nw = wpc * lm_kw(m1);
     const uint8_t* base = payload + poff[o];
     const uint32_t d = lm_dflt(m1);
-    int bad = 0;
+    uint32_t hi_acc = 0, zero_acc = 0;
     uint32_t* out = words + m1.off;
-    const uint32_t inv = 0xFFFFFFFFu / (uint32_t)wpc + 1u; // j / wpc == umulhi(j, inv): nw * wpc < 2^32 for every listed object
+    { // words j = tid, tid + THREADS, ...: (column, word) and the byte offset advance incrementally, all in 32 bits
+        const uint32_t tm = tail_mask(kh), dwd = dflt_word(d);
+        int c0 = tid / wpc, w = tid - c0 * wpc;
+        uint32_t off = (uint32_t)c0 * (uint32_t)kh + 16u * (uint32_t)w;
+        const int dc = THREADS / wpc, dwi = THREADS - dc * wpc;
+        const uint32_t doff = (uint32_t)dc * (uint32_t)kh + 16u * (uint32_t)dwi, carry = (uint32_t)kh - 16u * (uint32_t)wpc;
 #pragma unroll 4
-    for (int j = tid; j < nw; j += THREADS) {
-        int c = wpc > 1 ? (int)__umulhi((uint32_t)j, inv) : j, w = j - c * wpc; // (inv overflows for wpc == 1)
-        out[j] = pack_word(base + (size_t)c * kh, kh, w, d, bad);
+        for (int j = tid; j < nw; j += THREADS) {
+            out[j] = pack16(base + off, w == wpc - 1 ? tm : 0xFFFFFFFFu, dwd, hi_acc, zero_acc);
+            w += dwi; off += doff;
+            if (w >= wpc) { w -= wpc; off += carry; }
+        }
     }
-    if (bad) atomicOr(err, 1);
+    if ((hi_acc & 0xFCFCFCFCu) | zero_acc) atomicOr(err, 1);
     __syncthreads();
     if (tid >= 1 && tid < L) lm[(size_t)o * L + tid] = sm[tid];
     cta_build_levels<THREADS>(words, sm, L, 1, A, B);
