@@ -116,17 +116,17 @@ __device__ __forceinline__ int tail_level_from(int kh, int kw, int L, int from) 
     return t;
 }
 __global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ poff, const int32_t* __restrict__ list, int nlist,
-                                                          uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L, int* __restrict__ err) {
+                                                          uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L, int* __restrict__ err, int grp) {
     __shared__ uint32_t sbuf[8][2 * RB_HALF];
     const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
     uint32_t hi_acc = 0, zero_acc = 0;
-    for (int g = warp; g * 32 < nlist; g += nwarps) {
-        int my_i = g * 32 + lane;
-        int my_o = my_i < nlist ? list[my_i] : -1;
+    for (int g = warp; g * grp < nlist; g += nwarps) { // grp (4..32) objects per warp: enough groups to fill the GPU
+        int my_i = g * grp + lane;
+        int my_o = (lane < grp && my_i < nlist) ? list[my_i] : -1;
         // ---- phase A
-        for (int k = 0; k < 32; k++) {
+        for (int k = 0; k < grp; k++) {
             int o = __shfl_sync(FULLM, my_o, k);
             if (o < 0) break;
             LevelMeta mine = {};

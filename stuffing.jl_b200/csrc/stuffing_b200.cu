@@ -304,8 +304,9 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     // buildqtree!(t) for every object, fused with the level-1 pack: a warp per small object, a CTA per mid-size object;
     // big objects (mask-sized) are packed by a wide launch and built level by level with wide launches
     if (!l_small.empty()) {
-        int blocks = std::min(nblk((int64_t)l_small.size() * 32, 256), 148 * 8);
-        ctx->launches++, k_pack_build_small<<<blocks, 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list, (int)l_small.size(), ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->errflag.as<int>());
+        int grp = (int)std::min<int64_t>(32, std::max<int64_t>(4, (int64_t)l_small.size() / (148 * 40 * 2))); // >= 2 groups per resident warp
+        int blocks = std::min(nblk(((int64_t)l_small.size() + grp - 1) / grp * 32, 256), 148 * 8);
+        ctx->launches++, k_pack_build_small<<<blocks, 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list, (int)l_small.size(), ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->errflag.as<int>(), grp);
     }
     for (int k = 0; k < 2; k++) { // a CTA per mid-size object: 128 threads for a few KB, 512 for mask-sized ones
         size_t cnt = k ? l_mid.size() - n_mid1 : n_mid1;
