@@ -108,15 +108,21 @@ static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n +
 // entries per warp of the grouped rebuild kernels: one per warp while the GPU has warps to spare, up to 32 beyond that
 static inline int rebuild_group(int64_t n) { int64_t g = n / (148 * 64); return g < 4 ? 1 : (int)std::min<int64_t>(32, g); }
 
-enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_SURV = 13, C_N = 16 };
+enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_SURV = 13, C_STATUS = 14 /* path status bits (int) */, C_ERR = 15 /* error bits (int) */, C_N = 16 };
+#define ERRP(ctx) reinterpret_cast<int*>((ctx)->counts.as<unsigned long long>() + C_ERR)
+#define STATUSP(ctx) reinterpret_cast<int*>((ctx)->counts.as<unsigned long long>() + C_STATUS)
 
-static int32_t sync_counts(stf_ctx* ctx) {
+static int32_t sync_counts(stf_ctx* ctx) { // ONE read-back: counters, path status and error bits live in the same array
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(ctx->h_err, ctx->errflag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st)); // [0] error bits, [1] path status
     CK(cudaStreamSynchronize(ctx->st));
-    if (*ctx->h_err & 1) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st); FAIL(STF_E_BADCODE, "node code outside 1..3 in uploaded payload"); }
-    if (*ctx->h_err & 2) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st); FAIL(STF_E_RANGE, "spatial cell coordinate outside +-2^21"); }
-    if (*ctx->h_err & 4) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->st); FAIL(STF_E_CUDA, "internal: frontier scratch too small"); }
+    ctx->h_err[0] = (int)ctx->h_counts[C_ERR]; ctx->h_err[1] = (int)ctx->h_counts[C_STATUS];
+    if (ctx->h_err[0]) {
+        int e = ctx->h_err[0];
+        cudaMemsetAsync(ERRP(ctx), 0, sizeof(unsigned long long), ctx->st);
+        if (e & 1) FAIL(STF_E_BADCODE, "node code outside 1..3 in uploaded payload");
+        if (e & 2) FAIL(STF_E_RANGE, "spatial cell coordinate outside +-2^21");
+        if (e & 4) FAIL(STF_E_CUDA, "internal: frontier scratch too small");
+    }
     return STF_OK;
 }
 static int32_t upload_labels(stf_ctx* ctx, DevBuf& buf, int32_t nl, const int32_t* labels, const int32_t** dev) {
@@ -138,12 +144,11 @@ extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
     stf_ctx* ctx = new stf_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || cudaMallocHost(&ctx->h_err, 2 * sizeof(int)) != cudaSuccess ||
-        ctx->counts.ensure(C_N * sizeof(unsigned long long)) != cudaSuccess || ctx->errflag.ensure(2 * sizeof(int)) != cudaSuccess) {
+        cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || (ctx->h_err = (int*)calloc(2, sizeof(int))) == nullptr ||
+        ctx->counts.ensure(C_N * sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx; return STF_E_CUDA;
     }
     cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st);
-    cudaMemsetAsync(ctx->errflag.p, 0, 2 * sizeof(int), ctx->st);
     *out = ctx;
     return STF_OK;
 }
@@ -157,7 +162,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
                       &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
-    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->h_err) free(ctx->h_err);
     if (ctx->stg) cudaFreeHost(ctx->stg);
     if (ctx->stg_ev) cudaEventDestroy(ctx->stg_ev);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -306,7 +311,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     if (!l_small.empty()) {
         int grp = (int)std::min<int64_t>(32, std::max<int64_t>(4, (int64_t)l_small.size() / (148 * 40 * 2))); // >= 2 groups per resident warp
         int blocks = std::min(nblk(((int64_t)l_small.size() + grp - 1) / grp * 32, 256), 148 * 8);
-        ctx->launches++, k_pack_build_small<<<blocks, 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list, (int)l_small.size(), ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ctx->errflag.as<int>(), grp);
+        ctx->launches++, k_pack_build_small<<<blocks, 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list, (int)l_small.size(), ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ERRP(ctx), grp);
     }
     for (int k = 0; k < 2; k++) { // a CTA per mid-size object: 128 threads for a few KB, 512 for mask-sized ones
         size_t cnt = k ? l_mid.size() - n_mid1 : n_mid1;
@@ -320,13 +325,13 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
         int aw = (int)((midA[k] + 31) & ~31ull), bw = (int)((midB[k] + 31) & ~31ull);
         const int32_t* lst = d_list + l_small.size() + (k ? n_mid1 : 0);
         size_t smem = sizeof(uint32_t) * (size_t)(aw + bw);
-        if (k == 0) ctx->launches++, k_pack_build_mid<128><<<(int)cnt, 128, smem, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), lst, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, aw, ctx->errflag.as<int>());
-        else ctx->launches++, k_pack_build_mid<512><<<(int)cnt, 512, smem, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), lst, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, aw, ctx->errflag.as<int>());
+        if (k == 0) ctx->launches++, k_pack_build_mid<128><<<(int)cnt, 128, smem, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), lst, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, aw, ERRP(ctx));
+        else ctx->launches++, k_pack_build_mid<512><<<(int)cnt, 512, smem, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), lst, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, aw, ERRP(ctx));
     }
     if (!l_big.empty()) {
         uint64_t tw = big_woff.back();
         ctx->launches++, k_pack_level1<<<nblk((int64_t)tw, 256), 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list + l_small.size() + l_mid.size(), ctx->woff1.as<uint64_t>(), (int)l_big.size(),
-                                                                      ctx->lm.as<LevelMeta>(), L, ctx->words.as<uint32_t>(), tw, ctx->errflag.as<int>());
+                                                                      ctx->lm.as<LevelMeta>(), L, ctx->words.as<uint32_t>(), tw, ERRP(ctx));
     }
     KCHECK();
     for (int o : ctx->big_objs) { int32_t r = build_big(ctx, o, 1); if (r) return r; }
@@ -505,7 +510,7 @@ static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want
     A.overflow = ctx->overflow.as<uint32_t>(); A.overflow_cap = nmax;
     CK(ctx->surv.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nmax)));
     A.surv = ctx->surv.as<uint32_t>(); A.nsurv = ctx->counts.as<unsigned long long>() + C_SURV;
-    CK(cudaMemsetAsync(A.nsurv, 0, sizeof(unsigned long long), ctx->st));
+    if (n_host >= 0) CK(cudaMemsetAsync(A.nsurv, 0, sizeof(unsigned long long), ctx->st)); // (the latency path zeroes the whole counter array once)
     int per_block = NP_THREADS / NP_GROUP;
     int64_t want = n_host >= 0 ? n_host : std::max<int64_t>(ctx->hint_items, 4096);
     ctx->launches++, k_collide_first<<<(int)std::min<int64_t>(std::max<int64_t>(1, (want + 255) / 256), 148 * 16), 256, 0, ctx->st>>>(A);
@@ -513,7 +518,7 @@ static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want
     ctx->launches++, k_collide_small<<<blocks, NP_THREADS, 0, ctx->st>>>(A);
     KCHECK();
     CK(ctx->scratch.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->big_cap * ctx->big_ctas));
-    ctx->launches++, k_collide_big<<<ctx->big_ctas, NPB_THREADS, 0, ctx->st>>>(A, ctx->scratch.as<uint32_t>(), ctx->big_cap, ctx->errflag.as<int>());
+    ctx->launches++, k_collide_big<<<ctx->big_ctas, NPB_THREADS, 0, ctx->st>>>(A, ctx->scratch.as<uint32_t>(), ctx->big_cap, ERRP(ctx));
     KCHECK();
     return STF_OK;
 }
@@ -592,7 +597,7 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
         F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = nh;
         F.n_items_dev = nullptr; F.item_cap = 0; F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = unique;
         F.out5 = export_host_format ? ctx->out32.as<int32_t>() : nullptr; F.kept = ctx->counts.as<unsigned long long>() + C_KEPT;
-        F.do_prep = 0; F.status = ctx->errflag.as<int>() + 1;
+        F.do_prep = 0; F.status = STATUSP(ctx);
         ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
         KCHECK();
         stage_end(ctx);
@@ -730,23 +735,22 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     unsigned long long* nappend = ctx->counts.as<unsigned long long>() + C_NREC;
     if (fast) {
         set_smem_attrs();
-        CK(cudaMemsetAsync(nappend, 0, sizeof(unsigned long long), ctx->st));
         if (linked) {
             if (nl > 0) ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
-                                                                   ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>(), nullptr);
+                                                                   ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
             ctx->launches++, k_compact_records<<<nblk(nrec, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), nrec, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend);
         } else if (nl > 0) {
             ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
-                                                        ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ctx->errflag.as<int>(), nappend);
+                                                        ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ERRP(ctx), nappend);
         }
         KCHECK();
         stage_begin(ctx, STF_STAGE_SORT);
         if (getenv("STF_NO_CLUSTER")) // single-CTA variant (kept for comparison)
             ctx->launches++, k_sort_records<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
-                                                                                      linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, ctx->errflag.as<int>() + 1);
+                                                                                      linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, STATUSP(ctx));
         else // one cluster of 8 CTAs
             ctx->launches++, k_sort_records_cl<<<CS_CTAS, CS_THREADS, CS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
-                                                                                               linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, ctx->errflag.as<int>() + 1);
+                                                                                               linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, STATUSP(ctx));
         KCHECK();
         *keys = ctx->rk.as<uint64_t>(); *vals = ctx->rv.as<uint32_t>();
         stage_end(ctx);
@@ -756,12 +760,12 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
     if (linked) {
         if (nl > 0) ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
-                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>(), nullptr);
+                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
         CK(cudaMemcpyAsync(ctx->rk.p, ctx->lkk.p, sizeof(uint64_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->rv.p, ctx->lkv.p, sizeof(uint32_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
     } else if (nl > 0) {
         ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
-                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ctx->errflag.as<int>(), nullptr);
+                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ERRP(ctx), nullptr);
     }
     KCHECK();
     stage_begin(ctx, STF_STAGE_SORT);
@@ -822,7 +826,7 @@ extern "C" int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* la
     if (nl <= 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
     ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
-                                                ctx->lkv.as<uint32_t>(), ctx->errflag.as<int>(), nullptr);
+                                                ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
     KCHECK();
     return sync_counts(ctx);
 }
@@ -881,8 +885,7 @@ static int32_t spacial_core_fast(stf_ctx* ctx, int32_t nl, const int32_t* labels
     const int32_t* moved_pos = nullptr;
     if (linked) { r = upload_moved_pos(ctx, nl, labels, &moved_pos); if (r) return r; }
     int64_t nrec; uint64_t* keys; uint32_t* vals;
-    CK(cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st));
-    CK(cudaMemsetAsync(ctx->errflag.as<int>() + 1, 0, sizeof(int), ctx->st));
+    CK(cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st)); // every counter, the status and the error bits
     r = locate_and_sort(ctx, nl, dl, linked, true, &nrec, &keys, &vals); if (r) return r;
     int64_t want_items = std::max<int64_t>(std::max<int64_t>(1024, 32 * nrec / 4), ctx->hint_items + ctx->hint_items / 4 + 1024);
     if ((int64_t)(ctx->items.cap / sizeof(Item16)) < want_items) CK(ctx->items.ensure(sizeof(Item16) * (size_t)want_items));
@@ -897,7 +900,7 @@ static int32_t spacial_core_fast(stf_ctx* ctx, int32_t nl, const int32_t* labels
 static int fast_round_verdict(stf_ctx* ctx) {
     int st = ctx->h_err[1];
     if (!st) return 0;
-    cudaMemsetAsync(ctx->errflag.as<int>() + 1, 0, sizeof(int), ctx->st);
+    cudaMemsetAsync(STATUSP(ctx), 0, sizeof(unsigned long long), ctx->st);
     if (st & STF_ST_RETRY_BIG) ctx->force_big = true;
     if (st & STF_ST_RETRY_GROW) ctx->hint_items = (int64_t)ctx->h_counts[C_ITEMS]; // sizes the candidate list of the re-run
     return 1;
@@ -947,7 +950,7 @@ static int32_t manybody_export(stf_ctx* ctx, int32_t nl, const int32_t* labels, 
         F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
         F.n_items_dev = ctx->counts.as<unsigned long long>() + C_ITEMS; F.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
         F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = unique;
-        F.out5 = ctx->out32.as<int32_t>(); F.kept = ctx->counts.as<unsigned long long>() + C_KEPT; F.do_prep = 0; F.status = ctx->errflag.as<int>() + 1;
+        F.out5 = ctx->out32.as<int32_t>(); F.kept = ctx->counts.as<unsigned long long>() + C_KEPT; F.do_prep = 0; F.status = STATUSP(ctx);
         ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
         KCHECK();
         stage_end(ctx);
@@ -1091,7 +1094,7 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
         F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = 0; F.out5 = nullptr; F.kept = nullptr;
         F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
         F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
-        F.status = ctx->errflag.as<int>() + 1;
+        F.status = STATUSP(ctx);
         if (getenv("STF_NO_CLUSTER")) ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
         else {
             CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)(CS_CAP + 1024)));
@@ -1187,7 +1190,7 @@ extern "C" int32_t stf_shard_collide(stf_ctx* ctx, int32_t mode, int32_t nl, con
         r = spacial_core_fast(ctx, nl, labels, linked); if (r) break;
         r = sync_counts(ctx); if (r) break;
         int64_t items = (int64_t)ctx->h_counts[C_ITEMS], hits = (int64_t)ctx->h_counts[C_NHITS];
-        if (ctx->h_err[1] & STF_ST_RETRY_BIG) { cudaMemsetAsync(ctx->errflag.as<int>() + 1, 0, sizeof(int), ctx->st); ctx->force_big = true; break; }
+        if (ctx->h_err[1] & STF_ST_RETRY_BIG) { cudaMemsetAsync(STATUSP(ctx), 0, sizeof(unsigned long long), ctx->st); ctx->force_big = true; break; }
         if (items > (int64_t)(ctx->items.cap / sizeof(Item16))) { ctx->hint_items = items; continue; }
         if (hits > (int64_t)(ctx->hits.cap / sizeof(Item16))) { ctx->force_big = true; break; }
         read_round_counters(ctx); nh = hits; done = true;
