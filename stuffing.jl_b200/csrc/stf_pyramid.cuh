@@ -220,28 +220,47 @@ template <int THREADS> __global__ void __launch_bounds__(THREADS) k_pack_build_m
 
 // ---- warp-per-object build: worklist entry = (object, from_level): levels from+1..L.  32 entries per warp: the levels
 // with real width by the whole warp (warp_rebuild), the tail levels by one thread per entry (thread_tail_build) ----------
+// Fused shift!/setshift! (qtrees.jl:267-287): with `srs` != NULL entry i is (labels[i] or i, level): levels <= level move by
+// s*2^(level-l) (add) or are set to it, then levels > level are rebuilt — one launch instead of shift + rebuild.
 __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L,
-                                const int2* __restrict__ work, int nwork, const ObjMeta* __restrict__ om, int skip_big, int grp) {
+                                const int2* __restrict__ work, int nwork, const ObjMeta* __restrict__ om, int skip_big, int grp,
+                                const int32_t* __restrict__ labels = nullptr, const int32_t* __restrict__ srs = nullptr, const int32_t* __restrict__ scs = nullptr,
+                                int level = 0, int add = 0) {
     __shared__ uint32_t sbuf[8][2 * RB_HALF]; // blockDim.x == 256
     const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int g = warp; g * grp < nwork; g += nwarps) { // grp (1..32) entries per warp: few entries -> more warps, shorter chains
         int my_i = g * grp + lane;
-        int2 mine_w = (lane < grp && my_i < nwork) ? work[my_i] : make_int2(-1, 0);
-        if (mine_w.x >= 0 && ((skip_big && om[mine_w.x].big) || mine_w.y >= L)) mine_w.x = -1;
+        int2 mine_w = make_int2(-1, 0); int my_s1 = 0, my_s2 = 0;
+        if (lane < grp && my_i < nwork) {
+            if (srs) { mine_w = make_int2(labels ? labels[my_i] - 1 : my_i, level); my_s1 = srs[my_i]; my_s2 = scs[my_i]; }
+            else mine_w = work[my_i];
+        }
+        bool big_mine = mine_w.x >= 0 && skip_big && om[mine_w.x].big;
+        if (mine_w.x >= 0 && !srs && (big_mine || mine_w.y >= L)) mine_w.x = -1;
         for (int k = 0; k < grp; k++) {
             int o = __shfl_sync(FULLM, mine_w.x, k), from = __shfl_sync(FULLM, mine_w.y, k);
             if (o < 0) continue;
             LevelMeta mine = {};
             if (lane < L) mine = lm[(size_t)o * L + lane];
+            if (srs) { // the shift itself: level l <= `level` moves by s * 2^(level - l)
+                int s1 = __shfl_sync(FULLM, my_s1, k), s2 = __shfl_sync(FULLM, my_s2, k);
+                bool bigk = __shfl_sync(FULLM, (int)big_mine, k) != 0;
+                if (lane < from) {
+                    int f = 1 << (from - 1 - lane);
+                    if (add) { mine.rs += s1 * f; mine.cs += s2 * f; } else { mine.rs = s1 * f; mine.cs = s2 * f; }
+                    lm[(size_t)o * L + lane] = mine;
+                }
+                if (bigk || from >= L) { __syncwarp(); continue; } // mask-sized objects are rebuilt by wide launches
+            }
             LevelMeta mf = shfl_meta(mine, from - 1);
             int T = grp >= 4 ? tail_level_from(lm_kh(mf), lm_kw(mf), L, from) : L; // a thread tail pays off from ~4 objects per warp
             mine = warp_rebuild<false>(words, mine, L, from, lane, sbuf[threadIdx.x >> 5], T);
             if (lane >= from && lane < L) lm[(size_t)o * L + lane] = mine;
             __syncwarp();
         }
-        if (grp >= 4 && mine_w.x >= 0) thread_tail_build<false>(words, lm + (size_t)mine_w.x * L, L, mine_w.y);
+        if (grp >= 4 && mine_w.x >= 0 && !(srs && (big_mine || mine_w.y >= L))) thread_tail_build<false>(words, lm + (size_t)mine_w.x * L, L, mine_w.y);
         __syncwarp();
     }
 }

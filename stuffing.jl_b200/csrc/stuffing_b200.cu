@@ -456,10 +456,15 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
         CK(stage_h2d(ctx, ctx->lab3.p, cs, sizeof(int32_t) * (size_t)n));
         drs = ctx->lab2.as<int32_t>(); dcs = ctx->lab3.as<int32_t>();
     }
-    CK(ctx->work.ensure(sizeof(int2) * (size_t)n));
-    ctx->launches++, k_apply_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, dl, level, drs, dcs, mode & 1, ctx->work.as<int2>());
-    KCHECK();
-    r = rebuild_after(ctx, n, labels, level); if (r) return r;
+    { // one launch: shift + rebuild of every listed tree (mask-sized ones: shift here, rebuild by the wide launches below)
+        int grp = rebuild_group(n);
+        int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
+        ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, nullptr, n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
+                                                                     dl, drs, dcs, level, mode & 1);
+        KCHECK();
+        if (ctx->has_big && level < ctx->L)
+            for (int i = 0; i < n; i++) { int o = labels ? labels[i] - 1 : i; if (ctx->h_om[o].big) { r = build_big(ctx, o, level); if (r) return r; } }
+    }
     stage_end(ctx);
     return STF_OK; // stream-ordered: no output, inputs were staged
 }
