@@ -39,6 +39,7 @@ import workloads  # noqa: E402
 SEED, ITERATION = 1, 0
 FIXTURES = {"c1": "c1_word_n10000_seed1.npz", "c4": "c4_rect_n100000_seed4.npz"}
 NAMES = {"c1": "C1 fit iteration: 10k word masks + mask, 4096^2 canvas",
+         "c3": "C3 dynamic steps (dynamiccollisions.jl style): 10k word masks + mask, 4096^2 canvas, partialcollisions over the moved subset",
          "c4": "C4 fit iteration: 100k rect masks + mask, 16384^2 canvas",
          "c5": "C5 fit iteration: batch of 4096 scenes x (mask + 128 word masks), 512^2 canvas"}
 
@@ -439,18 +440,111 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_c3(args):
+    """BASELINE configs[2]: the dynamic loop of examples/dynamiccollisions.jl / trainepoch_D! (fit.jl:224-233) on the C1 scene.
+    One STEP = 1 % of the trees jittered by +-(1..8) px (shift!), partialcollisions over the moved subset (the labels of the
+    previous result + the jittered ones) through the LinkedSpacialQTree, the result returned to the HOST (the reference's
+    control flow needs it: moved := labels of the result), batchsteps! on it.  The state evolves, so steps differ; the line
+    reports totals over the K timed steps.  Every step crosses the boundary with host buffers: value == e2e."""
+    import torch
+    import _pkg
+    S = _pkg.load()
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = load_workload("c1")
+    s_ = W["mask_side"]
+    trees = [S.maskqtree(np.ones((s_, s_), bool))] + [S.qtree(o, W["canvas"]) for o in W["objs"]]
+    for t, r, c in zip(trees, W["rs"], W["cs"]):
+        t.shift1 = (int(r), int(c))
+    d = S.DeviceQTrees(trees, device=local)
+    lib, h, n_all = d.lib, d.h, len(trees)
+    stream = torch.cuda.ExternalStream(lib.stf_stream(h), device=torch.device("cuda", local))
+    lib.stf_set_optimiser(h, 2, 0.25, 0.5)
+    tree = S.linked_spacial_qtree(d)
+    S.locate(d, None, tree)
+    rng = np.random.default_rng(3)
+    moved = list(range(2, n_all + 1))
+    tot = dict(items=0, hits=0, moved=0, ms=0.0, h2d=0, d2h=0)
+    warm = max(3, args.warmup)
+    l0 = 0
+    sampler = None
+    for step in range(warm + args.steps):
+        timed = step >= warm
+        if step == warm:
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local) if rank == 0 else None
+            l0 = lib.stf_launch_count(h)
+        jit = rng.choice(np.arange(2, n_all + 1), size=n_all // 100, replace=False).astype(np.int32)
+        dr = (rng.integers(1, 9, len(jit)) * rng.choice([-1, 1], len(jit))).astype(np.int32)
+        dc = (rng.integers(1, 9, len(jit)) * rng.choice([-1, 1], len(jit))).astype(np.int32)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        d.shift(jit, 1, dr, dc)
+        labels = list(dict.fromkeys(moved + jit.tolist()))
+        colist = S.partialcollisions(d, tree, labels, unique=False, raw=True)
+        c = d.counters()
+        d._ck(lib.stf_batchsteps(h, len(colist), colist.ctypes.data, SEED, step))
+        b.record(stream)
+        b.synchronize()
+        moved = sorted({int(x) for r_ in colist for x in (r_["i1"], r_["i2"]) if x != 1})
+        if timed:
+            tot["ms"] += a.elapsed_time(b); tot["items"] += c["items"] + c["direct"]; tot["hits"] += len(colist); tot["moved"] += len(labels)
+            tot["h2d"] += 4 * len(labels) + 12 * len(jit) + 20 * len(colist); tot["d2h"] += 20 * len(colist) + 128
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    launches = lib.stf_launch_count(h) - l0
+    t = torch.tensor([tot["ms"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.steps
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    items = tot["items"] / args.steps
+    alg = 16.0 * items + 0.5 * 7.4 * items + 40.0 * tot["moved"] / args.steps + 100.0 * tot["hits"] / args.steps
+    line = {"metric": "collision_queries_per_sec", "value": world * items / (ms * 1e-3), "unit": "items/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "fit_iters_per_sec": world * 1e3 / ms,
+            "config": {"workload": NAMES["c3"], "objects": n_all, "items_per_step": int(items), "hits_per_step": int(tot["hits"] / args.steps),
+                       "moved_labels_per_step": int(tot["moved"] / args.steps), "l2": "not flushed: the state evolves from step to step (dynamic loop); the working set (5 MB) is L2-resident by design",
+                       "parallelism": f"scene replicas x{world}"},
+            "e2e": {"value": world * items / (ms * 1e-3), "unit": "items/s", "ms_per_step": ms, "h2d_bytes_per_step": int(tot["h2d"] / args.steps), "d2h_bytes_per_step": int(tot["d2h"] / args.steps)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole dynamic step", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "note": "latency-bound host-driven loop: two C-ABI calls with host lists per step"},
+            "cpu_baseline": {"value": None, "unit": "items/s", "cores": 0, "kind": "port", "sample": "see the c1 line: the same scene, one full round"}}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c1", choices=["c1", "c4", "c5"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c3", "c4", "c5"])
     ap.add_argument("--shard", default="scenes", choices=["scenes", "items"])
     ap.add_argument("--no-build-roofline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "c3":
+            raise SystemExit("bench.py: the reference arm covers c1, c4 and c5")
         run_reference(args)
+    elif args.workload == "c3":
+        run_c3(args)
     else:
         run_ours(args)
 
