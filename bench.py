@@ -13,7 +13,7 @@ Every step does identical work (same layout, same draws), so steps are comparabl
            shifts D2H every step.
 `roofline` : the slowest stage of the step against the measured HBM peak (algorithmic bytes), all other
            stages under `stages`, and under `bandwidth_shaped` the one kernel family of the path that streams HBM — the
-           fused pack+build of a 1024-scene batch (C5 shapes, 0.38 GB of u8 masks resident in HBM).
+           fused pack+build of the 4096-scene batch (C5, 1.5 GB of u8 masks resident in HBM).
 Other workloads (`--workload c4`: 100k masks / 16384^2; `c5`: 4096 scenes x 129 trees / 512^2 in one batch) run the same
 step through the multi-launch throughput path.
 N > 1    : c1 / c4 — scene replicas, every rank runs the step on its own copy ("weak"); c5 — the 4096 scenes are split
@@ -229,10 +229,10 @@ def cpu_baseline(which):
 
 # ---------------------------------------------------------------------------------------------- our arm (GPU)
 def build_roofline(S, torch, local, peak):
-    """the bandwidth-shaped kernels of the path: fused level-1 pack + pyramid build of a 1024-scene C5 batch whose u8
-    payload is resident in HBM (0.38 GB > L2).  Algorithmic bytes: the u8 read + 0.25 B per level-1 node
+    """the bandwidth-shaped kernels of the path: fused level-1 pack + pyramid build of the 4096-scene C5 batch whose u8
+    payload is resident in HBM (1.5 GB >> L2).  Algorithmic bytes: the u8 read + 0.25 B per level-1 node
     written + 5 x 0.25 B per upper node (4 children read, 1 written; the fused kernels never re-read them from HBM)."""
-    B = scene_batch(S, range(1024))
+    B = scene_batch(S, range(4096))
     dev = torch.from_numpy(np.concatenate([B["payload"], np.zeros(64, np.uint8)])).cuda(local)
     lib = S._lib.load()
     h = C.c_void_p()
@@ -254,7 +254,7 @@ def build_roofline(S, torch, local, peak):
         best = ms[8] if best is None else min(best, ms[8])
     lib.stf_destroy(h)
     ach = alg / (best * 1e-3) / 1e9
-    return {"kernel": "k_pack_build_small + k_pack_build_mid<128|512> (upload build of 1024 C5 scenes, 132k trees)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+    return {"kernel": "k_pack_build_small + k_pack_build_mid<128|512> (upload build of the 4096 C5 scenes, 528k trees)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
             "frac": ach / peak, "ms": float(best), "algorithmic_bytes": int(alg), "payload_bytes": int(B["payload"].size), "input": "u8 payload resident in HBM, larger than L2"}
 
 

@@ -8,7 +8,8 @@
 #   batchsteps!(dq, C, Momentum(η=1/4))              # grad2d + step! + rebuild on the GPU
 module StuffingB200
 export DeviceQTrees, totalcollisions_spacial, totalcollisions_native, partialcollisions, locate!, collision,
-       batchsteps!, fit_round!, getshift, setshift!, shift!, download!, grad2d
+       batchsteps!, fit_round!, getshift, setshift!, shift!, download!, grad2d, filttrain!, place!, ground_level,
+       shard_collide!, shard_pack!, shard_step!
 
 const LIB = get(ENV, "STUFFING_B200_LIB", joinpath(@__DIR__, "..", "stuffing.jl_b200", "libstuffing_b200.so"))
 const CoItem = Pair{Tuple{Int,Int},Tuple{Int,Int,Int}}
@@ -147,6 +148,59 @@ end
 function fit_round!(d::DeviceQTrees, labels=nothing; partial=false)
     lb, nl = _labels(labels); nh = Ref{Int64}(0); seed, it = _clock[]
     check(d, ccall((:stf_fit_round, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, UInt64, UInt64, Ptr{Int64}), d.h, partial ? 1 : 0, nl, lb, seed, it, nh))
+    _clock[] = (seed, it + 1)
+    Int(nh[])
+end
+
+# src/fit.jl:235-266 — one root BFS per pair of the pool (misses report -level: the nearness score), hits are stepped
+function filttrain!(d::DeviceQTrees, inpool::Vector{Tuple{Int,Int}}, outpool, nearlevel2; optimiser=nothing)
+    isempty(inpool) && return 0
+    L = Int(ccall((:stf_num_levels, LIB), Int32, (Ptr{Cvoid},), d.h))
+    items = [StfItem(i1, i2, L, 1, 1) for (i1, i2) in inpool]; out = similar(items)
+    check(d, ccall((:stf_collision_bfs, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{StfItem}, Ptr{StfItem}), d.h, length(items), items, out))
+    near = [o.l >= nearlevel2 for o in out]
+    outpool === nothing || append!(outpool, inpool[near])
+    colist = CoItem[CoItem(o) for (o, k) in zip(out, near) if k && o.l > 0]
+    batchsteps!(d, colist, optimiser)
+    length(colist)
+end
+
+# src/qtree_functions.jl:452-518 — the ground place!/reposition! search: deepcopy(mask) + every tree not in `inds`,
+# composed on the device; findroom_uniform (the reference's own, unchanged) then runs on the downloaded ground
+function ground_level(d::DeviceQTrees, l::Integer)
+    info = Vector{Int32}(undef, 5)
+    check(d, ccall((:stf_ground_level, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Ptr{Int32}), d.h, l, C_NULL, info))
+    m = Matrix{UInt8}(undef, info[1], info[2])
+    check(d, ccall((:stf_ground_level, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Ptr{Int32}), d.h, l, m, info))
+    m, (Int(info[3]), Int(info[4]))                       # payload and (rshift, cshift): fill a PaddedMat with it
+end
+function place!(d::DeviceQTrees, host_ground, qts, inds; kargs...)   # host_ground: a ShiftedQTree shaped like the mask
+    ex = Int32.(collect(inds))
+    check(d, ccall((:stf_ground_compose, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}), d.h, 1, length(ex), ex))
+    for l in 1:length(host_ground)
+        m, _ = ground_level(d, l); host_ground[l].kernel[2:size(m, 1) + 1, 2:size(m, 2) + 1] .= m
+    end
+    ind = nothing; Q = Vector{Tuple{Int,Int,Int}}()
+    for i in inds                                           # the reference's loop, qtree_functions.jl:512-517
+        ind = Main.Stuffing.QTrees.place!(host_ground, qts[i], Q; kargs...)
+        ind === nothing && return ind
+        Main.Stuffing.QTrees.overlap!(host_ground, qts[i])
+    end
+    rs = Int32[qts[i][1].rshift for i in inds]; cs = Int32[qts[i][1].cshift for i in inds]
+    check(d, ccall((:stf_set_shifts, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Int32), d.h, length(ex), ex, 1, rs, cs, 0))
+    ind
+end
+
+# item-parallel sharding of one scene (INTEGRATION.md "Multi-GPU from Julia"): the three calls around the all-gather
+function shard_collide!(d::DeviceQTrees, rank, nranks; labels=nothing, partial=false)
+    lb, nl = _labels(labels); n = Ref{Int64}(0)
+    check(d, ccall((:stf_shard_collide, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int32, Int32, Ptr{Int64}), d.h, partial ? 1 : 0, nl, lb, rank, nranks, n))
+    Int(n[])
+end
+shard_pack!(d::DeviceQTrees, send_dev, stride) = check(d, ccall((:stf_shard_pack, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), d.h, send_dev, stride))
+function shard_step!(d::DeviceQTrees, recv_dev, nranks, stride)
+    nh = Ref{Int64}(0); seed, it = _clock[]
+    check(d, ccall((:stf_shard_step, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, UInt64, UInt64, Ptr{Int64}), d.h, recv_dev, nranks, stride, seed, it, nh))
     _clock[] = (seed, it + 1)
     Int(nh[])
 end
