@@ -115,7 +115,7 @@ __device__ __forceinline__ int tail_level_from(int kh, int kw, int L, int from) 
     while ((kh > 16 || kw > 8) && t < L) { kh = kh / 2 + 1; kw = kw / 2 + 1; t++; }
     return t;
 }
-__global__ void __launch_bounds__(256) k_pack_build_small(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ poff, const int32_t* __restrict__ list, int nlist,
+__global__ void __launch_bounds__(256, 6) k_pack_build_small(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ poff, const int32_t* __restrict__ list, int nlist,
                                                           uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L, int* __restrict__ err, int grp) {
     __shared__ uint32_t sbuf[8][2 * RB_HALF];
     const unsigned FULLM = 0xffffffffu;
