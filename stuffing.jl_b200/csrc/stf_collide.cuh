@@ -97,6 +97,18 @@ __device__ __forceinline__ int64_t lower_bound_u64(const uint64_t* __restrict__ 
     return lo;
 }
 
+// (scene, level) index of the sorted records: idx[sl] = first record whose (scene << 5 | level) >= sl, idx[nsl] = n.
+// Batches of scenes search an ancestor cell inside its own (scene, level) slice (a few records) instead of the whole array.
+__global__ void k_level_index(const uint64_t* __restrict__ keys, const unsigned long long* __restrict__ n_dev, int64_t cap, int32_t* __restrict__ idx, int nsl) {
+    int64_t n = min((int64_t)*n_dev, cap);
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    int64_t prev = r == 0 ? -1 : (int64_t)(keys[r - 1] >> (2 * STF_CELL_W));
+    int64_t cur = r == n ? nsl : (int64_t)(keys[r] >> (2 * STF_CELL_W));
+    if (cur > nsl) cur = nsl;
+    for (int64_t x = prev + 1; x <= cur; x++) idx[x] = (int32_t)r;
+}
+
 struct EmitOut {
     Item16* items; int64_t item_cap;
     Item16* direct; int64_t direct_cap;   // direct hits go straight into the hit list ...
@@ -129,7 +141,8 @@ __device__ __forceinline__ int64_t upper_bound_u64(const uint64_t* __restrict__ 
 __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                            const unsigned long long* __restrict__ nrec_dev, int64_t nrec_cap, int L,
                                                            const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm,
-                                                           const int32_t* __restrict__ moved_pos, EmitOut out, int shard_rank, int shard_n) {
+                                                           const int32_t* __restrict__ moved_pos, EmitOut out, int shard_rank, int shard_n,
+                                                           const int32_t* __restrict__ lvl_index) {
     __shared__ int s_start[EM_THREADS / 32][16];
     __shared__ int s_pref[EM_THREADS / 32][17];
     const unsigned FULLM = 0xffffffffu;
@@ -144,17 +157,20 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
         int mp_low = moved_pos ? moved_pos[low - 1] : 0;
         // ---- per-lane candidate run
         int start = 0, cnt = 0;
+        const int64_t sl = (int64_t)(key >> (2 * STF_CELL_W)); // scene << 5 | level
         if (lane == 0) {
             start = (int)(r + 1);
-            cnt = (int)(upper_bound_u64(keys, r + 1, nrec, key) - (r + 1));
+            cnt = (int)(upper_bound_u64(keys, r + 1, lvl_index ? (int64_t)lvl_index[sl + 1] : nrec, key) - (r + 1));
         } else if (lane < L - 1 && l + lane <= L) {
             int pa = a, pb = b;
             for (int i = 0; i < lane; i++) { pa = (pa + 1) / 2; pb = (pb + 1) / 2; } // parent(): ÷ truncates toward zero
             uint64_t scene_bits = key >> (5 + 2 * STF_CELL_W);
             uint64_t akey = (scene_bits << (5 + 2 * STF_CELL_W)) | ((uint64_t)(uint32_t)(l + lane) << (2 * STF_CELL_W)) |
                             ((uint64_t)(uint32_t)(pa + STF_CELL_BIAS) << STF_CELL_W) | (uint64_t)(uint32_t)(pb + STF_CELL_BIAS);
-            int64_t h = lower_bound_u64(keys, nrec, akey);
-            if (h < nrec && keys[h] == akey) { start = (int)h; cnt = (int)(upper_bound_u64(keys, h + 1, nrec, akey) - h); }
+            int64_t lo = 0, hi = nrec;
+            if (lvl_index) { lo = lvl_index[sl + lane]; hi = lvl_index[sl + lane + 1]; } // the ancestor's own (scene, level) slice
+            int64_t h = lo + lower_bound_u64(keys + lo, hi - lo, akey);
+            if (h < hi && keys[h] == akey) { start = (int)h; cnt = (int)(upper_bound_u64(keys, h + 1, hi, akey) - h); }
         }
         int incl = cnt;
 #pragma unroll

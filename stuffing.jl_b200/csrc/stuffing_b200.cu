@@ -42,7 +42,7 @@ struct stf_ctx {
     DevBuf words, lm, om, payload, poff, woff1, work, lab, lab2, lab3, lab4, bytes_tmp;
     DevBuf rk, rv, rk2, rv2, hist, lkk, lkv;
     DevBuf items, direct, res, overflow, hits, hits2, hk, hv, hk2, hv2, keep, out32, scratch;
-    DevBuf gwords, glm, surv, dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
+    DevBuf lvlidx, gwords, glm, surv, dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
     unsigned long long* h_counts = nullptr; int* h_err = nullptr; // pinned
     OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
@@ -159,7 +159,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) free(ctx->h_err);
@@ -854,6 +854,13 @@ extern "C" int32_t stf_linked_collect(stf_ctx* ctx, stf_cellrec* out, int64_t ca
 }
 
 static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, const int32_t* moved_pos) {
+    const int32_t* lvl_index = nullptr;
+    if (ctx->multi_scene && nrec > 0) { // batches: (scene, level) index of the sorted records for the ancestor searches
+        int nsl = 32 << ctx->scene_bits;
+        CK(ctx->lvlidx.ensure(sizeof(int32_t) * (size_t)(nsl + 2)));
+        ctx->launches++, k_level_index<<<nblk(nrec + 1, 256), 256, 0, ctx->st>>>(keys, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->lvlidx.as<int32_t>(), nsl);
+        lvl_index = ctx->lvlidx.as<int32_t>();
+    }
     EmitOut eo; eo.items = ctx->items.as<Item16>(); eo.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
     eo.direct = ctx->hits.as<Item16>(); eo.direct_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
     eo.counts = ctx->counts.as<unsigned long long>(); eo.nhits = ctx->counts.as<unsigned long long>() + C_NHITS;
@@ -861,7 +868,7 @@ static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, con
     if (nrec > 0) {
         int blocks = (int)std::min<int64_t>((nrec / 4 + EM_THREADS / 32 - 1) / (EM_THREADS / 32) + 1, 148 * 8); // ~1 record per located object
         ctx->launches++, k_emit_items<<<blocks, EM_THREADS, 0, ctx->st>>>(keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
-                                                                        ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n);
+                                                                        ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n, lvl_index);
     }
     KCHECK();
     stage_end(ctx);
