@@ -292,6 +292,7 @@ struct NarrowArgs {
     uint32_t* overflow;              // item indices that need the big path
     int64_t overflow_cap;
     uint32_t* surv; unsigned long long* nsurv; // stage 1 -> stage 2: indices of the items that go below the first level
+    unsigned long long* cursor;      // stage 2 work cursor into surv (zeroed by stage 1)
 };
 
 // Stage 1, one THREAD per item: the four children of the start node.  Most candidate pairs end here (a FULL code =
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(256) k_collide_first(NarrowArgs A) {
     int64_t n = A.n_items_dev ? (int64_t)*A.n_items_dev : A.n_items_host;
     if (A.n_items_dev && n > A.n_items_host) n = A.n_items_host; // clamp to buffer capacity
     unsigned long long visited = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *A.cursor = 0ull;
     for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (int64_t)gridDim.x * blockDim.x) {
         Item16 item = A.items[it];
         int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
@@ -332,76 +334,105 @@ __global__ void __launch_bounds__(256) k_collide_first(NarrowArgs A) {
     if ((threadIdx.x & 31) == 0 && visited) atomicAdd(A.counts + 3, visited);
 }
 
+// Stage 2, one 4-lane GROUP per surviving item, one frontier node (its four children) per group and loop iteration.
+// The eight groups of a warp run ONE converged loop: a group that finishes its item takes the next one from the warp's
+// reserved chunk of the survivor list in the same iteration, so trip-count differences between items never idle lanes
+// (the earlier per-group loops ran with 11 of 32 lanes active on the batch workloads) and the votes are full-warp ballots.
 __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
     __shared__ uint32_t fr[NP_THREADS / NP_GROUP][2][NP_FCAP];
-    cg::thread_block_tile<NP_GROUP> g = cg::tiled_partition<NP_GROUP>(cg::this_thread_block());
-    int gl = g.thread_rank();
-    int gib = threadIdx.x / NP_GROUP;
-    int64_t n = (int64_t)*A.nsurv; // stage 2: only the items k_collide_first could not decide
-    int64_t ngroups = (int64_t)gridDim.x * (NP_THREADS / NP_GROUP);
+    const unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31, gl = lane & 3, g0 = lane & ~3;
+    const int gib = threadIdx.x / NP_GROUP;
+    const unsigned below = (1u << g0) - 1u; // lanes of the groups before mine
+    const int64_t n = (int64_t)*A.nsurv;    // only the items k_collide_first could not decide
+    const int64_t nwarps = (int64_t)gridDim.x * (NP_THREADS / 32);
+    const int chunk = (int)min((int64_t)64, max((int64_t)8, ((n / nwarps) + 7) & ~(int64_t)7));
+    // the warp's chunk of the survivor list (warp-uniform): the first one is static, later ones come from the cursor
+    int64_t cpos = ((int64_t)blockIdx.x * (NP_THREADS / 32) + (threadIdx.x >> 5)) * chunk, cend = min(cpos + chunk, n);
+    bool exhausted = cpos >= n;
+    if (exhausted) cpos = cend = 0;
+    // group state (identical in the four lanes)
+    bool active = false, newlevel = false;
+    int64_t it = 0;
+    int i1 = 0, i2 = 0, lev = 0, ata = 0, atb = 0, cnt = 0, cur = 0, depth = 0, q = 0, ncnt = 0;
+    LevelMeta m1 = {}, m2 = {};
     unsigned long long visited = 0;
-    for (int64_t j = (int64_t)blockIdx.x * (NP_THREADS / NP_GROUP) + gib; j < n; j += ngroups) {
-        int64_t it = A.surv[j];
-        Item16 item = A.items[it];
-        int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
-        int lev = item_l(item), ata = item.a, atb = item.b;
-        int cnt = 1, cur = 0, depth = 0;
-        if (gl == 0) fr[gib][0][0] = 0;
-        g.sync();
-        int4 result = make_int4(-lev, ata, atb, 0);
-        bool overflow = false;
-        for (;;) {
-            LevelMeta m1 = A.lm[(size_t)o1 * A.L + (lev - 2)], m2 = A.lm[(size_t)o2 * A.L + (lev - 2)];
-            int basea = ata << (depth + 1), baseb = atb << (depth + 1);
-            int ncnt = 0; bool hit = false;
-            int ntest = 4 * cnt;
-            for (int t0 = 0; t0 < ntest; t0 += NP_GROUP) {
-                int t = t0 + gl;
-                bool valid = t < ntest;
-                uint32_t code = 0, ab = 0; int a = 0, b = 0;
-                if (valid) {
-                    uint32_t node = fr[gib][cur][t >> 2]; int cn = t & 3;
-                    uint32_t al = ((node >> 16) << 1) + (cn & 1), be = ((node & 0xffffu) << 1) + (cn >> 1);
-                    ab = (al << 16) | be;
-                    a = basea - (int)al; b = baseb - (int)be;
-                    code = node_code<false>(A.words, m1, a, b) & node_code<false>(A.words, m2, a, b);
+    for (;;) {
+        unsigned need = __ballot_sync(FULLM, !active);
+        if (need) {
+            if (cpos >= cend && !exhausted) {
+                unsigned long long c0 = 0;
+                if (lane == 0) c0 = atomicAdd(A.cursor, (unsigned long long)chunk);
+                c0 = __shfl_sync(FULLM, c0, 0);
+                cpos = (int64_t)c0 + nwarps * chunk; cend = min(cpos + chunk, n);
+                if (cpos >= n) { exhausted = true; cpos = cend = 0; }
+            }
+            if (!active) {
+                int64_t j = cpos + (__popc(need & below) >> 2);
+                if (j < cend) {
+                    it = A.surv[j];
+                    Item16 item = A.items[it];
+                    i1 = item.i1; i2 = item_i2(item); lev = item_l(item); ata = item.a; atb = item.b;
+                    cnt = 1; cur = 0; depth = 0; q = 0; ncnt = 0; newlevel = true; active = true;
+                    if (gl == 0) fr[gib][0][0] = 0;
                 }
-                visited += valid;
-                unsigned hm = g.ballot(valid && code == CODE_FULL);
-                if (hm) {
-                    int src = __ffs(hm) - 1;
-                    result = make_int4(lev - 1, g.shfl(a, src), g.shfl(b, src), 0);
-                    hit = true; break;
-                }
-                bool push = valid && code == CODE_MIX && lev - 1 > 1;
-                unsigned pm = g.ballot(push);
+            }
+            cpos = min(cpos + (__popc(need) >> 2), cend);
+            if (!__any_sync(FULLM, active)) { if (exhausted) break; continue; }
+        }
+        __syncwarp(); // frontier writes of the previous iteration / the start node
+        if (newlevel) {
+            m1 = A.lm[(size_t)(i1 - 1) * A.L + (lev - 2)]; m2 = A.lm[(size_t)(i2 - 1) * A.L + (lev - 2)];
+            newlevel = false;
+        }
+        uint32_t code = 0, ab = 0; int a = 0, b = 0;
+        if (active) {
+            uint32_t node = fr[gib][cur][q];
+            uint32_t al = ((node >> 16) << 1) + (gl & 1), be = ((node & 0xffffu) << 1) + (gl >> 1);
+            ab = (al << 16) | be;
+            a = (ata << (depth + 1)) - (int)al; b = (atb << (depth + 1)) - (int)be;
+            code = node_code<false>(A.words, m1, a, b) & node_code<false>(A.words, m2, a, b);
+            visited++;
+        }
+        const unsigned hm = (__ballot_sync(FULLM, code == CODE_FULL) >> g0) & 0xFu;
+        const bool push = code == CODE_MIX && lev - 1 > 1;
+        const unsigned pm = (__ballot_sync(FULLM, push) >> g0) & 0xFu;
+        const int src = g0 + (hm ? __ffs(hm) - 1 : 0);
+        const int ha = __shfl_sync(FULLM, a, src), hb = __shfl_sync(FULLM, b, src);
+        if (active) {
+            int4 result = make_int4(0, 0, 0, 0); bool done = false, overflow = false;
+            if (hm) { result = make_int4(lev - 1, ha, hb, 0); done = true; }
+            else {
                 int np = __popc(pm);
-                if (ncnt + np > NP_FCAP) { overflow = true; break; }
-                if (push) fr[gib][cur ^ 1][ncnt + __popc(pm & ((1u << gl) - 1))] = ab;
-                ncnt += np;
+                if (ncnt + np > NP_FCAP) { overflow = true; done = true; }
+                else {
+                    if (push) fr[gib][cur ^ 1][ncnt + __popc(pm & ((1u << gl) - 1u))] = ab;
+                    ncnt += np; q++;
+                    if (q == cnt) { // level finished
+                        if (ncnt == 0) { // miss: -(level) and coordinates of the last node popped (:41)
+                            uint32_t node = fr[gib][cur][cnt - 1];
+                            result = make_int4(-lev, (ata << depth) - (int)(node >> 16), (atb << depth) - (int)(node & 0xffffu), 0);
+                            done = true;
+                        } else { cur ^= 1; cnt = ncnt; ncnt = 0; q = 0; lev -= 1; depth += 1; newlevel = true; }
+                    }
+                }
             }
-            if (hit || overflow) break;
-            if (ncnt == 0) { // miss: -(level) and coordinates of the last node popped (:41)
-                uint32_t node = fr[gib][cur][cnt - 1];
-                result = make_int4(-lev, (ata << depth) - (int)(node >> 16), (atb << depth) - (int)(node & 0xffffu), 0);
-                break;
+            if (done) {
+                if (gl == 0) {
+                    if (overflow) {
+                        unsigned long long s = atomicAdd(A.counts + 2, 1ull);
+                        if ((int64_t)s < A.overflow_cap) A.overflow[s] = (uint32_t)it;
+                        result = make_int4(-1, 0, 0, -1);
+                    }
+                    if (A.res) A.res[it] = result;
+                    if (A.hits && result.x >= 0) { // cp[1] >= 0  qtree_functions.jl:104-106
+                        unsigned long long s = atomicAdd(A.nhits, 1ull);
+                        if ((int64_t)s < A.hits_cap) A.hits[s] = make_item(i1, i2, result.x, result.y, result.z);
+                    }
+                }
+                active = false;
             }
-            g.sync();
-            cur ^= 1; cnt = ncnt; lev -= 1; depth += 1;
         }
-        if (gl == 0) {
-            if (overflow) {
-                unsigned long long s = atomicAdd(A.counts + 2, 1ull);
-                if ((int64_t)s < A.overflow_cap) A.overflow[s] = (uint32_t)it;
-                result = make_int4(-1, 0, 0, -1);
-            }
-            if (A.res) A.res[it] = result;
-            if (A.hits && result.x >= 0) { // cp[1] >= 0  qtree_functions.jl:104-106
-                unsigned long long s = atomicAdd(A.nhits, 1ull);
-                if ((int64_t)s < A.hits_cap) A.hits[s] = make_item(item.i1, item_i2(item), result.x, result.y, result.z);
-            }
-        }
-        g.sync();
     }
     // visited-node counter (algorithmic bytes of the roofline)
     for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, o);

@@ -108,7 +108,7 @@ static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n +
 // entries per warp of the grouped rebuild kernels: one per warp while the GPU has warps to spare, up to 32 beyond that
 static inline int rebuild_group(int64_t n) { int64_t g = n / (148 * 64); return g < 4 ? 1 : (int)std::min<int64_t>(32, g); }
 
-enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_SURV = 13, C_STATUS = 14 /* path status bits (int) */, C_ERR = 15 /* error bits (int) */, C_N = 16 };
+enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_SURV = 13, C_STATUS = 14 /* path status bits (int) */, C_ERR = 15 /* error bits (int) */, C_CURSOR = 16, C_N = 17 };
 #define ERRP(ctx) reinterpret_cast<int*>((ctx)->counts.as<unsigned long long>() + C_ERR)
 #define STATUSP(ctx) reinterpret_cast<int*>((ctx)->counts.as<unsigned long long>() + C_STATUS)
 
@@ -514,12 +514,12 @@ static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want
     A.hits = want_hits ? ctx->hits.as<Item16>() : nullptr; A.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16)); A.nhits = ctx->counts.as<unsigned long long>() + C_NHITS;
     A.overflow = ctx->overflow.as<uint32_t>(); A.overflow_cap = nmax;
     CK(ctx->surv.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nmax)));
-    A.surv = ctx->surv.as<uint32_t>(); A.nsurv = ctx->counts.as<unsigned long long>() + C_SURV;
+    A.surv = ctx->surv.as<uint32_t>(); A.nsurv = ctx->counts.as<unsigned long long>() + C_SURV; A.cursor = ctx->counts.as<unsigned long long>() + C_CURSOR;
     if (n_host >= 0) CK(cudaMemsetAsync(A.nsurv, 0, sizeof(unsigned long long), ctx->st)); // (the latency path zeroes the whole counter array once)
     int per_block = NP_THREADS / NP_GROUP;
     int64_t want = n_host >= 0 ? n_host : std::max<int64_t>(ctx->hint_items, 4096);
     ctx->launches++, k_collide_first<<<(int)std::min<int64_t>(std::max<int64_t>(1, (want + 255) / 256), 148 * 16), 256, 0, ctx->st>>>(A);
-    int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want / 2 + per_block - 1) / per_block), 148 * 32); // typically < half the items survive
+    int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want / 2 + per_block - 1) / per_block), 148 * 16); // typically < half the items survive; the warps share the list dynamically
     ctx->launches++, k_collide_small<<<blocks, NP_THREADS, 0, ctx->st>>>(A);
     KCHECK();
     CK(ctx->scratch.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->big_cap * ctx->big_ctas));
@@ -855,7 +855,7 @@ extern "C" int32_t stf_linked_collect(stf_ctx* ctx, stf_cellrec* out, int64_t ca
 
 static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, const int32_t* moved_pos) {
     const int32_t* lvl_index = nullptr;
-    if (ctx->multi_scene && nrec > 0) { // batches: (scene, level) index of the sorted records for the ancestor searches
+    if ((ctx->multi_scene || nrec > 65536) && nrec > 0) { // batches: (scene, level) index of the sorted records for the ancestor searches
         int nsl = 32 << ctx->scene_bits;
         CK(ctx->lvlidx.ensure(sizeof(int32_t) * (size_t)(nsl + 2)));
         ctx->launches++, k_level_index<<<nblk(nrec + 1, 256), 256, 0, ctx->st>>>(keys, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->lvlidx.as<int32_t>(), nsl);
