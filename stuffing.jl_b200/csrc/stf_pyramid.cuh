@@ -225,7 +225,7 @@ template <int THREADS> __global__ void __launch_bounds__(THREADS) k_pack_build_m
 __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L,
                                 const int2* __restrict__ work, int nwork, const ObjMeta* __restrict__ om, int skip_big, int grp,
                                 const int32_t* __restrict__ labels = nullptr, const int32_t* __restrict__ srs = nullptr, const int32_t* __restrict__ scs = nullptr,
-                                int level = 0, int add = 0) {
+                                int level = 0, int add = 0, int* __restrict__ built_from = nullptr, int skip_same = 0) {
     __shared__ uint32_t sbuf[8][2 * RB_HALF]; // blockDim.x == 256
     const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -247,13 +247,23 @@ __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restr
             if (srs) { // the shift itself: level l <= `level` moves by s * 2^(level - l)
                 int s1 = __shfl_sync(FULLM, my_s1, k), s2 = __shfl_sync(FULLM, my_s2, k);
                 bool bigk = __shfl_sync(FULLM, (int)big_mine, k) != 0;
+                if (skip_same && !add && !bigk && built_from[o] < from) {
+                    // the tree already sits there: its last rebuild started at or below `level` (so the rasters above are
+                    // the chain of that level's raster), every level at or below `level` has the requested shift and the
+                    // levels above carry its ÷2 chain: the rebuild would write what is there
+                    int prs = __shfl_up_sync(FULLM, mine.rs, 1), pcs = __shfl_up_sync(FULLM, mine.cs, 1);
+                    int f = 1 << max(from - 1 - lane, 0);
+                    bool same = lane >= L || (lane < from ? (mine.rs == s1 * f && mine.cs == s2 * f) : (mine.rs == prs / 2 && mine.cs == pcs / 2));
+                    if (__all_sync(FULLM, same)) { if (lane == k) mine_w.x = -1; continue; }
+                }
                 if (lane < from) {
                     int f = 1 << (from - 1 - lane);
                     if (add) { mine.rs += s1 * f; mine.cs += s2 * f; } else { mine.rs = s1 * f; mine.cs = s2 * f; }
                     lm[(size_t)o * L + lane] = mine;
                 }
+                if (built_from && lane == 0) built_from[o] = from - 1;
                 if (bigk || from >= L) { __syncwarp(); continue; } // mask-sized objects are rebuilt by wide launches
-            }
+            } else if (built_from && lane == 0) built_from[o] = from - 1;
             LevelMeta mf = shfl_meta(mine, from - 1);
             int T = grp >= 4 ? tail_level_from(lm_kh(mf), lm_kw(mf), L, from) : L; // a thread tail pays off from ~4 objects per warp
             mine = warp_rebuild<false>(words, mine, L, from, lane, sbuf[threadIdx.x >> 5], T);

@@ -60,7 +60,7 @@ struct StepArgs {
     const Item16* hits; int64_t n; const unsigned long long* n_dev; // n_dev != NULL: the step count lives on the device
     const uint32_t* prev; uint32_t* done; unsigned long long* ticket;
     const uint32_t* order; // optional: ticket t runs step order[t] (a topological order that interleaves independent chains)
-    double* vel; uint8_t* has_vel; uint8_t* moved_flag; int* dirty;
+    double* vel; uint8_t* has_vel; uint8_t* moved_flag; int* dirty; int* built_from; // built_from[o] = (level the last rebuild of o started from) - 1
     OptState opt; uint64_t seed, iter;
     unsigned long long* counts; // [4] number of moves
     unsigned long long* dbg_t;  // optional timeline (4 x u64 per step) when dbg & 16
@@ -110,7 +110,10 @@ __device__ __forceinline__ int3 move_decide(const StepArgs& A, double d0, double
 // ballots (the gradient sums are popcounts) -> the scalar arithmetic of step!/move!, done redundantly by every lane so
 // that nothing has to be broadcast -> stores, release fence, flag.  Everything that does not depend on tree state
 // (the hit, the draws, the mass-ratio tests) is computed before the wait.
-__global__ void __launch_bounds__(128) k_batchsteps(StepArgs A) {
+// MINB = resident CTAs per SM the register budget is sized for: 4 (120 registers, shortest dependent chain) for single
+// scenes, 6 (80 registers) for batches of scenes, where independent chains fill the extra warps
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_batchsteps(StepArgs A) {
     __shared__ uint32_t sbuf[4][2 * RB_HALF]; // only the rare eager materialisation uses it
     __shared__ uint64_t s_rnd[4][8];
     __shared__ int2 s_shift[4][32];
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(128) k_batchsteps(StepArgs A) {
                     LevelMeta tm = {};
                     if (lane < A.L) tm = ldmeta<true>(tl + lane);
                     warp_rebuild<true, true>(A.words, tm, A.L, dmt, lane, sbuf[wib]);
+                    if (lane == 0) A.built_from[ot] = dmt - 1;
                     __syncwarp();
                     dmt = A.L; if (t) dmB = dmt; else dmA = dmt;
                 }
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(128) k_batchsteps(StepArgs A) {
 
 // after the batch: rebuild the rasters of the levels above dirty[o] with the tracked shifts.  32 objects per warp: the
 // levels with real width by the whole warp, the tail levels by one thread per object.
-__global__ void __launch_bounds__(256) k_materialize(uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, int n, int* __restrict__ dirty, int grp) {
+__global__ void __launch_bounds__(256) k_materialize(uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, int n, int* __restrict__ dirty, int* __restrict__ built_from, int grp) {
     __shared__ uint32_t sbuf[8][2 * RB_HALF];
     const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(256) k_materialize(uint32_t* __restrict__ word
             warp_rebuild<false, true>(words, mine, L, m, lane, sbuf[threadIdx.x >> 5], T);
             __syncwarp();
         }
-        if (m_mine < L) { if (grp >= 4) thread_tail_build<true>(words, lm + (size_t)o_mine * L, L, m_mine); dirty[o_mine] = L; }
+        if (m_mine < L) { if (grp >= 4) thread_tail_build<true>(words, lm + (size_t)o_mine * L, L, m_mine); dirty[o_mine] = L; built_from[o_mine] = m_mine - 1; }
         __syncwarp();
     }
 }

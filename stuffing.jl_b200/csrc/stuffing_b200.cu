@@ -36,13 +36,14 @@ struct DevBuf {
 struct stf_ctx {
     int device = 0; cudaStream_t st = nullptr; std::string err;
     int n = 0, L = 0, canvas = 0; uint64_t total_words = 0;
+    bool raw_shift_edit = false; // stf_set_level_shift was used: shifts and rasters may disagree, never skip a rebuild
     int scene_bits = 0, label_bits = 1; bool multi_scene = false, sizelevel_ok = true, has_big = false;
     std::vector<ObjMeta> h_om; std::vector<uint32_t> h_off; // h_off[o*L + l-1]: word offsets (static)
     std::vector<int> big_objs;
     DevBuf words, lm, om, payload, poff, woff1, work, lab, lab2, lab3, lab4, bytes_tmp;
     DevBuf rk, rv, rk2, rv2, hist, lkk, lkv;
     DevBuf items, direct, res, overflow, hits, hits2, hk, hv, hk2, hv2, keep, out32, scratch;
-    DevBuf lvlidx, gwords, glm, surv, dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
+    DevBuf built_from, lvlidx, gwords, glm, surv, dbg_t, counts, errflag, vel, has_vel, moved_flag, moved_pos, prev, done, nat_flt, nat_m, dirty;
     unsigned long long* h_counts = nullptr; int* h_err = nullptr; // pinned
     OptState opt = { STF_OPT_MOMENTUM, 0.25, 0.5 };
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
@@ -159,7 +160,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) free(ctx->h_err);
@@ -203,7 +204,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     CK(cudaSetDevice(ctx->device));
     if (n < 0 || canvas < 2 || (canvas & (canvas - 1)) || canvas > 32768) FAIL(STF_E_ARG, "canvas must be a power of two in [2, 32768]");
     int L = 1; for (int s = canvas; s > 1; s >>= 1) L++;
-    ctx->n = n; ctx->L = L; ctx->canvas = canvas; ctx->items_valid = false; ctx->last_result = 0;
+    ctx->n = n; ctx->L = L; ctx->canvas = canvas; ctx->items_valid = false; ctx->last_result = 0; ctx->raw_shift_edit = false;
     ctx->label_bits = 1; while ((1ll << ctx->label_bits) <= n) ctx->label_bits++;
     if (n >= (1 << 26)) FAIL(STF_E_ARG, "too many objects");
     ctx->h_om.assign(n, ObjMeta());
@@ -266,6 +267,8 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     CK(ctx->moved_flag.ensure((size_t)std::max(1, n)));
     CK(ctx->moved_pos.ensure(sizeof(int32_t) * (size_t)std::max(1, n)));
     CK(ctx->dirty.ensure(sizeof(int32_t) * (size_t)std::max(1, n)));
+    CK(ctx->built_from.ensure(sizeof(int32_t) * (size_t)std::max(1, n)));
+    CK(cudaMemsetAsync(ctx->built_from.p, 0, sizeof(int32_t) * (size_t)std::max(1, n), ctx->st)); // the upload builds every tree from level 1
     CK(ctx->lkk.ensure(sizeof(uint64_t) * 4 * (size_t)std::max(1, n)));
     CK(ctx->lkv.ensure(sizeof(uint32_t) * 4 * (size_t)std::max(1, n)));
     CK(cudaMemsetAsync(ctx->has_vel.p, 0, (size_t)std::max(1, n), ctx->st));
@@ -437,7 +440,8 @@ static int32_t rebuild_after(stf_ctx* ctx, int n, const int32_t* labels_host, in
     if (from >= ctx->L) return STF_OK;
     int grp = rebuild_group(n);
     int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
-    ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp);
+    ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
+                                                                 nullptr, nullptr, nullptr, 0, 0, ctx->built_from.as<int>());
     KCHECK();
     if (ctx->has_big)
         for (int i = 0; i < n; i++) { int o = labels_host ? labels_host[i] - 1 : i; if (ctx->h_om[o].big) { int32_t r = build_big(ctx, o, from); if (r) return r; } }
@@ -460,7 +464,7 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
         int grp = rebuild_group(n);
         int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
         ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, nullptr, n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
-                                                                     dl, drs, dcs, level, mode & 1);
+                                                                     dl, drs, dcs, level, mode & 1, ctx->built_from.as<int>(), ctx->raw_shift_edit ? 0 : 1);
         KCHECK();
         if (ctx->has_big && level < ctx->L)
             for (int i = 0; i < n; i++) { int o = labels ? labels[i] - 1 : i; if (ctx->h_om[o].big) { r = build_big(ctx, o, level); if (r) return r; } }
@@ -472,6 +476,7 @@ extern "C" int32_t stf_set_level_shift(stf_ctx* ctx, int32_t label, int32_t l, i
     NEED_OBJS(); CHECK_LABEL(label);
     if (l < 1 || l > ctx->L) FAIL(STF_E_ARG, "level out of range");
     int32_t v[2] = { rs, cs };
+    ctx->raw_shift_edit = true;
     CK(stage_h2d(ctx, reinterpret_cast<char*>(ctx->lm.as<LevelMeta>() + (size_t)(label - 1) * ctx->L + (l - 1)) + 4, v, 8));
     return STF_OK;
 }
@@ -1026,17 +1031,19 @@ static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, co
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.om = ctx->om.as<ObjMeta>(); A.L = ctx->L;
     A.hits = hits; A.n = n_host; A.n_dev = n_dev; A.prev = ctx->prev.as<uint32_t>(); A.done = ctx->done.as<uint32_t>();
     A.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; A.order = order;
-    A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>(); A.dirty = ctx->dirty.as<int>();
+    A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>(); A.dirty = ctx->dirty.as<int>(); A.built_from = ctx->built_from.as<int>();
     A.opt = ctx->opt; A.seed = seed; A.iter = iter; A.counts = ctx->counts.as<unsigned long long>();
     { const char* e = getenv("STF_DEBUG_STEP"); A.dbg = e ? atoi(e) : 0; }
     A.dbg_t = nullptr;
     if (A.dbg & 16) { CK(ctx->dbg_t.ensure(sizeof(unsigned long long) * 4 * (size_t)std::max<int64_t>(n_host, BS_CAP))); A.dbg_t = ctx->dbg_t.as<unsigned long long>(); }
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (n_host + 3) / 4), 148 * 8);
     stage_begin(ctx, STF_STAGE_STEP);
-    ctx->launches++, k_batchsteps<<<blocks, 128, 0, ctx->st>>>(A);
+    ctx->launches++;
+    if (n_host > 32768) k_batchsteps<6><<<blocks, 128, 0, ctx->st>>>(A);
+    else k_batchsteps<4><<<blocks, 128, 0, ctx->st>>>(A);
     // the steps only moved the shifts: materialise the rasters of every moved tree once
     { int grp = rebuild_group(ctx->n);
-      ctx->launches++, k_materialize<<<std::min(nblk(((int64_t)ctx->n + grp - 1) / grp * 32, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->n, ctx->dirty.as<int>(), grp); }
+      ctx->launches++, k_materialize<<<std::min(nblk(((int64_t)ctx->n + grp - 1) / grp * 32, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->n, ctx->dirty.as<int>(), ctx->built_from.as<int>(), grp); }
     KCHECK();
     stage_end(ctx);
     return STF_OK;

@@ -549,3 +549,57 @@ def test_train_policy_reposition(S, orc):
     d.setshift(list(range(2, 47)), 1, [180] * 45, [180] * 45)
     ep, nc = S.train(d, 600, trainer=t.trainepoch_EM2, optimiser=S.Momentum(0.25), patience=5, seed=6)
     assert nc == 0 and S.totalcollisions(d) == [] and t.outofkernelbounds(d) == [], (ep, nc)
+
+
+@pytest.mark.gpu
+def test_set_shifts_leaves_unmoved_trees_alone_and_rebuilds_moved_ones(S, orc):
+    """stf_set_shifts skips a tree that already sits at the requested shift (the same rasters would be written); a tree
+    that moved, or any tree after a level shift was edited by hand (a bare setshift! on one level, qtrees.jl:150-156),
+    is rebuilt."""
+    rng = np.random.default_rng(77)
+    qo = []
+    for k in range(40):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        pic = rng.choice(np.array([1, 1, 2], np.uint8), size=(h, w)).astype(np.uint8)
+        t = orc.OTree(pic, 256, orc.EMPTY).build()
+        t.setshift(1, int(rng.integers(0, 150)), int(rng.integers(0, 150)))
+        qo.append(t)
+    d = device_from_oracle(S, qo, is_mask=np.zeros(len(qo), np.uint8))
+    labels = list(range(1, len(qo) + 1))
+    for level in (1, 3):
+        rs, cs = d.getshifts(labels, level)
+        d.setshift(labels, level, rs, cs)                                   # same shift at `level` (the finer levels may snap)
+        for t, r, c in zip(qo, rs, cs):
+            t.setshift(level, int(r), int(c))
+        d.setshift(labels, level, rs, cs)                                   # and now really nothing moves
+        assert_same_trees(d, qo)
+        new = [(int(r) + int(rng.integers(-9, 10)) * (k % 2), int(c) + int(rng.integers(-9, 10)) * (k % 2)) for k, (r, c) in enumerate(zip(rs, cs))]
+        d.setshift(labels, level, [p[0] for p in new], [p[1] for p in new])  # every other tree may move
+        for t, p in zip(qo, new):
+            t.setshift(level, p[0], p[1])
+        assert_same_trees(d, qo)
+    # the level-3 operations left the level 2-3 rasters as they were: a level-1 setshift! to the same place is NOT a no-op
+    rs, cs = d.getshifts(labels, 1)
+    d.setshift(labels, 1, rs, cs)
+    for t, r, c in zip(qo, rs, cs):
+        t.setshift(1, int(r), int(c))
+    assert_same_trees(d, qo)
+    # batchsteps! move trees at the hit levels; restoring the positions afterwards must give the oracle's state
+    oo, od, clock = orc.Opt("momentum", 0.25, 0.5, len(qo)), S.Momentum(0.25, 0.5), S.trainer.StepClock(seed=9)
+    hits = S.totalcollisions(d, unique=False)
+    assert hits == sorted(orc.totalcollisions(qo, unique=False))
+    if hits:
+        orc.batchsteps(qo, hits, oo, seed=9, iteration=0, is_mask=np.zeros(len(qo), np.uint8))
+        S.batchsteps(d, hits, od, clock)
+        assert_same_trees(d, qo)
+        d.setshift(labels, 1, rs, cs)
+        for t, r, c in zip(qo, rs, cs):
+            t.setshift(1, int(r), int(c))
+        assert_same_trees(d, qo)
+    # a hand-edited level shift: the next setshift! rebuilds everything again
+    rs, cs = d.getshifts(labels, 1)
+    d._ck(d.lib.stf_set_level_shift(d.h, 1, 3, 5, 7))
+    d.setshift(labels, 1, rs, cs)
+    for t, r, c in zip(qo, rs, cs):
+        t.setshift(1, int(r), int(c))
+    assert_same_trees(d, qo)
