@@ -158,19 +158,30 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
         // ---- per-lane candidate run
         int start = 0, cnt = 0;
         const int64_t sl = (int64_t)(key >> (2 * STF_CELL_W)); // scene << 5 | level
-        if (lane == 0) {
-            start = (int)(r + 1);
-            cnt = (int)(upper_bound_u64(keys, r + 1, lvl_index ? (int64_t)lvl_index[sl + 1] : nrec, key) - (r + 1));
-        } else if (lane < L - 1 && l + lane <= L) {
+        // every lane looks for the run of ONE key inside [lo, hi): lane 0 its own key after r, lane j the ancestor cell j
+        // levels up, inside that (scene, level) slice when the index is there.  One code path for all lanes (no serialised
+        // lane-0 branch); the run end is found by galloping (runs are one or two records long).
+        bool look = lane == 0 || (lane < L - 1 && l + lane <= L);
+        uint64_t akey = key;
+        int64_t lo = r + 1, hi = lvl_index ? (int64_t)lvl_index[sl + 1] : nrec;
+        if (look && lane > 0) {
             int pa = a, pb = b;
             for (int i = 0; i < lane; i++) { pa = (pa + 1) / 2; pb = (pb + 1) / 2; } // parent(): ÷ truncates toward zero
             uint64_t scene_bits = key >> (5 + 2 * STF_CELL_W);
-            uint64_t akey = (scene_bits << (5 + 2 * STF_CELL_W)) | ((uint64_t)(uint32_t)(l + lane) << (2 * STF_CELL_W)) |
-                            ((uint64_t)(uint32_t)(pa + STF_CELL_BIAS) << STF_CELL_W) | (uint64_t)(uint32_t)(pb + STF_CELL_BIAS);
-            int64_t lo = 0, hi = nrec;
+            akey = (scene_bits << (5 + 2 * STF_CELL_W)) | ((uint64_t)(uint32_t)(l + lane) << (2 * STF_CELL_W)) |
+                   ((uint64_t)(uint32_t)(pa + STF_CELL_BIAS) << STF_CELL_W) | (uint64_t)(uint32_t)(pb + STF_CELL_BIAS);
+            lo = 0; hi = nrec;
             if (lvl_index) { lo = lvl_index[sl + lane]; hi = lvl_index[sl + lane + 1]; } // the ancestor's own (scene, level) slice
-            int64_t h = lo + lower_bound_u64(keys + lo, hi - lo, akey);
-            if (h < hi && keys[h] == akey) { start = (int)h; cnt = (int)(upper_bound_u64(keys, h + 1, hi, akey) - h); }
+            int64_t x = lo, y = hi;
+            while (x < y) { int64_t mid = (x + y) >> 1; if (keys[mid] < akey) x = mid + 1; else y = mid; }
+            lo = x;
+        }
+        if (look && lo < hi && keys[lo] == akey) { // run [lo, e): gallop, then bisect the last stride
+            int64_t step = 1;
+            while (lo + step < hi && keys[lo + step] == akey) step <<= 1;
+            int64_t x = lo + (step >> 1) + 1, y = min(lo + step, hi); // keys[lo + step/2] == akey, keys[y] != akey (or y == hi)
+            while (x < y) { int64_t mid = (x + y) >> 1; if (keys[mid] == akey) x = mid + 1; else y = mid; }
+            start = (int)lo; cnt = (int)(x - lo);
         }
         int incl = cnt;
 #pragma unroll
