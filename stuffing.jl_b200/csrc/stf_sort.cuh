@@ -64,7 +64,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint64_t* __re
     for (int d = lane; d < 256; d += 32) cnt[w][d] = 0;
     __syncwarp();
     int64_t beg = (int64_t)vw * per_warp, end = min(n, beg + per_warp);
-    for (int64_t i = beg + lane; i < end; i += 32) atomicAdd(&cnt[w][digit_of(keys[i], P)], 1u);
+    for (int64_t i0 = beg + lane; i0 < end; i0 += 32 * 8) { // eight loads in flight per lane
+        uint64_t k[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { int64_t i = i0 + 32 * j; k[j] = i < end ? keys[i] : 0ull; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (i0 + 32 * j < end) atomicAdd(&cnt[w][digit_of(k[j], P)], 1u);
+    }
     __syncwarp();
     for (int d = lane; d < 256; d += 32) hist[(size_t)d * nvw + vw] = cnt[w][d];
 }
@@ -109,21 +115,38 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* _
     for (int d = lane; d < 256; d += 32) base[w][d] = hist[(size_t)d * nvw + vw] + dbase[d];
     __syncwarp();
     int64_t beg = (int64_t)vw * per_warp, end = min(n, beg + per_warp);
-    for (int64_t i0 = beg; i0 < end; i0 += 32) {
-        int64_t i = i0 + lane;
-        bool valid = i < end;
-        uint64_t k = valid ? keys[i] : 0;
-        uint32_t v = valid ? vals[i] : 0;
-        uint32_t d = valid ? digit_of(k, P) : 256u + lane; // invalid lanes never match
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t rank = __popc(peers & ((1u << lane) - 1));
-        uint32_t dst = 0;
-        if (valid) dst = base[w][d] + rank;
-        __syncwarp();
-        if (valid && rank == 0) base[w][d] += __popc(peers);
-        __syncwarp();
-        if (valid) { keys_out[dst] = k; vals_out[dst] = v; }
+    // SC_K chunks of 32 keys per round: the loads and the match.any votes of a round are independent (in flight
+    // together); only the running digit bases in shared memory chain one chunk to the next
+#define SC_K 8
+    const uint32_t lt = (1u << lane) - 1;
+    for (int64_t i0 = beg; i0 < end; i0 += 32 * SC_K) {
+        uint64_t k[SC_K]; uint32_t v[SC_K], d[SC_K], peers[SC_K], dst[SC_K];
+#pragma unroll
+        for (int j = 0; j < SC_K; j++) {
+            int64_t i = i0 + 32 * j + lane;
+            bool valid = i < end;
+            k[j] = valid ? keys[i] : 0ull; v[j] = valid ? vals[i] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < SC_K; j++) {
+            bool valid = i0 + 32 * j + lane < end;
+            d[j] = valid ? digit_of(k[j], P) : 256u + lane; // invalid lanes never match
+            peers[j] = __match_any_sync(0xffffffffu, d[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < SC_K; j++) {
+            bool valid = i0 + 32 * j + lane < end;
+            uint32_t rank = __popc(peers[j] & lt);
+            dst[j] = valid ? base[w][d[j]] + rank : 0u;
+            __syncwarp();
+            if (valid && rank == 0) base[w][d[j]] += __popc(peers[j]);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < SC_K; j++)
+            if (i0 + 32 * j + lane < end) { keys_out[dst[j]] = k[j]; vals_out[dst[j]] = v[j]; }
     }
+#undef SC_K
 }
 
 // Sorts (keys, vals) by the key bits set in `bits`.  Buffers ping-pong; returns 0 if the result is in (keys, vals),

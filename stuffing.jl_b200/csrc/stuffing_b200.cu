@@ -62,8 +62,30 @@ struct stf_ctx {
     int prof_open = -1; cudaEvent_t prof_open_ev = nullptr;
     // pinned staging for small host inputs (labels, shifts): the caller's buffer is only read during the call,
     // the H2D copy is a true async DMA, and calls without outputs need no stream synchronisation
+    char* h_out = nullptr; size_t h_out_cap = 0; // pinned landing area of small read-backs
     char* stg = nullptr; size_t stg_cap = 0, stg_off = 0; cudaEvent_t stg_ev = nullptr; bool stg_busy = false;
 };
+// several host arrays -> ONE contiguous device range with one copy (dst + sum of the earlier sizes, no padding)
+struct HostPart { const void* src; size_t bytes; };
+static cudaError_t stage_h2d_parts(stf_ctx* ctx, void* dst, const HostPart* parts, int nparts) {
+    size_t bytes = 0;
+    for (int i = 0; i < nparts; i++) bytes += parts[i].bytes;
+    if (bytes == 0) return cudaSuccess;
+    if (ctx->stg_busy && (ctx->stg_off + bytes > ctx->stg_cap || ctx->stg_off == 0)) { cudaEventSynchronize(ctx->stg_ev); ctx->stg_busy = false; ctx->stg_off = 0; }
+    if (ctx->stg_off + bytes > ctx->stg_cap) {
+        if (ctx->stg_busy) { cudaEventSynchronize(ctx->stg_ev); ctx->stg_busy = false; }
+        if (ctx->stg) cudaFreeHost(ctx->stg);
+        ctx->stg_cap = std::max(bytes * 2, (size_t)1 << 20); ctx->stg_off = 0;
+        cudaError_t e = cudaMallocHost(&ctx->stg, ctx->stg_cap); if (e != cudaSuccess) { ctx->stg = nullptr; ctx->stg_cap = 0; return e; }
+    }
+    if (!ctx->stg_ev) cudaEventCreateWithFlags(&ctx->stg_ev, cudaEventDisableTiming);
+    size_t o = 0;
+    for (int i = 0; i < nparts; i++) { memcpy(ctx->stg + ctx->stg_off + o, parts[i].src, parts[i].bytes); o += parts[i].bytes; }
+    cudaError_t e = cudaMemcpyAsync(dst, ctx->stg + ctx->stg_off, bytes, cudaMemcpyHostToDevice, ctx->st);
+    ctx->stg_off += (bytes + 255) & ~(size_t)255;
+    cudaEventRecord(ctx->stg_ev, ctx->st); ctx->stg_busy = true;
+    return e;
+}
 static cudaError_t stage_h2d(stf_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return cudaSuccess;
     if (ctx->stg_busy && (ctx->stg_off + bytes > ctx->stg_cap || ctx->stg_off == 0)) { cudaEventSynchronize(ctx->stg_ev); ctx->stg_busy = false; ctx->stg_off = 0; }
@@ -165,6 +187,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) free(ctx->h_err);
     if (ctx->stg) cudaFreeHost(ctx->stg);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->stg_ev) cudaEventDestroy(ctx->stg_ev);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
@@ -431,9 +454,22 @@ extern "C" int32_t stf_get_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
     CK(ctx->out32.ensure(sizeof(int32_t) * 2 * (size_t)n));
     ctx->launches++, k_get_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, dl, level, ctx->out32.as<int32_t>());
     KCHECK();
-    CK(cudaMemcpyAsync(rs, ctx->out32.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(cs, ctx->out32.as<int32_t>() + n, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    // one device->host copy into pinned memory, split into the caller's two arrays afterwards
+    const size_t nb = sizeof(int32_t) * (size_t)n;
+    if (n > 65536) { // large read-backs: straight into the caller's arrays (the extra host copy would cost more than a launch)
+        CK(cudaMemcpyAsync(rs, ctx->out32.p, nb, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(cs, ctx->out32.as<int32_t>() + n, nb, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        return STF_OK;
+    }
+    if (ctx->h_out_cap < 2 * nb) {
+        if (ctx->h_out) cudaFreeHost(ctx->h_out);
+        ctx->h_out = nullptr; ctx->h_out_cap = 0;
+        CK(cudaMallocHost(&ctx->h_out, 4 * nb)); ctx->h_out_cap = 4 * nb;
+    }
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->out32.p, 2 * nb, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    memcpy(rs, ctx->h_out, nb); memcpy(cs, ctx->h_out + nb, nb);
     return STF_OK;
 }
 static int32_t rebuild_after(stf_ctx* ctx, int n, const int32_t* labels_host, int from) { // ctx->work filled with (o, from)
@@ -452,14 +488,18 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
     if (level < 1 || level > ctx->L || n < 0 || (!labels && n > ctx->n)) FAIL(STF_E_ARG, "bad level or count");
     if (n == 0) return STF_OK;
     stage_begin(ctx, STF_STAGE_SHIFT);
-    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r;
+    const int32_t* dl = nullptr; int32_t r;
     const int32_t *drs = rs, *dcs = cs;
-    if (!(mode & STF_SHIFT_DEVICE_ARRAYS)) {
-        CK(ctx->lab2.ensure(sizeof(int32_t) * (size_t)n)); CK(ctx->lab3.ensure(sizeof(int32_t) * (size_t)n));
-        CK(stage_h2d(ctx, ctx->lab2.p, rs, sizeof(int32_t) * (size_t)n));
-        CK(stage_h2d(ctx, ctx->lab3.p, cs, sizeof(int32_t) * (size_t)n));
-        drs = ctx->lab2.as<int32_t>(); dcs = ctx->lab3.as<int32_t>();
-    }
+    if (!(mode & STF_SHIFT_DEVICE_ARRAYS)) { // host arrays: labels, rs and cs travel in ONE copy
+        if (labels) for (int i = 0; i < n; i++) if (labels[i] < 1 || labels[i] > ctx->n) FAIL(STF_E_ARG, "label out of range");
+        const size_t nb = sizeof(int32_t) * (size_t)n;
+        CK(ctx->lab.ensure(3 * nb));
+        HostPart parts[3] = { { labels, labels ? nb : 0 }, { rs, nb }, { cs, nb } };
+        CK(stage_h2d_parts(ctx, ctx->lab.p, parts, 3));
+        const int32_t* base = ctx->lab.as<int32_t>();
+        if (labels) { dl = base; base += n; }
+        drs = base; dcs = base + n;
+    } else { r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r; }
     { // one launch: shift + rebuild of every listed tree (mask-sized ones: shift here, rebuild by the wide launches below)
         int grp = rebuild_group(n);
         int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
