@@ -317,10 +317,12 @@ def run_ours(args):
         d._ck(lib.stf_reset_velocity(h, 0, None))
         if sharded is not None:
             nh.value = sharded.round(SEED, ITERATION)
-        else:
+            if not resident:
+                d._ck(lib.stf_get_shifts(h, n_all, None, 1, out_rs.data_ptr(), out_cs.data_ptr()))
+        elif resident:
             d._ck(lib.stf_fit_round(h, 0, 0, None, SEED, ITERATION, C.byref(nh)))
-        if not resident:
-            d._ck(lib.stf_get_shifts(h, n_all, None, 1, out_rs.data_ptr(), out_cs.data_ptr()))
+        else:  # the user-facing call: the round and the positions after it
+            d._ck(lib.stf_fit_round_positions(h, 0, 0, None, SEED, ITERATION, C.byref(nh), 1, out_rs.data_ptr(), out_cs.data_ptr()))
         return nh.value
 
     def timed(resident, steps):

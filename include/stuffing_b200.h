@@ -165,6 +165,12 @@ int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colist, uint64_t
  * partialcollisions over `labels`.  *nhits = length(colist). */
 int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels,
                       uint64_t seed, uint64_t iteration, int64_t* nhits);
+/* the same round followed by getshift(t, level) of EVERY tree (qtrees.jl:135-141): rs/cs (n each) receive the positions
+ * after the round.  On the single-scene path the read-back rides on the round's one synchronisation instead of a
+ * second call; otherwise it equals stf_fit_round + stf_get_shifts. */
+int32_t stf_fit_round_positions(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels,
+                                uint64_t seed, uint64_t iteration, int64_t* nhits,
+                                int32_t level, int32_t* rs, int32_t* cs);
 
 /* ---- ground composition for place! / reposition! (qtree_functions.jl:452-518, fit.jl:420-436).
  * ground = deepcopy(qtrees[mask_label]) with every other tree overlap!-ed except the `excl_labels` (the trees about to be

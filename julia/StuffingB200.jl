@@ -152,6 +152,17 @@ function fit_round!(d::DeviceQTrees, labels=nothing; partial=false)
     Int(nh[])
 end
 
+# the same round, then getshift(t, level) of every tree, read back with the round's own synchronisation
+function fit_round_positions!(d::DeviceQTrees, labels=nothing; partial=false, level=1)
+    lb, nl = _labels(labels); nh = Ref{Int64}(0); seed, it = _clock[]
+    n = Int(ccall((:stf_num_objects, LIB), Int32, (Ptr{Cvoid},), d.h))
+    rs = Vector{Int32}(undef, n); cs = Vector{Int32}(undef, n)
+    check(d, ccall((:stf_fit_round_positions, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, UInt64, UInt64, Ptr{Int64}, Int32, Ptr{Int32}, Ptr{Int32}),
+                   d.h, partial ? 1 : 0, nl, lb, seed, it, nh, level, rs, cs))
+    _clock[] = (seed, it + 1)
+    Int(nh[]), rs, cs
+end
+
 # src/fit.jl:235-266 — one root BFS per pair of the pool (misses report -level: the nearness score), hits are stepped
 function filttrain!(d::DeviceQTrees, inpool::Vector{Tuple{Int,Int}}, outpool, nearlevel2; optimiser=nothing)
     isempty(inpool) && return 0

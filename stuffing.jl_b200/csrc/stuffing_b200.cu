@@ -62,6 +62,7 @@ struct stf_ctx {
     int prof_open = -1; cudaEvent_t prof_open_ev = nullptr;
     // pinned staging for small host inputs (labels, shifts): the caller's buffer is only read during the call,
     // the H2D copy is a true async DMA, and calls without outputs need no stream synchronisation
+    int pos_level = 0; int32_t *pos_rs = nullptr, *pos_cs = nullptr; // stf_fit_round_positions: read-back folded into the round's one sync
     char* h_out = nullptr; size_t h_out_cap = 0; // pinned landing area of small read-backs
     char* stg = nullptr; size_t stg_cap = 0, stg_off = 0; cudaEvent_t stg_ev = nullptr; bool stg_busy = false;
 };
@@ -1135,6 +1136,35 @@ extern "C" int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colis
 }
 // One fit iteration on the device: many-body collision detection over the active labels, then batchsteps! on the result
 // (canonical list order = sorted by ((i1,i2),(l,a,b))).  Latency path: ~10 launches, ONE host synchronisation.
+// positions of every tree at ctx->pos_level -> pinned landing area (enqueue only); pos_deliver copies them out after the sync
+static int32_t pos_enqueue(stf_ctx* ctx) {
+    const int n = ctx->n; const size_t nb = sizeof(int32_t) * (size_t)n;
+    CK(ctx->out32.ensure(2 * nb));
+    if (ctx->h_out_cap < 2 * nb) {
+        if (ctx->h_out) cudaFreeHost(ctx->h_out);
+        ctx->h_out = nullptr; ctx->h_out_cap = 0;
+        CK(cudaMallocHost(&ctx->h_out, 4 * nb)); ctx->h_out_cap = 4 * nb;
+    }
+    ctx->launches++, k_get_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, nullptr, ctx->pos_level, ctx->out32.as<int32_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->out32.p, 2 * nb, cudaMemcpyDeviceToHost, ctx->st));
+    return STF_OK;
+}
+static void pos_deliver(stf_ctx* ctx) {
+    const size_t nb = sizeof(int32_t) * (size_t)ctx->n;
+    memcpy(ctx->pos_rs, ctx->h_out, nb); memcpy(ctx->pos_cs, ctx->h_out + nb, nb);
+}
+extern "C" int32_t stf_fit_round_positions(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits,
+                                           int32_t level, int32_t* rs, int32_t* cs) {
+    NEED_OBJS();
+    if (level < 1 || level > ctx->L || !rs || !cs) FAIL(STF_E_ARG, "bad level or output arrays");
+    ctx->pos_level = level; ctx->pos_rs = rs; ctx->pos_cs = cs;
+    int32_t r = stf_fit_round(ctx, mode, nl, labels, seed, iteration, nhits);
+    bool delivered = ctx->pos_level == 0;
+    ctx->pos_level = 0;
+    if (r) return r;
+    return delivered ? STF_OK : stf_get_shifts(ctx, ctx->n, nullptr, level, rs, cs); // paths without a folded read-back
+}
 extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits) {
     NEED_OBJS();
     if (nhits) *nhits = 0;
@@ -1161,8 +1191,11 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
         }
         KCHECK();
         r = launch_steps(ctx, ctx->hits2.as<Item16>(), std::max<int64_t>(ctx->ctr.hits, 2048), ctx->counts.as<unsigned long long>() + C_NSTEPS, seed, iteration); if (r) return r;
+        const bool fold = ctx->pos_level > 0 && ctx->n <= 65536;
+        if (fold) { r = pos_enqueue(ctx); if (r) return r; }
         r = sync_counts(ctx); if (r) return r;
         if (fast_round_verdict(ctx)) continue; // no step ran (n_steps == 0): nothing to undo
+        if (fold) { pos_deliver(ctx); ctx->pos_level = 0; }
         read_round_counters(ctx);
         ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES];
         if (nhits) *nhits = ctx->ctr.hits;

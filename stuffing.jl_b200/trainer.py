@@ -102,6 +102,21 @@ def fit_round(qts, labels=None, optimiser=None, clock: StepClock | None = None, 
     return nh.value
 
 
+def fit_round_positions(qts, labels=None, optimiser=None, clock: StepClock | None = None, partial=False, level=1):
+    """fit_round followed by getshift(t, level) of every tree, read back with the round's own synchronisation;
+    returns (length(colist), rs, cs)"""
+    d = _dev(qts)
+    clock = clock or _default_clock
+    _set_opt(d, optimiser)
+    lb = None if labels is None else i32(list(labels))
+    nh = C.c_int64(0)
+    rs, cs = np.zeros(d.n, np.int32), np.zeros(d.n, np.int32)
+    d._ck(d.lib.stf_fit_round_positions(d.h, 1 if partial else 0, 0 if lb is None else len(lb), ptr(lb), clock.seed, clock.iteration, C.byref(nh),
+                                        level, ptr(rs), ptr(cs)))
+    clock.iteration += 1
+    return nh.value, rs, cs
+
+
 def _labels_of(colist):
     seen, out = set(), []
     for r in colist:
