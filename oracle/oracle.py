@@ -93,6 +93,7 @@ def lib():
             "orc_batchsteps": (None, [vp, i32, vp, i64, vp, u64, u64]),
             "orc_batchsteps_masks": (None, [vp, i32, vp, i64, vp, u64, u64, vp]),
             "orc_place": (i32, [vp, i32, u64]),
+            "orc_place_gathering": (i32, [vp, i32, u64, i32, C.c_double]),
             "orc_overlap": (None, [vp, vp]),
         }
         for name, (res, args) in sig.items():
@@ -467,8 +468,11 @@ def batchsteps(qts, colist, opt: Opt | None, seed=0, iteration=0, is_mask=None):
     lib().orc_batchsteps_masks(_handles(qts), len(qts), _ptr(arr), len(arr), opt.h if opt else None, seed, iteration, _ptr(im))
 
 
-def place(qts, seed=1):
-    r = lib().orc_place(_handles(qts), len(qts), seed)
+def place(qts, seed=1, roomfinder="uniform", level=5, p=2):
+    if roomfinder == "gathering":
+        r = lib().orc_place_gathering(_handles(qts), len(qts), seed, level, float(p))
+    else:
+        r = lib().orc_place(_handles(qts), len(qts), seed)
     if r != 0:
         raise RuntimeError("no room for placement")
     return qts

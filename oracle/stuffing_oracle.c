@@ -658,6 +658,78 @@ static int findroom_uniform(const OrcTree* ground, IdxQ* q, Rng* rng, Idx* out) 
     }
     return 0;
 }
+/* shufflesort!(q, ground, p)  qtree_functions.jl:403-409: shuffle, then a STABLE sort by the elliptic p-norm of the cell's
+ * offset from the level's centre (Julia's default sort! is stable).  Integer p: repeated multiplication (exact for p = 2,
+ * the default); other p: pow(). */
+static double pnorm_term(double x, double p) {
+    if (p == 1.0) return x;
+    if (p == 2.0) return x * x;
+    if (p == 3.0) return x * x * x;
+    if (p == 4.0) { double y = x * x; return y * y; }
+    return pow(x, p);
+}
+typedef struct { double key; Idx i; } KeyedIdx;
+static void keyed_merge_sort(KeyedIdx* v, KeyedIdx* tmp, int64_t n) {
+    if (n < 2) return;
+    int64_t h = n / 2;
+    keyed_merge_sort(v, tmp, h); keyed_merge_sort(v + h, tmp, n - h);
+    int64_t a = 0, b = h, o = 0;
+    while (a < h && b < n) tmp[o++] = (v[b].key < v[a].key) ? v[b++] : v[a++]; /* ties keep the left element first */
+    while (a < h) tmp[o++] = v[a++];
+    while (b < n) tmp[o++] = v[b++];
+    memcpy(v, tmp, sizeof(KeyedIdx) * (size_t)n);
+}
+static void q_shufflesort(IdxQ* q, const OrcTree* ground, double p, Rng* rng) {
+    int64_t n = q->n - q->head; Idx* v = q->v + q->head;
+    double ce = (1 + (double)LV(ground, v[0].l).sz) / 2; /* size(ground[l], 1): the padded (virtual) size of the level */
+    double h = LV(ground, 1).kh, w = LV(ground, 1).kw;
+    q_shuffle(q, rng);
+    KeyedIdx* kv = (KeyedIdx*)malloc(sizeof(KeyedIdx) * (size_t)(2 * n));
+    for (int64_t k = 0; k < n; k++) {
+        kv[k].i = v[k];
+        kv[k].key = pnorm_term(fabs((v[k].a - ce) / h), p) + pnorm_term(fabs(v[k].b - ce) / w, p);
+    }
+    keyed_merge_sort(kv, kv + n, n);
+    for (int64_t k = 0; k < n; k++) v[k] = kv[k].i;
+    free(kv);
+}
+static int findroom_gathering(const OrcTree* ground, IdxQ* q, Rng* rng, int level, double p, Idx* out) { /* qtree_functions.jl:410-441 */
+    if (q_empty(q)) {
+        int l = ground->L - level; if (l < 1) l = 1;
+        int s = LV(ground, l).sz;
+        for (int i = 1; i <= s; i++) for (int j = 1; j <= s; j++) { Idx c = { l, i, j }; if (rdi(ground, c) != ORC_FULL) q_push(q, c); }
+        if (!q_empty(q)) q_shufflesort(q, ground, p, rng);
+    }
+    while (!q_empty(q)) {
+        Idx i = q_pop(q);
+        if (i.l == 1) { if (rdi(ground, i) == ORC_EMPTY) { *out = i; return 1; } }
+        else {
+            int has = 0; Idx ans = i;
+            const int8_t* perm = PERM4[rng_below(rng, 24)];
+            for (int k = 0; k < 4; k++) {
+                Idx ci = child(i, perm[k]); uint8_t g = rdi(ground, ci);
+                if (g == ORC_EMPTY) { if (rng_f64(rng) < 0.7) { ans = ci; has = 1; } q_push(q, ci); }
+                else if (g == ORC_MIX) q_push(q, ci);
+            }
+            if (!q_empty(q) && q->v[q->head].l != i.l) q_shufflesort(q, ground, p, rng);
+            if (has) { *out = ans; return 1; }
+        }
+    }
+    return 0;
+}
+int orc_place_gathering(OrcTree* const* trees, int n, uint64_t seed, int level, double p) { /* place!(...; roomfinder=findroom_gathering) */
+    OrcTree* ground = orc_tree_copy(trees[0]);
+    IdxQ q; q_init(&q); Rng rng = { seed }; int ok = 0;
+    for (int i = 1; i < n; i++) {
+        Idx ind;
+        if (!findroom_gathering(ground, &q, &rng, level, p, &ind)) { ok = -1; break; }
+        int64_t ca, cb; indexcenter(ind.l, ind.a, ind.b, &ca, &cb);
+        orc_setshift(trees[i], 1, (int)ca - LV(trees[i], 1).kh / 2, (int)cb - LV(trees[i], 1).kw / 2);
+        orc_overlap(ground, trees[i]);
+    }
+    q_free(&q); orc_tree_free(ground);
+    return ok;
+}
 int orc_place(OrcTree* const* trees, int n, uint64_t seed) { /* Stuffing.jl:64-68 + qtree_functions.jl:503-543 */
     OrcTree* ground = orc_tree_copy(trees[0]);
     IdxQ q; q_init(&q); Rng rng = { seed }; int ok = 0;

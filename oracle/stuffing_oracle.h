@@ -114,6 +114,8 @@ void orc_batchsteps_masks(OrcTree* const* trees, int n, const OrcItem* colist, i
 /* ---- input generation (not on the hot path) ---- */
 /* place!(qtrees) of Stuffing.jl:64-68: trees[0] is the mask; returns 0, or -1 "no room" */
 int orc_place(OrcTree* const* trees, int n, uint64_t seed);
+/* place!(...; roomfinder=findroom_gathering, level, p)  qtree_functions.jl:403-441 */
+int orc_place_gathering(OrcTree* const* trees, int n, uint64_t seed, int level, double p);
 void orc_overlap(OrcTree* ground, const OrcTree* t); /* overlap!(tree1, tree2) */
 
 #ifdef __cplusplus

@@ -58,9 +58,14 @@ class HostGround:
 
     def __init__(self, levels, default):
         self.levels, self.default = levels, int(default)  # levels[l-1] = [codes, rs, cs]
+        self.canvas = 1 << (len(levels) - 1)  # the padded side of level 1 (L = log2(canvas) + 1 levels)
 
     def __len__(self):
         return len(self.levels)
+
+    def size(self, l):
+        """size(ground[l], 1): the padded (virtual) side of level l"""
+        return self.canvas >> (l - 1)
 
     @classmethod
     def from_device(cls, d: DeviceQTrees, default):
@@ -150,7 +155,63 @@ def findroom_uniform(ground: HostGround, q: list, rng: Rng):
     return None
 
 
-def place(d: DeviceQTrees, inds=None, seed=1, mask_label=1):
+def _pnorm_term(x, p):
+    if p == 1:
+        return x
+    if p == 2:
+        return x * x
+    if p == 3:
+        return x * x * x
+    if p == 4:
+        y = x * x
+        return y * y
+    return x ** float(p)
+
+
+def _shufflesort(q: list, ground: HostGround, p, rng: Rng):
+    """shufflesort!(q, ground, p)  qtree_functions.jl:403-409: shuffle, then a stable sort by the elliptic p-norm of the
+    offset from the level's centre (the padded size of the level, the kernel size of level 1)"""
+    ce = (1 + ground.size(q[0][0])) / 2
+    h, w = ground.levels[0][0].shape
+    for k in range(len(q) - 1, 0, -1):
+        j = rng.u64() % (k + 1)
+        q[k], q[j] = q[j], q[k]
+    q.sort(key=lambda i: _pnorm_term(abs((i[1] - ce) / h), p) + _pnorm_term(abs(i[2] - ce) / w, p))
+
+
+def findroom_gathering(ground: HostGround, q: list, rng: Rng, level=5, p=2):
+    """findroom_gathering(ground, q; level, p)  qtree_functions.jl:410-441: the search starts from every non-FULL cell of
+    level max(1, L - level), nearest to the centre first, and re-sorts the queue the same way at every level change"""
+    if not q:
+        l = max(1, len(ground) - level)
+        s = ground.size(l)
+        q.extend((l, i, j) for i in range(1, s + 1) for j in range(1, s + 1) if ground.get(l, i, j) != FULL)
+        if q:
+            _shufflesort(q, ground, p, rng)
+    while q:
+        i = q.pop(0)
+        if i[0] == 1:
+            if ground.get(*i) == EMPTY:
+                return i
+            continue
+        ans = None
+        for cn in PERM4[rng.below(24)]:
+            ci = (i[0] - 1, 2 * i[1] - (cn & 1), 2 * i[2] - (cn >> 1))
+            gcode = ground.get(*ci)
+            if gcode == EMPTY:
+                if rng.f64() < 0.7:
+                    ans = ci
+                q.append(ci)
+            elif gcode == MIX:
+                q.append(ci)
+        if q and q[0][0] != i[0]:
+            _shufflesort(q, ground, p, rng)
+        if ans is not None:
+            return ans
+    return None
+
+
+def place(d: DeviceQTrees, inds=None, seed=1, mask_label=1, roomfinder="uniform", level=5, p=2):
     """place!(qtrees[, inds])  Stuffing.jl:64-73: ground = deepcopy(mask) + every tree NOT in `inds` (device), then the
     trees of `inds` (default: all but the mask) are centred one after the other on the room the search finds and
     overlapped into the ground.  Moves the trees on the device; returns the list of placed labels."""
@@ -161,7 +222,7 @@ def place(d: DeviceQTrees, inds=None, seed=1, mask_label=1):
     rng, q = Rng(seed), []
     new_rs, new_cs = [], []
     for lb in labels:
-        ind = findroom_uniform(ground, q, rng)
+        ind = findroom_gathering(ground, q, rng, level, p) if roomfinder == "gathering" else findroom_uniform(ground, q, rng)
         if ind is None:
             raise RuntimeError("no room for placement")
         ca, cb = indexcenter(*ind)

@@ -606,3 +606,27 @@ def test_set_shifts_leaves_unmoved_trees_alone_and_rebuilds_moved_ones(S, orc):
     for t, r, c in zip(qo, rs, cs):
         t.setshift(1, int(r), int(c))
     assert_same_trees(d, qo)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level,p", [(5, 2), (3, 1), (8, 4)])
+def test_place_with_findroom_gathering(S, orc, level, p):
+    """place!(...; roomfinder=findroom_gathering, level, p) (qtree_functions.jl:403-441): device ground + host search give
+    the oracle's shifts for the same seed — the start cells of level max(1, L - level), the centre-first shufflesort!"""
+    rng = np.random.default_rng(31)
+    objs = workloads.rect_objects(40, 40, rng)
+    qo = orc.qtrees(objs, mask=np.ones((260, 300), bool))
+    d = device_from_oracle(S, qo)
+    S.place(d, seed=11, roomfinder="gathering", level=level, p=p)
+    orc.place(qo, 11, roomfinder="gathering", level=level, p=p)
+    rs, cs = d.getshifts()
+    want = np.array([t.getshift() for t in qo])
+    assert np.array_equal(rs, want[:, 0]) and np.array_equal(cs, want[:, 1])
+    assert_same_trees(d, qo, labels=range(1, 8))
+    # gathering packs towards the centre: the mean distance to the canvas centre is smaller than with the uniform search
+    qu = orc.qtrees(objs, mask=np.ones((260, 300), bool)); orc.place(qu, 11)
+    def spread(qs):
+        c = np.array([t.getcenter() for t in qs[1:]], float); m = np.array(qs[0].getcenter(), float)
+        return float(np.mean(np.hypot(*(c - m).T)))
+    if (level, p) == (5, 2):
+        assert spread(qo) < spread(qu)

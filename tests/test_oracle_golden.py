@@ -300,3 +300,30 @@ def test_fit_converges(orc):
         orc.batchsteps(qts, c, opt, seed=3, iteration=it)
     assert nc == 0
     assert all(t.testqtree() == 0 for t in qts[1:])
+
+
+def test_place_roomfinders(orc):
+    """place! (Stuffing.jl:64-68) with both room finders (qtree_functions.jl:372-441): every tree lands with its centre on
+    a cell that was EMPTY in the ground built so far, the result depends on the seed only, and findroom_gathering packs
+    towards the centre (its queue is sorted by the distance from the centre)."""
+    import workloads
+    rng = np.random.default_rng(31)
+    objs = workloads.rect_objects(40, 40, rng)
+
+    def run(**kw):
+        qs = orc.qtrees(objs, mask=np.ones((260, 300), bool))
+        ground = qs[0].copy()
+        orc.place(qs, 11, **kw)
+        for t in qs[1:]:
+            ca, cb = t.getcenter()
+            assert ground.get(1, ca, cb) == orc.EMPTY
+            orc.overlap(ground, t)
+        c = np.array([t.getcenter() for t in qs[1:]], float); m = np.array(qs[0].getcenter(), float)
+        return [t.getshift() for t in qs], float(np.mean(np.hypot(*(c - m).T)))
+
+    su, du = run()
+    sg, dg = run(roomfinder="gathering")
+    assert run() == (su, du) and run(roomfinder="gathering") == (sg, dg)
+    assert su != sg and dg < du
+    run(roomfinder="gathering", level=3, p=1)
+    run(roomfinder="gathering", level=20, p=4)  # level beyond the pyramid: starts from level 1
