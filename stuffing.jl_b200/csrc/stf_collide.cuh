@@ -22,6 +22,7 @@ namespace cg = cooperative_groups;
 __global__ void k_locate(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
                          int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                          int* __restrict__ err, unsigned long long* __restrict__ n_append) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0; uint64_t ck[4]; int o = 0, slot = 0;
     if (j < nl) {
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
                                                            const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm,
                                                            const int32_t* __restrict__ moved_pos, EmitOut out, int shard_rank, int shard_n,
                                                            const int32_t* __restrict__ lvl_index) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     __shared__ int s_start[EM_THREADS / 32][16];
     __shared__ int s_pref[EM_THREADS / 32][17];
     const unsigned FULLM = 0xffffffffu;
@@ -310,6 +312,7 @@ struct NarrowArgs {
 // the hit the sequential BFS returns first; no MIX child = miss at the start node, qtree_functions.jl:27-41), with every
 // lane busy; only the pairs with a MIX-in-both child go on to the group-per-item frontier kernel below.
 __global__ void __launch_bounds__(256) k_collide_first(NarrowArgs A) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     int64_t n = A.n_items_dev ? (int64_t)*A.n_items_dev : A.n_items_host;
     if (A.n_items_dev && n > A.n_items_host) n = A.n_items_host; // clamp to buffer capacity
     unsigned long long visited = 0;
@@ -350,6 +353,7 @@ __global__ void __launch_bounds__(256) k_collide_first(NarrowArgs A) {
 // reserved chunk of the survivor list in the same iteration, so trip-count differences between items never idle lanes
 // (the earlier per-group loops ran with 11 of 32 lanes active on the batch workloads) and the votes are full-warp ballots.
 __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     __shared__ uint32_t fr[NP_THREADS / NP_GROUP][2][NP_FCAP];
     const unsigned FULLM = 0xffffffffu;
     const int lane = threadIdx.x & 31, gl = lane & 3, g0 = lane & ~3;
@@ -453,6 +457,7 @@ __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
 // large-frontier path: one CTA per overflowed item, frontier double-buffered in global scratch
 #define NPB_THREADS 256
 __global__ void __launch_bounds__(NPB_THREADS) k_collide_big(NarrowArgs A, uint32_t* __restrict__ scratch, int64_t cap_per_cta, int* __restrict__ err) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     __shared__ int w_push[NPB_THREADS / 32];
     __shared__ int w_hit[NPB_THREADS / 32];
     __shared__ int4 s_result;

@@ -49,6 +49,15 @@ template <bool CG> __device__ __forceinline__ LevelMeta ldmeta(const LevelMeta* 
     LevelMeta m; m.off = v.x; m.rs = (int)v.y; m.cs = (int)v.z; m.dims = v.w; return m;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may be
+// scheduled while its predecessor in the stream is still running.  Every such kernel starts with pdl_sync(): it lets its
+// own successor be scheduled early (all CTAs of this grid are resident or done by the time the last one gets here), then
+// waits until the predecessor grid has completed and its writes are visible.  Launched normally, both are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // t[l][a,b] — PaddedMat getindex (qtrees.jl:156-162) on the packed store
 template <bool CG> __device__ __forceinline__ uint32_t node_code(const uint32_t* __restrict__ words, const LevelMeta& m, int a, int b) {
     int r = a - m.rs - 1, c = b - m.cs - 1;

@@ -49,6 +49,7 @@ __global__ void __cluster_dims__(CS_CTAS, 1, 1) __launch_bounds__(CS_THREADS) k_
                                                              const unsigned long long* __restrict__ n_dev, int64_t cap, int key_bits, int vbits,
                                                              const int32_t* __restrict__ val_map, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                              unsigned long long* __restrict__ n_out, int* __restrict__ status) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClusterSortSmem& S = *reinterpret_cast<ClusterSortSmem*>(smem_raw);
     const int c = (int)cg::this_cluster().block_rank();
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_step_links(const Item16* __restr
 // step-dependency links.  CTA c owns slice c of every sorted sequence; neighbours across a slice boundary are read from
 // global memory (sorted keys) or from the previous CTA's shared memory (endpoint records).
 __global__ void __cluster_dims__(CS_CTAS, 1, 1) __launch_bounds__(CS_THREADS) k_finalize_prep_cl(FinalizeArgs A, uint64_t* __restrict__ skey) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClusterSortSmem& S = *reinterpret_cast<ClusterSortSmem*>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();

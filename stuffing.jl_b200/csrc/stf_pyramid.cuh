@@ -226,6 +226,7 @@ __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restr
                                 const int2* __restrict__ work, int nwork, const ObjMeta* __restrict__ om, int skip_big, int grp,
                                 const int32_t* __restrict__ labels = nullptr, const int32_t* __restrict__ srs = nullptr, const int32_t* __restrict__ scs = nullptr,
                                 int level = 0, int add = 0, int* __restrict__ built_from = nullptr, int skip_same = 0) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     __shared__ uint32_t sbuf[8][2 * RB_HALF]; // blockDim.x == 256
     const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

@@ -114,6 +114,7 @@ __device__ __forceinline__ int3 move_decide(const StepArgs& A, double d0, double
 // scenes, 6 (80 registers) for batches of scenes, where independent chains fill the extra warps
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_batchsteps(StepArgs A) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     __shared__ uint32_t sbuf[4][2 * RB_HALF]; // only the rare eager materialisation uses it
     __shared__ uint64_t s_rnd[4][8];
     __shared__ int2 s_shift[4][32];
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(128, MINB) k_batchsteps(StepArgs A) {
 // after the batch: rebuild the rasters of the levels above dirty[o] with the tracked shifts.  32 objects per warp: the
 // levels with real width by the whole warp, the tail levels by one thread per object.
 __global__ void __launch_bounds__(256) k_materialize(uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, int n, int* __restrict__ dirty, int* __restrict__ built_from, int grp) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     __shared__ uint32_t sbuf[8][2 * RB_HALF];
     const unsigned FULLM = 0xffffffffu;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

@@ -36,6 +36,7 @@ struct DevBuf {
 struct stf_ctx {
     int device = 0; cudaStream_t st = nullptr; std::string err;
     int n = 0, L = 0, canvas = 0; uint64_t total_words = 0;
+    bool pdl = true; // programmatic dependent launch between the kernels of a round (STF_NO_PDL=1: plain stream order)
     bool raw_shift_edit = false; // stf_set_level_shift was used: shifts and rasters may disagree, never skip a rebuild
     int scene_bits = 0, label_bits = 1; bool multi_scene = false, sizelevel_ok = true, has_big = false;
     std::vector<ObjMeta> h_om; std::vector<uint32_t> h_off; // h_off[o*L + l-1]: word offsets (static)
@@ -66,6 +67,16 @@ struct stf_ctx {
     char* h_out = nullptr; size_t h_out_cap = 0; // pinned landing area of small read-backs
     char* stg = nullptr; size_t stg_cap = 0, stg_off = 0; cudaEvent_t stg_ev = nullptr; bool stg_busy = false;
 };
+// launch with the programmatic-dependent-launch attribute (the kernel must start with pdl_sync()); STF_NO_PDL=1 disables
+#define LAUNCH_PDL(ctx, kern, grid, block, smem, ...) do { \
+    (ctx)->launches++; \
+    if ((ctx)->pdl) { \
+        cudaLaunchConfig_t cfg_ = {}; cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block); cfg_.dynamicSmemBytes = (smem); cfg_.stream = (ctx)->st; \
+        cudaLaunchAttribute at_[1]; at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at_[0].val.programmaticStreamSerializationAllowed = 1; \
+        cfg_.attrs = at_; cfg_.numAttrs = 1; \
+        cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__); \
+    } else kern<<<grid, block, smem, (ctx)->st>>>(__VA_ARGS__); } while (0)
+
 // several host arrays -> ONE contiguous device range with one copy (dst + sum of the earlier sizes, no padding)
 struct HostPart { const void* src; size_t bytes; };
 static cudaError_t stage_h2d_parts(stf_ctx* ctx, void* dst, const HostPart* parts, int nparts) {
@@ -167,6 +178,7 @@ extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return STF_E_CUDA;
     stf_ctx* ctx = new stf_ctx();
     ctx->device = device;
+    if (getenv("STF_NO_PDL")) ctx->pdl = false;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || (ctx->h_err = (int*)calloc(2, sizeof(int))) == nullptr ||
         ctx->counts.ensure(C_N * sizeof(unsigned long long)) != cudaSuccess) {
@@ -441,6 +453,7 @@ extern "C" int32_t stf_grad2d(stf_ctx* ctx, int32_t n, const int32_t* labels, co
     return STF_OK;
 }
 __global__ void k_get_shifts(const LevelMeta* __restrict__ lm, int L, int n, const int32_t* __restrict__ labels, int level, int32_t* __restrict__ out) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int o = labels ? labels[i] - 1 : i;
@@ -453,7 +466,7 @@ extern "C" int32_t stf_get_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
     if (n == 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r;
     CK(ctx->out32.ensure(sizeof(int32_t) * 2 * (size_t)n));
-    ctx->launches++, k_get_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, dl, level, ctx->out32.as<int32_t>());
+    LAUNCH_PDL(ctx, k_get_shifts, nblk(n, 256), 256, 0, ctx->lm.as<LevelMeta>(), ctx->L, n, dl, level, ctx->out32.as<int32_t>());
     KCHECK();
     // one device->host copy into pinned memory, split into the caller's two arrays afterwards
     const size_t nb = sizeof(int32_t) * (size_t)n;
@@ -477,8 +490,8 @@ static int32_t rebuild_after(stf_ctx* ctx, int n, const int32_t* labels_host, in
     if (from >= ctx->L) return STF_OK;
     int grp = rebuild_group(n);
     int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
-    ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
-                                                                 nullptr, nullptr, nullptr, 0, 0, ctx->built_from.as<int>());
+    LAUNCH_PDL(ctx, k_build_objects, blocks, 256, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
+                                                                 nullptr, nullptr, nullptr, 0, 0, ctx->built_from.as<int>(), 0);
     KCHECK();
     if (ctx->has_big)
         for (int i = 0; i < n; i++) { int o = labels_host ? labels_host[i] - 1 : i; if (ctx->h_om[o].big) { int32_t r = build_big(ctx, o, from); if (r) return r; } }
@@ -504,7 +517,7 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
     { // one launch: shift + rebuild of every listed tree (mask-sized ones: shift here, rebuild by the wide launches below)
         int grp = rebuild_group(n);
         int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
-        ctx->launches++, k_build_objects<<<blocks, 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, nullptr, n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
+        LAUNCH_PDL(ctx, k_build_objects, blocks, 256, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, nullptr, n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
                                                                      dl, drs, dcs, level, mode & 1, ctx->built_from.as<int>(), ctx->raw_shift_edit ? 0 : 1);
         KCHECK();
         if (ctx->has_big && level < ctx->L)
@@ -564,12 +577,12 @@ static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want
     if (n_host >= 0) CK(cudaMemsetAsync(A.nsurv, 0, sizeof(unsigned long long), ctx->st)); // (the latency path zeroes the whole counter array once)
     int per_block = NP_THREADS / NP_GROUP;
     int64_t want = n_host >= 0 ? n_host : std::max<int64_t>(ctx->hint_items, 4096);
-    ctx->launches++, k_collide_first<<<(int)std::min<int64_t>(std::max<int64_t>(1, (want + 255) / 256), 148 * 16), 256, 0, ctx->st>>>(A);
+    LAUNCH_PDL(ctx, k_collide_first, (int)std::min<int64_t>(std::max<int64_t>(1, (want + 255) / 256), 148 * 16), 256, 0, A);
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want / 2 + per_block - 1) / per_block), 148 * 16); // typically < half the items survive; the warps share the list dynamically
-    ctx->launches++, k_collide_small<<<blocks, NP_THREADS, 0, ctx->st>>>(A);
+    LAUNCH_PDL(ctx, k_collide_small, blocks, NP_THREADS, 0, A);
     KCHECK();
     CK(ctx->scratch.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->big_cap * ctx->big_ctas));
-    ctx->launches++, k_collide_big<<<ctx->big_ctas, NPB_THREADS, 0, ctx->st>>>(A, ctx->scratch.as<uint32_t>(), ctx->big_cap, ERRP(ctx));
+    LAUNCH_PDL(ctx, k_collide_big, ctx->big_ctas, NPB_THREADS, 0, A, ctx->scratch.as<uint32_t>(), ctx->big_cap, ERRP(ctx));
     KCHECK();
     return STF_OK;
 }
@@ -787,11 +800,11 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     if (fast) {
         set_smem_attrs();
         if (linked) {
-            if (nl > 0) ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
+            if (nl > 0) LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
                                                                    ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
             ctx->launches++, k_compact_records<<<nblk(nrec, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), nrec, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend);
         } else if (nl > 0) {
-            ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
+            LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
                                                         ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ERRP(ctx), nappend);
         }
         KCHECK();
@@ -800,7 +813,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
             ctx->launches++, k_sort_records<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
                                                                                       linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, STATUSP(ctx));
         else // one cluster of 8 CTAs
-            ctx->launches++, k_sort_records_cl<<<CS_CTAS, CS_THREADS, CS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
+            LAUNCH_PDL(ctx, k_sort_records_cl, CS_CTAS, CS_THREADS, CS_SMEM_BYTES, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
                                                                                                linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, STATUSP(ctx));
         KCHECK();
         *keys = ctx->rk.as<uint64_t>(); *vals = ctx->rv.as<uint32_t>();
@@ -810,12 +823,12 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     }
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
     if (linked) {
-        if (nl > 0) ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
+        if (nl > 0) LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
                                                                ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
         CK(cudaMemcpyAsync(ctx->rk.p, ctx->lkk.p, sizeof(uint64_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->rv.p, ctx->lkv.p, sizeof(uint32_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
     } else if (nl > 0) {
-        ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
+        LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
                                                     ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ERRP(ctx), nullptr);
     }
     KCHECK();
@@ -876,7 +889,7 @@ extern "C" int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* la
     if (!labels) nl = ctx->n;
     if (nl <= 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
-    ctx->launches++, k_locate<<<nblk(nl, 128), 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
+    LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
                                                 ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
     KCHECK();
     return sync_counts(ctx);
@@ -913,7 +926,7 @@ static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, con
     stage_begin(ctx, STF_STAGE_EMIT);
     if (nrec > 0) {
         int blocks = (int)std::min<int64_t>((nrec / 4 + EM_THREADS / 32 - 1) / (EM_THREADS / 32) + 1, 148 * 8); // ~1 record per located object
-        ctx->launches++, k_emit_items<<<blocks, EM_THREADS, 0, ctx->st>>>(keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
+        LAUNCH_PDL(ctx, k_emit_items, blocks, EM_THREADS, 0, keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
                                                                         ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n, lvl_index);
     }
     KCHECK();
@@ -1079,12 +1092,11 @@ static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, co
     if (A.dbg & 16) { CK(ctx->dbg_t.ensure(sizeof(unsigned long long) * 4 * (size_t)std::max<int64_t>(n_host, BS_CAP))); A.dbg_t = ctx->dbg_t.as<unsigned long long>(); }
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (n_host + 3) / 4), 148 * 8);
     stage_begin(ctx, STF_STAGE_STEP);
-    ctx->launches++;
-    if (n_host > 32768) k_batchsteps<6><<<blocks, 128, 0, ctx->st>>>(A);
-    else k_batchsteps<4><<<blocks, 128, 0, ctx->st>>>(A);
+    if (n_host > 32768) LAUNCH_PDL(ctx, k_batchsteps<6>, blocks, 128, 0, A);
+    else LAUNCH_PDL(ctx, k_batchsteps<4>, blocks, 128, 0, A);
     // the steps only moved the shifts: materialise the rasters of every moved tree once
     { int grp = rebuild_group(ctx->n);
-      ctx->launches++, k_materialize<<<std::min(nblk(((int64_t)ctx->n + grp - 1) / grp * 32, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->n, ctx->dirty.as<int>(), ctx->built_from.as<int>(), grp); }
+      LAUNCH_PDL(ctx, k_materialize, std::min(nblk(((int64_t)ctx->n + grp - 1) / grp * 32, 256), 148 * 8), 256, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->n, ctx->dirty.as<int>(), ctx->built_from.as<int>(), grp); }
     KCHECK();
     stage_end(ctx);
     return STF_OK;
@@ -1145,7 +1157,7 @@ static int32_t pos_enqueue(stf_ctx* ctx) {
         ctx->h_out = nullptr; ctx->h_out_cap = 0;
         CK(cudaMallocHost(&ctx->h_out, 4 * nb)); ctx->h_out_cap = 4 * nb;
     }
-    ctx->launches++, k_get_shifts<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->lm.as<LevelMeta>(), ctx->L, n, nullptr, ctx->pos_level, ctx->out32.as<int32_t>());
+    LAUNCH_PDL(ctx, k_get_shifts, nblk(n, 256), 256, 0, ctx->lm.as<LevelMeta>(), ctx->L, n, nullptr, ctx->pos_level, ctx->out32.as<int32_t>());
     KCHECK();
     CK(cudaMemcpyAsync(ctx->h_out, ctx->out32.p, 2 * nb, cudaMemcpyDeviceToHost, ctx->st));
     return STF_OK;
@@ -1187,7 +1199,7 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
         if (getenv("STF_NO_CLUSTER")) ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
         else {
             CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)(CS_CAP + 1024)));
-            ctx->launches++, k_finalize_prep_cl<<<CS_CTAS, CS_THREADS, CS_SMEM_BYTES, ctx->st>>>(F, ctx->hk.as<uint64_t>());
+            LAUNCH_PDL(ctx, k_finalize_prep_cl, CS_CTAS, CS_THREADS, CS_SMEM_BYTES, F, ctx->hk.as<uint64_t>());
         }
         KCHECK();
         r = launch_steps(ctx, ctx->hits2.as<Item16>(), std::max<int64_t>(ctx->ctr.hits, 2048), ctx->counts.as<unsigned long long>() + C_NSTEPS, seed, iteration); if (r) return r;
