@@ -72,6 +72,7 @@ __global__ void k_locate(const uint32_t* __restrict__ words, const LevelMeta* __
 // LinkedSpacialQTree table (4 slots per object) -> compact (key, label) records, unordered
 __global__ void k_compact_records(const uint64_t* __restrict__ tk, const uint32_t* __restrict__ tv, int64_t nslots,
                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_append) {
+    pdl_sync();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t k = i < nslots ? tk[i] : STF_KEY_INVALID;
     bool v = k != STF_KEY_INVALID;
@@ -101,6 +102,7 @@ __device__ __forceinline__ int64_t lower_bound_u64(const uint64_t* __restrict__ 
 // (scene, level) index of the sorted records: idx[sl] = first record whose (scene << 5 | level) >= sl, idx[nsl] = n.
 // Batches of scenes search an ancestor cell inside its own (scene, level) slice (a few records) instead of the whole array.
 __global__ void k_level_index(const uint64_t* __restrict__ keys, const unsigned long long* __restrict__ n_dev, int64_t cap, int32_t* __restrict__ idx, int nsl) {
+    pdl_sync();
     int64_t n = min((int64_t)*n_dev, cap);
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n) return;
@@ -565,10 +567,12 @@ __global__ void k_collision_dfs(const uint32_t* __restrict__ words, const LevelM
 // result ordering: sort!(r) and unique!(minmax∘first, ·)  (qtree_functions.jl:252)
 // =============================================================================================
 __global__ void k_hit_keys(const Item16* __restrict__ hits, int64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    pdl_sync();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { keys[i] = ((uint64_t)(uint32_t)hits[i].i1 << 32) | (uint32_t)item_i2(hits[i]); vals[i] = (uint32_t)i; }
 }
 __global__ void k_gather_hits(const Item16* __restrict__ hits, const uint32_t* __restrict__ vals, int64_t n, Item16* __restrict__ out) {
+    pdl_sync();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = hits[vals[i]];
 }
@@ -579,6 +583,7 @@ __device__ __forceinline__ bool lab_less(const Item16& x, const Item16& y) {
 // hits of one ordered pair (i1,i2) are adjacent after the radix sort; order them by (l,a,b) and mark what
 // unique! keeps: the first entry of a run, unless the swapped pair (i2,i1) sorts earlier (i1 > i2 and it exists)
 __global__ void k_fix_ties(Item16* __restrict__ hits, const uint64_t* __restrict__ keys, int64_t n, int unique, uint32_t* __restrict__ keep) {
+    pdl_sync();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t key = keys[i];
@@ -603,6 +608,7 @@ __global__ void k_fix_ties(Item16* __restrict__ hits, const uint64_t* __restrict
     }
 }
 __global__ void k_export_hits(const Item16* __restrict__ hits, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, int64_t n, int32_t* __restrict__ out /*5 ints each*/) {
+    pdl_sync();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !keep[i]) return;
     int32_t* o = out + 5 * (size_t)pos[i];

@@ -50,12 +50,15 @@ template <bool CG> __device__ __forceinline__ LevelMeta ldmeta(const LevelMeta* 
 }
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may be
-// scheduled while its predecessor in the stream is still running.  Every such kernel starts with pdl_sync(): it lets its
-// own successor be scheduled early (all CTAs of this grid are resident or done by the time the last one gets here), then
-// waits until the predecessor grid has completed and its writes are visible.  Launched normally, both are no-ops.
+// scheduled while its predecessor in the stream is still running.  Every such kernel starts with pdl_sync(): wait until
+// the predecessor grid has completed and its writes are visible, THEN let the own successor be scheduled (it parks in
+// its wait while this grid runs: its launch latency and prologue are off the critical path).  The order matters:
+// triggering before the wait lets a chain A -> B -> C schedule C while A still runs, and on B200 C's wait was then
+// observed to return before A's writes were complete (a second call on one context lost its candidate list).
+// Launched without the attribute, both instructions are no-ops.
 __device__ __forceinline__ void pdl_sync() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // t[l][a,b] — PaddedMat getindex (qtrees.jl:156-162) on the packed store

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_records(const uint64_t* __r
                                                              const unsigned long long* __restrict__ n_dev, int64_t cap, int key_bits, int vbits,
                                                              const int32_t* __restrict__ val_map, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                              unsigned long long* __restrict__ n_out, int* __restrict__ status) {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockSortSmem& S = *reinterpret_cast<BlockSortSmem*>(smem_raw);
     int64_t n64 = (int64_t)*n_dev;
@@ -128,6 +129,7 @@ __device__ __forceinline__ void fin_step_links(BlockSortSmem& S, const Item16* _
 }
 
 __global__ void __launch_bounds__(BS_THREADS) k_finalize_hits(FinalizeArgs A) {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockSortSmem& S = *reinterpret_cast<BlockSortSmem*>(smem_raw);
     __shared__ uint32_t s_kept;
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_finalize_hits(FinalizeArgs A) {
 // links only, for a caller-ordered list (stf_batchsteps: the list order is the canonical step order); n <= BS_CAP/2
 __global__ void __launch_bounds__(BS_THREADS) k_step_links(const Item16* __restrict__ list, int n, int lb, const ObjMeta* __restrict__ om,
                                                            uint32_t* __restrict__ prev, uint32_t* __restrict__ done, unsigned long long* __restrict__ ticket) {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockSortSmem& S = *reinterpret_cast<BlockSortSmem*>(smem_raw);
     fin_step_links(S, list, n, lb, om, prev, done);

@@ -58,6 +58,7 @@ static inline std::vector<DigitPass> plan_digits(uint64_t bits) {
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint64_t* __restrict__ keys, int64_t n, DigitPass P, int per_warp, int nvw, uint32_t* __restrict__ hist) {
+    pdl_sync();
     __shared__ uint32_t cnt[SORT_WARPS_PER_BLOCK][256];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int vw = blockIdx.x * SORT_WARPS_PER_BLOCK + w;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint64_t* __re
 }
 // CTA d: exclusive scan of digit d's per-warp counts (in place), digit total -> dtot[d]
 __global__ void __launch_bounds__(256) k_sort_scan_digit(uint32_t* __restrict__ hist, int nvw, uint32_t* __restrict__ dtot) {
+    pdl_sync();
     __shared__ uint32_t wsum[8];
     uint32_t* row = hist + (size_t)blockIdx.x * nvw;
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(256) k_sort_scan_digit(uint32_t* __restrict__ 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, DigitPass P,
                                                                int per_warp, int nvw, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ dtot,
                                                                uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    pdl_sync();
     __shared__ uint32_t base[SORT_WARPS_PER_BLOCK][256];
     __shared__ uint32_t dbase[256];
     __shared__ uint32_t wsum[8];
@@ -151,8 +154,18 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* _
 
 // Sorts (keys, vals) by the key bits set in `bits`.  Buffers ping-pong; returns 0 if the result is in (keys, vals),
 // 1 if it is in (keys_alt, vals_alt).  `hist` holds >= 256*nvw + 256 uint32 (the last 256: digit totals).
+template <typename... KArgs, typename... Args>
+static inline void sort_launch(bool pdl, cudaStream_t st, void (*kern)(KArgs...), int grid, int block, Args... args) {
+    if (!pdl) { kern<<<grid, block, 0, st>>>(args...); return; }
+    cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.stream = st;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+}
 static inline int radix_sort_pairs(cudaStream_t st, int64_t* launches, uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
-                                   int64_t n, uint64_t bits, uint32_t* hist) {
+                                   int64_t n, uint64_t bits, uint32_t* hist, bool pdl = false, bool* after_kernel = nullptr) {
+    // *after_kernel: the stream's last operation is a kernel (a copy or memset before a programmatic launch is not waited for)
+    bool pdl_first = after_kernel && *after_kernel;
     if (n <= 1) return 0;
     SortPlan p = sort_plan(n);
     uint32_t* dtot = hist + (size_t)256 * p.nvw;
@@ -160,10 +173,11 @@ static inline int radix_sort_pairs(cudaStream_t st, int64_t* launches, uint64_t*
     for (const DigitPass& P : plan_digits(bits)) {
         uint64_t* kin = flip ? keys_alt : keys; uint32_t* vin = flip ? vals_alt : vals;
         uint64_t* kout = flip ? keys : keys_alt; uint32_t* vout = flip ? vals : vals_alt;
-        k_sort_hist<<<p.blocks, SORT_THREADS, 0, st>>>(kin, n, P, p.per_warp, p.nvw, hist);
-        k_sort_scan_digit<<<256, 256, 0, st>>>(hist, p.nvw, dtot);
-        k_sort_scatter<<<p.blocks, SORT_THREADS, 0, st>>>(kin, vin, n, P, p.per_warp, p.nvw, hist, dtot, kout, vout);
+        sort_launch(pdl && pdl_first, st, k_sort_hist, p.blocks, SORT_THREADS, (const uint64_t*)kin, n, P, p.per_warp, p.nvw, hist);
+        sort_launch(pdl, st, k_sort_scan_digit, 256, 256, hist, p.nvw, dtot);
+        sort_launch(pdl, st, k_sort_scatter, p.blocks, SORT_THREADS, (const uint64_t*)kin, (const uint32_t*)vin, n, P, p.per_warp, p.nvw, (const uint32_t*)hist, (const uint32_t*)dtot, kout, vout);
         flip ^= 1; if (launches) *launches += 3;
+        pdl_first = true; if (after_kernel) *after_kernel = true;
     }
     return flip;
 }
@@ -172,6 +186,7 @@ static inline size_t radix_sort_hist_words(int64_t n) { return (size_t)256 * sor
 
 // exclusive scan of `m` uint32 by ONE block (small m only: per-block counts of a compaction)
 __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, int64_t m, uint32_t* __restrict__ total) {
+    pdl_sync();
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry, btot;
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -208,12 +223,14 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, 
 // ---- order-preserving compaction of the 4-slot record table (INVALID keys dropped) + the OR of all key differences
 #define CMP_BLOCK 1024
 __global__ void __launch_bounds__(CMP_BLOCK) k_compact_count(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ blockcnt) {
+    pdl_sync();
     int64_t i = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
     int c = __syncthreads_count(i < n && keys[i] != STF_KEY_INVALID);
     if (threadIdx.x == 0) blockcnt[blockIdx.x] = (uint32_t)c;
 }
 __global__ void __launch_bounds__(CMP_BLOCK) k_compact_write(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, const uint32_t* __restrict__ blockoff,
                                                              uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    pdl_sync();
     __shared__ uint32_t wsum[32];
     int64_t i = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -228,6 +245,7 @@ __global__ void __launch_bounds__(CMP_BLOCK) k_compact_write(const uint64_t* __r
 }
 // vary |= OR over i < n of keys[i] ^ keys[0]  (n on the device): the bits the sort has to look at
 __global__ void __launch_bounds__(256) k_vary_or(const uint64_t* __restrict__ keys, const unsigned long long* __restrict__ n_dev, int64_t cap, unsigned long long* __restrict__ vary) {
+    pdl_sync();
     __shared__ unsigned long long wor[8];
     int64_t n = min((int64_t)*n_dev, cap);
     unsigned long long x = 0;

@@ -18,6 +18,7 @@ struct OptState { int kind; double eta, rho; };
 // endpoints: one per (step k, side s) with a movable object; key = object, stable-sorted so that the
 // entries of one object are in list order.  prev[2k+s] = index of the previous step of that object (+1), 0 = none.
 __global__ void k_step_endpoints(const Item16* __restrict__ hits, int64_t n, const ObjMeta* __restrict__ om, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    pdl_sync();
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= 2 * n) return;
     int64_t k = e >> 1; int s = (int)(e & 1);
@@ -26,6 +27,7 @@ __global__ void k_step_endpoints(const Item16* __restrict__ hits, int64_t n, con
     vals[e] = (uint32_t)e;
 }
 __global__ void k_step_prev(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const unsigned long long* __restrict__ m_dev, int64_t m_cap, uint32_t* __restrict__ prev) {
+    pdl_sync();
     int64_t m = m_dev ? min((int64_t)*m_dev, m_cap) : m_cap;
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m) return;
@@ -41,6 +43,7 @@ __global__ void k_step_prev(const uint64_t* __restrict__ keys, const uint32_t* _
 // tickets in that order puts all steps without a pending predecessor first: independent chains (e.g. the scenes of a
 // batch) overlap instead of being walked one after the other.
 __global__ void k_step_level(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ lin, uint32_t* __restrict__ lout, int64_t n) {
+    pdl_sync();
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t p0 = prev[2 * k], p1 = prev[2 * k + 1], l = 0;
@@ -49,6 +52,7 @@ __global__ void k_step_level(const uint32_t* __restrict__ prev, const uint32_t* 
     lout[k] = l;
 }
 __global__ void k_step_level_keys(const uint32_t* __restrict__ lvl, int64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    pdl_sync();
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) { keys[k] = lvl[k]; vals[k] = (uint32_t)k; }
 }

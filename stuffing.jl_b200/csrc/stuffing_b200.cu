@@ -36,6 +36,8 @@ struct DevBuf {
 struct stf_ctx {
     int device = 0; cudaStream_t st = nullptr; std::string err;
     int n = 0, L = 0, canvas = 0; uint64_t total_words = 0;
+    const char* pdl_skip = getenv("STF_PDL_SKIP"); // debugging: kernels (by name) launched without the attribute
+    bool after_kernel = false; // the last operation enqueued on the stream was one of our kernel launches
     bool pdl = true; // programmatic dependent launch between the kernels of a round (STF_NO_PDL=1: plain stream order)
     bool raw_shift_edit = false; // stf_set_level_shift was used: shifts and rasters may disagree, never skip a rebuild
     int scene_bits = 0, label_bits = 1; bool multi_scene = false, sizelevel_ok = true, has_big = false;
@@ -67,15 +69,22 @@ struct stf_ctx {
     char* h_out = nullptr; size_t h_out_cap = 0; // pinned landing area of small read-backs
     char* stg = nullptr; size_t stg_cap = 0, stg_off = 0; cudaEvent_t stg_ev = nullptr; bool stg_busy = false;
 };
+// Copies, memsets and event records are not grids: to stay on documented ground, a kernel gets the programmatic attribute
+// only when the operation enqueued right before it was one of our kernels.  Every copy/memset/event call in this file
+// clears after_kernel.
+#define cudaMemsetAsync(...) (ctx->after_kernel = false, cudaMemsetAsync(__VA_ARGS__))
+#define cudaMemcpyAsync(...) (ctx->after_kernel = false, cudaMemcpyAsync(__VA_ARGS__))
+#define cudaEventRecord(...) (ctx->after_kernel = false, cudaEventRecord(__VA_ARGS__))
 // launch with the programmatic-dependent-launch attribute (the kernel must start with pdl_sync()); STF_NO_PDL=1 disables
 #define LAUNCH_PDL(ctx, kern, grid, block, smem, ...) do { \
     (ctx)->launches++; \
-    if ((ctx)->pdl) { \
+    if ((ctx)->pdl && (ctx)->after_kernel && !((ctx)->pdl_skip && strstr((ctx)->pdl_skip, #kern))) { \
         cudaLaunchConfig_t cfg_ = {}; cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block); cfg_.dynamicSmemBytes = (smem); cfg_.stream = (ctx)->st; \
         cudaLaunchAttribute at_[1]; at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at_[0].val.programmaticStreamSerializationAllowed = 1; \
         cfg_.attrs = at_; cfg_.numAttrs = 1; \
         cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__); \
-    } else kern<<<grid, block, smem, (ctx)->st>>>(__VA_ARGS__); } while (0)
+    } else kern<<<grid, block, smem, (ctx)->st>>>(__VA_ARGS__); \
+    (ctx)->after_kernel = true; } while (0)
 
 // several host arrays -> ONE contiguous device range with one copy (dst + sum of the earlier sizes, no padding)
 struct HostPart { const void* src; size_t bytes; };
@@ -662,7 +671,7 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
         F.n_items_dev = nullptr; F.item_cap = 0; F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = unique;
         F.out5 = export_host_format ? ctx->out32.as<int32_t>() : nullptr; F.kept = ctx->counts.as<unsigned long long>() + C_KEPT;
         F.do_prep = 0; F.status = STATUSP(ctx);
-        ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
+        LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
         KCHECK();
         stage_end(ctx);
         if (!export_host_format) { *nout = nh; return STF_OK; }
@@ -673,23 +682,23 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
     size_t kb = sizeof(uint64_t) * (size_t)nh, vb = sizeof(uint32_t) * (size_t)nh;
     CK(ctx->hk.ensure(kb)); CK(ctx->hk2.ensure(kb)); CK(ctx->hv.ensure(vb)); CK(ctx->hv2.ensure(vb)); CK(ctx->keep.ensure(vb + 16));
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(nh)));
-    ctx->launches++, k_hit_keys<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+    LAUNCH_PDL(ctx, k_hit_keys, nblk(nh, 256), 256, 0, ctx->hits.as<Item16>(), nh, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
     uint64_t* ks; uint32_t* vs;
     { // (i1, i2) = bits [32, 32+lb) and [0, lb): one LSD sort over exactly those bits
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh,
-                                 bit_range(0, ctx->label_bits) | bit_range(32, 32 + ctx->label_bits), ctx->hist.as<uint32_t>());
+                                 bit_range(0, ctx->label_bits) | bit_range(32, 32 + ctx->label_bits), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
         ks = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(); vs = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
     }
-    ctx->launches++, k_gather_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits.as<Item16>(), vs, nh, ctx->hits2.as<Item16>());
-    ctx->launches++, k_fix_ties<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ks, nh, unique, ctx->keep.as<uint32_t>());
+    LAUNCH_PDL(ctx, k_gather_hits, nblk(nh, 256), 256, 0, ctx->hits.as<Item16>(), vs, nh, ctx->hits2.as<Item16>());
+    LAUNCH_PDL(ctx, k_fix_ties, nblk(nh, 256), 256, 0, ctx->hits2.as<Item16>(), ks, nh, unique, ctx->keep.as<uint32_t>());
     KCHECK();
     if (!export_host_format && !unique) { *nout = nh; stage_end(ctx); return STF_OK; }
     // positions = exclusive scan of keep (reuse the other value buffer)
     uint32_t* pos = (vs == ctx->hv.as<uint32_t>()) ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
     CK(cudaMemcpyAsync(pos, ctx->keep.p, vb, cudaMemcpyDeviceToDevice, ctx->st));
-    ctx->launches++, k_scan_u32<<<1, 1024, 0, ctx->st>>>(pos, nh, reinterpret_cast<uint32_t*>(ctx->counts.as<unsigned long long>() + C_KEPT));
+    LAUNCH_PDL(ctx, k_scan_u32, 1, 1024, 0, pos, nh, reinterpret_cast<uint32_t*>(ctx->counts.as<unsigned long long>() + C_KEPT));
     CK(ctx->out32.ensure(sizeof(int32_t) * 5 * (size_t)nh));
-    ctx->launches++, k_export_hits<<<nblk(nh, 256), 256, 0, ctx->st>>>(ctx->hits2.as<Item16>(), ctx->keep.as<uint32_t>(), pos, nh, ctx->out32.as<int32_t>());
+    LAUNCH_PDL(ctx, k_export_hits, nblk(nh, 256), 256, 0, ctx->hits2.as<Item16>(), ctx->keep.as<uint32_t>(), pos, nh, ctx->out32.as<int32_t>());
     KCHECK();
     stage_end(ctx);
     int32_t r = sync_counts(ctx); if (r) return r;
@@ -802,7 +811,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
         if (linked) {
             if (nl > 0) LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
                                                                    ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
-            ctx->launches++, k_compact_records<<<nblk(nrec, 256), 256, 0, ctx->st>>>(ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), nrec, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend);
+            LAUNCH_PDL(ctx, k_compact_records, nblk(nrec, 256), 256, 0, ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), nrec, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend);
         } else if (nl > 0) {
             LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
                                                         ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ERRP(ctx), nappend);
@@ -810,7 +819,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
         KCHECK();
         stage_begin(ctx, STF_STAGE_SORT);
         if (getenv("STF_NO_CLUSTER")) // single-CTA variant (kept for comparison)
-            ctx->launches++, k_sort_records<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
+            LAUNCH_PDL(ctx, k_sort_records, 1, BS_THREADS, BS_SMEM_BYTES, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
                                                                                       linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, STATUSP(ctx));
         else // one cluster of 8 CTAs
             LAUNCH_PDL(ctx, k_sort_records_cl, CS_CTAS, CS_THREADS, CS_SMEM_BYTES, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
@@ -838,15 +847,15 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
         CK(ctx->keep.ensure(sizeof(uint32_t) * (size_t)(nb + 16)));
         unsigned long long* vary = ctx->counts.as<unsigned long long>() + C_VARY;
         CK(cudaMemsetAsync(nvalid, 0, sizeof(unsigned long long), ctx->st)); CK(cudaMemsetAsync(vary, 0, sizeof(unsigned long long), ctx->st));
-        ctx->launches++, k_compact_count<<<nb, CMP_BLOCK, 0, ctx->st>>>(ctx->rk.as<uint64_t>(), nrec, ctx->keep.as<uint32_t>());
-        ctx->launches++, k_scan_u32<<<1, 1024, 0, ctx->st>>>(ctx->keep.as<uint32_t>(), nb, reinterpret_cast<uint32_t*>(nvalid));
-        ctx->launches++, k_compact_write<<<nb, CMP_BLOCK, 0, ctx->st>>>(ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nrec, ctx->keep.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>());
-        ctx->launches++, k_vary_or<<<std::min(nblk(nrec / 4 + 1, 256), 148 * 4), 256, 0, ctx->st>>>(ctx->rk2.as<uint64_t>(), nvalid, nrec, vary);
+        LAUNCH_PDL(ctx, k_compact_count, nb, CMP_BLOCK, 0, ctx->rk.as<uint64_t>(), nrec, ctx->keep.as<uint32_t>());
+        LAUNCH_PDL(ctx, k_scan_u32, 1, 1024, 0, ctx->keep.as<uint32_t>(), nb, reinterpret_cast<uint32_t*>(nvalid));
+        LAUNCH_PDL(ctx, k_compact_write, nb, CMP_BLOCK, 0, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nrec, ctx->keep.as<uint32_t>(), ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>());
+        LAUNCH_PDL(ctx, k_vary_or, std::min(nblk(nrec / 4 + 1, 256), 148 * 4), 256, 0, ctx->rk2.as<uint64_t>(), nvalid, nrec, vary);
         KCHECK();
         int32_t r = sync_counts(ctx); if (r) return r;
         int64_t nv = (int64_t)ctx->h_counts[C_NVALID];
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nv,
-                                 (uint64_t)ctx->h_counts[C_VARY] & bit_range(0, bits), ctx->hist.as<uint32_t>());
+                                 (uint64_t)ctx->h_counts[C_VARY] & bit_range(0, bits), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
         *keys = f ? ctx->rk.as<uint64_t>() : ctx->rk2.as<uint64_t>();
         *vals = f ? ctx->rv.as<uint32_t>() : ctx->rv2.as<uint32_t>();
     }
@@ -917,7 +926,7 @@ static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, con
     if ((ctx->multi_scene || nrec > 65536) && nrec > 0) { // batches: (scene, level) index of the sorted records for the ancestor searches
         int nsl = 32 << ctx->scene_bits;
         CK(ctx->lvlidx.ensure(sizeof(int32_t) * (size_t)(nsl + 2)));
-        ctx->launches++, k_level_index<<<nblk(nrec + 1, 256), 256, 0, ctx->st>>>(keys, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->lvlidx.as<int32_t>(), nsl);
+        LAUNCH_PDL(ctx, k_level_index, nblk(nrec + 1, 256), 256, 0, keys, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->lvlidx.as<int32_t>(), nsl);
         lvl_index = ctx->lvlidx.as<int32_t>();
     }
     EmitOut eo; eo.items = ctx->items.as<Item16>(); eo.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
@@ -1022,7 +1031,7 @@ static int32_t manybody_export(stf_ctx* ctx, int32_t nl, const int32_t* labels, 
         F.n_items_dev = ctx->counts.as<unsigned long long>() + C_ITEMS; F.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
         F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = unique;
         F.out5 = ctx->out32.as<int32_t>(); F.kept = ctx->counts.as<unsigned long long>() + C_KEPT; F.do_prep = 0; F.status = STATUSP(ctx);
-        ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
+        LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
         KCHECK();
         stage_end(ctx);
         r = sync_counts(ctx); if (r) return r;
@@ -1111,25 +1120,25 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
     if (m <= BS_CAP && ctx->label_bits + 1 + FIN_IDX_BITS <= 64) { // one CTA: endpoints, sort, links
         set_smem_attrs();
-        ctx->launches++, k_step_links<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(hits, (int)n, ctx->label_bits, ctx->om.as<ObjMeta>(), ctx->prev.as<uint32_t>(), ctx->done.as<uint32_t>(),
+        LAUNCH_PDL(ctx, k_step_links, 1, BS_THREADS, BS_SMEM_BYTES, hits, (int)n, ctx->label_bits, ctx->om.as<ObjMeta>(), ctx->prev.as<uint32_t>(), ctx->done.as<uint32_t>(),
                                                                                  ctx->counts.as<unsigned long long>() + C_TICKET);
     } else {
         CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)m)); CK(ctx->hk2.ensure(sizeof(uint64_t) * (size_t)m));
         CK(ctx->hv.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->hv2.ensure(sizeof(uint32_t) * (size_t)m));
         CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(m)));
-        ctx->launches++, k_step_endpoints<<<nblk(m, 256), 256, 0, ctx->st>>>(hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+        LAUNCH_PDL(ctx, k_step_endpoints, nblk(m, 256), 256, 0, hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->prev.p, 0, sizeof(uint32_t) * (size_t)m, ctx->st));
-        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, bit_range(0, ctx->label_bits + 1), ctx->hist.as<uint32_t>());
-        ctx->launches++, k_step_prev<<<nblk(m, 256), 256, 0, ctx->st>>>(f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, bit_range(0, ctx->label_bits + 1), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
+        LAUNCH_PDL(ctx, k_step_prev, nblk(m, 256), 256, 0, f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
         CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
         if (n >= 16384) { // many chains (a batch of scenes): claim the steps level by level
             CK(ctx->keep.ensure(sizeof(uint32_t) * 2 * (size_t)n));
             uint32_t* la = ctx->keep.as<uint32_t>(); uint32_t* lb = la + n;
             CK(cudaMemsetAsync(la, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
-            for (int sweep = 0; sweep < 16; sweep++) { ctx->launches++, k_step_level<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->prev.as<uint32_t>(), la, lb, n); std::swap(la, lb); }
-            ctx->launches++, k_step_level_keys<<<nblk(n, 256), 256, 0, ctx->st>>>(la, n, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
-            int f2 = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), n, bit_range(0, 5), ctx->hist.as<uint32_t>());
+            for (int sweep = 0; sweep < 16; sweep++) { LAUNCH_PDL(ctx, k_step_level, nblk(n, 256), 256, 0, ctx->prev.as<uint32_t>(), la, lb, n); std::swap(la, lb); }
+            LAUNCH_PDL(ctx, k_step_level_keys, nblk(n, 256), 256, 0, la, n, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
+            int f2 = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), n, bit_range(0, 5), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
             order = f2 ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
         }
     }
@@ -1196,7 +1205,7 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
         F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
         F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
         F.status = STATUSP(ctx);
-        if (getenv("STF_NO_CLUSTER")) ctx->launches++, k_finalize_hits<<<1, BS_THREADS, BS_SMEM_BYTES, ctx->st>>>(F);
+        if (getenv("STF_NO_CLUSTER")) LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
         else {
             CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)(CS_CAP + 1024)));
             LAUNCH_PDL(ctx, k_finalize_prep_cl, CS_CTAS, CS_THREADS, CS_SMEM_BYTES, F, ctx->hk.as<uint64_t>());
