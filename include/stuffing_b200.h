@@ -200,7 +200,7 @@ int64_t stf_launch_count(const stf_ctx* ctx);
 
 /* ---- per-stage device timers (CUDA events on the context's stream; for bench.py's roofline) ---- */
 #define STF_NSTAGES 9
-#define STF_STAGE_SHIFT 0     /* stf_set_shifts: shift update + pyramid rebuild (k_apply_shifts, k_build_objects) */
+#define STF_STAGE_SHIFT 0     /* stf_set_shifts: shift update + pyramid rebuild (k_build_objects) */
 #define STF_STAGE_LOCATE 1    /* k_locate */
 #define STF_STAGE_SORT 2      /* radix sort of the (cell,label) records */
 #define STF_STAGE_EMIT 3      /* k_emit_items: candidate generation */

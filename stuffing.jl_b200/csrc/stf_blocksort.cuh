@@ -105,14 +105,10 @@ __device__ __forceinline__ void bs_pass(BlockSortSmem& S, uint64_t (&x)[BS_ITEMS
             int e = w * per + c * 32 + lane;
             bool valid = e < n;
             uint32_t d = (uint32_t)(x[c] >> shift) & 255u;
-#ifndef STF_BS_MATCH
-            uint32_t peers = __ballot_sync(FULLM, valid);
+            uint32_t peers = __ballot_sync(FULLM, valid); // eight ballots: measured faster than match.any here (many distinct digits)
             if (!valid) peers = ~peers;
 #pragma unroll
             for (int b = 0; b < 8; b++) { uint32_t bal = __ballot_sync(FULLM, (d >> b) & 1u); peers &= ((d >> b) & 1u) ? bal : ~bal; }
-#else
-            uint32_t peers = __match_any_sync(FULLM, valid ? d : 256u + (uint32_t)lane); // invalid lanes match nobody
-#endif
             int leader = __ffs(peers) - 1;
             uint32_t old = 0;
             if (valid && lane == leader) { old = my[d]; my[d] = old + __popc(peers); }

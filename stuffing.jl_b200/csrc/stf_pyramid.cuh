@@ -339,20 +339,7 @@ __global__ void __launch_bounds__(256) k_overlap_level1(const uint32_t* __restri
     }
 }
 
-// ---- shift!/setshift! (qtrees.jl:267-287): levels <= level move by s*2^(level-i); build list -----
-__global__ void k_apply_shifts(LevelMeta* __restrict__ lm, int L, int n, const int32_t* __restrict__ labels, int level,
-                               const int32_t* __restrict__ rs, const int32_t* __restrict__ cs, int add, int2* __restrict__ work) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int o = labels ? labels[i] - 1 : i;
-    int s1 = rs[i], s2 = cs[i];
-    for (int l = level; l >= 1; l--) {
-        LevelMeta* m = lm + (size_t)o * L + (l - 1);
-        if (add) { m->rs += s1; m->cs += s2; } else { m->rs = s1; m->cs = s2; }
-        s1 *= 2; s2 *= 2;
-    }
-    work[i] = make_int2(o, level);
-}
+// ---- work list of stf_build: (object, from-level) entries; shift!/setshift! (qtrees.jl:267-287) are fused into k_build_objects
 __global__ void k_fill_worklist(int n, const int32_t* __restrict__ labels, int from, int2* __restrict__ work) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) work[i] = make_int2(labels ? labels[i] - 1 : i, from);
