@@ -12,14 +12,103 @@ namespace cg = cooperative_groups;
 // (2) broad phase
 // =============================================================================================
 
-// one thread per label: <= 4 cells.
+// FOUR lanes per label (<= 4 cells): the four top cells, then the four children of every positionlower step, are read by
+// the four lanes at once and decided by one ballot, so a descent costs one round trip per level instead of up to five
+// (the thread-per-label version spent 19 us of a 300 us round in this dependent chain).  The warp runs one converged loop.
 // Slot mode (n_append == NULL): written to slots 4*slot..4*slot+3 (unused slots = INVALID key).
 //   linked != 0: LinkedSpacialQTree semantics — slot = object, cells outside the root (L,1,1) dropped (qtrees.jl:506).
 //   linked == 0: HashSpacialQTree semantics — slot = position in `labels`.
 // Append mode (n_append != NULL, hash semantics): the valid records are appended compactly (one atomic per warp) as
 //   (key, tie) with tie = position in `labels` (or the label itself when labels == NULL); a sort by (key, tie)
 //   reproduces the insertion order of the reference's Dict of Vectors (qtrees.jl:411-415) whatever the append order.
-__global__ void k_locate(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
+#define LOC_THREADS 128
+__global__ void __launch_bounds__(LOC_THREADS) k_locate(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
+                         int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                         int* __restrict__ err, unsigned long long* __restrict__ n_append) {
+    pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
+    const unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31, gl = lane & 3, g0 = lane & ~3;
+    const int j = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
+    const bool have = j < nl;
+    int cnt = 0; uint64_t ck0 = STF_KEY_INVALID, ck1 = STF_KEY_INVALID, ck2 = STF_KEY_INVALID, ck3 = STF_KEY_INVALID;
+    int o = 0, slot = 0, scene = 0;
+    const LevelMeta* olm = lm;
+    unsigned topmask = 0; LevelMeta top = {};
+    if (have) {
+        o = labels ? labels[j] - 1 : j;
+        slot = linked ? o : j;
+        olm = lm + (size_t)o * L;
+        top = olm[L - 1]; // sizelevel(qt) == length(qt)  qtrees.jl:191-193
+        scene = om[o].scene;
+    }
+    { // the four top cells (1,1),(1,2),(2,1),(2,2) of the top kernel, lane k reads cell k  qtree_functions.jl:167-170
+        bool ne = have && node_code<false>(words, top, top.rs + 1 + (gl >> 1), top.cs + 1 + (gl & 1)) != CODE_EMPTY;
+        topmask = (__ballot_sync(FULLM, ne) >> g0) & 0xFu;
+    }
+    bool indesc = false; int l = 0, a = 0, b = 0;
+    LevelMeta nextm = {}; // meta of the level the NEXT iteration reads: loaded one iteration ahead, off the node-read chain
+    if (have && L > 2) nextm = olm[L - 2];
+    for (;;) {
+        if (!indesc && topmask) { // next non-empty top cell, in order
+            int k = __ffs(topmask) - 1; topmask &= topmask - 1;
+            if (l != 0 && L > 2) nextm = olm[L - 2]; // a second top cell restarts from the top (rare)
+            l = L; a = top.rs + 1 + (k >> 1); b = top.cs + 1 + (k & 1); indesc = true;
+        }
+        if (!__any_sync(FULLM, indesc)) break;
+        const bool go = indesc && l > 2; // positionlower  :141-158: one level per iteration, lane i tests child i
+        bool ne = false;
+        if (go) {
+            LevelMeta cm = nextm;             // = olm[l - 2]
+            if (l > 3) nextm = olm[l - 3];    // the level after this one, in flight together with the node read
+            ne = node_code<false>(words, cm, 2 * a - (gl & 1), 2 * b - (gl >> 1)) != CODE_EMPTY;
+        }
+        const unsigned nem = (__ballot_sync(FULLM, ne) >> g0) & 0xFu;
+        if (indesc) {
+            bool fin = !go;
+            if (go) {
+                if (__popc(nem) == 1) { int i = __ffs(nem) - 1; a = 2 * a - (i & 1); b = 2 * b - (i >> 1); l -= 1; } // the only non-empty child
+                else fin = true; // two non-empty children: stay; none: inconsistent pyramid (the oracle stops the same way)
+            }
+            if (fin) {
+                bool keep = true;
+                if (linked) { int r = 1 << (L - l); keep = (a >= 1 && a <= r && b >= 1 && b <= r); }
+                if (a <= -STF_CELL_BIAS || a >= STF_CELL_BIAS || b <= -STF_CELL_BIAS || b >= STF_CELL_BIAS) { if (gl == 0) atomicOr(err, 2); keep = false; }
+                if (keep) {
+                    uint64_t key = cell_key(scene, l, a, b);
+                    if (cnt == 0) ck0 = key; else if (cnt == 1) ck1 = key; else if (cnt == 2) ck2 = key; else ck3 = key;
+                    cnt++;
+                }
+                indesc = false;
+            }
+        }
+    }
+    const uint64_t mine = gl == 0 ? ck0 : gl == 1 ? ck1 : gl == 2 ? ck2 : ck3; // lane k of the group holds record k
+    if (n_append) {
+        int c = gl == 0 ? cnt : 0, incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULLM, incl, d); if (lane >= d) incl += t; }
+        int total = __shfl_sync(FULLM, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 31 && total) base = atomicAdd(n_append, (unsigned long long)total);
+        base = __shfl_sync(FULLM, base, 31);
+        int excl = __shfl_sync(FULLM, incl - c, g0); // records of the groups before mine in this warp
+        uint32_t tie = labels ? (uint32_t)j : (uint32_t)(o + 1);
+        if (gl < cnt) { keys[base + excl + gl] = mine; vals[base + excl + gl] = tie; }
+        return;
+    }
+    if (!have) return;
+    keys[4 * (size_t)slot + gl] = gl < cnt ? mine : STF_KEY_INVALID; vals[4 * (size_t)slot + gl] = (uint32_t)(o + 1);
+}
+
+// Throughput version, one THREAD per label (<= 4 cells): batches of scenes and very large scenes, where every SM is
+// busy anyway and the four-lane version would only multiply the instruction count.
+// Slot mode (n_append == NULL): written to slots 4*slot..4*slot+3 (unused slots = INVALID key).
+//   linked != 0: LinkedSpacialQTree semantics — slot = object, cells outside the root (L,1,1) dropped (qtrees.jl:506).
+//   linked == 0: HashSpacialQTree semantics — slot = position in `labels`.
+// Append mode (n_append != NULL, hash semantics): the valid records are appended compactly (one atomic per warp) as
+//   (key, tie) with tie = position in `labels` (or the label itself when labels == NULL); a sort by (key, tie)
+//   reproduces the insertion order of the reference's Dict of Vectors (qtrees.jl:411-415) whatever the append order.
+__global__ void k_locate_wide(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
                          int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                          int* __restrict__ err, unsigned long long* __restrict__ n_append) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this

@@ -86,6 +86,10 @@ struct stf_ctx {
     } else kern<<<grid, block, smem, (ctx)->st>>>(__VA_ARGS__); \
     (ctx)->after_kernel = true; } while (0)
 
+// locate: four lanes per label while the labels alone cannot fill the machine, one thread per label beyond that
+#define LAUNCH_LOCATE(ctx, nl_, ...) do { \
+    if ((int64_t)(nl_) <= 65536) LAUNCH_PDL(ctx, k_locate, nblk(4ll * (nl_), LOC_THREADS), LOC_THREADS, 0, __VA_ARGS__); \
+    else LAUNCH_PDL(ctx, k_locate_wide, nblk((nl_), 128), 128, 0, __VA_ARGS__); } while (0)
 // several host arrays -> ONE contiguous device range with one copy (dst + sum of the earlier sizes, no padding)
 struct HostPart { const void* src; size_t bytes; };
 static cudaError_t stage_h2d_parts(stf_ctx* ctx, void* dst, const HostPart* parts, int nparts) {
@@ -809,11 +813,11 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     if (fast) {
         set_smem_attrs();
         if (linked) {
-            if (nl > 0) LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
+            if (nl > 0) LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
                                                                    ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
             LAUNCH_PDL(ctx, k_compact_records, nblk(nrec, 256), 256, 0, ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), nrec, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend);
         } else if (nl > 0) {
-            LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
+            LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
                                                         ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ERRP(ctx), nappend);
         }
         KCHECK();
@@ -832,12 +836,12 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     }
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
     if (linked) {
-        if (nl > 0) LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
+        if (nl > 0) LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
                                                                ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
         CK(cudaMemcpyAsync(ctx->rk.p, ctx->lkk.p, sizeof(uint64_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->rv.p, ctx->lkv.p, sizeof(uint32_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
     } else if (nl > 0) {
-        LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
+        LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
                                                     ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ERRP(ctx), nullptr);
     }
     KCHECK();
@@ -898,7 +902,7 @@ extern "C" int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* la
     if (!labels) nl = ctx->n;
     if (nl <= 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
-    LAUNCH_PDL(ctx, k_locate, nblk(nl, 128), 128, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
+    LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
                                                 ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
     KCHECK();
     return sync_counts(ctx);
