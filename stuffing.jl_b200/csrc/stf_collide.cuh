@@ -292,11 +292,12 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
             bool is_item = false, is_direct = false, want_code = false;
             int i1 = low, i2 = 0;
             if (valid) {
-                int k = 0;
-#pragma unroll
-                for (int j = 1; j < 16; j++) if (s_pref[wib][j] <= c) k = j; // runs are in lane order; empty runs share a prefix
-                // the LAST j with pref <= c and a non-empty run: pref[j] <= c < pref[j+1]
-                while (s_pref[wib][k + 1] <= c) k++; // (never taken: kept as a guard for empty trailing runs)
+                // the run candidate c belongs to: the LAST k with pref[k] <= c (runs are in lane order, empty runs share a
+                // prefix with their successor, pref[0] = 0): four bisection steps over the 16 prefixes
+                int k = s_pref[wib][8] <= c ? 8 : 0;
+                k += s_pref[wib][k + 4] <= c ? 4 : 0;
+                k += s_pref[wib][k + 2] <= c ? 2 : 0;
+                k += s_pref[wib][k + 1] <= c ? 1 : 0;
                 int other = (int)vals[s_start[wib][k] + (c - s_pref[wib][k])];
                 if (k == 0) {
                     is_item = true; i2 = other;
