@@ -303,6 +303,7 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(lib.stf_stream(h), device=torch.device("cuda", local))
     rs_h = torch.from_numpy(np.ascontiguousarray(rs0[movable - 1])).pin_memory(); cs_h = torch.from_numpy(np.ascontiguousarray(cs0[movable - 1])).pin_memory()
     rs_d, cs_d = rs_h.cuda(), cs_h.cuda()
+    movable_d = torch.from_numpy(movable).cuda()  # resident runs: the label list lives in HBM like the positions
     out_rs = torch.empty(n_all, dtype=torch.int32).pin_memory(); out_cs = torch.empty(n_all, dtype=torch.int32).pin_memory()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     lib.stf_set_optimiser(h, 2, 0.25, 0.5)
@@ -311,7 +312,7 @@ def run_ours(args):
 
     def step(resident):
         if resident:
-            d._ck(lib.stf_set_shifts(h, nm, movable.ctypes.data, 1, rs_d.data_ptr(), cs_d.data_ptr(), 0 | 2))
+            d._ck(lib.stf_set_shifts(h, nm, movable_d.data_ptr(), 1, rs_d.data_ptr(), cs_d.data_ptr(), 0 | 2 | 4))
         else:
             d._ck(lib.stf_set_shifts(h, nm, movable.ctypes.data, 1, rs_h.data_ptr(), cs_h.data_ptr(), 0))
         d._ck(lib.stf_reset_velocity(h, 0, None))

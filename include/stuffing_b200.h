@@ -103,8 +103,12 @@ int32_t stf_read_nodes(stf_ctx* ctx, int32_t n, const int32_t* labels, const int
 int32_t stf_get_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level, int32_t* rs, int32_t* cs);
 /* mode 0: setshift!(t, level, rs, cs) (qtrees.jl:277-285); mode 1: shift!(t, level, rs, cs) (:267-275).
  * Levels <= level move, levels > level are rebuilt.  labels == NULL: objects 1..n.
- * mode | STF_SHIFT_DEVICE_ARRAYS: rs/cs are device pointers (inputs already resident in HBM). */
+ * mode | STF_SHIFT_DEVICE_ARRAYS: rs/cs are device pointers (inputs already resident in HBM).
+ * mode | STF_SHIFT_DEVICE_ARRAYS | STF_SHIFT_DEVICE_LABELS: `labels` is a device pointer too (a resident list: no host pass
+ * over it, no copy).  The kernel validates it: an out-of-range label or a mask-sized object in the list is dropped and
+ * reported as STF_E_ARG by the next synchronising call. */
 #define STF_SHIFT_DEVICE_ARRAYS 2
+#define STF_SHIFT_DEVICE_LABELS 4
 int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level,
                        const int32_t* rs, const int32_t* cs, int32_t mode);
 /* setrshift!(t[l], v) / setcshift!(t[l], v) on one PaddedMat, no rebuild  qtrees.jl:134-135 */

@@ -225,7 +225,8 @@ template <int THREADS> __global__ void __launch_bounds__(THREADS) k_pack_build_m
 __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restrict__ lm, int L,
                                 const int2* __restrict__ work, int nwork, const ObjMeta* __restrict__ om, int skip_big, int grp,
                                 const int32_t* __restrict__ labels = nullptr, const int32_t* __restrict__ srs = nullptr, const int32_t* __restrict__ scs = nullptr,
-                                int level = 0, int add = 0, int* __restrict__ built_from = nullptr, int skip_same = 0) {
+                                int level = 0, int add = 0, int* __restrict__ built_from = nullptr, int skip_same = 0,
+                                int check_nobj = 0, int* __restrict__ err = nullptr) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
     __shared__ uint32_t sbuf[8][2 * RB_HALF]; // blockDim.x == 256
     const unsigned FULLM = 0xffffffffu;
@@ -237,6 +238,9 @@ __global__ void k_build_objects(uint32_t* __restrict__ words, LevelMeta* __restr
         if (lane < grp && my_i < nwork) {
             if (srs) { mine_w = make_int2(labels ? labels[my_i] - 1 : my_i, level); my_s1 = srs[my_i]; my_s2 = scs[my_i]; }
             else mine_w = work[my_i];
+            // device-resident label lists were not seen by the host: out-of-range labels and mask-sized objects (rebuilt by
+            // host-driven wide launches) are rejected here, the entry is dropped and the error surfaces at the next sync
+            if (check_nobj && ((unsigned)mine_w.x >= (unsigned)check_nobj || om[mine_w.x].big)) { atomicOr(err, 8); mine_w.x = -1; }
         }
         bool big_mine = mine_w.x >= 0 && skip_big && om[mine_w.x].big;
         if (mine_w.x >= 0 && !srs && (big_mine || mine_w.y >= L)) mine_w.x = -1;

@@ -170,6 +170,7 @@ static int32_t sync_counts(stf_ctx* ctx) { // ONE read-back: counters, path stat
         if (e & 1) FAIL(STF_E_BADCODE, "node code outside 1..3 in uploaded payload");
         if (e & 2) FAIL(STF_E_RANGE, "spatial cell coordinate outside +-2^21");
         if (e & 4) FAIL(STF_E_CUDA, "internal: frontier scratch too small");
+        if (e & 8) FAIL(STF_E_ARG, "device-resident label list: label out of range or mask-sized object");
     }
     return STF_OK;
 }
@@ -504,7 +505,7 @@ static int32_t rebuild_after(stf_ctx* ctx, int n, const int32_t* labels_host, in
     int grp = rebuild_group(n);
     int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
     LAUNCH_PDL(ctx, k_build_objects, blocks, 256, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, ctx->work.as<int2>(), n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
-                                                                 nullptr, nullptr, nullptr, 0, 0, ctx->built_from.as<int>(), 0);
+                                                                 nullptr, nullptr, nullptr, 0, 0, ctx->built_from.as<int>(), 0, 0, nullptr);
     KCHECK();
     if (ctx->has_big)
         for (int i = 0; i < n; i++) { int o = labels_host ? labels_host[i] - 1 : i; if (ctx->h_om[o].big) { int32_t r = build_big(ctx, o, from); if (r) return r; } }
@@ -513,6 +514,7 @@ static int32_t rebuild_after(stf_ctx* ctx, int n, const int32_t* labels_host, in
 extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels, int32_t level, const int32_t* rs, const int32_t* cs, int32_t mode) {
     NEED_OBJS();
     if (level < 1 || level > ctx->L || n < 0 || (!labels && n > ctx->n)) FAIL(STF_E_ARG, "bad level or count");
+    if ((mode & STF_SHIFT_DEVICE_LABELS) && !(mode & STF_SHIFT_DEVICE_ARRAYS)) FAIL(STF_E_ARG, "a device label list needs device rs/cs arrays");
     if (n == 0) return STF_OK;
     stage_begin(ctx, STF_STAGE_SHIFT);
     const int32_t* dl = nullptr; int32_t r;
@@ -526,14 +528,16 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
         const int32_t* base = ctx->lab.as<int32_t>();
         if (labels) { dl = base; base += n; }
         drs = base; dcs = base + n;
-    } else { r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r; }
+    } else if (mode & STF_SHIFT_DEVICE_LABELS) dl = labels; // resident list: validated by the kernel
+    else { r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r; }
+    const bool dev_labels = (mode & STF_SHIFT_DEVICE_LABELS) && (mode & STF_SHIFT_DEVICE_ARRAYS) && labels;
     { // one launch: shift + rebuild of every listed tree (mask-sized ones: shift here, rebuild by the wide launches below)
         int grp = rebuild_group(n);
         int blocks = std::min(nblk(((int64_t)n + grp - 1) / grp * 32, 256), 148 * 8);
         LAUNCH_PDL(ctx, k_build_objects, blocks, 256, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, nullptr, n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
-                                                                     dl, drs, dcs, level, mode & 1, ctx->built_from.as<int>(), ctx->raw_shift_edit ? 0 : 1);
+                                                                     dl, drs, dcs, level, mode & 1, ctx->built_from.as<int>(), ctx->raw_shift_edit ? 0 : 1, dev_labels ? ctx->n : 0, ERRP(ctx));
         KCHECK();
-        if (ctx->has_big && level < ctx->L)
+        if (ctx->has_big && level < ctx->L && !dev_labels)
             for (int i = 0; i < n; i++) { int o = labels ? labels[i] - 1 : i; if (ctx->h_om[o].big) { r = build_big(ctx, o, level); if (r) return r; } }
     }
     stage_end(ctx);
@@ -969,7 +973,7 @@ static int32_t spacial_core_fast(stf_ctx* ctx, int32_t nl, const int32_t* labels
     const int32_t* moved_pos = nullptr;
     if (linked) { r = upload_moved_pos(ctx, nl, labels, &moved_pos); if (r) return r; }
     int64_t nrec; uint64_t* keys; uint32_t* vals;
-    CK(cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st)); // every counter, the status and the error bits
+    CK(cudaMemsetAsync(ctx->counts.p, 0, C_ERR * sizeof(unsigned long long), ctx->st)); // every counter and the status; pending error bits stay until a sync reads them
     r = locate_and_sort(ctx, nl, dl, linked, true, &nrec, &keys, &vals); if (r) return r;
     int64_t want_items = std::max<int64_t>(std::max<int64_t>(1024, 32 * nrec / 4), ctx->hint_items + ctx->hint_items / 4 + 1024);
     if ((int64_t)(ctx->items.cap / sizeof(Item16)) < want_items) CK(ctx->items.ensure(sizeof(Item16) * (size_t)want_items));

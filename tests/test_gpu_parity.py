@@ -630,3 +630,34 @@ def test_place_with_findroom_gathering(S, orc, level, p):
         return float(np.mean(np.hypot(*(c - m).T)))
     if (level, p) == (5, 2):
         assert spread(qo) < spread(qu)
+
+
+@pytest.mark.gpu
+def test_set_shifts_with_resident_label_list(S, orc):
+    """STF_SHIFT_DEVICE_LABELS: labels, rs and cs all live in HBM; same state as the host-list call, and a bad label in
+    the resident list is dropped and reported by the next synchronising call."""
+    import torch
+    rng = np.random.default_rng(5)
+    qo = rect_scene(orc, 60, 44, sz=60, masksize=(400, 400))
+    d = device_from_oracle(S, qo)
+    labels = np.array(sorted(rng.choice(np.arange(2, len(qo) + 1), 25, replace=False)), np.int32)
+    rs, cs = d.getshifts(list(labels), 1)
+    nrs = (rs + rng.integers(-7, 8, len(labels))).astype(np.int32); ncs = (cs + rng.integers(-7, 8, len(labels))).astype(np.int32)
+    tl, tr, tc = (torch.from_numpy(x).cuda() for x in (labels, nrs, ncs))
+    d._ck(d.lib.stf_set_shifts(d.h, len(labels), tl.data_ptr(), 1, tr.data_ptr(), tc.data_ptr(), 0 | 2 | 4))
+    for lb, r, c in zip(labels, nrs, ncs):
+        qo[lb - 1].setshift(1, int(r), int(c))
+    assert_same_trees(d, qo)
+    # shift! (relative) through the same path
+    d._ck(d.lib.stf_set_shifts(d.h, len(labels), tl.data_ptr(), 2, tr.data_ptr(), tc.data_ptr(), 1 | 2 | 4))
+    for lb, r, c in zip(labels, nrs, ncs):
+        qo[lb - 1].shift(2, int(r), int(c))
+    assert_same_trees(d, qo)
+    # a label outside 1..n: dropped, reported at the next sync, the rest of the list is applied
+    bad = labels.copy(); bad[3] = len(qo) + 7
+    tb = torch.from_numpy(bad).cuda()
+    d._ck(d.lib.stf_set_shifts(d.h, len(bad), tb.data_ptr(), 1, tr.data_ptr(), tc.data_ptr(), 0 | 2 | 4))
+    with pytest.raises(Exception):
+        d.getshifts()
+        S.totalcollisions(d)
+    assert d.lib.stf_set_shifts(d.h, len(labels), tl.data_ptr(), 1, tr.data_ptr(), tc.data_ptr(), 0 | 4) != 0  # needs device arrays
