@@ -221,31 +221,37 @@ __device__ __forceinline__ int64_t upper_bound_u64(const uint64_t* __restrict__ 
     return lo;
 }
 
-// candidate generation, one WARP per sorted record r (low label in cell (l,a,b)).
+// candidate generation, W lanes (a warp, or a half warp for batches of small scenes) per sorted record r (low label in
+// cell (l,a,b)).
 //  lane 0      : the later records of r's own cell            (same-cell pairs, qtree_functions.jl:233-239)
 //  lane k >= 1 : the records of the k-th ancestor cell, found by binary search (:241-248)
-// A warp scan turns the per-lane run lengths into one candidate range; the warp then walks that range 32
-// candidates at a time (balanced even when an ancestor holds hundreds of labels), applies
-// collisions_boundsfilter (:203-223) and reserves output slots with one atomic per 32 candidates.
+// A scan turns the per-lane run lengths into one candidate range; the lanes then walk that range W candidates at a time
+// (balanced even when an ancestor holds hundreds of labels), apply collisions_boundsfilter (:203-223) and reserve output
+// slots with one atomic per warp iteration.  W = 16 when records have few candidates (a scene of a batch has ~10 per
+// record and at most 16 levels): two records per warp keep twice as many lanes busy in the searches and in the filter.
 // moved_pos != NULL selects partialcollisions semantics (:285-326): a pair is generated iff at least one
 // side is in `labels` (moved_pos[o] >= 0); two moved labels of one cell are oriented (later, earlier).
 #define EM_THREADS 256
+template <int W>
 __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                            const unsigned long long* __restrict__ nrec_dev, int64_t nrec_cap, int L,
                                                            const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm,
                                                            const int32_t* __restrict__ moved_pos, EmitOut out, int shard_rank, int shard_n,
                                                            const int32_t* __restrict__ lvl_index) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
-    __shared__ int s_start[EM_THREADS / 32][16];
-    __shared__ int s_pref[EM_THREADS / 32][17];
+    constexpr int RPW = 32 / W; // records per warp
+    __shared__ int s_start[EM_THREADS / 32][RPW][16];
+    __shared__ int s_pref[EM_THREADS / 32][RPW][17];
     const unsigned FULLM = 0xffffffffu;
-    int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / W, sl_ = lane % W;
     int64_t nrec = min((int64_t)*nrec_dev, nrec_cap); // valid records (sorted, compacted)
     int64_t nwarps = (int64_t)gridDim.x * (EM_THREADS / 32);
     // item-parallel sharding: rank k of shard_n generates the candidates of the records k, k+shard_n, ...
-    for (int64_t r = ((int64_t)blockIdx.x * (EM_THREADS / 32) + wib) * shard_n + shard_rank; r < nrec; r += nwarps * shard_n) {
-        uint64_t key = keys[r];
-        int low = (int)vals[r];
+    for (int64_t idx0 = ((int64_t)blockIdx.x * (EM_THREADS / 32) + wib) * RPW; idx0 * shard_n + shard_rank < nrec; idx0 += nwarps * RPW) {
+        const int64_t r = (idx0 + sub) * shard_n + shard_rank;
+        const bool rec = r < nrec; // (the second half of the last warp may have no record)
+        uint64_t key = rec ? keys[r] : 0ull;
+        int low = rec ? (int)vals[r] : 1;
         int l, a, b; cell_unkey(key, &l, &a, &b);
         int mp_low = moved_pos ? moved_pos[low - 1] : 0;
         // ---- per-lane candidate run
@@ -254,17 +260,17 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
         // every lane looks for the run of ONE key inside [lo, hi): lane 0 its own key after r, lane j the ancestor cell j
         // levels up, inside that (scene, level) slice when the index is there.  One code path for all lanes (no serialised
         // lane-0 branch); the run end is found by galloping (runs are one or two records long).
-        bool look = lane == 0 || (lane < L - 1 && l + lane <= L);
+        bool look = rec && (sl_ == 0 || (sl_ < L - 1 && l + sl_ <= L));
         uint64_t akey = key;
-        int64_t lo = r + 1, hi = lvl_index ? (int64_t)lvl_index[sl + 1] : nrec;
-        if (look && lane > 0) {
+        int64_t lo = r + 1, hi = (lvl_index && rec) ? (int64_t)lvl_index[sl + 1] : nrec;
+        if (look && sl_ > 0) {
             int pa = a, pb = b;
-            for (int i = 0; i < lane; i++) { pa = (pa + 1) / 2; pb = (pb + 1) / 2; } // parent(): ÷ truncates toward zero
+            for (int i = 0; i < sl_; i++) { pa = (pa + 1) / 2; pb = (pb + 1) / 2; } // parent(): ÷ truncates toward zero
             uint64_t scene_bits = key >> (5 + 2 * STF_CELL_W);
-            akey = (scene_bits << (5 + 2 * STF_CELL_W)) | ((uint64_t)(uint32_t)(l + lane) << (2 * STF_CELL_W)) |
+            akey = (scene_bits << (5 + 2 * STF_CELL_W)) | ((uint64_t)(uint32_t)(l + sl_) << (2 * STF_CELL_W)) |
                    ((uint64_t)(uint32_t)(pa + STF_CELL_BIAS) << STF_CELL_W) | (uint64_t)(uint32_t)(pb + STF_CELL_BIAS);
             lo = 0; hi = nrec;
-            if (lvl_index) { lo = lvl_index[sl + lane]; hi = lvl_index[sl + lane + 1]; } // the ancestor's own (scene, level) slice
+            if (lvl_index) { lo = lvl_index[sl + sl_]; hi = lvl_index[sl + sl_ + 1]; } // the ancestor's own (scene, level) slice
             int64_t x = lo, y = hi;
             while (x < y) { int64_t mid = (x + y) >> 1; if (keys[mid] < akey) x = mid + 1; else y = mid; }
             lo = x;
@@ -278,27 +284,31 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
         }
         int incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULLM, incl, o); if (lane >= o) incl += t; }
-        int total = __shfl_sync(FULLM, incl, 31);
-        if (total == 0) continue;
-        if (lane < 16) { s_start[wib][lane] = start; s_pref[wib][lane] = incl - cnt; }
-        if (lane == 16) s_pref[wib][16] = total;
+        for (int o = 1; o < W; o <<= 1) { int t = __shfl_up_sync(FULLM, incl, o, W); if (sl_ >= o) incl += t; }
+        const int total = __shfl_sync(FULLM, incl, W - 1, W);
+        int tmax = total;
+        if (W == 16) tmax = max(tmax, __shfl_xor_sync(FULLM, total, 16));
+        if (tmax == 0) continue;
+        if (sl_ < 16) { s_start[wib][sub][sl_] = start; s_pref[wib][sub][sl_] = incl - cnt; }
+        if (sl_ == 0) s_pref[wib][sub][16] = total;
         __syncwarp();
-        LevelMeta lowm = lm[(size_t)(low - 1) * L + (l - 1)];
+        LevelMeta lowm = {};
+        if (rec) lowm = lm[(size_t)(low - 1) * L + (l - 1)];
         int lowcode = -1;
-        for (int c0 = 0; c0 < total; c0 += 32) {
-            int c = c0 + lane;
+        const int* pref = s_pref[wib][sub]; const int* sstart = s_start[wib][sub];
+        for (int c0 = 0; c0 < tmax; c0 += W) {
+            int c = c0 + sl_;
             bool valid = c < total;
             bool is_item = false, is_direct = false, want_code = false;
             int i1 = low, i2 = 0;
             if (valid) {
                 // the run candidate c belongs to: the LAST k with pref[k] <= c (runs are in lane order, empty runs share a
                 // prefix with their successor, pref[0] = 0): four bisection steps over the 16 prefixes
-                int k = s_pref[wib][8] <= c ? 8 : 0;
-                k += s_pref[wib][k + 4] <= c ? 4 : 0;
-                k += s_pref[wib][k + 2] <= c ? 2 : 0;
-                k += s_pref[wib][k + 1] <= c ? 1 : 0;
-                int other = (int)vals[s_start[wib][k] + (c - s_pref[wib][k])];
+                int k = pref[8] <= c ? 8 : 0;
+                k += pref[k + 4] <= c ? 4 : 0;
+                k += pref[k + 2] <= c ? 2 : 0;
+                k += pref[k + 1] <= c ? 1 : 0;
+                int other = (int)vals[sstart[k] + (c - pref[k])];
                 if (k == 0) {
                     is_item = true; i2 = other;
                     if (moved_pos) {
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
                 }
             }
             if (__any_sync(FULLM, want_code)) {
-                if (lowcode < 0) lowcode = (int)node_code<false>(words, lowm, a, b);
+                if (lowcode < 0 && rec) lowcode = (int)node_code<false>(words, lowm, a, b);
                 is_direct = want_code && lowcode != (int)CODE_EMPTY;
             }
             unsigned im = __ballot_sync(FULLM, is_item), dm = __ballot_sync(FULLM, is_direct);
