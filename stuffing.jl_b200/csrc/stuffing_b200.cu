@@ -944,7 +944,7 @@ static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, con
     if (nrec > 0) {
         int blocks = (int)std::min<int64_t>((nrec / 4 + EM_THREADS / 32 - 1) / (EM_THREADS / 32) + 1, 148 * 8); // ~1 record per located object
         // batches of scenes: few candidates per record and L <= 16 -> two records per warp
-        if (ctx->multi_scene && ctx->L <= 16) LAUNCH_PDL(ctx, k_emit_items<16>, (blocks + 1) / 2, EM_THREADS, 0, keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
+        if ((ctx->multi_scene || nrec > 65536) && ctx->L <= 16) LAUNCH_PDL(ctx, k_emit_items<16>, (blocks + 1) / 2, EM_THREADS, 0, keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
                                                                         ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n, lvl_index);
         else LAUNCH_PDL(ctx, k_emit_items<32>, blocks, EM_THREADS, 0, keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
                                                                         ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n, lvl_index);
