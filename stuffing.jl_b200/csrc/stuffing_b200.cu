@@ -405,7 +405,7 @@ extern "C" int32_t stf_upload_packed(stf_ctx* ctx, int32_t n, const uint8_t* pay
 }
 
 // ------------------------------------------------------------------------------------------------ tree state
-#define NEED_OBJS() do { if (!ctx) return STF_E_ARG; if (ctx->L == 0) FAIL(STF_E_STATE, "nothing uploaded"); CK(cudaSetDevice(ctx->device)); stage_reset(ctx); } while (0)
+#define NEED_OBJS() do { if (!ctx) return STF_E_ARG; if (ctx->L == 0) FAIL(STF_E_STATE, "nothing uploaded"); CK(cudaSetDevice(ctx->device)); stage_reset(ctx); ctx->after_kernel = false; /* the caller may have put work of its own on the stream */ } while (0)
 #define CHECK_LABEL(x) do { if ((x) < 1 || (x) > ctx->n) FAIL(STF_E_ARG, "label out of range"); } while (0)
 
 extern "C" int32_t stf_get_level_info(stf_ctx* ctx, int32_t label, int32_t l, int32_t out[5]) {
