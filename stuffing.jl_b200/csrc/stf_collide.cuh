@@ -406,7 +406,7 @@ struct NarrowArgs {
     unsigned long long* counts;      // [2] overflow count, [3] visited
     uint32_t* overflow;              // item indices that need the big path
     int64_t overflow_cap;
-    uint32_t* surv; unsigned long long* nsurv; // stage 1 -> stage 2: indices of the items that go below the first level
+    uint32_t* surv; unsigned long long* nsurv; // stage 1 -> stage 2: item index (28 bits) | MIX-in-both children of the start node (4 bits)
     unsigned long long* cursor;      // stage 2 work cursor into surv (zeroed by stage 1)
 };
 
@@ -430,15 +430,15 @@ __global__ void __launch_bounds__(256) k_collide_first(NarrowArgs A) {
             int ca = 2 * a - (cn & 1), cb = 2 * b - (cn >> 1);
             code[cn] = node_code<false>(A.words, m1, ca, cb) & node_code<false>(A.words, m2, ca, cb);
         }
-        int hit = -1; bool mix = false;
+        int hit = -1; uint32_t mixmask = 0;
 #pragma unroll
-        for (int cn = 3; cn >= 0; cn--) { if (code[cn] == CODE_FULL) hit = cn; mix |= (code[cn] == CODE_MIX); }
-        if (hit < 0 && mix && lev - 1 > 1) { // undecided: the frontier kernel restarts it from the start node
+        for (int cn = 3; cn >= 0; cn--) { if (code[cn] == CODE_FULL) hit = cn; mixmask |= (uint32_t)(code[cn] == CODE_MIX) << cn; }
+        visited += 4;
+        if (hit < 0 && mixmask && lev - 1 > 1) { // undecided: the frontier kernel continues from the MIX children (bits 28..31)
             unsigned long long s_ = atomicAdd(A.nsurv, 1ull);
-            A.surv[s_] = (uint32_t)it;
+            A.surv[s_] = (uint32_t)it | (mixmask << 28);
             continue;
         }
-        visited += 4;
         int4 result = hit >= 0 ? make_int4(lev - 1, 2 * a - (hit & 1), 2 * b - (hit >> 1), 0) : make_int4(-lev, a, b, 0);
         if (A.res) A.res[it] = result;
         if (A.hits && result.x >= 0) {
@@ -487,11 +487,12 @@ __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
             if (!active) {
                 int64_t j = cpos + (__popc(need & below) >> 2);
                 if (j < cend) {
-                    it = A.surv[j];
+                    const uint32_t sv = A.surv[j], mm = sv >> 28; // stage 1 already tested the start node's children: mm = the MIX ones
+                    it = sv & 0x0FFFFFFFu;
                     Item16 item = A.items[it];
-                    i1 = item.i1; i2 = item_i2(item); lev = item_l(item); ata = item.a; atb = item.b;
-                    cnt = 1; cur = 0; depth = 0; q = 0; ncnt = 0; newlevel = true; active = true;
-                    if (gl == 0) fr[gib][0][0] = 0;
+                    i1 = item.i1; i2 = item_i2(item); lev = item_l(item) - 1; ata = item.a; atb = item.b;
+                    cnt = __popc(mm); cur = 0; depth = 1; q = 0; ncnt = 0; newlevel = true; active = true;
+                    if ((mm >> gl) & 1u) fr[gib][0][__popc(mm & ((1u << gl) - 1u))] = ((uint32_t)(gl & 1) << 16) | (uint32_t)(gl >> 1);
                 }
             }
             cpos = min(cpos + (__popc(need) >> 2), cend);

@@ -582,6 +582,7 @@ static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want
     if (want_res) CK(ctx->res.ensure(sizeof(int4) * (size_t)std::max<int64_t>(1, nmax)));
     CK(ctx->overflow.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nmax)));
     if (nmax == 0) return STF_OK;
+    if (nmax >= (1ll << 28)) FAIL(STF_E_ARG, "more than 2^28 candidate pairs in one call"); // stage 1 -> 2 list: 28-bit item index + 4 flag bits
     NarrowArgs A;
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.L = ctx->L;
     A.items = ctx->items.as<Item16>();
