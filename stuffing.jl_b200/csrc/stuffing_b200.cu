@@ -570,6 +570,10 @@ static void set_smem_attrs() {
     cudaFuncSetAttribute(k_sort_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
     cudaFuncSetAttribute(k_sort_records_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BYTES);
     cudaFuncSetAttribute(k_finalize_prep_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BYTES);
+#if CS_CTAS > 8
+    cudaFuncSetAttribute(k_sort_records_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(k_finalize_prep_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+#endif
     cudaFuncSetAttribute(k_finalize_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
     cudaFuncSetAttribute(k_step_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
     done = true;
