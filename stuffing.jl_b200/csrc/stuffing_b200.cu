@@ -111,6 +111,27 @@ static cudaError_t stage_h2d_parts(stf_ctx* ctx, void* dst, const HostPart* part
     cudaEventRecord(ctx->stg_ev, ctx->st); ctx->stg_busy = true;
     return e;
 }
+// small inputs: no copy engine at all — the arrays are gathered into the pinned staging area and the consuming kernel reads
+// them from there over PCIe (pinned allocations are device-accessible at the same address under unified addressing).
+// *dev = that address; the caller launches its kernel and then calls stage_mark() so the area is not reused before it ran.
+static cudaError_t stage_zero_copy(stf_ctx* ctx, const HostPart* parts, int nparts, const void** dev) {
+    size_t bytes = 0;
+    for (int i = 0; i < nparts; i++) bytes += parts[i].bytes;
+    if (ctx->stg_busy && (ctx->stg_off + bytes > ctx->stg_cap || ctx->stg_off == 0)) { cudaEventSynchronize(ctx->stg_ev); ctx->stg_busy = false; ctx->stg_off = 0; }
+    if (ctx->stg_off + bytes > ctx->stg_cap) {
+        if (ctx->stg_busy) { cudaEventSynchronize(ctx->stg_ev); ctx->stg_busy = false; }
+        if (ctx->stg) cudaFreeHost(ctx->stg);
+        ctx->stg_cap = std::max(bytes * 2, (size_t)1 << 20); ctx->stg_off = 0;
+        cudaError_t e = cudaMallocHost(&ctx->stg, ctx->stg_cap); if (e != cudaSuccess) { ctx->stg = nullptr; ctx->stg_cap = 0; return e; }
+    }
+    if (!ctx->stg_ev) cudaEventCreateWithFlags(&ctx->stg_ev, cudaEventDisableTiming);
+    size_t o = 0;
+    for (int i = 0; i < nparts; i++) { memcpy(ctx->stg + ctx->stg_off + o, parts[i].src, parts[i].bytes); o += parts[i].bytes; }
+    *dev = ctx->stg + ctx->stg_off;
+    ctx->stg_off += (bytes + 255) & ~(size_t)255;
+    return cudaSuccess;
+}
+static void stage_mark(stf_ctx* ctx) { cudaEventRecord(ctx->stg_ev, ctx->st); ctx->stg_busy = true; }
 static cudaError_t stage_h2d(stf_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return cudaSuccess;
     if (ctx->stg_busy && (ctx->stg_off + bytes > ctx->stg_cap || ctx->stg_off == 0)) { cudaEventSynchronize(ctx->stg_ev); ctx->stg_busy = false; ctx->stg_off = 0; }
@@ -519,13 +540,15 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
     stage_begin(ctx, STF_STAGE_SHIFT);
     const int32_t* dl = nullptr; int32_t r;
     const int32_t *drs = rs, *dcs = cs;
+    bool zero_copy = false;
     if (!(mode & STF_SHIFT_DEVICE_ARRAYS)) { // host arrays: labels, rs and cs travel in ONE copy
         if (labels) for (int i = 0; i < n; i++) if (labels[i] < 1 || labels[i] > ctx->n) FAIL(STF_E_ARG, "label out of range");
         const size_t nb = sizeof(int32_t) * (size_t)n;
-        CK(ctx->lab.ensure(3 * nb));
         HostPart parts[3] = { { labels, labels ? nb : 0 }, { rs, nb }, { cs, nb } };
-        CK(stage_h2d_parts(ctx, ctx->lab.p, parts, 3));
-        const int32_t* base = ctx->lab.as<int32_t>();
+        const int32_t* base;
+        zero_copy = n <= 65536 && !getenv("STF_NO_ZERO_COPY"); // up to 768 KB: read by the kernel straight from pinned memory
+        if (zero_copy) { const void* zp = nullptr; CK(stage_zero_copy(ctx, parts, 3, &zp)); base = static_cast<const int32_t*>(zp); }
+        else { CK(ctx->lab.ensure(3 * nb)); CK(stage_h2d_parts(ctx, ctx->lab.p, parts, 3)); base = ctx->lab.as<int32_t>(); }
         if (labels) { dl = base; base += n; }
         drs = base; dcs = base + n;
     } else if (mode & STF_SHIFT_DEVICE_LABELS) dl = labels; // resident list: validated by the kernel
@@ -537,6 +560,7 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
         LAUNCH_PDL(ctx, k_build_objects, blocks, 256, 0, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, nullptr, n, ctx->om.as<ObjMeta>(), ctx->has_big ? 1 : 0, grp,
                                                                      dl, drs, dcs, level, mode & 1, ctx->built_from.as<int>(), ctx->raw_shift_edit ? 0 : 1, dev_labels ? ctx->n : 0, ERRP(ctx));
         KCHECK();
+        if (zero_copy) stage_mark(ctx); // the staging area is free again once this kernel has run
         if (ctx->has_big && level < ctx->L && !dev_labels)
             for (int i = 0; i < n; i++) { int o = labels ? labels[i] - 1 : i; if (ctx->h_om[o].big) { r = build_big(ctx, o, level); if (r) return r; } }
     }
@@ -1182,6 +1206,11 @@ static int32_t pos_enqueue(stf_ctx* ctx) {
         if (ctx->h_out) cudaFreeHost(ctx->h_out);
         ctx->h_out = nullptr; ctx->h_out_cap = 0;
         CK(cudaMallocHost(&ctx->h_out, 4 * nb)); ctx->h_out_cap = 4 * nb;
+    }
+    if (!getenv("STF_NO_ZERO_COPY")) { // posted writes over PCIe into the pinned landing area: no copy-engine operation before the sync
+        LAUNCH_PDL(ctx, k_get_shifts, nblk(n, 256), 256, 0, ctx->lm.as<LevelMeta>(), ctx->L, n, nullptr, ctx->pos_level, reinterpret_cast<int32_t*>(ctx->h_out));
+        KCHECK();
+        return STF_OK;
     }
     LAUNCH_PDL(ctx, k_get_shifts, nblk(n, 256), 256, 0, ctx->lm.as<LevelMeta>(), ctx->L, n, nullptr, ctx->pos_level, ctx->out32.as<int32_t>());
     KCHECK();
