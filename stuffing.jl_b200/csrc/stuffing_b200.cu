@@ -181,8 +181,15 @@ enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_
 #define ERRP(ctx) reinterpret_cast<int*>((ctx)->counts.as<unsigned long long>() + C_ERR)
 #define STATUSP(ctx) reinterpret_cast<int*>((ctx)->counts.as<unsigned long long>() + C_STATUS)
 
+// the counter array -> pinned host memory by posted writes (no copy-engine operation in front of the synchronisation)
+__global__ void k_copy_counts(const unsigned long long* __restrict__ counts, unsigned long long* __restrict__ host, int n) {
+    pdl_sync();
+    if ((int)threadIdx.x < n) host[threadIdx.x] = counts[threadIdx.x];
+}
 static int32_t sync_counts(stf_ctx* ctx) { // ONE read-back: counters, path status and error bits live in the same array
-    CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
+    static const bool zc = !getenv("STF_NO_ZERO_COPY");
+    if (zc) { LAUNCH_PDL(ctx, k_copy_counts, 1, 32, 0, (const unsigned long long*)ctx->counts.as<unsigned long long>(), ctx->h_counts, (int)C_N); }
+    else CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->h_err[0] = (int)ctx->h_counts[C_ERR]; ctx->h_err[1] = (int)ctx->h_counts[C_STATUS];
     if (ctx->h_err[0]) {
