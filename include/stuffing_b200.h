@@ -97,6 +97,10 @@ int32_t stf_num_levels(const stf_ctx* ctx); /* length(t)  qtrees.jl:217 */
 int32_t stf_get_level_info(stf_ctx* ctx, int32_t label, int32_t l, int32_t out[5]);
 /* kh*kw payload bytes of level l, column-major: t[l].kernel[2:end-2,2:end-2] */
 int32_t stf_download_level(stf_ctx* ctx, int32_t label, int32_t l, uint8_t* out);
+/* every level of the listed trees (labels == NULL: all) in one call: for each tree, levels 1..L back to back, each
+ * kh_l*kw_l bytes column-major (the payloads of t[1..L]; kh_{l+1} = kh_l ÷ 2 + 1, qtrees.jl:185).  *count = total bytes
+ * (two-call pattern with cap).  One kernel launch instead of one per (tree, level). */
+int32_t stf_download_trees(stf_ctx* ctx, int32_t n, const int32_t* labels, uint8_t* out, int64_t cap, int64_t* count);
 /* t[l, a, b] for n coordinates: PaddedMat getindex, `default` outside the kernel  qtrees.jl:156-162 */
 int32_t stf_read_nodes(stf_ctx* ctx, int32_t n, const int32_t* labels, const int32_t* l,
                        const int32_t* a, const int32_t* b, uint8_t* out);

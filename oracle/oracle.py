@@ -67,6 +67,8 @@ def lib():
             "orc_shift": (None, [vp, i32, i32, i32]),
             "orc_setshift": (None, [vp, i32, i32, i32]),
             "orc_shift_axis": (None, [vp, i32, i32, i32, i32]),
+            "orc_setshifts": (i64, [vp, vp, i32, i32, vp, vp, i32, i32]),
+            "orc_getshifts": (None, [vp, vp, i32, i32, vp, vp]),
             "orc_testqtree": (i32, [vp]),
             "orc_inkernelbounds": (i32, [vp, i32, i32, i32]),
             "orc_collision_dfs": (None, [vp, vp, i32, i32, i32, vp]),
@@ -239,14 +241,44 @@ def qtrees(pics, mask=None, size=None, background=None, maskbackground=None):
     return ts
 
 
+class TreeList(list):
+    """a list of OTrees that keeps its ctypes handle array (timed loops: no per-call marshalling of 10k handles);
+    do not mutate it after the first call"""
+    _harr = None
+
+
 def _handles(qts):
+    if isinstance(qts, TreeList):
+        if qts._harr is None or len(qts._harr) != max(1, len(qts)):
+            qts._harr = (C.c_void_p * max(1, len(qts)))(*[t.h for t in qts])
+        return qts._harr
     arr = (C.c_void_p * max(1, len(qts)))(*[t.h for t in qts])
     return arr
+
+
+def setshifts(qts, labels, level, rs, cs, skip_same=True, nthreads=1):
+    """setshift!(qts[labels[i]], level, (rs[i], cs[i])) for the whole list in one C call; returns the number of trees rebuilt"""
+    lb, nl = _labels(labels)
+    rs = np.ascontiguousarray(rs, np.int32); cs = np.ascontiguousarray(cs, np.int32)
+    if lb is None:
+        nl = len(rs)
+    return int(lib().orc_setshifts(_handles(qts), _ptr(lb), nl, level, _ptr(rs), _ptr(cs), int(skip_same), nthreads))
+
+
+def getshifts(qts, labels=None, level=1):
+    lb, nl = _labels(labels)
+    if lb is None:
+        nl = len(qts)
+    rs = np.zeros(nl, np.int32); cs = np.zeros(nl, np.int32)
+    lib().orc_getshifts(_handles(qts), _ptr(lb), nl, level, _ptr(rs), _ptr(cs))
+    return rs, cs
 
 
 def _labels(labels):
     if labels is None:
         return None, 0
+    if isinstance(labels, np.ndarray) and labels.dtype == np.int32 and labels.flags.c_contiguous:
+        return labels, len(labels)
     a = np.ascontiguousarray(np.asarray(list(labels), dtype=np.int32))
     return a, len(a)
 
@@ -373,7 +405,7 @@ class LinkedTree:
         return d
 
 
-def partialcollisions(qts, tree=None, labels=None, unique=True, perm_seed=0, nthreads=1, details=False):
+def partialcollisions(qts, tree=None, labels=None, unique=True, perm_seed=0, nthreads=1, details=False, raw=False):
     tree = tree if tree is not None else LinkedTree(qts)
     lb, nl = _labels(range(1, len(qts) + 1) if labels is None else labels)
     cap = 1 << 12
@@ -387,6 +419,8 @@ def partialcollisions(qts, tree=None, labels=None, unique=True, perm_seed=0, nth
         if m >= 0 and (not details or ni.value <= cap):
             break
         cap = max(-m if m < 0 else 0, ni.value, cap * 2) + 16
+    if raw:
+        return out[:m], dict(n_items=ni.value, n_direct=nd.value)
     res = _items_out(out, m)
     if details:
         return res, dict(items=_items_out(items, ni.value), n_direct=nd.value)

@@ -84,7 +84,8 @@ static inline int inrange(Idx a, Idx b) { /* qtrees.jl:38-49; caller guarantees 
 
 /* ------------------------------------------------------------------ PaddedMat / ShiftedQTree */
 typedef struct { int kh, kw, rs, cs, sz; uint8_t* k; } Level; /* payload only: kernel[2:end-2,2:end-2] */
-struct OrcTree { int L, sizelevel; uint8_t dflt; Level* lv; };
+struct OrcTree { int L, sizelevel; uint8_t dflt; Level* lv;
+    int built_from, raw_edit; /* bookkeeping of orc_setshifts' skip: level the last rebuild started from; a raw PaddedMat shift edit happened */ };
 #define LV(t, l) ((t)->lv[(l) - 1])
 
 static inline int lv_inkernel(const Level* m, int r, int c) { /* inkernelbounds  qtrees.jl:140-149 */
@@ -104,7 +105,7 @@ OrcTree* orc_tree_new(const uint8_t* pic, int kh, int kw, int pitch, int canvas,
     int L = 1; for (int s = canvas; s > 1; s >>= 1) L++;
     OrcTree* t = (OrcTree*)calloc(1, sizeof(OrcTree));
     t->L = L; t->dflt = (uint8_t)dflt; t->lv = (Level*)calloc((size_t)L, sizeof(Level));
-    int m = kh, n = kw, sz = canvas; t->sizelevel = -1;
+    int m = kh, n = kw, sz = canvas; t->sizelevel = -1; t->built_from = L + 1; /* nothing built yet */
     for (int l = 1; l <= L; l++) {
         Level* v = &LV(t, l);
         v->kh = m; v->kw = n; v->rs = v->cs = 0; v->sz = sz;
@@ -142,9 +143,10 @@ int orc_tree_set(OrcTree* t, int l, int a, int b, int v) { /* setindex!  qtrees.
     if (!lv_inkernel(m, a, b)) return -1;
     m->k[(size_t)(b - m->cs - 1) * m->kh + (a - m->rs - 1)] = (uint8_t)v; return 0;
 }
-void orc_level_setshift(OrcTree* t, int l, int rs, int cs) { LV(t, l).rs = rs; LV(t, l).cs = cs; }
+void orc_level_setshift(OrcTree* t, int l, int rs, int cs) { LV(t, l).rs = rs; LV(t, l).cs = cs; t->raw_edit = 1; }
 
 void orc_build(OrcTree* t, int layer) { /* buildqtree!(t::ShiftedQTree, layer)  qtrees.jl:221-237 */
+    t->built_from = layer - 1;
     for (int l = layer; l <= t->L; l++) {
         int m2 = LV(t, l - 1).rs / 2, n2 = LV(t, l - 1).cs / 2; /* ÷ toward zero */
         Level* v = &LV(t, l);
@@ -165,6 +167,33 @@ void orc_shift(OrcTree* t, int l, int s1, int s2) { /* shift!  qtrees.jl:267-275
 void orc_setshift(OrcTree* t, int l, int s1, int s2) { /* setshift!  qtrees.jl:277-285 */
     for (int i = l; i >= 1; i--) { LV(t, i).rs = s1; LV(t, i).cs = s2; s1 *= 2; s2 *= 2; }
     orc_build(t, l + 1);
+}
+/* setshift!(qtrees[labels[i]], level, (rs[i], cs[i])) for a whole list in ONE call (bench scaffolding: the restore of a
+ * seeded layout between timed steps; labels == NULL: trees 1..nl).  skip_same != 0: a tree that already sits there is left
+ * alone — exact, not an approximation: its last rebuild started at or below `level`, every level <= level has the
+ * requested shift and the levels above carry its ÷2 chain, so buildqtree! would rewrite what is there.  The device side
+ * applies the same rule (k_build_objects); both arms of bench.py therefore rebuild the same trees.  Returns the number of
+ * trees rebuilt. */
+int64_t orc_setshifts(OrcTree* const* trees, const int32_t* labels, int nl, int level, const int32_t* rs, const int32_t* cs, int skip_same, int nthreads) {
+    int64_t rebuilt = 0;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads) reduction(+ : rebuilt)
+    for (int i = 0; i < nl; i++) {
+        OrcTree* t = trees[labels ? labels[i] - 1 : i];
+        if (skip_same && !t->raw_edit && t->built_from <= level) {
+            int same = 1, s1 = rs[i], s2 = cs[i];
+            for (int l = level; l >= 1 && same; l--) { same = LV(t, l).rs == s1 && LV(t, l).cs == s2; s1 *= 2; s2 *= 2; }
+            for (int l = level + 1; l <= t->L && same; l++) same = LV(t, l).rs == LV(t, l - 1).rs / 2 && LV(t, l).cs == LV(t, l - 1).cs / 2;
+            if (same) continue;
+        }
+        orc_setshift(t, level, rs[i], cs[i]);
+        rebuilt++;
+    }
+    return rebuilt;
+}
+/* getshift(qtrees[labels[i]], level) for a list  qtrees.jl:288 */
+void orc_getshifts(OrcTree* const* trees, const int32_t* labels, int nl, int level, int32_t* rs, int32_t* cs) {
+    for (int i = 0; i < nl; i++) { const OrcTree* t = trees[labels ? labels[i] - 1 : i]; rs[i] = LV(t, level).rs; cs[i] = LV(t, level).cs; }
 }
 void orc_shift_axis(OrcTree* t, int l, int st, int axis, int set) { /* qtrees.jl:238-265 */
     for (int i = l; i >= 1; i--) {

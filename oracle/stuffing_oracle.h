@@ -59,6 +59,10 @@ void orc_build(OrcTree* t, int layer);                             /* buildqtree
 void orc_shift(OrcTree* t, int l, int s1, int s2);                 /* shift! */
 void orc_setshift(OrcTree* t, int l, int s1, int s2);              /* setshift! */
 void orc_shift_axis(OrcTree* t, int l, int st, int axis, int set); /* rshift!/cshift!/setrshift!/setcshift! */
+/* setshift! / getshift over a label list in one call (labels == NULL: trees 1..nl); skip_same leaves a tree that already
+ * sits at the requested place alone (exact); returns the number of trees rebuilt */
+int64_t orc_setshifts(OrcTree* const* trees, const int32_t* labels, int nl, int level, const int32_t* rs, const int32_t* cs, int skip_same, int nthreads);
+void orc_getshifts(OrcTree* const* trees, const int32_t* labels, int nl, int level, int32_t* rs, int32_t* cs);
 int orc_testqtree(const OrcTree* t);                               /* utils.jl:7-24; 0 ok */
 int orc_inkernelbounds(const OrcTree* t, int l, int a, int b);
 

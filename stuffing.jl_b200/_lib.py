@@ -30,6 +30,7 @@ EXPORTS = {
     "stf_num_levels": (C.c_int32, [C.c_void_p]),
     "stf_get_level_info": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "stf_download_level": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "stf_download_trees": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stf_read_nodes": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "stf_get_shifts": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "stf_set_shifts": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),

@@ -360,6 +360,21 @@ __global__ void k_unpack_level(const uint32_t* __restrict__ words, const LevelMe
     }
 }
 
+// every level of the listed trees in ONE launch (stf_download_trees): block x handles (tree x / L, level x % L + 1);
+// boff[x] = byte offset of that level in `out` (host-computed prefix sums of kh*kw)
+__global__ void k_unpack_trees(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, const int32_t* __restrict__ labels,
+                               const uint64_t* __restrict__ boff, uint8_t* __restrict__ out) {
+    int i = blockIdx.x / L, l = blockIdx.x % L;
+    int o = labels ? labels[i] - 1 : i;
+    LevelMeta m = lm[(size_t)o * L + l];
+    int kh = lm_kh(m), kw = lm_kw(m), wpc = wpc_of(kh);
+    uint8_t* dst = out + boff[blockIdx.x];
+    for (int j = threadIdx.x; j < kh * kw; j += blockDim.x) {
+        int c = j / kh, r = j - c * kh;
+        dst[j] = (uint8_t)((words[m.off + (size_t)c * wpc + (r >> 4)] >> ((r & 15) << 1)) & 3u);
+    }
+}
+
 // t[l,a,b] for n queries (stf_read_nodes) and grad2d (fit_helper.jl:51-66)
 __global__ void k_read_nodes(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, int L, int n,
                              const int32_t* __restrict__ labels, const int32_t* __restrict__ l, const int32_t* __restrict__ a,

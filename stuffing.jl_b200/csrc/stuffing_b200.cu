@@ -25,7 +25,7 @@ struct DevBuf {
         void* q = nullptr;
         cudaError_t e = cudaMalloc(&q, ncap);
         if (e != cudaSuccess) return e;
-        if (keep && p && cap) { e = cudaMemcpyAsync(q, p, cap, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; cudaStreamSynchronize(st); }
+        if (keep && p && cap) { e = cudaMemcpyAsync(q, p, cap, cudaMemcpyDeviceToDevice, st); if (e == cudaSuccess) e = cudaStreamSynchronize(st); if (e != cudaSuccess) { cudaFree(q); return e; } }
         if (p) cudaFree(p);
         p = q; cap = ncap; return cudaSuccess;
     }
@@ -36,7 +36,12 @@ struct DevBuf {
 struct stf_ctx {
     int device = 0; cudaStream_t st = nullptr; std::string err;
     int n = 0, L = 0, canvas = 0; uint64_t total_words = 0;
-    const char* pdl_skip = getenv("STF_PDL_SKIP"); // debugging: kernels (by name) launched without the attribute
+    // environment switches, read ONCE in stf_create (never on the hot path)
+    const char* pdl_skip = nullptr; // STF_PDL_SKIP: kernels (by name) launched without the programmatic attribute (debugging)
+    bool zero_copy = true;   // STF_NO_ZERO_COPY=1: small host arrays / read-backs go through the copy engine instead of pinned-memory accesses
+    bool env_force_big = false; // STF_FORCE_BIG=1: always the multi-launch throughput path
+    bool no_cluster = false; // STF_NO_CLUSTER=1: single-CTA sorts instead of the 8-CTA cluster kernels
+    int dbg_step = 0;        // STF_DEBUG_STEP: k_batchsteps experiments
     bool after_kernel = false; // the last operation enqueued on the stream was one of our kernel launches
     bool pdl = true; // programmatic dependent launch between the kernels of a round (STF_NO_PDL=1: plain stream order)
     bool raw_shift_edit = false; // stf_set_level_shift was used: shifts and rasters may disagree, never skip a rebuild
@@ -187,8 +192,7 @@ __global__ void k_copy_counts(const unsigned long long* __restrict__ counts, uns
     if ((int)threadIdx.x < n) host[threadIdx.x] = counts[threadIdx.x];
 }
 static int32_t sync_counts(stf_ctx* ctx) { // ONE read-back: counters, path status and error bits live in the same array
-    static const bool zc = !getenv("STF_NO_ZERO_COPY");
-    if (zc) { LAUNCH_PDL(ctx, k_copy_counts, 1, 32, 0, (const unsigned long long*)ctx->counts.as<unsigned long long>(), ctx->h_counts, (int)C_N); }
+    if (ctx->zero_copy) { LAUNCH_PDL(ctx, k_copy_counts, 1, 32, 0, (const unsigned long long*)ctx->counts.as<unsigned long long>(), ctx->h_counts, (int)C_N); }
     else CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->h_err[0] = (int)ctx->h_counts[C_ERR]; ctx->h_err[1] = (int)ctx->h_counts[C_STATUS];
@@ -213,6 +217,28 @@ static int32_t upload_labels(stf_ctx* ctx, DevBuf& buf, int32_t nl, const int32_
 }
 
 // ------------------------------------------------------------------------------------------------ lifetime
+// Function attributes (> 48 KB of dynamic shared memory, non-portable cluster sizes) are PER DEVICE: they are set for the
+// context's device every time a context is created (a host driving several GPUs from one process creates one context per
+// device), and a failure fails stf_create instead of surfacing later as a launch error.
+static cudaError_t set_func_attrs() {
+    cudaError_t e;
+#define STF_ATTR(f, a, v) do { e = cudaFuncSetAttribute(f, a, (int)(v)); if (e != cudaSuccess) return e; } while (0)
+    const size_t pbm = sizeof(uint32_t) * (PBM_A + PBM_B);
+    STF_ATTR(k_build_tail_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, pbm);
+    STF_ATTR(k_pack_build_mid<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, pbm);
+    STF_ATTR(k_pack_build_mid<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, pbm);
+    STF_ATTR(k_sort_records, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM_BYTES);
+    STF_ATTR(k_sort_records_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BYTES);
+    STF_ATTR(k_finalize_prep_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BYTES);
+#if CS_CTAS > 8
+    STF_ATTR(k_sort_records_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    STF_ATTR(k_finalize_prep_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+#endif
+    STF_ATTR(k_finalize_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM_BYTES);
+    STF_ATTR(k_step_links, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM_BYTES);
+#undef STF_ATTR
+    return cudaSuccess;
+}
 extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
     if (!out) return STF_E_ARG;
     *out = nullptr;
@@ -221,10 +247,15 @@ extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
     stf_ctx* ctx = new stf_ctx();
     ctx->device = device;
     if (getenv("STF_NO_PDL")) ctx->pdl = false;
+    ctx->pdl_skip = getenv("STF_PDL_SKIP");
+    ctx->zero_copy = !getenv("STF_NO_ZERO_COPY");
+    ctx->env_force_big = getenv("STF_FORCE_BIG") != nullptr;
+    ctx->no_cluster = getenv("STF_NO_CLUSTER") != nullptr;
+    { const char* e = getenv("STF_DEBUG_STEP"); ctx->dbg_step = e ? atoi(e) : 0; }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || (ctx->h_err = (int*)calloc(2, sizeof(int))) == nullptr ||
-        ctx->counts.ensure(C_N * sizeof(unsigned long long)) != cudaSuccess) {
-        delete ctx; return STF_E_CUDA;
+        ctx->counts.ensure(C_N * sizeof(unsigned long long)) != cudaSuccess || set_func_attrs() != cudaSuccess) {
+        stf_destroy(ctx); return STF_E_CUDA;
     }
     cudaMemsetAsync(ctx->counts.p, 0, C_N * sizeof(unsigned long long), ctx->st);
     *out = ctx;
@@ -257,8 +288,6 @@ __global__ void k_fill_i32(int* __restrict__ p, int n, int v) { int i = blockIdx
 // ------------------------------------------------------------------------------------------------ build helpers
 // levels from+1..L of one big object living in (words, lm) at meta index `mi`: wide launches while a level is large, then one CTA
 static int32_t build_big_on(stf_ctx* ctx, uint32_t* words, LevelMeta* lm, int mi, int kh1, int kw1, int from) {
-    static bool attr = false;
-    if (!attr) { CK(cudaFuncSetAttribute(k_build_tail_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * (PBM_A + PBM_B)))); attr = true; }
     auto words_of = [&](int l) { int kh = ((kh1 - 2) >> (l - 1)) + 2, kw = ((kw1 - 2) >> (l - 1)) + 2; if (l == 1) { kh = kh1; kw = kw1; } return (int64_t)wpc_of(kh) * kw; };
     for (int l = from + 1; l <= ctx->L; l++) {
         int64_t nw = words_of(l);
@@ -283,6 +312,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     if (n < 0 || canvas < 2 || (canvas & (canvas - 1)) || canvas > 32768) FAIL(STF_E_ARG, "canvas must be a power of two in [2, 32768]");
     int L = 1; for (int s = canvas; s > 1; s >>= 1) L++;
     ctx->n = n; ctx->L = L; ctx->canvas = canvas; ctx->items_valid = false; ctx->last_result = 0; ctx->raw_shift_edit = false;
+    ctx->ground_of = -1; ctx->force_big = false; ctx->hint_items = 0; ctx->ctr = stf_counters_t(); // per-scene state of a previous upload
     ctx->label_bits = 1; while ((1ll << ctx->label_bits) <= n) ctx->label_bits++;
     if (n >= (1 << 26)) FAIL(STF_E_ARG, "too many objects");
     ctx->h_om.assign(n, ObjMeta());
@@ -397,12 +427,6 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     for (int k = 0; k < 2; k++) { // a CTA per mid-size object: 128 threads for a few KB, 512 for mask-sized ones
         size_t cnt = k ? l_mid.size() - n_mid1 : n_mid1;
         if (!cnt) continue;
-        static bool attr = false;
-        if (!attr) {
-            CK(cudaFuncSetAttribute(k_pack_build_mid<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * (PBM_A + PBM_B))));
-            CK(cudaFuncSetAttribute(k_pack_build_mid<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * (PBM_A + PBM_B))));
-            attr = true;
-        }
         int aw = (int)((midA[k] + 31) & ~31ull), bw = (int)((midB[k] + 31) & ~31ull);
         const int32_t* lst = d_list + l_small.size() + (k ? n_mid1 : 0);
         size_t smem = sizeof(uint32_t) * (size_t)(aw + bw);
@@ -457,6 +481,32 @@ extern "C" int32_t stf_download_level(stf_ctx* ctx, int32_t label, int32_t l, ui
     ctx->launches++, k_unpack_level<<<std::min(nblk((int64_t)nb, 256), 148 * 8), 256, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->L, o, l, ctx->bytes_tmp.as<uint8_t>());
     KCHECK();
     CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, nb, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return STF_OK;
+}
+extern "C" int32_t stf_download_trees(stf_ctx* ctx, int32_t n, const int32_t* labels, uint8_t* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (count) *count = 0;
+    if (!labels) n = ctx->n;
+    if (n <= 0) return STF_OK;
+    const int L = ctx->L;
+    std::vector<uint64_t> off((size_t)n * L + 1, 0);
+    for (int i = 0; i < n; i++) {
+        int lb = labels ? labels[i] : i + 1; CHECK_LABEL(lb);
+        int a = ctx->h_om[lb - 1].kh1, b = ctx->h_om[lb - 1].kw1;
+        for (int l = 0; l < L; l++) { off[(size_t)i * L + l + 1] = off[(size_t)i * L + l] + (uint64_t)a * b; a = a / 2 + 1; b = b / 2 + 1; }
+    }
+    const uint64_t total = off.back();
+    if (count) *count = (int64_t)total;
+    if ((int64_t)total > cap) FAIL(STF_E_CAPACITY, "output buffer too small");
+    if (total == 0) return STF_OK;
+    if (!out) FAIL(STF_E_ARG, "null output buffer");
+    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, n, labels, &dl); if (r) return r;
+    CK(ctx->bytes_tmp.ensure((size_t)total)); CK(ctx->woff1.ensure(sizeof(uint64_t) * off.size()));
+    CK(cudaMemcpyAsync(ctx->woff1.p, off.data(), sizeof(uint64_t) * off.size(), cudaMemcpyHostToDevice, ctx->st));
+    ctx->launches++, k_unpack_trees<<<n * L, 128, 0, ctx->st>>>(ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, dl, ctx->woff1.as<uint64_t>(), ctx->bytes_tmp.as<uint8_t>());
+    KCHECK();
+    CK(cudaMemcpyAsync(out, ctx->bytes_tmp.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return STF_OK;
 }
@@ -553,7 +603,7 @@ extern "C" int32_t stf_set_shifts(stf_ctx* ctx, int32_t n, const int32_t* labels
         const size_t nb = sizeof(int32_t) * (size_t)n;
         HostPart parts[3] = { { labels, labels ? nb : 0 }, { rs, nb }, { cs, nb } };
         const int32_t* base;
-        zero_copy = n <= 65536 && !getenv("STF_NO_ZERO_COPY"); // up to 768 KB: read by the kernel straight from pinned memory
+        zero_copy = n <= 65536 && ctx->zero_copy; // up to 768 KB: read by the kernel straight from pinned memory
         if (zero_copy) { const void* zp = nullptr; CK(stage_zero_copy(ctx, parts, 3, &zp)); base = static_cast<const int32_t*>(zp); }
         else { CK(ctx->lab.ensure(3 * nb)); CK(stage_h2d_parts(ctx, ctx->lab.p, parts, 3)); base = ctx->lab.as<int32_t>(); }
         if (labels) { dl = base; base += n; }
@@ -595,20 +645,6 @@ extern "C" int32_t stf_build(stf_ctx* ctx, int32_t n, const int32_t* labels, int
 }
 
 // ------------------------------------------------------------------------------------------------ narrow phase
-static void set_smem_attrs() {
-    static bool done = false;
-    if (done) return;
-    cudaFuncSetAttribute(k_sort_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
-    cudaFuncSetAttribute(k_sort_records_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BYTES);
-    cudaFuncSetAttribute(k_finalize_prep_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BYTES);
-#if CS_CTAS > 8
-    cudaFuncSetAttribute(k_sort_records_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(k_finalize_prep_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-#endif
-    cudaFuncSetAttribute(k_finalize_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
-    cudaFuncSetAttribute(k_step_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES);
-    done = true;
-}
 // runs the BFS over ctx->items.  n_host >= 0: host-known item count; n_host < 0: the count is on the device
 // (counts[C_ITEMS], clamped to `cap`).  want_res: per-item results into ctx->res; want_hits: hits (l >= 0) appended to
 // ctx->hits through counts[C_NHITS].
@@ -706,7 +742,6 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
     if (nh == 0) return STF_OK;
     stage_begin(ctx, STF_STAGE_RESULT);
     if (nh <= BS_CAP && 2 * ctx->label_bits + FIN_IDX_BITS <= 64) { // one CTA: sort, tie order, unique, export
-        set_smem_attrs();
         if (export_host_format) CK(ctx->out32.ensure(sizeof(int32_t) * 5 * (size_t)nh));
         unsigned long long v = (unsigned long long)nh;
         CK(stage_h2d(ctx, ctx->counts.as<unsigned long long>() + C_NHITS, &v, sizeof(v)));
@@ -834,7 +869,7 @@ extern "C" int32_t stf_totalcollisions_native(stf_ctx* ctx, int32_t nl, const in
 // ------------------------------------------------------------------------------------------------ broad phase
 static bool fast_path_ok(const stf_ctx* ctx, int64_t nl) {
     int key_bits = 2 * STF_CELL_W + 5 + ctx->scene_bits;
-    return !ctx->force_big && nl <= BS_CAP && key_bits + ctx->label_bits <= 64 && 2 * ctx->label_bits + FIN_IDX_BITS <= 64 && !getenv("STF_FORCE_BIG");
+    return !ctx->force_big && nl <= BS_CAP && key_bits + ctx->label_bits <= 64 && 2 * ctx->label_bits + FIN_IDX_BITS <= 64 && !ctx->env_force_big;
 }
 // locate + sort; on return *keys/*vals point at the sorted records, their number is in counts[C_NVALID] (device);
 // *nrec_out = capacity bound (4 slots per located object).  `labels_dev` = the device copy of `labels` (or NULL).
@@ -851,7 +886,6 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     unsigned long long* nvalid = ctx->counts.as<unsigned long long>() + C_NVALID;
     unsigned long long* nappend = ctx->counts.as<unsigned long long>() + C_NREC;
     if (fast) {
-        set_smem_attrs();
         if (linked) {
             if (nl > 0) LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
                                                                    ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
@@ -862,7 +896,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
         }
         KCHECK();
         stage_begin(ctx, STF_STAGE_SORT);
-        if (getenv("STF_NO_CLUSTER")) // single-CTA variant (kept for comparison)
+        if (ctx->no_cluster) // single-CTA variant (kept for comparison)
             LAUNCH_PDL(ctx, k_sort_records, 1, BS_THREADS, BS_SMEM_BYTES, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, nrec, bits, ctx->label_bits,
                                                                                       linked ? nullptr : dl, ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nvalid, STATUSP(ctx));
         else // one cluster of 8 CTAs
@@ -871,8 +905,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
         KCHECK();
         *keys = ctx->rk.as<uint64_t>(); *vals = ctx->rv.as<uint32_t>();
         stage_end(ctx);
-        ctx->ctr.records = nrec;
-        return STF_OK;
+        return STF_OK; // ctr.records: from counts[C_NVALID] at the round's one synchronisation (read_round_counters)
     }
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
     if (linked) {
@@ -898,6 +931,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
         KCHECK();
         int32_t r = sync_counts(ctx); if (r) return r;
         int64_t nv = (int64_t)ctx->h_counts[C_NVALID];
+        ctx->ctr.records = nv; // valid (cell, label) records
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nv,
                                  (uint64_t)ctx->h_counts[C_VARY] & bit_range(0, bits), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
         *keys = f ? ctx->rk.as<uint64_t>() : ctx->rk2.as<uint64_t>();
@@ -905,7 +939,6 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     }
     KCHECK();
     stage_end(ctx);
-    ctx->ctr.records = nrec;
     return STF_OK;
 }
 static int32_t export_cells(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, stf_cellrec* out, int64_t cap, int64_t* count) {
@@ -1001,6 +1034,7 @@ static int32_t upload_moved_pos(stf_ctx* ctx, int32_t nl, const int32_t* labels,
 static void read_round_counters(stf_ctx* ctx) {
     ctx->ctr.items = (int64_t)ctx->h_counts[C_ITEMS]; ctx->ctr.direct = (int64_t)ctx->h_counts[C_DIRECT]; ctx->ctr.hits = (int64_t)ctx->h_counts[C_NHITS];
     ctx->ctr.overflow = (int64_t)ctx->h_counts[C_OVERFLOW]; ctx->ctr.visited = (int64_t)ctx->h_counts[C_VISITED];
+    ctx->ctr.records = (int64_t)ctx->h_counts[C_NVALID]; // valid (cell, label) records of the round's sort
     ctx->last_items = ctx->ctr.items; ctx->items_valid = true; ctx->hint_items = ctx->ctr.items;
 }
 
@@ -1144,7 +1178,7 @@ static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, co
     A.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; A.order = order;
     A.vel = ctx->vel.as<double>(); A.has_vel = ctx->has_vel.as<uint8_t>(); A.moved_flag = ctx->moved_flag.as<uint8_t>(); A.dirty = ctx->dirty.as<int>(); A.built_from = ctx->built_from.as<int>();
     A.opt = ctx->opt; A.seed = seed; A.iter = iter; A.counts = ctx->counts.as<unsigned long long>();
-    { const char* e = getenv("STF_DEBUG_STEP"); A.dbg = e ? atoi(e) : 0; }
+    A.dbg = ctx->dbg_step;
     A.dbg_t = nullptr;
     if (A.dbg & 16) { CK(ctx->dbg_t.ensure(sizeof(unsigned long long) * 4 * (size_t)std::max<int64_t>(n_host, BS_CAP))); A.dbg_t = ctx->dbg_t.as<unsigned long long>(); }
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (n_host + 3) / 4), 148 * 8);
@@ -1167,7 +1201,6 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     stage_begin(ctx, STF_STAGE_STEP_PREP);
     CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
     if (m <= BS_CAP && ctx->label_bits + 1 + FIN_IDX_BITS <= 64) { // one CTA: endpoints, sort, links
-        set_smem_attrs();
         LAUNCH_PDL(ctx, k_step_links, 1, BS_THREADS, BS_SMEM_BYTES, hits, (int)n, ctx->label_bits, ctx->om.as<ObjMeta>(), ctx->prev.as<uint32_t>(), ctx->done.as<uint32_t>(),
                                                                                  ctx->counts.as<unsigned long long>() + C_TICKET);
     } else {
@@ -1214,7 +1247,7 @@ static int32_t pos_enqueue(stf_ctx* ctx) {
         ctx->h_out = nullptr; ctx->h_out_cap = 0;
         CK(cudaMallocHost(&ctx->h_out, 4 * nb)); ctx->h_out_cap = 4 * nb;
     }
-    if (!getenv("STF_NO_ZERO_COPY")) { // posted writes over PCIe into the pinned landing area: no copy-engine operation before the sync
+    if (ctx->zero_copy) { // posted writes over PCIe into the pinned landing area: no copy-engine operation before the sync
         LAUNCH_PDL(ctx, k_get_shifts, nblk(n, 256), 256, 0, ctx->lm.as<LevelMeta>(), ctx->L, n, nullptr, ctx->pos_level, reinterpret_cast<int32_t*>(ctx->h_out));
         KCHECK();
         return STF_OK;
@@ -1258,7 +1291,7 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
         F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
         F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
         F.status = STATUSP(ctx);
-        if (getenv("STF_NO_CLUSTER")) LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
+        if (ctx->no_cluster) LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
         else {
             CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)(CS_CAP + 1024)));
             LAUNCH_PDL(ctx, k_finalize_prep_cl, CS_CTAS, CS_THREADS, CS_SMEM_BYTES, F, ctx->hk.as<uint64_t>());

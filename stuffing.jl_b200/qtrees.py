@@ -251,6 +251,28 @@ class DeviceQTrees:
         self._ck(self.lib.stf_read_nodes(self.h, len(labels), ptr(labels), ptr(l), ptr(a), ptr(b), ptr(out)))
         return out
 
+    def download_trees(self, labels=None):
+        """every level of the listed trees with ONE kernel launch (stf_download_trees): a list (per tree) of lists
+        (per level 1..L) of kh x kw uint8 code matrices"""
+        lb = None if labels is None else i32(labels)
+        n = self.n if lb is None else len(lb)
+        cnt = C.c_int64(0)
+        rc = self.lib.stf_download_trees(self.h, n, ptr(lb), None, 0, C.byref(cnt))
+        if rc not in (0, _lib.STF_E_CAPACITY):
+            self._ck(rc)
+        buf = np.zeros(max(1, cnt.value), np.uint8)
+        self._ck(self.lib.stf_download_trees(self.h, n, ptr(lb), ptr(buf), len(buf), C.byref(cnt)))
+        out, pos = [], 0
+        for i in range(n):
+            o = (int(lb[i]) if lb is not None else i + 1) - 1
+            a, b, lv = int(self.kh1[o]), int(self.kw1[o]), []
+            for _ in range(self.nlevels):
+                lv.append(buf[pos:pos + a * b].reshape((a, b), order="F"))
+                pos += a * b
+                a, b = a // 2 + 1, b // 2 + 1
+            out.append(lv)
+        return out
+
     def getshifts(self, labels=None, level=1):
         n = self.n if labels is None else len(labels)
         lb = None if labels is None else i32(labels)
@@ -549,9 +571,11 @@ class DynamicColliders:
         self.moved = list(range(1, len(self.qtrees) + 1))
         self.unlocated = []
 
-    def union(self, c):  # union!(dc, c)
+    def union(self, c):  # union!(dc, c): ordered-set union, O(|moved| + |c|)
+        seen = set(self.moved)
         for x in c:
-            if x not in self.moved:
+            if x not in seen:
+                seen.add(x)
                 self.moved.append(x)
 
     def dynamiccollisions(self, **kw):

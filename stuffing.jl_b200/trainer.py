@@ -428,7 +428,13 @@ def randommove(qts, colist, rng):
     d = _dev(qts)
     rows = list(colist) if not isinstance(colist, np.ndarray) else [r for r in colist]
     pairs = _pairs_of(colist)
-    order = sorted(range(len(pairs)), key=lambda k: -max(pairs[k]))
+    # sort!(colist, by=maximum, rev=true) (fit.jl:438): `maximum` of a CoItem (a Pair) is the lexicographic maximum of its
+    # two tuples (i1, i2) and (l, a, b); of a bare pair it is max(i1, i2).  Stable, like Julia's default for `by` sorts.
+    if isinstance(colist, np.ndarray):
+        keys = [max(pairs[k], (int(rows[k]["l"]), int(rows[k]["a"]), int(rows[k]["b"]))) for k in range(len(pairs))]
+    else:
+        keys = [max(p) for p in pairs]
+    order = sorted(range(len(pairs)), key=lambda k: keys[k], reverse=True)
     sel = order[max(0, len(order) - 3):]
     moved = []
     for k in sel:
@@ -520,7 +526,9 @@ def train(qts, epochs=-1, trainer=trainepoch_EM2, patience=None, optimiser=None,
                 last_eta, _ = eta_list.pop()
                 set_eta(optimiser, last_eta)
             indi_s.reset()
-        if indi_g.age > max(2, 2 * patience, epochs / 50 * max(1, len(d) / max(1, indi_g.min))):
+        # length(ts) / indi_g.min is Inf when the best count is 0 (Julia float division): the test never fires then (fit.jl:547)
+        ratio = float("inf") if indi_g.min == 0 else len(d) / indi_g.min
+        if indi_g.age > max(2, 2 * patience, epochs / 50 * max(1, ratio)):
             break
     return ep, nc
 

@@ -33,16 +33,23 @@ def device_from_oracle(S, qts_orc, **kw):
 
 
 def assert_same_trees(d, qts_orc, labels=None):
-    """every level of every tree: same kernel size, same shift, same node codes"""
-    labels = range(1, len(qts_orc) + 1) if labels is None else labels
-    for lb in labels:
-        to, td = qts_orc[lb - 1], d[lb - 1]
-        assert len(to) == len(td)
-        for l in range(1, len(to) + 1):
-            io, idv = to.info(l), td.info(l)
-            assert io == idv, (lb, l, io, idv)
-            lo, ld = to.level(l), td.level(l)
-            assert np.array_equal(lo, ld), (lb, l)
+    """every level of every listed tree: same kernel size, same shift, same node codes.  The device side is read with one
+    batched download (stf_download_trees) and one stf_get_shifts per level — a handful of launches, not one per level"""
+    labels = list(range(1, len(qts_orc) + 1)) if labels is None else list(labels)
+    if not labels:
+        return
+    L = d.nlevels
+    dev = d.download_trees(labels)
+    shifts = [d.getshifts(labels, l) for l in range(1, L + 1)]
+    for k, lb in enumerate(labels):
+        to = qts_orc[lb - 1]
+        assert len(to) == L
+        for l in range(1, L + 1):
+            io = to.info(l)
+            ld = dev[k][l - 1]
+            idv = (ld.shape[0], ld.shape[1], int(shifts[l - 1][0][k]), int(shifts[l - 1][1][k]), d.canvas >> (l - 1))
+            assert tuple(io) == idv, (lb, l, io, idv)
+            assert np.array_equal(to.level(l), ld), (lb, l)
 
 
 def rect_scene(orc, n, seed, sz=100, masksize=(1000, 1000), place=True):

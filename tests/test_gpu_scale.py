@@ -1,6 +1,8 @@
-"""Full-size GPU tests of the other BASELINE.json configurations (C4: 100k masks on a 16384^2 canvas,
-C5: 4096 independent 512^2 scenes in one batch): bit-exact against the oracle where the oracle finishes in
-seconds, size-independent properties at the full size."""
+"""Full-size GPU tests of every BASELINE.json configuration (C1: 10k word masks on 4096^2; C2: the 1k / 1024^2 fit loop;
+C3: the dynamic loop at 10k; C4: 100k masks on a 16384^2 canvas; C5: 4096 independent 512^2 scenes in one batch):
+bit-exact against the oracle where the oracle finishes in seconds, size-independent properties at the full size."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -18,6 +20,174 @@ def S():
 @pytest.fixture(scope="module")
 def orc():
     return oracle()
+
+
+def _sorted_hits(orc, qo, labels=None, partial_tree=None):
+    if partial_tree is not None:
+        h, info = orc.partialcollisions(qo, partial_tree, labels, unique=False, raw=True)
+    else:
+        h, info = orc.totalcollisions_spacial(qo, labels, unique=False, raw=True)
+    h = h.copy()
+    orc.lib().orc_sort_unique(h.ctypes.data, C.byref(C.c_int64(len(h))), 0)
+    return h, info
+
+
+def test_c1_10k_words_4096_canvas(S, orc):
+    """the headline scene of bench.py (BASELINE configs[0]/metric): full hit list, item multiset, fixture counts, three fit
+    rounds of fitted positions, and the pyramids of moved trees — all against the oracle"""
+    W = workloads.load_workload("c1")
+    qo = workloads.oracle_scene(orc, W)
+    d = workloads.device_scene(S, W)
+    assert len(d) == 10_001 and d.nlevels == 13
+    want, info = orc.totalcollisions_spacial(qo, unique=False, details=True, raw=True)
+    got = S.totalcollisions_spacial(d, unique=False, raw=True)
+    c = d.counters()
+    assert c["items"] == info["n_items"] == W["n_items"] and c["direct"] == info["n_direct"] and len(got) == W["n_hits"]
+    assert c["records"] == 10_004                                   # 10 000 objects in one cell each + the mask in four
+    hs, _ = _sorted_hits(orc, qo)
+    assert np.array_equal(got, hs)                                  # every hit, (i1, i2) => (l, a, b), canonical order
+    items_dev = np.sort(d.fetch_items(), order=["i1", "i2", "l", "a", "b"])
+    items_orc = np.sort(info["items"], order=["i1", "i2", "l", "a", "b"])
+    assert np.array_equal(items_dev, items_orc)                     # the narrow-phase item multiset
+    # mask excluded (examples/collision_benchmark.jl:22-37), unique
+    lab = np.arange(2, len(qo) + 1, dtype=np.int32)
+    assert S.items_to_list(S.totalcollisions_spacial(d, lab, raw=True)) == orc.totalcollisions_spacial(qo, lab)
+    # three device-resident fit rounds: hit counts and every position after each round
+    opt = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    clock = S.trainer.StepClock(seed=1)
+    for it in range(3):
+        hs, _ = _sorted_hits(orc, qo)
+        nh, rs, cs = S.trainer.fit_round_positions(d, None, S.Momentum(0.25, 0.5), clock)
+        orc.batchsteps(qo, hs, opt, seed=1, iteration=it)
+        ro, co = orc.getshifts(qo)
+        assert nh == len(hs) and np.array_equal(rs, ro) and np.array_equal(cs, co), it
+    moved = sorted({int(x) for x in np.concatenate([hs["i1"], hs["i2"]]) if x != 1})[:300]
+    assert_same_trees(d, qo, labels=moved + [2, 3, 5000, 10_001])
+
+
+def test_c2_fit_loop_1k_rects_1024_canvas(S, orc):
+    """BASELINE configs[1] (examples/packing.jl): 50 fixed rounds of totalcollisions + batchsteps on 1 000 rect masks;
+    per-round hit counts and fitted positions against the committed golden vector AND a live oracle run"""
+    W = workloads.load_workload("c2")
+    qo = workloads.oracle_scene(orc, W)
+    d = workloads.device_scene(S, W)
+    assert len(d) == 1001 and d.nlevels == 11
+    opt = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    clock = S.trainer.StepClock(seed=W["seed"])
+    hits_dev = []
+    for k in range(W["rounds"]):
+        hs, info = _sorted_hits(orc, qo)
+        nh, rs, cs = S.trainer.fit_round_positions(d, None, S.Momentum(0.25, 0.5), clock)
+        c = d.counters()
+        assert nh == len(hs) == W["round_hits"][k] and c["items"] + c["direct"] == info["n_items"] + info["n_direct"] == W["round_items"][k], k
+        orc.batchsteps(qo, hs, opt, seed=W["seed"], iteration=k)
+        ro, co = orc.getshifts(qo)
+        assert np.array_equal(rs, ro) and np.array_equal(cs, co), k
+        hits_dev.append(nh)
+    assert np.array_equal(rs, W["final_rs"]) and np.array_equal(cs, W["final_cs"])
+    assert hits_dev[0] > 100 and hits_dev[-1] == 0                   # the loop converges (test/runtests.jl:48-68)
+    assert_same_trees(d, qo, labels=list(range(1, 1002, 7)))
+
+
+def _orc_trainepoch_E(orc, qo, opt, seed, it0):
+    """trainepoch_E! (fit.jl:85-99) on the oracle in canonical mode, the twin of trainer.trainepoch_E"""
+    def total(labels=None):  # the dispatcher (qtree_functions.jl:270-276): native below the threshold, spacial above
+        h = orc.items_array(orc.totalcollisions(qo, labels, unique=False))
+        orc.lib().orc_sort_unique(h.ctypes.data, C.byref(C.c_int64(len(h))), 0)
+        return h
+    it = it0
+    hs = total()
+    nc = len(hs)
+    if nc == 0:
+        return nc, it
+    orc.batchsteps(qo, hs, opt, seed=seed, iteration=it); it += 1
+    inds = S_labels(hs)
+    for ni in range(1, len(qo) // len(inds) + 1):
+        hs = total(inds)
+        orc.batchsteps(qo, hs, opt, seed=seed, iteration=it); it += 1
+        if ni > 8 * len(hs):
+            break
+    return nc, it
+
+
+def S_labels(colist):
+    seen, out = set(), []
+    for r in colist:
+        for x in (int(r["i1"]), int(r["i2"])):
+            if x not in seen:
+                seen.add(x); out.append(x)
+    return out
+
+
+def test_c2_trainepoch_E_policy_parity(S, orc):
+    """the reference's element-wise trainer (fit.jl:85-99: total round, then rounds over the moved labels until
+    ni > 8 |colist|) at the C2 size: same epochs, same collision counts, same fitted positions as the oracle"""
+    W = workloads.load_workload("c2")
+    qo = workloads.oracle_scene(orc, W)
+    d = workloads.device_scene(S, W)
+    opt = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    clock = S.trainer.StepClock(seed=7)
+    it = 0
+    for ep in range(6):
+        nc_o, it = _orc_trainepoch_E(orc, qo, opt, 7, it)
+        nc_d = S.trainer.trainepoch_E(d, S.Momentum(0.25, 0.5), clock)
+        assert nc_d == nc_o and clock.iteration == it, (ep, nc_d, nc_o, clock.iteration, it)
+        rs, cs = d.getshifts()
+        ro, co = orc.getshifts(qo)
+        assert np.array_equal(rs, ro) and np.array_equal(cs, co), ep
+    assert nc_o < W["round_hits"][0] // 4
+
+
+def test_c3_dynamic_loop_10k(S, orc):
+    """BASELINE configs[2]: 20 steps of the scripted dynamic loop of bench.py --workload c3 on the 10k scene — per step the
+    partialcollisions result through the linked tree and every position after batchsteps, against the oracle"""
+    import bench
+    W = workloads.load_workload("c1")
+    qo = workloads.oracle_scene(orc, W)
+    d = workloads.device_scene(S, W)
+    n_all = len(d)
+    tree_d = S.linked_spacial_qtree(d); S.locate(d, None, tree_d)
+    tree_o = orc.LinkedTree(qo); tree_o.locate(qo)
+    opt = orc.Opt("momentum", 0.25, 0.5, n_all)
+    S.trainer._set_opt(d, S.Momentum(0.25, 0.5))
+    moved = list(range(2, n_all + 1))
+    total_hits = 0
+    for step, (jit, dr, dc) in enumerate(bench.c3_script(n_all, 20)):
+        d.shift(jit, 1, dr, dc)
+        for lb, a, b in zip(jit.tolist(), dr.tolist(), dc.tolist()):
+            qo[lb - 1].shift(1, a, b)
+        labels = list(dict.fromkeys(moved + jit.tolist()))
+        got = S.partialcollisions(d, tree_d, labels, unique=False, raw=True)
+        want, info = _sorted_hits(orc, qo, labels, tree_o)
+        c = d.counters()
+        assert np.array_equal(got, want), step
+        assert c["items"] == info["n_items"] and c["direct"] == info["n_direct"], step
+        d._ck(d.lib.stf_batchsteps(d.h, len(got), got.ctypes.data, 1, step))
+        orc.batchsteps(qo, want, opt, seed=1, iteration=step)
+        rs, cs = d.getshifts()
+        ro, co = orc.getshifts(qo)
+        assert np.array_equal(rs, ro) and np.array_equal(cs, co), step
+        moved = bench.labels_of_result(got)
+        total_hits += len(got)
+    assert total_hits > 5000 and len(moved) < n_all // 2
+
+
+def test_two_contexts_in_one_process(S, orc):
+    """a host that drives several contexts from one process (SURVEY §8b threading row): function attributes are set per
+    context/device in stf_create; two live contexts give identical, oracle-exact results (on a multi-GPU box the second one
+    sits on device 1)"""
+    import torch
+    ndev = torch.cuda.device_count()
+    W = workloads.load_workload("c1k")
+    qo = workloads.oracle_scene(orc, W)
+    want = sorted(orc.totalcollisions_spacial(qo, unique=False))
+    ds = [workloads.device_scene(S, W, device=(k % ndev)) for k in range(2)]
+    for d in ds:
+        assert S.totalcollisions_spacial(d, unique=False) == want and len(want) == W["n_hits"]
+    clock = [S.trainer.StepClock(seed=3), S.trainer.StepClock(seed=3)]
+    for it in range(2):
+        res = [S.trainer.fit_round_positions(d, None, S.Momentum(0.25, 0.5), clock[k]) for k, d in enumerate(ds)]
+        assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
 
 
 def test_c4_100k_objects_16384_canvas(S, orc):

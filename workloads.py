@@ -8,8 +8,13 @@ G-word : word-like binary blobs imitating examples/collision_benchmark.jl:32 (Wo
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+# committed place! layouts + oracle counts (tools/make_bench_fixture.py)
+FIXTURES = {"c1": "c1_word_n10000_seed1.npz", "c1k": "c1_word_n1000_seed1.npz", "c2": "c2_rect_n1000_seed2.npz", "c4": "c4_rect_n100000_seed4.npz"}
 
 EMPTY, FULL, MIX = 1, 2, 3
 
@@ -83,3 +88,59 @@ def uniform_shifts(objs, mask_side, canvas, rng):
 
 def codes_of(obj):
     return np.where(obj, FULL, EMPTY).astype(np.uint8)
+
+
+def load_workload(which="c1"):
+    """single-scene workloads of BASELINE.json: seeded objects + the committed place! layout (tools/make_bench_fixture.py).
+    c1 (also the c3 scene): 10 000 word masks, 3500^2 mask, canvas 4096; c1k: 1 000 word masks, canvas 2048;
+    c2: 1 000 rect masks sz 36, 1000^2 mask, canvas 1024 (+ the golden vector of its 50 fit rounds);
+    c4: 100 000 rect masks sz 30, 15900^2 mask, canvas 16384."""
+    fx = np.load(os.path.join(ROOT, "bench_data", FIXTURES[which]))
+    n, seed, s = int(fx["n"]), int(fx["seed"]), int(fx["mask_side"])
+    rng = np.random.default_rng(seed)
+    objs = rect_objects(n, 30, rng) if which == "c4" else rect_objects(n, 36, rng) if which == "c2" else word_objects(n, rng)
+    W = dict(n=n, seed=seed, mask_side=s, canvas=int(fx["canvas"]), objs=objs, rs=fx["rs"].astype(np.int32), cs=fx["cs"].astype(np.int32),
+             n_items=int(fx["n_items"]), n_hits=int(fx["n_hits"]), visited=int(fx["visited"]))
+    for k in ("rounds", "round_items", "round_hits", "round_visited", "final_rs", "final_cs"):
+        if k in fx:
+            W[k] = fx[k] if fx[k].ndim else int(fx[k])
+    return W
+
+
+def scene_batch(S, scenes, per_scene=128, seed=5, side=490, canvas=512):
+    """C5: `scenes` = iterable of scene ids; every scene = a side^2 mask + per_scene word masks at uniform positions.
+    S = the product package (qtree / maskqtree host constructors).  Returns the packed upload (payload, kh, kw, rs, cs,
+    dflt, is_mask, scene ids 0..len-1, canvas)."""
+    pool_rng = np.random.default_rng(seed)
+    pool = [S.qtree(o, canvas) for o in word_objects(2000, pool_rng)]
+    mask = S.maskqtree(np.ones((side, side), bool))
+    mflat = np.asfortranarray(mask.codes).ravel(order="F")
+    pflat = [np.asfortranarray(t.codes).ravel(order="F") for t in pool]
+    ph, pw = np.array([t.codes.shape[0] for t in pool]), np.array([t.codes.shape[1] for t in pool])
+    off = (canvas - side) // 2
+    chunks, kh, kw, rs, cs, dflt, is_mask, scene = [], [], [], [], [], [], [], []
+    for k, s in enumerate(scenes):
+        rng = np.random.default_rng(50_000 + int(s))
+        pick = rng.integers(0, len(pool), per_scene)
+        chunks.append(mflat); kh.append(side); kw.append(side); rs.append(mask.shift1[0]); cs.append(mask.shift1[1]); dflt.append(mask.default); is_mask.append(1); scene.append(k)
+        for j in pick:
+            chunks.append(pflat[j]); kh.append(ph[j]); kw.append(pw[j]); dflt.append(pool[j].default); is_mask.append(0); scene.append(k)
+            rs.append(off + int(rng.integers(0, max(1, side - ph[j])))); cs.append(off + int(rng.integers(0, max(1, side - pw[j]))))
+    return dict(payload=np.concatenate(chunks), kh=np.array(kh, np.int32), kw=np.array(kw, np.int32), rs=np.array(rs, np.int32), cs=np.array(cs, np.int32),
+                dflt=np.array(dflt, np.uint8), is_mask=np.array(is_mask, np.uint8), scene=np.array(scene, np.int32), canvas=canvas)
+
+
+def device_scene(S, W, device=0):
+    """the single-scene workload W on the GPU: mask (label 1) + objects at the fixture's place! layout"""
+    s = W["mask_side"]
+    trees = [S.maskqtree(np.ones((s, s), bool))] + [S.qtree(o, W["canvas"]) for o in W["objs"]]
+    for t, r, c in zip(trees, W["rs"], W["cs"]):
+        t.shift1 = (int(r), int(c))
+    return S.DeviceQTrees(trees, device=device)
+
+
+def oracle_scene(orc, W):
+    """the same scene on the CPU oracle (test infrastructure / the reference arm of bench.py)"""
+    qts = orc.TreeList(orc.qtrees(W["objs"], mask=np.ones((W["mask_side"], W["mask_side"]), bool)))
+    orc.setshifts(qts, None, 1, W["rs"], W["cs"], skip_same=False)
+    return qts
