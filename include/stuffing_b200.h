@@ -142,7 +142,11 @@ int32_t stf_locate(stf_ctx* ctx, int32_t nl, const int32_t* labels, stf_cellrec*
  * unique == 0: all hits, same sort order (the reference's order is arbitrary). */
 int32_t stf_totalcollisions_spacial(stf_ctx* ctx, int32_t nl, const int32_t* labels, int32_t unique,
                                     stf_item* out, int64_t cap, int64_t* count);
-/* the narrow-phase item list of the last spacial/partial call (the reference's `itemlist`), unordered */
+/* the narrow-phase item list of the last spacial/partial call (the reference's `itemlist` keyword buffer,
+ * qtree_functions.jl:225-249), unordered.  By default the candidate pairs are tested where they are generated and never
+ * stored (only counted: stf_counters_t.items); stf_set_keep_items(ctx, 1) makes the following many-body calls
+ * materialise the list so that it can be fetched. */
+int32_t stf_set_keep_items(stf_ctx* ctx, int32_t on);
 int32_t stf_fetch_items(stf_ctx* ctx, stf_item* out, int64_t cap, int64_t* count);
 int32_t stf_fetch_result(stf_ctx* ctx, stf_item* out, int64_t cap, int64_t* count);
 

@@ -43,6 +43,7 @@ EXPORTS = {
     "stf_totalcollisions_native": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stf_locate": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stf_totalcollisions_spacial": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "stf_set_keep_items": (C.c_int32, [C.c_void_p, C.c_int32]),
     "stf_fetch_items": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stf_fetch_result": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stf_linked_reset": (C.c_int32, [C.c_void_p]),

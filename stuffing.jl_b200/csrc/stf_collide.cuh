@@ -6,6 +6,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include "stf_common.cuh"
+#include "stf_narrow.cuh"
 namespace cg = cooperative_groups;
 
 // =============================================================================================
@@ -201,11 +202,18 @@ __global__ void k_level_index(const uint64_t* __restrict__ keys, const unsigned 
     for (int64_t x = prev + 1; x <= cur; x++) idx[x] = (int32_t)r;
 }
 
+// a candidate pair the word-parallel part could not decide (or that overflowed the small frontier): the item, its
+// frontier `front` (Morton order of the child-number paths) at `depth` levels below the start node, and — for explicit
+// item lists — the index its result is stored under
+struct __align__(16) SurvRec { Item16 item; uint64_t front; uint32_t depth; uint32_t it; };
+
 struct EmitOut {
-    Item16* items; int64_t item_cap;
-    Item16* direct; int64_t direct_cap;   // direct hits go straight into the hit list ...
-    unsigned long long* counts;           // [0] items, [1] direct hits (statistics)
+    Item16* items; int64_t item_cap;      // materialised candidate list (only when FUSED == false)
+    Item16* direct; int64_t direct_cap;   // direct hits AND (fused) narrow-phase hits go straight into the hit list ...
+    unsigned long long* counts;           // [0] items, [1] direct hits, [3] node tests (statistics)
     unsigned long long* nhits;            // ... whose fill counter this is
+    SurvRec* surv; int64_t surv_cap; unsigned long long* nsurv; // fused: pairs still undecided after depth 3
+    unsigned long long* cursor;           // work cursor of the frontier kernel (zeroed here)
 };
 __device__ __forceinline__ void emit_push(Item16* buf, int64_t cap, unsigned long long* counter, const Item16& it) {
     cg::coalesced_group g = cg::coalesced_threads();
@@ -231,8 +239,13 @@ __device__ __forceinline__ int64_t upper_bound_u64(const uint64_t* __restrict__ 
 // record and at most 16 levels): two records per warp keep twice as many lanes busy in the searches and in the filter.
 // moved_pos != NULL selects partialcollisions semantics (:285-326): a pair is generated iff at least one
 // side is in `labels` (moved_pos[o] >= 0); two moved labels of one cell are oriented (later, earlier).
+// FUSED: the narrow phase of every generated pair runs right here, in the lane that generated it (nw_collide3: the
+// first three levels below the cell as bitwise plane tests on whole node blocks): the candidate list is never written
+// or re-read, the blocks of the LOW tree (the same for every candidate of the record) are fetched once per record by 14
+// lanes (2 + 4 + 8 columns) and handed round by shuffles; decided pairs end here (hits appended to the hit list), the few
+// that are still undecided after depth 3 go to the frontier kernel with their frontier mask.
 #define EM_THREADS 256
-template <int W>
+template <int W, bool FUSED>
 __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                            const unsigned long long* __restrict__ nrec_dev, int64_t nrec_cap, int L,
                                                            const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm,
@@ -246,6 +259,8 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / W, sl_ = lane % W;
     int64_t nrec = min((int64_t)*nrec_dev, nrec_cap); // valid records (sorted, compacted)
     int64_t nwarps = (int64_t)gridDim.x * (EM_THREADS / 32);
+    unsigned long long visited = 0;
+    if (FUSED && blockIdx.x == 0 && threadIdx.x == 0) *out.cursor = 0ull;
     // item-parallel sharding: rank k of shard_n generates the candidates of the records k, k+shard_n, ...
     for (int64_t idx0 = ((int64_t)blockIdx.x * (EM_THREADS / 32) + wib) * RPW; idx0 * shard_n + shard_rank < nrec; idx0 += nwarps * RPW) {
         const int64_t r = (idx0 + sub) * shard_n + shard_rank;
@@ -295,6 +310,23 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
         LevelMeta lowm = {};
         if (rec) lowm = lm[(size_t)(low - 1) * L + (l - 1)];
         int lowcode = -1;
+        NwLowRegs lowb = {};
+        if (FUSED) { // the low tree's blocks of depth 1..3 below the cell: lane t < 14 of the record's group fetches one column
+            const int d = sl_ < 2 ? 1 : (sl_ < 6 ? 2 : 3), j = sl_ < 2 ? sl_ : (sl_ < 6 ? sl_ - 2 : sl_ - 6);
+            uint32_t fv = 0;
+            if (rec && sl_ < 14 && l - d >= 1) {
+                const LevelMeta m = lm[(size_t)(low - 1) * L + (l - d - 1)];
+                const int n = 1 << d;
+                fv = fields32_at<false>(words, m, n * b - (n - 1) - m.cs - 1 + j, n * a - (n - 1) - m.rs - 1, n);
+            }
+            const int g0 = sub * W;
+#define STF_F(k) __shfl_sync(FULLM, fv, g0 + (k))
+            lowb.B.p1 = (STF_F(0) & 0xFu) | ((STF_F(1) & 0xFu) << 4);
+            lowb.B.p2 = (STF_F(2) & 0xFFu) | ((STF_F(3) & 0xFFu) << 8) | ((STF_F(4) & 0xFFu) << 16) | ((STF_F(5) & 0xFFu) << 24);
+#pragma unroll
+            for (int q = 0; q < 4; q++) lowb.B.p3[q] = (STF_F(6 + 2 * q) & 0xFFFFu) | (STF_F(7 + 2 * q) << 16);
+#undef STF_F
+        }
         const int* pref = s_pref[wib][sub]; const int* sstart = s_start[wib][sub];
         for (int c0 = 0; c0 < tmax; c0 += W) {
             int c = c0 + sl_;
@@ -336,10 +368,26 @@ __global__ void __launch_bounds__(EM_THREADS) k_emit_items(const uint64_t* __res
             }
             ibase = __shfl_sync(FULLM, ibase, 0); dbase = __shfl_sync(FULLM, dbase, 0);
             unsigned lt = (1u << lane) - 1;
-            if (is_item) { int64_t slot = (int64_t)ibase + __popc(im & lt); if (slot < out.item_cap) out.items[slot] = make_item(i1, i2, l, a, b); }
+            if (!FUSED) { if (is_item) { int64_t slot = (int64_t)ibase + __popc(im & lt); if (slot < out.item_cap) out.items[slot] = make_item(i1, i2, l, a, b); } }
+            else if (is_item) { // narrow phase in place: `low` against the other tree of the pair (the AND is symmetric)
+                const int other = i1 == low ? i2 : i1;
+                const NwResult R = nw_collide3<false>(words, lowb, lm + (size_t)(other - 1) * L, l, a, b);
+                visited += (unsigned long long)R.visited;
+                if (R.undecided) {
+                    unsigned long long s_ = atomicAdd(out.nsurv, 1ull);
+                    if ((int64_t)s_ < out.surv_cap) { SurvRec sr; sr.item = make_item(i1, i2, l, a, b); sr.front = R.front; sr.depth = 3u; sr.it = 0u; out.surv[s_] = sr; }
+                } else if (R.l >= 0) { // cp[1] >= 0  qtree_functions.jl:104-106
+                    unsigned long long s_ = atomicAdd(out.nhits, 1ull);
+                    if ((int64_t)s_ < out.direct_cap) out.direct[s_] = make_item(i1, i2, R.l, R.a, R.b);
+                }
+            }
             if (is_direct) { int64_t slot = (int64_t)dbase + __popc(dm & lt); if (slot < out.direct_cap) out.direct[slot] = make_item(low, i2, l, a, b); }
         }
         __syncwarp();
+    }
+    if (FUSED) {
+        for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(FULLM, visited, o);
+        if (lane == 0 && visited) atomicAdd(out.counts + 3, visited);
     }
 }
 
@@ -394,83 +442,150 @@ __global__ void k_native_pairs(const int32_t* __restrict__ flt, const int* __res
 // order; a ballot finds the first FULL code (= the node the sequential BFS returns) and an ordered
 // ballot/popc compaction appends the MIX children to the next frontier.
 // Frontier entries are (alpha,beta) offsets below the start node: a = at.a*2^d - alpha.
-#define NP_GROUP 4
-#define NP_FCAP 64
 #define NP_THREADS 128
 
 struct NarrowArgs {
     const uint32_t* words; const LevelMeta* lm; int L;
-    const Item16* items; const unsigned long long* n_items_dev; int64_t n_items_host; // device count if non-null
+    const Item16* items; const unsigned long long* n_items_dev; int64_t n_items_host; // explicit item list (k_narrow_items); device count if non-null
     int4* res;                       // per item (l,a,b,0); l < 0 = miss (NULL: not wanted)
     Item16* hits; int64_t hits_cap; unsigned long long* nhits; // hits (l >= 0) appended here (NULL: not wanted)
-    unsigned long long* counts;      // [2] overflow count, [3] visited
-    uint32_t* overflow;              // item indices that need the big path
+    unsigned long long* counts;      // [2] overflow count, [3] node tests
+    SurvRec* overflow;               // pairs that need the big path
     int64_t overflow_cap;
-    uint32_t* surv; unsigned long long* nsurv; // stage 1 -> stage 2: item index (28 bits) | MIX-in-both children of the start node (4 bits)
-    unsigned long long* cursor;      // stage 2 work cursor into surv (zeroed by stage 1)
+    SurvRec* surv; int64_t surv_cap; unsigned long long* nsurv; // word-parallel part -> frontier kernel
+    unsigned long long* cursor;      // frontier-kernel work cursor into surv (zeroed by the kernel that fills surv)
+    int* status;                     // latency path: STF_ST_RETRY_GROW when the survivor list was too small
 };
 
-// Stage 1, one THREAD per item: the four children of the start node.  Most candidate pairs end here (a FULL code =
-// the hit the sequential BFS returns first; no MIX child = miss at the start node, qtree_functions.jl:27-41), with every
-// lane busy; only the pairs with a MIX-in-both child go on to the group-per-item frontier kernel below.
-__global__ void __launch_bounds__(256) k_collide_first(NarrowArgs A) {
+// Word-parallel part over a compact item list (the candidate list of the broad phase, or an explicit list of
+// stf_collision_bfs / stf_collide_items / totalcollisions_native): nw_depth1..3, one THREAD per pair and depth.  The pairs
+// that go one level deeper are COMPACTED per warp between the depths (two small shared-memory queues per warp, ballot
+// ranks, no block barrier): a warp runs depth 1 on 32 fresh pairs, and whenever 32 pairs wait for depth 2 (or depth 3)
+// it runs that depth on them with every lane busy — instead of dragging its few deep pairs through all three depths.
+// Warps never wait for each other, so the gathers of one warp hide behind the arithmetic of the others.  Pairs still
+// undecided after depth 3 go on to the frontier kernel below with their depth-3 frontier.
+#define NW_THREADS 256
+#define NW_QCAP 64
+struct NwQEntry { Item16 item; uint32_t mix; int vis; uint32_t it; uint32_t pad; };
+__global__ void __launch_bounds__(NW_THREADS) k_narrow_items(NarrowArgs A) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
+    __shared__ NwQEntry s_q[NW_THREADS / 32][2][NW_QCAP];
+    const unsigned FULLM = 0xffffffffu;
     int64_t n = A.n_items_dev ? (int64_t)*A.n_items_dev : A.n_items_host;
     if (A.n_items_dev && n > A.n_items_host) n = A.n_items_host; // clamp to buffer capacity
     unsigned long long visited = 0;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) *A.cursor = 0ull;
-    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (int64_t)gridDim.x * blockDim.x) {
-        Item16 item = A.items[it];
-        int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
-        int lev = item_l(item), a = item.a, b = item.b;
-        LevelMeta m1 = A.lm[(size_t)o1 * A.L + (lev - 2)], m2 = A.lm[(size_t)o2 * A.L + (lev - 2)];
-        uint32_t code[4];
-#pragma unroll
-        for (int cn = 0; cn < 4; cn++) {
-            int ca = 2 * a - (cn & 1), cb = 2 * b - (cn >> 1);
-            code[cn] = node_code<false>(A.words, m1, ca, cb) & node_code<false>(A.words, m2, ca, cb);
-        }
-        int hit = -1; uint32_t mixmask = 0;
-#pragma unroll
-        for (int cn = 3; cn >= 0; cn--) { if (code[cn] == CODE_FULL) hit = cn; mixmask |= (uint32_t)(code[cn] == CODE_MIX) << cn; }
-        visited += 4;
-        if (hit < 0 && mixmask && lev - 1 > 1) { // undecided: the frontier kernel continues from the MIX children (bits 28..31)
+    NwQEntry* q2 = s_q[wib][0]; NwQEntry* q3 = s_q[wib][1];
+    int n2 = 0, n3 = 0; // queue fills (warp-uniform)
+    auto finish = [&](uint32_t it, const Item16& item, const NwResult& R) {
+        visited += (unsigned long long)R.visited;
+        if (R.undecided) {
             unsigned long long s_ = atomicAdd(A.nsurv, 1ull);
-            A.surv[s_] = (uint32_t)it | (mixmask << 28);
+            if ((int64_t)s_ < A.surv_cap) { SurvRec sr; sr.item = item; sr.front = R.front; sr.depth = 3u; sr.it = it; A.surv[s_] = sr; }
+            return;
+        }
+        if (A.res) A.res[it] = make_int4(R.l, R.a, R.b, 0);
+        if (A.hits && R.l >= 0) {
+            unsigned long long s_ = atomicAdd(A.nhits, 1ull);
+            if ((int64_t)s_ < A.hits_cap) A.hits[s_] = make_item(item.i1, item_i2(item), R.l, R.a, R.b);
+        }
+    };
+    const int64_t nwarps = (int64_t)gridDim.x * (NW_THREADS / 32);
+    int64_t base = ((int64_t)blockIdx.x * (NW_THREADS / 32) + wib) * 32;
+    for (;;) {
+        const bool more = base < n;
+        if (n3 >= 32 || (!more && n2 == 0 && n3 > 0)) { // ---- depth 3 on (up to) 32 queued pairs
+            const int take = min(n3, 32), e = n3 - take + lane;
+            if (lane < take) {
+                const NwQEntry q = q3[e];
+                const int l = item_l(q.item), a = q.item.a, b = q.item.b;
+                const LevelMeta m1 = ldmeta<false>(A.lm + (size_t)(q.item.i1 - 1) * A.L + (l - 4)), m2 = ldmeta<false>(A.lm + (size_t)(item_i2(q.item) - 1) * A.L + (l - 4));
+                uint32_t pa[4], pb[4];
+                nw_block3<false>(A.words, m1, a, b, pa); nw_block3<false>(A.words, m2, a, b, pb);
+                NwResult R; R.visited = q.vis; R.undecided = 0; R.front = 0;
+                nw_depth3(pa, pb, q.mix, l, a, b, R);
+                finish(q.it, q.item, R);
+            }
+            n3 -= take;
+            __syncwarp();
             continue;
         }
-        int4 result = hit >= 0 ? make_int4(lev - 1, 2 * a - (hit & 1), 2 * b - (hit >> 1), 0) : make_int4(-lev, a, b, 0);
-        if (A.res) A.res[it] = result;
-        if (A.hits && result.x >= 0) {
-            unsigned long long s_ = atomicAdd(A.nhits, 1ull);
-            if ((int64_t)s_ < A.hits_cap) A.hits[s_] = make_item(item.i1, item_i2(item), result.x, result.y, result.z);
+        if (n2 >= 32 || (!more && n2 > 0)) { // ---- depth 2
+            const int take = min(n2, 32), e = n2 - take + lane;
+            bool deeper = false; NwQEntry q = {}; 
+            if (lane < take) {
+                q = q2[e];
+                const int l = item_l(q.item), a = q.item.a, b = q.item.b;
+                const LevelMeta m1 = ldmeta<false>(A.lm + (size_t)(q.item.i1 - 1) * A.L + (l - 3)), m2 = ldmeta<false>(A.lm + (size_t)(item_i2(q.item) - 1) * A.L + (l - 3));
+                NwResult R; R.visited = q.vis; R.undecided = 0; R.front = 0; uint32_t mix;
+                deeper = nw_depth2(nw_block2<false>(A.words, m1, a, b), nw_block2<false>(A.words, m2, a, b), q.mix, l, a, b, R, &mix) != 0;
+                if (deeper) { q.mix = mix; q.vis = R.visited; } else finish(q.it, q.item, R);
+            }
+            n2 -= take;
+            const unsigned dm = __ballot_sync(FULLM, deeper);
+            __syncwarp(); // q2 reads of this round are done before anything is pushed again
+            if (deeper) q3[n3 + __popc(dm & ((1u << lane) - 1u))] = q;
+            n3 += __popc(dm);
+            __syncwarp();
+            continue;
+        }
+        if (!more) break;
+        { // ---- depth 1 on 32 fresh pairs
+            const int64_t it = base + lane;
+            bool deeper = false; NwQEntry q = {};
+            if (it < n) {
+                q.item = A.items[it]; q.it = (uint32_t)it;
+                const int l = item_l(q.item), a = q.item.a, b = q.item.b;
+                const LevelMeta m1 = ldmeta<false>(A.lm + (size_t)(q.item.i1 - 1) * A.L + (l - 2)), m2 = ldmeta<false>(A.lm + (size_t)(item_i2(q.item) - 1) * A.L + (l - 2));
+                NwResult R; uint32_t mix;
+                deeper = nw_depth1(nw_block1<false>(A.words, m1, a, b), nw_block1<false>(A.words, m2, a, b), l, a, b, R, &mix) != 0;
+                if (deeper) { q.mix = mix; q.vis = R.visited; } else finish(q.it, q.item, R);
+            }
+            const unsigned dm = __ballot_sync(FULLM, deeper);
+            if (deeper) q2[n2 + __popc(dm & ((1u << lane) - 1u))] = q;
+            n2 += __popc(dm);
+            __syncwarp();
+            base += nwarps * 32;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, o);
-    if ((threadIdx.x & 31) == 0 && visited) atomicAdd(A.counts + 3, visited);
+    for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(FULLM, visited, o);
+    if (lane == 0 && visited) atomicAdd(A.counts + 3, visited);
 }
 
-// Stage 2, one 4-lane GROUP per surviving item, one frontier node (its four children) per group and loop iteration.
-// The eight groups of a warp run ONE converged loop: a group that finishes its item takes the next one from the warp's
-// reserved chunk of the survivor list in the same iteration, so trip-count differences between items never idle lanes
-// (the earlier per-group loops ran with 11 of 32 lanes active on the batch workloads) and the votes are full-warp ballots.
+// Frontier kernel, one G-lane GROUP per pair the word-parallel part left undecided, G / 4 frontier nodes (their four
+// children each) per group and loop iteration.  G = 4 for batches (many pairs: throughput, eight pairs per warp); G = 32
+// for single scenes (few pairs, each a long dependent chain: a whole warp expands eight frontier nodes per round trip, and
+// the frontier buffer is eight times larger, so fewer pairs fall through to the CTA-per-pair path).
+// The groups of a warp run ONE converged loop: a group that finishes its pair takes the next one from the warp's reserved
+// chunk of the survivor list in the same iteration, so trip-count differences between pairs never idle lanes, and the
+// votes are full-warp ballots.  Lanes are ordered (frontier node, child number) = BFS order: the first FULL code among
+// the group's lanes is the node the sequential BFS returns, and the ballot/popc compaction keeps the next frontier in order.
+template <int G> struct NpCfg { static constexpr int FCAP = G == 4 ? 64 : 512; };
+template <int G>
 __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
-    __shared__ uint32_t fr[NP_THREADS / NP_GROUP][2][NP_FCAP];
+    constexpr int FCAP = NpCfg<G>::FCAP, NPI = G / 4; // frontier nodes per iteration
+    __shared__ uint32_t fr[NP_THREADS / G][2][FCAP];
     const unsigned FULLM = 0xffffffffu;
-    const int lane = threadIdx.x & 31, gl = lane & 3, g0 = lane & ~3;
-    const int gib = threadIdx.x / NP_GROUP;
-    const unsigned below = (1u << g0) - 1u; // lanes of the groups before mine
-    const int64_t n = (int64_t)*A.nsurv;    // only the items k_collide_first could not decide
+    const int lane = threadIdx.x & 31, gl_ = lane % G, g0 = lane - gl_, gl = gl_ & 3, slot = gl_ >> 2;
+    const int gib = threadIdx.x / G;
+    const unsigned gmask = G == 32 ? FULLM : ((1u << G) - 1u);
+    const unsigned below = G == 32 ? 0u : ((1u << g0) - 1u); // lanes of the groups before mine
+    int64_t n = (int64_t)*A.nsurv;          // only the pairs the word-parallel part could not decide
+    if (n > A.surv_cap) { // the list was too small: the round is re-run with a larger one (latency path) / the host re-runs
+        if (A.status && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(A.status, 1 /* STF_ST_RETRY_GROW */);
+        n = A.surv_cap;
+    }
     const int64_t nwarps = (int64_t)gridDim.x * (NP_THREADS / 32);
-    const int chunk = (int)min((int64_t)64, max((int64_t)8, ((n / nwarps) + 7) & ~(int64_t)7));
+    const int chunk = G == 32 ? 1 : (int)min((int64_t)64, max((int64_t)8, ((n / nwarps) + 7) & ~(int64_t)7));
     // the warp's chunk of the survivor list (warp-uniform): the first one is static, later ones come from the cursor
     int64_t cpos = ((int64_t)blockIdx.x * (NP_THREADS / 32) + (threadIdx.x >> 5)) * chunk, cend = min(cpos + chunk, n);
     bool exhausted = cpos >= n;
     if (exhausted) cpos = cend = 0;
-    // group state (identical in the four lanes)
+    // group state (identical in the lanes of a group)
     bool active = false, newlevel = false;
-    int64_t it = 0;
+    uint32_t it = 0; int lev0 = 0; // result index (explicit lists) and start level of the pair
     int i1 = 0, i2 = 0, lev = 0, ata = 0, atb = 0, cnt = 0, cur = 0, depth = 0, q = 0, ncnt = 0;
     LevelMeta m1 = {}, m2 = {};
     unsigned long long visited = 0;
@@ -485,36 +600,41 @@ __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
                 if (cpos >= n) { exhausted = true; cpos = cend = 0; }
             }
             if (!active) {
-                int64_t j = cpos + (__popc(need & below) >> 2);
+                int64_t j = cpos + (__popc(need & below) / G);
                 if (j < cend) {
-                    const uint32_t sv = A.surv[j], mm = sv >> 28; // stage 1 already tested the start node's children: mm = the MIX ones
-                    it = sv & 0x0FFFFFFFu;
-                    Item16 item = A.items[it];
-                    i1 = item.i1; i2 = item_i2(item); lev = item_l(item) - 1; ata = item.a; atb = item.b;
-                    cnt = __popc(mm); cur = 0; depth = 1; q = 0; ncnt = 0; newlevel = true; active = true;
-                    if ((mm >> gl) & 1u) fr[gib][0][__popc(mm & ((1u << gl) - 1u))] = ((uint32_t)(gl & 1) << 16) | (uint32_t)(gl >> 1);
+                    const SurvRec sr = A.surv[j]; // the word-parallel part already tested `depth` levels: `front` = its last frontier
+                    it = sr.it; lev0 = item_l(sr.item);
+                    i1 = sr.item.i1; i2 = item_i2(sr.item); depth = (int)sr.depth; lev = lev0 - depth; ata = sr.item.a; atb = sr.item.b;
+                    cnt = __popcll(sr.front); cur = 0; q = 0; ncnt = 0; newlevel = true; active = true;
+                    uint64_t f = sr.front; int idx = 0; // Morton order = BFS order: set bit number idx is frontier entry idx
+                    while (f) {
+                        const int k = __ffsll((long long)f) - 1; f &= f - 1;
+                        if (idx % G == gl_) { int al, be; nw_unkey((uint32_t)k, &al, &be); fr[gib][0][idx] = ((uint32_t)al << 16) | (uint32_t)be; }
+                        idx++;
+                    }
                 }
             }
-            cpos = min(cpos + (__popc(need) >> 2), cend);
+            cpos = min(cpos + (__popc(need) / G), cend);
             if (!__any_sync(FULLM, active)) { if (exhausted) break; continue; }
         }
-        __syncwarp(); // frontier writes of the previous iteration / the start node
+        __syncwarp(); // frontier writes of the previous iteration / the start frontier
         if (newlevel) {
             m1 = A.lm[(size_t)(i1 - 1) * A.L + (lev - 2)]; m2 = A.lm[(size_t)(i2 - 1) * A.L + (lev - 2)];
             newlevel = false;
         }
         uint32_t code = 0, ab = 0; int a = 0, b = 0;
-        if (active) {
-            uint32_t node = fr[gib][cur][q];
+        const bool valid = active && q + slot < cnt;
+        if (valid) {
+            uint32_t node = fr[gib][cur][q + slot];
             uint32_t al = ((node >> 16) << 1) + (gl & 1), be = ((node & 0xffffu) << 1) + (gl >> 1);
             ab = (al << 16) | be;
             a = (ata << (depth + 1)) - (int)al; b = (atb << (depth + 1)) - (int)be;
             code = node_code<false>(A.words, m1, a, b) & node_code<false>(A.words, m2, a, b);
-            visited++;
         }
-        const unsigned hm = (__ballot_sync(FULLM, code == CODE_FULL) >> g0) & 0xFu;
+        const unsigned hm = (__ballot_sync(FULLM, code == CODE_FULL) >> g0) & gmask;
+        if (valid && (!hm || gl_ < __ffs(hm))) visited++; // the sequential BFS stops at the first FULL child
         const bool push = code == CODE_MIX && lev - 1 > 1;
-        const unsigned pm = (__ballot_sync(FULLM, push) >> g0) & 0xFu;
+        const unsigned pm = (__ballot_sync(FULLM, push) >> g0) & gmask;
         const int src = g0 + (hm ? __ffs(hm) - 1 : 0);
         const int ha = __shfl_sync(FULLM, a, src), hb = __shfl_sync(FULLM, b, src);
         if (active) {
@@ -522,11 +642,11 @@ __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
             if (hm) { result = make_int4(lev - 1, ha, hb, 0); done = true; }
             else {
                 int np = __popc(pm);
-                if (ncnt + np > NP_FCAP) { overflow = true; done = true; }
+                if (ncnt + np > FCAP) { overflow = true; done = true; }
                 else {
-                    if (push) fr[gib][cur ^ 1][ncnt + __popc(pm & ((1u << gl) - 1u))] = ab;
-                    ncnt += np; q++;
-                    if (q == cnt) { // level finished
+                    if (push) fr[gib][cur ^ 1][ncnt + __popc(pm & ((1u << gl_) - 1u))] = ab;
+                    ncnt += np; q += NPI;
+                    if (q >= cnt) { // level finished
                         if (ncnt == 0) { // miss: -(level) and coordinates of the last node popped (:41)
                             uint32_t node = fr[gib][cur][cnt - 1];
                             result = make_int4(-lev, (ata << depth) - (int)(node >> 16), (atb << depth) - (int)(node & 0xffffu), 0);
@@ -536,13 +656,13 @@ __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
                 }
             }
             if (done) {
-                if (gl == 0) {
+                if (gl_ == 0) {
                     if (overflow) {
                         unsigned long long s = atomicAdd(A.counts + 2, 1ull);
-                        if ((int64_t)s < A.overflow_cap) A.overflow[s] = (uint32_t)it;
+                        if ((int64_t)s < A.overflow_cap) { SurvRec sr; sr.item = make_item(i1, i2, lev0, ata, atb); sr.front = 0; sr.depth = 0u; sr.it = it; A.overflow[s] = sr; }
                         result = make_int4(-1, 0, 0, -1);
                     }
-                    if (A.res) A.res[it] = result;
+                    if (A.res && !overflow) A.res[it] = result;
                     if (A.hits && result.x >= 0) { // cp[1] >= 0  qtree_functions.jl:104-106
                         unsigned long long s = atomicAdd(A.nhits, 1ull);
                         if ((int64_t)s < A.hits_cap) A.hits[s] = make_item(i1, i2, result.x, result.y, result.z);
@@ -552,7 +672,7 @@ __global__ void __launch_bounds__(NP_THREADS) k_collide_small(NarrowArgs A) {
             }
         }
     }
-    // visited-node counter (algorithmic bytes of the roofline)
+    // node-test counter (algorithmic bytes of the roofline)
     for (int o = 16; o > 0; o >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, o);
     if ((threadIdx.x & 31) == 0 && visited) atomicAdd(A.counts + 3, visited);
 }
@@ -570,9 +690,10 @@ __global__ void __launch_bounds__(NPB_THREADS) k_collide_big(NarrowArgs A, uint3
     uint32_t* fbuf[2] = { f0, f0 + cap_per_cta };
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned long long visited = 0;
-    for (int64_t ov = blockIdx.x; ov < nov; ov += gridDim.x) {
-        int64_t it = A.overflow[ov];
-        Item16 item = A.items[it];
+    for (int64_t ov = blockIdx.x; ov < nov; ov += gridDim.x) { // (restarts from the start node: the nodes the small path tested are counted twice)
+        const SurvRec sr = A.overflow[ov];
+        const uint32_t it = sr.it;
+        const Item16 item = sr.item;
         int o1 = item.i1 - 1, o2 = item_i2(item) - 1;
         int lev = item_l(item), ata = item.a, atb = item.b;
         int64_t cnt = 1; int cur = 0, depth = 0;

@@ -60,6 +60,9 @@ struct stf_ctx {
     int shard_rank = 0, shard_n = 1; // item-parallel sharding of the candidate generation (stf_shard_*)
     bool force_big = false; // the single-CTA latency path overflowed once: stay on the multi-launch path
     int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
+    int64_t hint_surv = 0;  // pairs the word-parallel narrow phase handed to the frontier kernel in the previous round
+    bool fused_narrow = false; // STF_FUSED_NARROW=1: candidates are tested inside the candidate kernel and never stored (measured slower: DESIGN.md)
+    bool keep_items = false; // stf_set_keep_items: the candidate list (the reference's `itemlist`) must be fetchable: never the fused variant
     stf_counters_t ctr = {};
     int64_t launches = 0; // kernels launched by this context (bench.py gpu_launches)
     // per-stage device timers (stf_profile_*): pairs of events recorded on ctx->st
@@ -251,6 +254,7 @@ extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
     ctx->zero_copy = !getenv("STF_NO_ZERO_COPY");
     ctx->env_force_big = getenv("STF_FORCE_BIG") != nullptr;
     ctx->no_cluster = getenv("STF_NO_CLUSTER") != nullptr;
+    ctx->fused_narrow = getenv("STF_FUSED_NARROW") != nullptr;
     { const char* e = getenv("STF_DEBUG_STEP"); ctx->dbg_step = e ? atoi(e) : 0; }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || (ctx->h_err = (int*)calloc(2, sizeof(int))) == nullptr ||
@@ -312,7 +316,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     if (n < 0 || canvas < 2 || (canvas & (canvas - 1)) || canvas > 32768) FAIL(STF_E_ARG, "canvas must be a power of two in [2, 32768]");
     int L = 1; for (int s = canvas; s > 1; s >>= 1) L++;
     ctx->n = n; ctx->L = L; ctx->canvas = canvas; ctx->items_valid = false; ctx->last_result = 0; ctx->raw_shift_edit = false;
-    ctx->ground_of = -1; ctx->force_big = false; ctx->hint_items = 0; ctx->ctr = stf_counters_t(); // per-scene state of a previous upload
+    ctx->ground_of = -1; ctx->force_big = false; ctx->hint_items = 0; ctx->hint_surv = 0; ctx->ctr = stf_counters_t(); // per-scene state of a previous upload
     ctx->label_bits = 1; while ((1ll << ctx->label_bits) <= n) ctx->label_bits++;
     if (n >= (1 << 26)) FAIL(STF_E_ARG, "too many objects");
     ctx->h_om.assign(n, ObjMeta());
@@ -645,35 +649,56 @@ extern "C" int32_t stf_build(stf_ctx* ctx, int32_t n, const int32_t* labels, int
 }
 
 // ------------------------------------------------------------------------------------------------ narrow phase
-// runs the BFS over ctx->items.  n_host >= 0: host-known item count; n_host < 0: the count is on the device
-// (counts[C_ITEMS], clamped to `cap`).  want_res: per-item results into ctx->res; want_hits: hits (l >= 0) appended to
-// ctx->hits through counts[C_NHITS].
-static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want_res, bool want_hits) {
-    int64_t nmax = n_host >= 0 ? n_host : cap;
-    if (want_res) CK(ctx->res.ensure(sizeof(int4) * (size_t)std::max<int64_t>(1, nmax)));
-    CK(ctx->overflow.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nmax)));
-    if (nmax == 0) return STF_OK;
-    if (nmax >= (1ll << 28)) FAIL(STF_E_ARG, "more than 2^28 candidate pairs in one call"); // stage 1 -> 2 list: 28-bit item index + 4 flag bits
-    NarrowArgs A;
+// survivor / overflow lists of the narrow phase (SurvRec, 32 B): sized for `want` pairs
+static int32_t ensure_surv(stf_ctx* ctx, int64_t want) {
+    CK(ctx->surv.ensure(sizeof(SurvRec) * (size_t)std::max<int64_t>(1024, want)));
+    CK(ctx->overflow.ensure(sizeof(SurvRec) * (size_t)std::max<int64_t>(1024, want)));
+    return STF_OK;
+}
+static void fill_narrow_args(stf_ctx* ctx, NarrowArgs& A, bool want_res, bool want_hits, bool device_counts) {
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.L = ctx->L;
-    A.items = ctx->items.as<Item16>();
-    A.n_items_dev = n_host >= 0 ? nullptr : ctx->counts.as<unsigned long long>() + C_ITEMS; A.n_items_host = nmax;
+    A.items = ctx->items.as<Item16>(); A.n_items_dev = nullptr; A.n_items_host = 0;
     A.res = want_res ? ctx->res.as<int4>() : nullptr; A.counts = ctx->counts.as<unsigned long long>();
     A.hits = want_hits ? ctx->hits.as<Item16>() : nullptr; A.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16)); A.nhits = ctx->counts.as<unsigned long long>() + C_NHITS;
-    A.overflow = ctx->overflow.as<uint32_t>(); A.overflow_cap = nmax;
-    CK(ctx->surv.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nmax)));
-    A.surv = ctx->surv.as<uint32_t>(); A.nsurv = ctx->counts.as<unsigned long long>() + C_SURV; A.cursor = ctx->counts.as<unsigned long long>() + C_CURSOR;
-    if (n_host >= 0) CK(cudaMemsetAsync(A.nsurv, 0, sizeof(unsigned long long), ctx->st)); // (the latency path zeroes the whole counter array once)
-    int per_block = NP_THREADS / NP_GROUP;
-    int64_t want = n_host >= 0 ? n_host : std::max<int64_t>(ctx->hint_items, 4096);
-    LAUNCH_PDL(ctx, k_collide_first, (int)std::min<int64_t>(std::max<int64_t>(1, (want + 255) / 256), 148 * 16), 256, 0, A);
-    int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want / 2 + per_block - 1) / per_block), 148 * 16); // typically < half the items survive; the warps share the list dynamically
-    LAUNCH_PDL(ctx, k_collide_small, blocks, NP_THREADS, 0, A);
+    A.overflow = ctx->overflow.as<SurvRec>(); A.overflow_cap = (int64_t)(ctx->overflow.cap / sizeof(SurvRec));
+    A.surv = ctx->surv.as<SurvRec>(); A.surv_cap = (int64_t)(ctx->surv.cap / sizeof(SurvRec));
+    A.nsurv = ctx->counts.as<unsigned long long>() + C_SURV; A.cursor = ctx->counts.as<unsigned long long>() + C_CURSOR;
+    A.status = device_counts ? STATUSP(ctx) : nullptr;
+}
+// the frontier kernels over the survivor list (filled by k_narrow_items or by the fused candidate kernel): `want` = expected
+// number of survivors (grid sizing only; the kernels read the real count from the device)
+static int32_t launch_frontier(stf_ctx* ctx, const NarrowArgs& A, int64_t want) {
+    // few pairs (a single scene): a whole warp per pair shortens the dependent chain of the deep ones; many pairs (a batch):
+    // four lanes per pair for throughput
+    if (want <= 32768) {
+        int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want + 3) / 4), 148 * 16);
+        LAUNCH_PDL(ctx, k_collide_small<32>, blocks, NP_THREADS, 0, A);
+    } else {
+        int per_block = NP_THREADS / 4;
+        int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (want + per_block - 1) / per_block), 148 * 16); // the warps share the list dynamically
+        LAUNCH_PDL(ctx, k_collide_small<4>, blocks, NP_THREADS, 0, A);
+    }
     KCHECK();
     CK(ctx->scratch.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->big_cap * ctx->big_ctas));
     LAUNCH_PDL(ctx, k_collide_big, ctx->big_ctas, NPB_THREADS, 0, A, ctx->scratch.as<uint32_t>(), ctx->big_cap, ERRP(ctx));
     KCHECK();
     return STF_OK;
+}
+// runs the narrow phase over the explicit list ctx->items.  n_host >= 0: host-known item count; n_host < 0: the count is on
+// the device (counts[C_ITEMS], clamped to `cap`).  want_res: per-item results into ctx->res; want_hits: hits (l >= 0)
+// appended to ctx->hits through counts[C_NHITS].
+static int32_t narrow_phase(stf_ctx* ctx, int64_t n_host, int64_t cap, bool want_res, bool want_hits) {
+    int64_t nmax = n_host >= 0 ? n_host : cap;
+    if (want_res) CK(ctx->res.ensure(sizeof(int4) * (size_t)std::max<int64_t>(1, nmax)));
+    if (nmax == 0) return STF_OK;
+    if (nmax >= (1ll << 32)) FAIL(STF_E_ARG, "more than 2^32 candidate pairs in one call");
+    int32_t r = ensure_surv(ctx, nmax); if (r) return r; // every item may survive: never too small
+    NarrowArgs A; fill_narrow_args(ctx, A, want_res, want_hits, n_host < 0);
+    A.n_items_dev = n_host >= 0 ? nullptr : ctx->counts.as<unsigned long long>() + C_ITEMS; A.n_items_host = nmax;
+    if (n_host >= 0) CK(cudaMemsetAsync(A.nsurv, 0, sizeof(unsigned long long), ctx->st)); // (the latency path zeroes the whole counter array once)
+    int64_t want = n_host >= 0 ? n_host : std::max<int64_t>(ctx->hint_items, 4096);
+    LAUNCH_PDL(ctx, k_narrow_items, (int)std::min<int64_t>(std::max<int64_t>(1, (want + NW_THREADS - 1) / NW_THREADS), 148 * 8), NW_THREADS, 0, A);
+    return launch_frontier(ctx, A, std::max<int64_t>(want / 16, 256));
 }
 static int32_t import_items(stf_ctx* ctx, int64_t n, const stf_item* items, DevBuf& dst) {
     for (int64_t i = 0; i < n; i++) {
@@ -799,9 +824,14 @@ extern "C" int32_t stf_fetch_result(stf_ctx* ctx, stf_item* out, int64_t cap, in
     NEED_OBJS();
     return deliver(ctx, ctx->last_result, out, cap, count);
 }
+extern "C" int32_t stf_set_keep_items(stf_ctx* ctx, int32_t on) {
+    if (!ctx) return STF_E_ARG;
+    ctx->keep_items = on != 0; ctx->items_valid = false; // (only matters with STF_FUSED_NARROW=1: the default path always materialises the list)
+    return STF_OK;
+}
 extern "C" int32_t stf_fetch_items(stf_ctx* ctx, stf_item* out, int64_t cap, int64_t* count) {
     NEED_OBJS();
-    if (!ctx->items_valid) FAIL(STF_E_STATE, "no item list available");
+    if (!ctx->items_valid) FAIL(STF_E_STATE, "no item list available: call stf_set_keep_items(ctx, 1) before the many-body call");
     int64_t n = ctx->last_items;
     if (count) *count = n;
     if (n > cap) FAIL(STF_E_CAPACITY, "output buffer too small");
@@ -998,7 +1028,9 @@ extern "C" int32_t stf_linked_collect(stf_ctx* ctx, stf_cellrec* out, int64_t ca
     return export_cells(ctx, nrec, keys, vals, out, cap, count);
 }
 
-static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, const int32_t* moved_pos) {
+// candidate generation.  fused: the narrow phase runs inside (decided pairs never become items; hits go to ctx->hits,
+// undecided pairs to ctx->surv for launch_frontier); else the candidate list is materialised in ctx->items.
+static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, const uint32_t* vals, const int32_t* moved_pos, bool fused) {
     const int32_t* lvl_index = nullptr;
     if ((ctx->multi_scene || nrec > 65536) && nrec > 0) { // batches: (scene, level) index of the sorted records for the ancestor searches
         int nsl = 32 << ctx->scene_bits;
@@ -1009,14 +1041,18 @@ static int32_t launch_emit(stf_ctx* ctx, int64_t nrec, const uint64_t* keys, con
     EmitOut eo; eo.items = ctx->items.as<Item16>(); eo.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
     eo.direct = ctx->hits.as<Item16>(); eo.direct_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
     eo.counts = ctx->counts.as<unsigned long long>(); eo.nhits = ctx->counts.as<unsigned long long>() + C_NHITS;
+    eo.surv = ctx->surv.as<SurvRec>(); eo.surv_cap = (int64_t)(ctx->surv.cap / sizeof(SurvRec)); eo.nsurv = ctx->counts.as<unsigned long long>() + C_SURV;
+    eo.cursor = ctx->counts.as<unsigned long long>() + C_CURSOR;
     stage_begin(ctx, STF_STAGE_EMIT);
     if (nrec > 0) {
         int blocks = (int)std::min<int64_t>((nrec / 4 + EM_THREADS / 32 - 1) / (EM_THREADS / 32) + 1, 148 * 8); // ~1 record per located object
         // batches of scenes: few candidates per record and L <= 16 -> two records per warp
-        if ((ctx->multi_scene || nrec > 65536) && ctx->L <= 16) LAUNCH_PDL(ctx, k_emit_items<16>, (blocks + 1) / 2, EM_THREADS, 0, keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
-                                                                        ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n, lvl_index);
-        else LAUNCH_PDL(ctx, k_emit_items<32>, blocks, EM_THREADS, 0, keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(),
-                                                                        ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n, lvl_index);
+        const bool half = (ctx->multi_scene || nrec > 65536) && ctx->L <= 16;
+#define STF_EMIT(W_, F_, B_) LAUNCH_PDL(ctx, (k_emit_items<W_, F_>), B_, EM_THREADS, 0, keys, vals, ctx->counts.as<unsigned long long>() + C_NVALID, nrec, ctx->L, ctx->words.as<uint32_t>(), \
+                                        ctx->lm.as<LevelMeta>(), moved_pos, eo, ctx->shard_rank, ctx->shard_n, lvl_index)
+        if (half) { if (fused) STF_EMIT(16, true, (blocks + 1) / 2); else STF_EMIT(16, false, (blocks + 1) / 2); }
+        else { if (fused) STF_EMIT(32, true, blocks); else STF_EMIT(32, false, blocks); }
+#undef STF_EMIT
 
     }
     KCHECK();
@@ -1035,7 +1071,14 @@ static void read_round_counters(stf_ctx* ctx) {
     ctx->ctr.items = (int64_t)ctx->h_counts[C_ITEMS]; ctx->ctr.direct = (int64_t)ctx->h_counts[C_DIRECT]; ctx->ctr.hits = (int64_t)ctx->h_counts[C_NHITS];
     ctx->ctr.overflow = (int64_t)ctx->h_counts[C_OVERFLOW]; ctx->ctr.visited = (int64_t)ctx->h_counts[C_VISITED];
     ctx->ctr.records = (int64_t)ctx->h_counts[C_NVALID]; // valid (cell, label) records of the round's sort
-    ctx->last_items = ctx->ctr.items; ctx->items_valid = true; ctx->hint_items = ctx->ctr.items;
+    ctx->last_items = ctx->ctr.items; ctx->items_valid = !ctx->fused_narrow || ctx->keep_items; ctx->hint_items = ctx->ctr.items;
+    ctx->hint_surv = (int64_t)ctx->h_counts[C_SURV];
+}
+// which list the finalize kernel checks for overflow before it lets the steps run: the candidate list when it is
+// materialised, the survivor list of the fused narrow phase otherwise
+static void set_overflow_check(stf_ctx* ctx, FinalizeArgs& F) {
+    if (!ctx->fused_narrow || ctx->keep_items) { F.n_items_dev = ctx->counts.as<unsigned long long>() + C_ITEMS; F.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16)); }
+    else { F.n_items_dev = ctx->counts.as<unsigned long long>() + C_SURV; F.item_cap = (int64_t)(ctx->surv.cap / sizeof(SurvRec)); }
 }
 
 // Latency path of one many-body round: every count stays on the device, the host only enqueues.  Broad phase
@@ -1049,10 +1092,19 @@ static int32_t spacial_core_fast(stf_ctx* ctx, int32_t nl, const int32_t* labels
     int64_t nrec; uint64_t* keys; uint32_t* vals;
     CK(cudaMemsetAsync(ctx->counts.p, 0, C_ERR * sizeof(unsigned long long), ctx->st)); // every counter and the status; pending error bits stay until a sync reads them
     r = locate_and_sort(ctx, nl, dl, linked, true, &nrec, &keys, &vals); if (r) return r;
+    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)(BS_CAP + 1024))); // more hits than BS_CAP leave the fast path anyway
+    if (ctx->fused_narrow && !ctx->keep_items) { // fused: candidates are tested where they are generated; only the undecided pairs are stored
+        r = ensure_surv(ctx, std::max<int64_t>(2 * nrec / 4, ctx->hint_surv + ctx->hint_surv / 4 + 1024)); if (r) return r;
+        r = launch_emit(ctx, nrec, keys, vals, moved_pos, true); if (r) return r;
+        stage_begin(ctx, STF_STAGE_NARROW);
+        NarrowArgs A; fill_narrow_args(ctx, A, false, true, true);
+        r = launch_frontier(ctx, A, std::max<int64_t>(ctx->hint_surv, 512)); if (r) return r;
+        stage_end(ctx);
+        return STF_OK;
+    }
     int64_t want_items = std::max<int64_t>(std::max<int64_t>(1024, 32 * nrec / 4), ctx->hint_items + ctx->hint_items / 4 + 1024);
     if ((int64_t)(ctx->items.cap / sizeof(Item16)) < want_items) CK(ctx->items.ensure(sizeof(Item16) * (size_t)want_items));
-    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)(BS_CAP + 1024))); // more hits than BS_CAP leave the fast path anyway
-    r = launch_emit(ctx, nrec, keys, vals, moved_pos); if (r) return r;
+    r = launch_emit(ctx, nrec, keys, vals, moved_pos, false); if (r) return r;
     stage_begin(ctx, STF_STAGE_NARROW);
     r = narrow_phase(ctx, -1, (int64_t)(ctx->items.cap / sizeof(Item16)), false, true); if (r) return r;
     stage_end(ctx);
@@ -1064,7 +1116,7 @@ static int fast_round_verdict(stf_ctx* ctx) {
     if (!st) return 0;
     cudaMemsetAsync(STATUSP(ctx), 0, sizeof(unsigned long long), ctx->st);
     if (st & STF_ST_RETRY_BIG) ctx->force_big = true;
-    if (st & STF_ST_RETRY_GROW) ctx->hint_items = (int64_t)ctx->h_counts[C_ITEMS]; // sizes the candidate list of the re-run
+    if (st & STF_ST_RETRY_GROW) { ctx->hint_items = (int64_t)ctx->h_counts[C_ITEMS]; ctx->hint_surv = (int64_t)ctx->h_counts[C_SURV]; } // size the lists of the re-run
     return 1;
 }
 
@@ -1077,23 +1129,36 @@ static int32_t spacial_core(stf_ctx* ctx, int32_t nl, const int32_t* labels, int
     int64_t nrec; uint64_t* keys; uint32_t* vals;
     r = locate_and_sort(ctx, nl, dl, linked, false, &nrec, &keys, &vals); if (r) return r;
     int64_t n_items = 0, n_direct = 0;
+    const bool fused = ctx->fused_narrow && !ctx->keep_items;
+    unsigned long long* nsurv_dev = ctx->counts.as<unsigned long long>() + C_SURV;
     for (int attempt = 0; attempt < 3; attempt++) {
         r = zero_counts(ctx); if (r) return r;
-        if (ctx->items.cap < sizeof(Item16) * 1024) CK(ctx->items.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, 32 * nrec)));
+        CK(cudaMemsetAsync(nsurv_dev, 0, sizeof(unsigned long long), ctx->st));
+        if (ctx->items.cap < sizeof(Item16) * 1024 && !fused) CK(ctx->items.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, 32 * nrec)));
         if (ctx->hits.cap < sizeof(Item16) * 1024) CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1024, nrec)));
-        int64_t item_cap = (int64_t)(ctx->items.cap / sizeof(Item16)), direct_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
-        r = launch_emit(ctx, nrec, keys, vals, moved_pos); if (r) return r;
+        if (fused) { r = ensure_surv(ctx, std::max<int64_t>(nrec, ctx->hint_surv + ctx->hint_surv / 4 + 1024)); if (r) return r; }
+        int64_t item_cap = (int64_t)(ctx->items.cap / sizeof(Item16)), hit_cap = (int64_t)(ctx->hits.cap / sizeof(Item16)), surv_cap = (int64_t)(ctx->surv.cap / sizeof(SurvRec));
+        r = launch_emit(ctx, nrec, keys, vals, moved_pos, fused); if (r) return r;
         r = sync_counts(ctx); if (r) return r;
         n_items = (int64_t)ctx->h_counts[C_ITEMS]; n_direct = (int64_t)ctx->h_counts[C_DIRECT];
-        if (n_items <= item_cap && n_direct <= direct_cap) break;
-        if (attempt == 2) FAIL(STF_E_CUDA, "internal: item buffer did not converge");
-        CK(ctx->items.ensure(sizeof(Item16) * (size_t)(n_items + n_items / 4 + 1024)));
-        CK(ctx->hits.ensure(sizeof(Item16) * (size_t)(n_direct + n_direct / 4 + 1024)));
+        const int64_t n_surv = (int64_t)ctx->h_counts[C_SURV], n_hits = (int64_t)ctx->h_counts[C_NHITS]; // fused: direct + narrow-phase hits so far
+        if (fused ? (n_surv <= surv_cap && n_hits <= hit_cap) : (n_items <= item_cap && n_direct <= hit_cap)) break;
+        if (attempt == 2) FAIL(STF_E_CUDA, "internal: candidate buffers did not converge");
+        if (!fused) CK(ctx->items.ensure(sizeof(Item16) * (size_t)(n_items + n_items / 4 + 1024)));
+        ctx->hint_surv = n_surv;
+        CK(ctx->hits.ensure(sizeof(Item16) * (size_t)(n_hits + n_hits / 4 + 1024)));
     }
-    // direct hits are already at the front of ctx->hits (counts[C_NHITS] == n_direct); keep them while growing
-    CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n_items + n_direct), true, ctx->st));
     stage_begin(ctx, STF_STAGE_NARROW);
-    r = narrow_phase(ctx, n_items, n_items, false, true); if (r) return r;
+    if (fused) { // the frontier kernels append at most one more hit per surviving pair
+        const int64_t n_surv = (int64_t)ctx->h_counts[C_SURV], n_hits = (int64_t)ctx->h_counts[C_NHITS];
+        CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n_hits + n_surv), true, ctx->st));
+        NarrowArgs A; fill_narrow_args(ctx, A, false, true, false);
+        r = launch_frontier(ctx, A, n_surv); if (r) return r;
+    } else {
+        // direct hits are already at the front of ctx->hits (counts[C_NHITS] == n_direct); keep them while growing
+        CK(ctx->hits.ensure(sizeof(Item16) * (size_t)std::max<int64_t>(1, n_items + n_direct), true, ctx->st));
+        r = narrow_phase(ctx, n_items, n_items, false, true); if (r) return r;
+    }
     stage_end(ctx);
     r = sync_counts(ctx); if (r) return r;
     read_round_counters(ctx);
@@ -1110,7 +1175,7 @@ static int32_t manybody_export(stf_ctx* ctx, int32_t nl, const int32_t* labels, 
         stage_begin(ctx, STF_STAGE_RESULT);
         FinalizeArgs F = {};
         F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
-        F.n_items_dev = ctx->counts.as<unsigned long long>() + C_ITEMS; F.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
+        set_overflow_check(ctx, F);
         F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = unique;
         F.out5 = ctx->out32.as<int32_t>(); F.kept = ctx->counts.as<unsigned long long>() + C_KEPT; F.do_prep = 0; F.status = STATUSP(ctx);
         LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
@@ -1286,7 +1351,7 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
         stage_begin(ctx, STF_STAGE_RESULT);
         FinalizeArgs F = {};
         F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
-        F.n_items_dev = ctx->counts.as<unsigned long long>() + C_ITEMS; F.item_cap = (int64_t)(ctx->items.cap / sizeof(Item16));
+        set_overflow_check(ctx, F);
         F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = 0; F.out5 = nullptr; F.kept = nullptr;
         F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
         F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
@@ -1390,7 +1455,8 @@ extern "C" int32_t stf_shard_collide(stf_ctx* ctx, int32_t mode, int32_t nl, con
         r = sync_counts(ctx); if (r) break;
         int64_t items = (int64_t)ctx->h_counts[C_ITEMS], hits = (int64_t)ctx->h_counts[C_NHITS];
         if (ctx->h_err[1] & STF_ST_RETRY_BIG) { cudaMemsetAsync(STATUSP(ctx), 0, sizeof(unsigned long long), ctx->st); ctx->force_big = true; break; }
-        if (items > (int64_t)(ctx->items.cap / sizeof(Item16))) { ctx->hint_items = items; continue; }
+        if (items > (int64_t)(ctx->items.cap / sizeof(Item16)) && (!ctx->fused_narrow || ctx->keep_items)) { ctx->hint_items = items; continue; }
+        if (ctx->fused_narrow && !ctx->keep_items && (int64_t)ctx->h_counts[C_SURV] > (int64_t)(ctx->surv.cap / sizeof(SurvRec))) { ctx->hint_surv = (int64_t)ctx->h_counts[C_SURV]; cudaMemsetAsync(STATUSP(ctx), 0, sizeof(unsigned long long), ctx->st); continue; }
         if (hits > (int64_t)(ctx->hits.cap / sizeof(Item16))) { ctx->force_big = true; break; }
         read_round_counters(ctx); nh = hits; done = true;
     }

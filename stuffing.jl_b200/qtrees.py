@@ -314,6 +314,11 @@ class DeviceQTrees:
         self._ck(self.lib.stf_counters(self.h, ptr(out)))
         return dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in out)))
 
+    def keep_items(self, on=True):
+        """materialise the candidate list (`itemlist`) in the following many-body calls so that fetch_items() can return it"""
+        self._ck(self.lib.stf_set_keep_items(self.h, int(bool(on))))
+        return self
+
     def fetch_items(self):
         cnt = C.c_int64(0)
         rc = self.lib.stf_fetch_items(self.h, None, 0, C.byref(cnt))

@@ -206,11 +206,16 @@ def test_spacial_native_partial_parity(S, orc, scene200):
     qo, d = scene200
     for unique in (True, False):
         want, det = orc.totalcollisions_spacial(qo, unique=unique, details=True)
-        got = S.totalcollisions_spacial(d, unique=unique)
-        assert got == sorted(want)
-        c = d.counters()
-        assert c["items"] == len(det["items"]) and c["direct"] == det["n_direct"]
-        assert sorted(S.items_to_list(d.fetch_items())) == sorted(det["items"])
+        for keep in (False, True):  # fused narrow phase (default) / materialised candidate list (the reference's itemlist)
+            d.keep_items(keep)
+            got = S.totalcollisions_spacial(d, unique=unique)
+            assert got == sorted(want)
+            c = d.counters()
+            assert c["items"] == len(det["items"]) and c["direct"] == det["n_direct"]
+            assert c["overflow"] > 0 or c["visited"] == det["visited"]  # node tests of the sequential BFS, early exits included
+            if keep:
+                assert sorted(S.items_to_list(d.fetch_items())) == sorted(det["items"])
+        d.keep_items(False)
     labels = [1, 3, 6, 99, 100, 150, 42]
     assert S.totalcollisions_spacial(d, labels) == sorted(orc.totalcollisions_spacial(qo, labels))
     assert S.totalcollisions_native(d) == sorted(orc.totalcollisions_native(qo))
@@ -224,11 +229,44 @@ def test_spacial_native_partial_parity(S, orc, scene200):
     lo = orc.LinkedTree(qo).locate(qo)
     for lbs in ([1, 3, 6, 99], [200, 5, 17, 18, 19, 1], list(range(1, 201))):
         want, det = orc.partialcollisions(qo, lo, lbs, details=True)
-        got = S.partialcollisions(d, spt, lbs)
-        assert got == sorted(want)
-        assert sorted(S.items_to_list(d.fetch_items())) == sorted(det["items"])
+        for keep in (False, True):
+            d.keep_items(keep)
+            got = S.partialcollisions(d, spt, lbs)
+            assert got == sorted(want)
+            if keep:
+                assert sorted(S.items_to_list(d.fetch_items())) == sorted(det["items"])
+        d.keep_items(False)
     c2 = {frozenset(p) for p, _ in S.totalcollisions(d) if set(p) & {1, 3, 6, 99}}
     assert c2 == pairset(S.partialcollisions(d, spt, [1, 3, 6, 99]))
+
+
+def test_fused_narrow_variant_parity(S, orc, monkeypatch):
+    """STF_FUSED_NARROW=1 (read at stf_create): candidates are tested inside the candidate kernel and never stored — same
+    hits, same counts, same node-test count as the oracle; the item list is only there after keep_items(True)"""
+    monkeypatch.setenv("STF_FUSED_NARROW", "1")
+    qo = rect_scene(orc, 200, 7, sz=100)
+    d = device_from_oracle(S, qo)
+    monkeypatch.delenv("STF_FUSED_NARROW")
+    want, det = orc.totalcollisions_spacial(qo, unique=False, details=True)
+    assert S.totalcollisions_spacial(d, unique=False) == sorted(want)
+    c = d.counters()
+    assert c["items"] == len(det["items"]) and c["direct"] == det["n_direct"] and (c["overflow"] > 0 or c["visited"] == det["visited"])
+    with pytest.raises(S._lib.StuffingError):
+        d.fetch_items()
+    d.keep_items(True)
+    assert S.totalcollisions_spacial(d, unique=False) == sorted(want)
+    assert sorted(S.items_to_list(d.fetch_items())) == sorted(det["items"])
+    d.keep_items(False)
+    lo = orc.LinkedTree(qo).locate(qo)
+    spt = S.locate(d, S.linked_spacial_qtree(d))
+    for lbs in ([1, 3, 6, 99], list(range(1, 201))):
+        assert S.partialcollisions(d, spt, lbs) == sorted(orc.partialcollisions(qo, lo, lbs))
+    opt = orc.Opt("momentum", 0.25, 0.5, len(qo)); clock = S.trainer.StepClock(seed=9)
+    for it in range(3):
+        hits = sorted(orc.totalcollisions_spacial(qo, unique=False))
+        assert S.trainer.fit_round(d, None, S.Momentum(0.25, 0.5), clock) == len(hits)
+        orc.batchsteps(qo, hits, opt, seed=9, iteration=it)
+    assert_same_trees(d, qo)
 
 
 def test_large_frontier_path(S, orc):
@@ -240,12 +278,12 @@ def test_large_frontier_path(S, orc):
     qo[1].setshift(1, 13, 7); qo[2].setshift(1, 100, 120); qo[3].setshift(1, 30, 30)
     d = device_from_oracle(S, qo, is_mask=np.zeros(4, np.uint8))
     # thin diagonal lines never produce a FULL code above level 1: the BFS must carry wide frontiers
-    n = 400
+    n = 1500  # (the frontier buffer of the warp-per-pair kernel holds 512 nodes: the diagonals must be longer than that)
     diag1 = np.zeros((n, n), np.int64); diag2 = np.zeros((n, n), np.int64)
     idx = np.arange(n)
     diag1[idx, idx] = 1
     diag2[idx, n - 1 - idx] = 1; diag2[idx, idx] = 1
-    qo2 = orc.qtrees([diag1, diag2, diag1.copy()], size=512, background=0)
+    qo2 = orc.qtrees([diag1, diag2, diag1.copy()], size=2048, background=0)
     qo2[2].setshift(1, 1, 0)
     d2 = device_from_oracle(S, qo2, is_mask=np.zeros(3, np.uint8))
     for (dd, oo) in ((d, qo), (d2, qo2)):

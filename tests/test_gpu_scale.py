@@ -46,7 +46,11 @@ def test_c1_10k_words_4096_canvas(S, orc):
     assert c["records"] == 10_004                                   # 10 000 objects in one cell each + the mask in four
     hs, _ = _sorted_hits(orc, qo)
     assert np.array_equal(got, hs)                                  # every hit, (i1, i2) => (l, a, b), canonical order
+    assert c["overflow"] > 0 or c["visited"] == info["visited"] == W["visited"]   # node tests of the sequential BFS
+    d.keep_items(True)                                              # materialise the reference's itemlist instead of testing in place
+    assert np.array_equal(S.totalcollisions_spacial(d, unique=False, raw=True), hs)
     items_dev = np.sort(d.fetch_items(), order=["i1", "i2", "l", "a", "b"])
+    d.keep_items(False)
     items_orc = np.sort(info["items"], order=["i1", "i2", "l", "a", "b"])
     assert np.array_equal(items_dev, items_orc)                     # the narrow-phase item multiset
     # mask excluded (examples/collision_benchmark.jl:22-37), unique
