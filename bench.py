@@ -406,7 +406,7 @@ class DevScene:
         self.out_rs = torch.empty(self.n_all, dtype=torch.int32).pin_memory(); self.out_cs = torch.empty(self.n_all, dtype=torch.int32).pin_memory()
         self.lib.stf_set_optimiser(self.h, 2, 0.25, 0.5)
         self.nh = C.c_int64(0)
-        self.sharded = parallel.ShardedFit(d, rank, world, dist) if shard_items else None
+        self.sharded = None
         self.rounds = int(self.W["rounds"]) if which == "c2" else 1
         self.round_hits = np.zeros(max(1, self.rounds), np.int64)
         self.tot = {}
@@ -422,22 +422,13 @@ class DevScene:
     def step(self, resident, count=False):
         d, lib, h, nh = self.d, self.lib, self.h, self.nh
         self.restore(resident)
-        if self.which == "c2":
-            seed = self.W["seed"]
-            tot = dict(items=0, hits=0, visited=0, moved=0, records=0)
-            for k in range(self.rounds):
-                last = k == self.rounds - 1
-                if last and not resident:  # the user-facing call of the last round also returns the positions
-                    d._ck(lib.stf_fit_round_positions(h, 0, 0, None, seed, k, C.byref(nh), 1, self.out_rs.data_ptr(), self.out_cs.data_ptr()))
-                else:
-                    d._ck(lib.stf_fit_round(h, 0, 0, None, seed, k, C.byref(nh)))
-                self.round_hits[k] = nh.value
-                if count:
-                    c = d.counters()
-                    tot["items"] += c["items"] + c["direct"]; tot["hits"] += nh.value; tot["visited"] += c["visited"]; tot["records"] += c["records"]
-                    tot["moved"] += c["moved"] if nh.value else 0
+        if self.which == "c2":  # 50 rounds, ONE call and one host synchronisation (stf_fit_rounds)
+            tot8 = np.zeros(8, np.int64)
+            d._ck(lib.stf_fit_rounds(h, 0, 0, None, int(self.W["seed"]), 0, self.rounds, self.round_hits.ctypes.data, tot8.ctypes.data,
+                                     0 if resident else 1, None if resident else self.out_rs.data_ptr(), None if resident else self.out_cs.data_ptr()))
             if count:
-                self.tot = tot
+                t8 = dict(zip(self.S._lib.COUNTER_FIELDS, (int(x) for x in tot8)))
+                self.tot = dict(items=t8["items"], hits=t8["hits"], visited=t8["visited"], moved=t8["moved"], records=t8["records"] * self.rounds)
             return int(self.round_hits.sum())
         if self.sharded is not None:
             nh.value = self.sharded.round(SEED, ITERATION)
@@ -489,7 +480,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     which = args.workload
-    shard_items = args.shard == "items" and which not in ("c5", "c2")
+    shard_items = False  # (`--shard items` is run_group: one process drives all GPUs)
     sc = DevScene(S, torch, which, local, rank, world, shard_items, dist)
     d, lib, h = sc.d, sc.lib, sc.h
     stream = sc.stream
@@ -625,7 +616,7 @@ def run_ours(args):
                         "visited_nodes_per_step": int(float(t[4])) if which == "c5" or shard_items else T["visited"] * world,
                         "parallelism": sc.par, "upload_build_s": round(sc.t_up, 3),
                         "counts_asserted": "items/hits == fixture (oracle) counts" if which in ("c1", "c4") else ("per-round hits and final positions == golden vector" if which == "c2" else "steps do identical work")},
-            "e2e": {"value": items_job / (ms_e2e * 1e-3), "unit": "items/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(12 * sc.nm), "d2h_bytes_per_step": int(8 * sc.n_all + (8 + 136) * R)},
+            "e2e": {"value": items_job / (ms_e2e * 1e-3), "unit": "items/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(12 * sc.nm), "d2h_bytes_per_step": int(8 * sc.n_all + 8 * R + 136 + (32 * (R + 2) if which == "c2" else 0))},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     if collide_only:
         line["collide_only"] = collide_only
@@ -634,6 +625,99 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def group_bench(S, torch, which, devices, steps, warm):
+    """item-parallel sharding of ONE scene over `devices`, driven from THIS process through stf_group_* (the way a Julia
+    host would drive several GPUs): every GPU holds a replica, generates and tests the candidate pairs of its share of the
+    sorted records, the GPUs exchange their hit lists themselves over NVLink peer memory (device-side flag barrier), every
+    GPU runs the same batchsteps.  One step = the c1 step (restore + reset + round) on every replica.  Timed with CUDA
+    events on every GPU's stream (max over GPUs); L2 flushed on every GPU between iterations."""
+    from stuffing_b200 import parallel
+    W = load_workload(which)
+    s = W["mask_side"]
+    trees = [S.maskqtree(np.ones((s, s), bool))] + [S.qtree(o, W["canvas"]) for o in W["objs"]]
+    for t, r, c in zip(trees, W["rs"], W["cs"]):
+        t.shift1 = (int(r), int(c))
+    g = parallel.GpuGroup(trees, devices)
+    lib = g.lib
+    movable = np.arange(2, len(trees) + 1, dtype=np.int32)
+    rs = np.ascontiguousarray(W["rs"][1:]); cs = np.ascontiguousarray(W["cs"][1:])
+    streams = [torch.cuda.ExternalStream(lib.stf_stream(d.h), device=torch.device("cuda", dv)) for d, dv in zip(g.replicas, g.devices)]
+    flush = [torch.empty(512 << 20, dtype=torch.uint8, device=torch.device("cuda", dv)) for dv in g.devices]
+    for d in g.replicas:
+        lib.stf_set_optimiser(d.h, 2, 0.25, 0.5)
+
+    def step():
+        for d in g.replicas:
+            d._ck(lib.stf_set_shifts(d.h, len(movable), movable.ctypes.data, 1, rs.ctypes.data, cs.ctypes.data, 0))
+            d._ck(lib.stf_reset_velocity(d.h, 0, None))
+        return g.fit_round(SEED, ITERATION)
+
+    for _ in range(warm):
+        nh = step()
+    assert nh == W["n_hits"], (nh, W["n_hits"])
+    items = sum(d.counters()["items"] + d.counters()["direct"] for d in g.replicas)
+    assert items == W["n_items"], (items, W["n_items"])
+    tot = 0.0
+    for _ in range(steps):
+        for st, f in zip(streams, flush):
+            with torch.cuda.stream(st):
+                f.zero_()
+        for dv in g.devices:
+            torch.cuda.synchronize(dv)
+        ev = []
+        for st in streams:
+            a = torch.cuda.Event(enable_timing=True); a.record(st); ev.append(a)
+        step()
+        ms = 0.0
+        for st, a in zip(streams, ev):
+            b = torch.cuda.Event(enable_timing=True); b.record(st); b.synchronize()
+            ms = max(ms, a.elapsed_time(b))
+        tot += ms
+    out = {"workload": which, "gpus": len(devices), "ms_per_step": tot / steps, "items_per_s": items / (tot / steps * 1e-3), "items_per_step": int(items), "hits_per_step": int(nh),
+           "nvlink_bytes_per_step": g.nvlink_bytes, "host_syncs_per_step": len(devices), "exchange": "peer stores over NVLink + device-side flag barrier (stf_group_fit_round), one process drives all GPUs"}
+    g.close()
+    return out
+
+
+def run_group(args):
+    """`--shard items`: rank 0 drives ALL N GPUs of the box from one process (stf_group_*); the other ranks of a torchrun
+    launch only keep the barrier.  Reports the N-GPU group next to the 1-GPU group of the same step (strong scaling)."""
+    import torch
+    import _pkg
+    S = _pkg.load()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = None
+    if rank == 0:
+        n = max(world, args.gpus)
+        n = min(n, torch.cuda.device_count())
+        warm = max(3, args.warmup)
+        sampler = ClockSampler(0)
+        one = group_bench(S, torch, args.workload, [0], args.steps, warm)
+        many = group_bench(S, torch, args.workload, list(range(n)), args.steps, warm) if n > 1 else one
+        clocks = sampler.stop()
+        peak, peak_src = peaks()
+        line = {"metric": "collision_queries_per_sec", "value": many["items_per_s"], "unit": "items/s", "n_gpus": n, "steps": args.steps, "warmup": warm,
+                "ms_per_step": many["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "fit_iters_per_sec": 1e3 / many["ms_per_step"], "julia": julia_probe(), "config": {"workload": NAMES[args.workload], "l2": L2_NOTE},
+                "details": {"parallelism": f"item-parallel group of {n} GPUs driven by one process", "one_gpu": one, "n_gpu": many, "speedup_vs_one_gpu": one["ms_per_step"] / many["ms_per_step"]},
+                "e2e": {"value": many["items_per_s"], "unit": "items/s", "ms_per_step": many["ms_per_step"], "h2d_bytes_per_step": int(12 * 10000 * n), "d2h_bytes_per_step": int(136 * n)},
+                "nvlink_bytes_per_step": many["nvlink_bytes_per_step"], "gpu_launches": None, "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                             "note": "latency-bound round; see the default bench line for the per-stage roofline"},
+                "cpu_baseline": {"value": None, "unit": "items/s", "cores": 0, "kind": "port", "sample": "see the default bench line"}}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line:
+        print(json.dumps(line), flush=True)
 
 
 def run_c3(args):
@@ -733,6 +817,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.shard == "items" and args.workload in ("c1", "c4"):
+        run_group(args)
     elif args.workload == "c3":
         run_c3(args)
     else:

@@ -184,6 +184,16 @@ int32_t stf_fit_round_positions(stf_ctx* ctx, int32_t mode, int32_t nl, const in
                                 uint64_t seed, uint64_t iteration, int64_t* nhits,
                                 int32_t level, int32_t* rs, int32_t* cs);
 
+/* `n_rounds` fit rounds back to back WITHOUT a host round trip between them — the inner loops of the reference's trainers
+ * (trainepoch_E!: fit.jl:91-96; any fixed number of rounds of totalcollisions(qtrees[, labels]) -> batchsteps!) stay on the
+ * device: round k uses the draws of iteration0 + k.  The rounds are enqueued blindly; a round that cannot run on the
+ * device's current buffers cancels itself and everything after it, the host grows the buffers and continues from that
+ * round, so the result always equals n_rounds calls of stf_fit_round.  ONE synchronisation per call on the single-scene
+ * latency path.  nhits_per_round[k] = length(colist) of round k; totals (nullable) = sums of items / node tests / hits /
+ * moves over the rounds; level > 0: rs/cs (n each) receive getshift(t, level) of every tree after the last round. */
+int32_t stf_fit_rounds(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration0,
+                       int32_t n_rounds, int64_t* nhits_per_round, stf_counters_t* totals, int32_t level, int32_t* rs, int32_t* cs);
+
 /* ---- ground composition for place! / reposition! (qtree_functions.jl:452-518, fit.jl:420-436).
  * ground = deepcopy(qtrees[mask_label]) with every other tree overlap!-ed except the `excl_labels` (the trees about to be
  * re-placed).  The room search itself (findroom_uniform: a sequential BFS driven by one RNG stream) stays on the host
@@ -205,6 +215,25 @@ int32_t stf_ground_level(stf_ctx* ctx, int32_t l, uint8_t* out, int32_t info[5])
 int32_t stf_shard_collide(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, int32_t rank, int32_t nranks, int64_t* nlocal);
 int32_t stf_shard_pack(stf_ctx* ctx, void* send_dev, int64_t stride);
 int32_t stf_shard_step(stf_ctx* ctx, const void* recv_dev, int32_t nranks, int64_t stride, uint64_t seed, uint64_t iteration, int64_t* nhits);
+
+/* ---- the same sharding for a host that drives SEVERAL GPUs FROM ONE PROCESS (SURVEY §8b threading row: the way a Julia
+ * host would; the reference's counterpart is its Threads.@spawn over index chunks, qtree_functions.jl:52-110).
+ * stf_group_create makes one context per listed device and enables peer access between them; the caller uploads the SAME
+ * scene into every context (stf_group_ctx(g, i) with any stf_upload_*) and applies state changes (stf_set_shifts,
+ * stf_set_optimiser, ...) to every context.  stf_group_fit_round = stf_fit_round over the group: GPU i generates and tests
+ * the candidate pairs of the sorted records i, i+n, ..., the GPUs exchange their hit lists THEMSELVES (peer stores over
+ * NVLink into every peer's gather buffer + a device-side flag barrier, no collective call and no host synchronisation in
+ * between), and every GPU runs the same canonical batchsteps on the union, so the replicas stay bit-identical.  One host
+ * synchronisation per GPU and round.  *nhits = length(colist).  Needs a scene that fits the single-scene latency path. */
+typedef struct stf_group stf_group;
+int32_t stf_group_create(int32_t n, const int32_t* devices, stf_group** out);
+void stf_group_destroy(stf_group* g);
+int32_t stf_group_size(const stf_group* g);
+stf_ctx* stf_group_ctx(stf_group* g, int32_t i);
+const char* stf_group_last_error(const stf_group* g);
+int32_t stf_group_fit_round(stf_group* g, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits);
+/* bytes the last stf_group_fit_round moved between GPUs (hit records and flags pushed to peers) */
+int64_t stf_group_nvlink_bytes(const stf_group* g);
 
 int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out);
 /* number of kernels this context has launched since stf_create (bench.py's gpu_launches) */

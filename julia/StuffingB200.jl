@@ -1,218 +1,321 @@
-# StuffingB200.jl — the reference-side binding: thin `ccall` glue over libstuffing_b200.so that keeps
-# Stuffing.jl's own signatures.  NOT EXECUTED in the build image (no Julia there); it is a 1:1 mirror of
-# the Python host layer (stuffing.jl_b200/qtrees.py, trainer.py), which is what the tests exercise.
+# StuffingB200.jl — the reference-side binding: `ccall` glue over libstuffing_b200.so that KEEPS Stuffing.jl's own
+# signatures for the hot path (SURVEY §8b).  NOT EXECUTED in the build image (Julia is absent there); it is a 1:1 mirror
+# of the Python host layer (stuffing.jl_b200/qtrees.py, trainer.py), which is what the tests exercise, and
+# tests/test_abi_and_host.py checks every `ccall` argument tuple in this file against the library's exports.
 #
-# Usage inside Stuffing.jl:   include("StuffingB200.jl"); using .StuffingB200
-#   dq  = DeviceQTrees(qtrees(objs, mask=mask))      # upload + build on the GPU
-#   C   = totalcollisions_spacial(dq; unique=false)  # Vector{CoItem}, 1-based, like the reference
-#   batchsteps!(dq, C, Momentum(η=1/4))              # grad2d + step! + rebuild on the GPU
+# Drop-in use inside Stuffing.jl (src/Stuffing.jl would `include` this file next to qtrees.jl):
+#   qts  = qtrees(objs, mask=mask)                   # the reference's own host trees (Vector{U8SQTree})
+#   dqts = DeviceQTrees(qts)                         # upload + build on the GPU; dqts isa AbstractVector{DeviceTree}
+#   C    = totalcollisions(dqts)                     # same dispatcher, same keywords, Vector{CoItem}
+#   collision(dqts[2], dqts[3]); grad2d(dqts[2], l, a, b); shift!(dqts[2], 1, 2, 3); getshift(dqts[2])
+#   fit!(dqts, 100; trainer=trainepoch_EM2!)         # the reference's train! loop, unchanged, over the device trainers
+#   sync_to_host!(dqts, qts)                         # shifts + levels back into the host trees (before place!/getpositions on them)
+#
+# Every function below cites the reference definition it stands in for (src/...:line).  Integers cross the boundary as
+# the reference prints them (1-based labels and (l, a, b)); matrices are column-major on both sides.
 module StuffingB200
-export DeviceQTrees, totalcollisions_spacial, totalcollisions_native, partialcollisions, locate!, collision,
-       batchsteps!, fit_round!, getshift, setshift!, shift!, download!, grad2d, filttrain!, place!, ground_level,
-       shard_collide!, shard_pack!, shard_step!
+import ..QTrees: AbstractStackedQTree, U8SQTree, CoItem, Index, collision, collision_dfs, totalcollisions, totalcollisions_native,
+                 totalcollisions_spacial, partialcollisions, dynamiccollisions, locate!, hash_spacial_qtree, linked_spacial_qtree,
+                 shift!, setshift!, setcenter!, getshift, getcenter, kernelsize, buildqtree!, inkernelbounds, EMPTY, FULL, MIX
+import ..Trainer: grad2d, batchsteps!, Momentum, SGD, eta, eta!, reset!
+export DeviceQTrees, DeviceTree, DeviceHashTree, DeviceLinkedTree, DeviceColliders, sync_to_host!, fit_round!, fit_rounds!, GpuGroup
 
 const LIB = get(ENV, "STUFFING_B200_LIB", joinpath(@__DIR__, "..", "stuffing.jl_b200", "libstuffing_b200.so"))
-const CoItem = Pair{Tuple{Int,Int},Tuple{Int,Int,Int}}
 
 struct StfItem            # include/stuffing_b200.h: stf_item
     i1::Int32; i2::Int32; l::Int32; a::Int32; b::Int32
 end
-CoItem(x::StfItem) = (Int(x.i1), Int(x.i2)) => (Int(x.l), Int(x.a), Int(x.b))
+_coitem(x::StfItem) = (Int(x.i1), Int(x.i2)) => (Int(x.l), Int(x.a), Int(x.b))
 StfItem(c::CoItem) = StfItem(c.first[1], c.first[2], c.second[1], c.second[2], c.second[3])
 
-mutable struct DeviceQTrees
+# ------------------------------------------------------------------------------------------------ the vector of trees
+"Vector{U8SQTree} resident on one GPU (one context of the C ABI).  Indexing yields DeviceTree handles."
+mutable struct DeviceQTrees <: AbstractVector{AbstractStackedQTree}
     h::Ptr{Cvoid}
     n::Int
-    function DeviceQTrees(qts::AbstractVector; device::Integer=0)   # qts::Vector{U8SQTree} of the reference
+    L::Int
+    clock::Tuple{UInt64,UInt64}                   # (seed, iteration) of the canonical-mode draws, one tick per batchsteps!
+    function DeviceQTrees(qts::AbstractVector; device::Integer=0, seed::Integer=0)   # qts::Vector{U8SQTree} of the reference
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:stf_create, LIB), Int32, (Int32, Ptr{Ptr{Cvoid}}), device, h)
         rc == 0 || error("stf_create failed ($rc): no CUDA device — there is no CPU fallback")
-        n = length(qts)
-        kernels = [qt[1].kernel for qt in qts]                       # PaddedMat.kernel :: Matrix{UInt8}, (kh+3)x(kw+3)
-        GC.@preserve kernels begin
-            pics  = [pointer(k, LinearIndices(k)[2, 2]) for k in kernels]   # payload starts at kernel[2,2]
-            kh    = Int32[size(k, 1) - 3 for k in kernels]
-            kw    = Int32[size(k, 2) - 3 for k in kernels]
-            pitch = Int32[size(k, 1) for k in kernels]
-            rs    = Int32[qt[1].rshift for qt in qts]
-            cs    = Int32[qt[1].cshift for qt in qts]
-            dflt  = UInt8[qt[1].default for qt in qts]
-            canvas = n > 0 ? size(qts[1][1], 1) : 2
-            rc = ccall((:stf_upload_objects, LIB), Int32,
-                       (Ptr{Cvoid}, Int32, Ptr{Ptr{UInt8}}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}, Int32, Ptr{UInt8}, Ptr{Int32}),
-                       h[], n, pics, kh, kw, pitch, rs, cs, dflt, canvas, C_NULL, C_NULL)
-        end
-        d = new(h[], n)
-        check(d, rc)
+        d = new(h[], length(qts), 0, (UInt64(seed), UInt64(0)))
         finalizer(x -> ccall((:stf_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), d)
+        upload!(d, qts)
     end
 end
-Base.length(d::DeviceQTrees) = d.n
+function upload!(d::DeviceQTrees, qts::AbstractVector)
+    n = length(qts)
+    kernels = [qt[1].kernel for qt in qts]                       # PaddedMat.kernel :: Matrix{UInt8}, (kh+3)x(kw+3)  qtrees.jl:109-128
+    GC.@preserve kernels begin
+        pics  = [pointer(k, LinearIndices(k)[2, 2]) for k in kernels]   # payload starts at kernel[2,2]
+        kh    = Int32[size(k, 1) - 3 for k in kernels]
+        kw    = Int32[size(k, 2) - 3 for k in kernels]
+        pitch = Int32[size(k, 1) for k in kernels]
+        rs    = Int32[qt[1].rshift for qt in qts]
+        cs    = Int32[qt[1].cshift for qt in qts]
+        dflt  = UInt8[qt[1].default for qt in qts]
+        canvas = n > 0 ? size(qts[1][1], 1) : 2
+        rc = ccall((:stf_upload_objects, LIB), Int32,
+                   (Ptr{Cvoid}, Int32, Ptr{Ptr{UInt8}}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}, Int32, Ptr{UInt8}, Ptr{Int32}),
+                   d.h, n, pics, kh, kw, pitch, rs, cs, dflt, canvas, C_NULL, C_NULL)
+    end
+    check(d, rc)
+    d.n = n
+    d.L = Int(ccall((:stf_num_levels, LIB), Int32, (Ptr{Cvoid},), d.h))
+    d
+end
 check(d::DeviceQTrees, rc) = rc == 0 || error(unsafe_string(ccall((:stf_last_error, LIB), Cstring, (Ptr{Cvoid},), d.h)))
+Base.size(d::DeviceQTrees) = (d.n,)
+Base.getindex(d::DeviceQTrees, i::Int) = DeviceTree(d, i)
+Base.IndexStyle(::Type{DeviceQTrees}) = IndexLinear()
 
-# two-call pattern for result lists
-function _list(f::Symbol, d::DeviceQTrees, args...; cap=1 << 14)
-    buf = Vector{StfItem}(undef, cap); cnt = Ref{Int64}(0)
-    rc = _call(f, d, args..., buf, cap, cnt)
-    if rc == -3                                  # STF_E_CAPACITY
+# ------------------------------------------------------------------------------------------------ one tree (qtrees.jl:58-105, 170-294)
+"One ShiftedQTree of a DeviceQTrees: the AbstractStackedQTree interface over the C ABI."
+struct DeviceTree <: AbstractStackedQTree
+    owner::DeviceQTrees
+    label::Int
+end
+Base.length(t::DeviceTree) = t.owner.L                                      # qtrees.jl:217
+function levelinfo(t::DeviceTree, l::Integer)                                # kh, kw, rshift, cshift, canvas size of level l
+    out = Vector{Int32}(undef, 5)
+    check(t.owner, ccall((:stf_get_level_info, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}), t.owner.h, t.label, l, out))
+    Int.(out)
+end
+Base.size(t::DeviceTree) = (s = levelinfo(t, 1)[5]; (s, s))
+function Base.getindex(t::DeviceTree, l::Integer)                            # t[l] -> Matrix{UInt8} payload of level l  qtrees.jl:98
+    kh, kw = levelinfo(t, l)[1:2]
+    m = Matrix{UInt8}(undef, kh, kw)
+    check(t.owner, ccall((:stf_download_level, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), t.owner.h, t.label, l, m))
+    m
+end
+function Base.getindex(t::DeviceTree, l::Integer, a::Integer, b::Integer)    # t[l, a, b]: PaddedMat getindex, default outside  qtrees.jl:156-162
+    out = Vector{UInt8}(undef, 1)
+    check(t.owner, ccall((:stf_read_nodes, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}),
+                         t.owner.h, 1, Int32[t.label], Int32[l], Int32[a], Int32[b], out))
+    out[1]
+end
+Base.getindex(t::DeviceTree, ind::Index) = t[ind[1], ind[2], ind[3]]
+kernelsize(t::DeviceTree, l::Integer=1) = (i = levelinfo(t, l); (i[1], i[2]))       # qtrees.jl:152
+getshift(t::DeviceTree, l::Integer=1) = (i = levelinfo(t, l); (i[3], i[4]))         # qtrees.jl:288
+getcenter(t::DeviceTree) = getshift(t) .+ kernelsize(t) .÷ 2                        # qtrees.jl:290
+inkernelbounds(t::DeviceTree, l::Integer, a::Integer, b::Integer) = (i = levelinfo(t, l); i[3] < a <= i[3] + i[1] && i[4] < b <= i[4] + i[2])  # qtrees.jl:140-149
+function _shifts!(d::DeviceQTrees, labels, l, s1, s2, mode)
+    lb = Int32.(collect(labels))
+    check(d, ccall((:stf_set_shifts, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Int32),
+                   d.h, length(lb), lb, l, Int32.(collect(s1)), Int32.(collect(s2)), mode))
+end
+shift!(t::DeviceTree, l::Integer, s1::Integer, s2::Integer) = (_shifts!(t.owner, (t.label,), l, (s1,), (s2,), 1); t)        # qtrees.jl:267-275
+setshift!(t::DeviceTree, l::Integer, s1::Integer, s2::Integer) = (_shifts!(t.owner, (t.label,), l, (s1,), (s2,), 0); t)     # qtrees.jl:277-285
+setshift!(t::DeviceTree, l::Integer, st::Tuple{Integer,Integer}) = setshift!(t, l, st...)
+setshift!(t::DeviceTree, st::Tuple{Integer,Integer}) = setshift!(t, 1, st...)
+setcenter!(t::DeviceTree, c) = setshift!(t, 1, (c .- kernelsize(t) .÷ 2)...)                                                # qtrees.jl:293-294
+function buildqtree!(t::DeviceTree, layer::Integer=2)                                                                       # qtrees.jl:221-237
+    check(t.owner, ccall((:stf_build, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32), t.owner.h, 1, Int32[t.label], layer)); t
+end
+# whole vectors at once (one launch): the batched forms the host mirror uses
+setshift!(d::DeviceQTrees, labels, l::Integer, s1, s2) = _shifts!(d, labels, l, s1, s2, 0)
+shift!(d::DeviceQTrees, labels, l::Integer, s1, s2) = _shifts!(d, labels, l, s1, s2, 1)
+function getshift(d::DeviceQTrees, labels=1:d.n, l::Integer=1)
+    lb = Int32.(collect(labels)); rs = Vector{Int32}(undef, length(lb)); cs = similar(rs)
+    check(d, ccall((:stf_get_shifts, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}), d.h, length(lb), lb, l, rs, cs))
+    collect(zip(Int.(rs), Int.(cs)))
+end
+"device -> host: shifts of every level and the level payloads of `labels` into the reference's own trees (before host-side place!/reposition!)"
+function sync_to_host!(d::DeviceQTrees, qts::AbstractVector, labels=1:d.n)
+    lb = Int32.(collect(labels)); cnt = Ref{Int64}(0)
+    ccall((:stf_download_trees, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{UInt8}, Int64, Ptr{Int64}), d.h, length(lb), lb, C_NULL, 0, cnt)
+    buf = Vector{UInt8}(undef, cnt[])
+    check(d, ccall((:stf_download_trees, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{UInt8}, Int64, Ptr{Int64}), d.h, length(lb), lb, buf, length(buf), cnt))
+    pos = 0
+    for i in lb, l in 1:d.L
+        m = qts[i][l]; kh, kw = size(m.kernel) .- 3
+        m.kernel[2:kh+1, 2:kw+1] .= reshape(view(buf, pos+1:pos+kh*kw), kh, kw); pos += kh * kw
+        m.rshift, m.cshift = getshift(DeviceTree(d, i), l)
+    end
+    qts
+end
+"getpositions / setpositions!  (Stuffing.jl:78-99): (x, y) of every object relative to the mask (label 1)"
+function getpositions(d::DeviceQTrees, inds=1:d.n-1)
+    s = getshift(d); m = s[1]
+    [(s[i+1][2] - m[2] + 1, s[i+1][1] - m[1] + 1) for i in inds]
+end
+function setpositions!(d::DeviceQTrees, inds, x_y)
+    m = getshift(d, (1,))[1]; inds = collect(inds)
+    xy = x_y isa Tuple ? fill(x_y, length(inds)) : collect(x_y)
+    setshift!(d, inds .+ 1, 1, [p[2] - 1 + m[1] for p in xy], [p[1] - 1 + m[2] for p in xy]); x_y
+end
+
+# ------------------------------------------------------------------------------------------------ pair collision (qtree_functions.jl:2-51)
+function collision(Q1::DeviceTree, Q2::DeviceTree)                                        # qtree_functions.jl:43-51
+    @assert Q1.owner === Q2.owner
+    out = Vector{Int32}(undef, 3)
+    check(Q1.owner, ccall((:stf_collision, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}), Q1.owner.h, Q1.label, Q2.label, out))
+    (Int(out[1]), Int(out[2]), Int(out[3]))
+end
+function _pairs(f::Symbol, d::DeviceQTrees, items::Vector{StfItem})
+    out = similar(items)
+    rc = f === :stf_collision_dfs ?
+        ccall((:stf_collision_dfs, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{StfItem}, Ptr{StfItem}), d.h, length(items), items, out) :
+        ccall((:stf_collision_bfs, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{StfItem}, Ptr{StfItem}), d.h, length(items), items, out)
+    check(d, rc); out
+end
+function collision_dfs(Q1::DeviceTree, Q2::DeviceTree, i::Index=(length(Q1), 1, 1))       # qtree_functions.jl:2-20
+    o = _pairs(:stf_collision_dfs, Q1.owner, [StfItem(Q1.label, Q2.label, i...)])[1]; (Int(o.l), Int(o.a), Int(o.b))
+end
+
+# ------------------------------------------------------------------------------------------------ many-body (qtree_functions.jl:52-370)
+function _list(d::DeviceQTrees, colist::Vector{CoItem}, call)                             # two-call pattern of the ABI
+    cap = 1 << 14; buf = Vector{StfItem}(undef, cap); cnt = Ref{Int64}(0)
+    rc = call(buf, cap, cnt)
+    if rc == -3                                                                            # STF_E_CAPACITY
         resize!(buf, cnt[])
         rc = ccall((:stf_fetch_result, LIB), Int32, (Ptr{Cvoid}, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, buf, cnt[], cnt)
     end
     check(d, rc)
-    CoItem.(@view buf[1:cnt[]])
+    append!(colist, _coitem.(@view buf[1:cnt[]]))
 end
-_labels(::Nothing) = (C_NULL, Int32(0))
-_labels(l) = (v = Int32.(collect(l)); (v, Int32(length(v))))
-function _call(f::Symbol, d, labels, unique, buf, cap, cnt)
-    lb, nl = _labels(labels)
-    f === :stf_totalcollisions_spacial ?
-        ccall((:stf_totalcollisions_spacial, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, nl, lb, unique, buf, cap, cnt) :
-    f === :stf_partialcollisions ?
-        ccall((:stf_partialcollisions, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, nl, lb, unique, buf, cap, cnt) :
-        ccall((:stf_totalcollisions_native, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, nl, lb, buf, cap, cnt)
+_lb(::Nothing) = (C_NULL, Int32(0))
+_lb(l) = (v = Int32.(collect(l)); (v, Int32(length(v))))
+function totalcollisions_native(d::DeviceQTrees, labels=nothing; colist=Vector{CoItem}(), kargs...)            # qtree_functions.jl:126-131
+    lb, nl = _lb(labels)
+    _list(d, colist, (buf, cap, cnt) -> ccall((:stf_totalcollisions_native, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, nl, lb, buf, cap, cnt))
 end
-
-# src/qtree_functions.jl:225-263
-totalcollisions_spacial(d::DeviceQTrees, labels=nothing; unique=true, kargs...) = _list(:stf_totalcollisions_spacial, d, labels, Int32(unique))
-# src/qtree_functions.jl:111-131
-totalcollisions_native(d::DeviceQTrees, labels=nothing; kargs...) = _list(:stf_totalcollisions_native, d, labels, Int32(0))
-# src/qtree_functions.jl:277-330 (the linked tree lives in the context; stf_linked_locate = locate!(qts, labels, tree))
-partialcollisions(d::DeviceQTrees, labels; unique=true, kargs...) = _list(:stf_partialcollisions, d, labels, Int32(unique))
-
-# src/qtree_functions.jl:43-51
-function collision(d::DeviceQTrees, i1::Integer, i2::Integer)
-    out = Vector{Int32}(undef, 3)
-    check(d, ccall((:stf_collision, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}), d.h, i1, i2, out))
-    (Int(out[1]), Int(out[2]), Int(out[3]))
+"HashSpacialQTree stand-in (qtrees.jl:399-422): the device keeps the cells as sorted records; `qtree` is filled by locate!"
+struct DeviceHashTree; qtree::Dict{Index,Vector{Int}}; end
+"LinkedSpacialQTree stand-in (qtrees.jl:424-552): the persistent 4-slot table lives in the context"
+struct DeviceLinkedTree; owner::DeviceQTrees; end
+hash_spacial_qtree(::DeviceQTrees) = DeviceHashTree(Dict{Index,Vector{Int}}())           # qtree_functions.jl:139-140
+function linked_spacial_qtree(d::DeviceQTrees)                                            # qtree_functions.jl:132-138
+    check(d, ccall((:stf_linked_reset, LIB), Int32, (Ptr{Cvoid},), d.h)); DeviceLinkedTree(d)
 end
-
-# src/qtree_functions.jl:190-201 → Dict{Index,Vector{Int}} like HashSpacialQTree.qtree
-function locate!(d::DeviceQTrees, labels=nothing)
-    lb, nl = _labels(labels)
+Base.empty!(t::DeviceHashTree) = (empty!(t.qtree); t)
+function locate!(d::DeviceQTrees, labels, t::DeviceHashTree)                              # qtree_functions.jl:190-201
+    lb, nl = _lb(labels)
     cap = 4 * (labels === nothing ? d.n : Int(nl)) + 4
     buf = Matrix{Int32}(undef, 4, cap); cnt = Ref{Int64}(0)
     check(d, ccall((:stf_locate, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Int64, Ptr{Int64}), d.h, nl, lb, buf, cap, cnt))
-    t = Dict{Tuple{Int,Int,Int},Vector{Int}}()
     for k in 1:cnt[]
-        push!(get!(Vector{Int}, t, (Int(buf[1, k]), Int(buf[2, k]), Int(buf[3, k]))), Int(buf[4, k]))
+        push!(get!(Vector{Int}, t.qtree, (Int(buf[1, k]), Int(buf[2, k]), Int(buf[3, k]))), Int(buf[4, k]))
     end
     t
 end
-
-# src/qtrees.jl:267-288
-function _shifts!(d, labels, l, s1, s2, mode)
-    lb, n = _labels(labels)
-    check(d, ccall((:stf_set_shifts, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Int32),
-                   d.h, n, lb, l, Int32.(collect(s1)), Int32.(collect(s2)), mode))
+locate!(d::DeviceQTrees, t::DeviceHashTree=hash_spacial_qtree(d)) = locate!(d, nothing, t)
+function locate!(d::DeviceQTrees, labels, t::DeviceLinkedTree)
+    lb, nl = _lb(labels)
+    check(d, ccall((:stf_linked_locate, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}), d.h, nl, lb)); t
 end
-setshift!(d::DeviceQTrees, label::Integer, l::Integer, s1::Integer, s2::Integer) = _shifts!(d, (label,), l, (s1,), (s2,), 0)
-shift!(d::DeviceQTrees, label::Integer, l::Integer, s1::Integer, s2::Integer) = _shifts!(d, (label,), l, (s1,), (s2,), 1)
-function getshift(d::DeviceQTrees, labels=1:d.n, l::Integer=1)
-    lb, n = _labels(labels); rs = Vector{Int32}(undef, n); cs = similar(rs)
-    check(d, ccall((:stf_get_shifts, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}), d.h, n, lb, l, rs, cs))
-    collect(zip(Int.(rs), Int.(cs)))
+locate!(d::DeviceQTrees, t::DeviceLinkedTree) = locate!(d, nothing, t)
+function totalcollisions_spacial(d::DeviceQTrees, labels=nothing; colist=Vector{CoItem}(), unique=true, kargs...)  # qtree_functions.jl:225-263
+    lb, nl = _lb(labels)
+    _list(d, colist, (buf, cap, cnt) -> ccall((:stf_totalcollisions_spacial, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, nl, lb, Int32(unique), buf, cap, cnt))
 end
-# refresh a host tree from the device before place!/reposition!/getpositions (host code stays the reference's)
-function download!(d::DeviceQTrees, label::Integer, qt)
-    for l in 1:length(qt)
-        info = Vector{Int32}(undef, 5)
-        check(d, ccall((:stf_get_level_info, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}), d.h, label, l, info))
-        qt[l].rshift, qt[l].cshift = info[3], info[4]
-        payload = Matrix{UInt8}(undef, info[1], info[2])
-        check(d, ccall((:stf_download_level, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), d.h, label, l, payload))
-        qt[l].kernel[2:end-2, 2:end-2] .= payload
+const SPACIAL_ENABLE_THRESHOLD = round(Int, 10 + 10log2(Threads.nthreads()))               # qtree_functions.jl:265
+function totalcollisions(d::DeviceQTrees, labels=nothing; itemlist=nothing, pairlist=nothing, queue=nothing, spqtree=nothing, linkedspqtree=nothing,
+                         treenodestack=nothing, unique=true, kargs...)                   # dispatcher + _kw shims  qtree_functions.jl:266-276,331-338
+    n = labels === nothing ? d.n : length(labels)
+    n > SPACIAL_ENABLE_THRESHOLD ? totalcollisions_spacial(d, labels; unique=unique, kargs...) : totalcollisions_native(d, labels; kargs...)
+end
+function partialcollisions(d::DeviceQTrees, t::DeviceLinkedTree=locate!(d, linked_spacial_qtree(d)), labels=1:d.n;
+                           colist=Vector{CoItem}(), unique=true, kargs...)               # qtree_functions.jl:277-330
+    lb, nl = _lb(labels)
+    _list(d, colist, (buf, cap, cnt) -> ccall((:stf_partialcollisions, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, nl, lb, Int32(unique), buf, cap, cnt))
+end
+function dynamiccollisions(d::DeviceQTrees, t::DeviceLinkedTree, moved::AbstractVector{Int}; unlocated::AbstractVector{Int}, colist=Vector{CoItem}(), kargs...)  # qtree_functions.jl:340-356
+    if length(moved) / d.n > 0.6
+        r = totalcollisions(d; colist=colist, kargs...)
+        union!(unlocated, moved)
+    else
+        ms = Set(moved)
+        locate!(d, [i for i in unlocated if !(i in ms)], t)
+        empty!(unlocated)
+        r = partialcollisions(d, t, moved; colist=colist, kargs...)
     end
-    qt
+    empty!(moved)
+    union!(moved, Iterators.flatten(first.(r)))
+    r
 end
+"DynamicColliders (qtree_functions.jl:357-370) over device trees"
+struct DeviceColliders; qtrees::DeviceQTrees; spqtree::DeviceLinkedTree; moved::Vector{Int}; unlocated::Vector{Int}; end
+DeviceColliders(d::DeviceQTrees) = DeviceColliders(d, linked_spacial_qtree(d), collect(1:d.n), Int[])
+Base.union!(dc::DeviceColliders, c) = union!(dc.moved, c)
+dynamiccollisions(dc::DeviceColliders; kargs...) = dynamiccollisions(dc.qtrees, dc.spqtree, dc.moved; unlocated=dc.unlocated, kargs...)
 
-# src/fit_helper.jl:51-66
-function grad2d(d::DeviceQTrees, label::Integer, l::Integer, a::Integer, b::Integer)
+# ------------------------------------------------------------------------------------------------ fit step (fit_helper.jl, fit.jl:11-75)
+function grad2d(t::DeviceTree, l::Integer, a::Integer, b::Integer)                        # fit_helper.jl:51-66
     out = Vector{Int32}(undef, 2)
-    check(d, ccall((:stf_grad2d, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
-                   d.h, 1, Int32[label], Int32[l], Int32[a], Int32[b], out))
+    check(t.owner, ccall((:stf_grad2d, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+                         t.owner.h, 1, Int32[t.label], Int32[l], Int32[a], Int32[b], out))
     (Int(out[1]), Int(out[2]))
 end
-
-# src/fit.jl:69-75; optimiser = the reference's Momentum/SGD structs (only η, ρ cross the boundary)
-const _clock = Ref((UInt64(0), UInt64(0)))   # (seed, iteration) of the canonical-mode draws
-_optkind(o) = hasproperty(o, :rho) ? (Int32(2), o.eta, o.rho) : hasproperty(o, :eta) ? (Int32(1), o.eta, 0.0) : (Int32(0), 0.0, 0.0)
-function batchsteps!(d::DeviceQTrees, colist::Vector{CoItem}, optimiser=nothing)
-    kind, eta, rho = optimiser === nothing ? (Int32(0), 0.0, 0.0) : _optkind(optimiser)
-    check(d, ccall((:stf_set_optimiser, LIB), Int32, (Ptr{Cvoid}, Int32, Float64, Float64), d.h, kind, eta, rho))
-    seed, it = _clock[]
+_optkind(o::Momentum) = (Int32(2), Float64(o.eta), Float64(o.rho))
+_optkind(o::SGD) = (Int32(1), Float64(o.eta), 0.0)
+_optkind(::Any) = (Int32(0), 0.0, 0.0)                                                   # (t, Δ) -> Δ ./ 6  fit.jl:25
+_setopt!(d::DeviceQTrees, o) = (k = _optkind(o); check(d, ccall((:stf_set_optimiser, LIB), Int32, (Ptr{Cvoid}, Int32, Float64, Float64), d.h, k[1], k[2], k[3])))
+function reset!(o::Momentum, ts::AbstractVector{DeviceTree})                              # reset!.(optimiser, ts[repositioned])  fit.jl:508
+    isempty(ts) && return
+    lb = Int32[t.label for t in ts]
+    check(ts[1].owner, ccall((:stf_reset_velocity, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}), ts[1].owner.h, length(lb), lb))
+end
+function batchsteps!(d::DeviceQTrees, colist::Vector{CoItem}, optimiser=(t, Δ) -> Δ ./ 6)  # fit.jl:69-75 (canonical mode: list order)
+    _setopt!(d, optimiser)
+    seed, it = d.clock
     check(d, ccall((:stf_batchsteps, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{StfItem}, UInt64, UInt64), d.h, length(colist), StfItem.(colist), seed, it))
-    _clock[] = (seed, it + 1)
+    d.clock = (seed, it + 1)
     nothing
 end
-# device-resident totalcollisions(...; unique=false) → batchsteps!; returns length(colist)
-function fit_round!(d::DeviceQTrees, labels=nothing; partial=false)
-    lb, nl = _labels(labels); nh = Ref{Int64}(0); seed, it = _clock[]
+"one device-resident round: totalcollisions(qtrees[, labels]; unique=false) -> batchsteps!; returns length(colist)  (fit.jl:87-96)"
+function fit_round!(d::DeviceQTrees, labels=nothing; optimiser=(t, Δ) -> Δ ./ 6, partial=false)
+    _setopt!(d, optimiser)
+    lb, nl = _lb(labels); nh = Ref{Int64}(0); seed, it = d.clock
     check(d, ccall((:stf_fit_round, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, UInt64, UInt64, Ptr{Int64}), d.h, partial ? 1 : 0, nl, lb, seed, it, nh))
-    _clock[] = (seed, it + 1)
+    d.clock = (seed, it + 1)
     Int(nh[])
 end
-
-# the same round, then getshift(t, level) of every tree, read back with the round's own synchronisation
-function fit_round_positions!(d::DeviceQTrees, labels=nothing; partial=false, level=1)
-    lb, nl = _labels(labels); nh = Ref{Int64}(0); seed, it = _clock[]
-    n = Int(ccall((:stf_num_objects, LIB), Int32, (Ptr{Cvoid},), d.h))
-    rs = Vector{Int32}(undef, n); cs = Vector{Int32}(undef, n)
-    check(d, ccall((:stf_fit_round_positions, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, UInt64, UInt64, Ptr{Int64}, Int32, Ptr{Int32}, Ptr{Int32}),
-                   d.h, partial ? 1 : 0, nl, lb, seed, it, nh, level, rs, cs))
-    _clock[] = (seed, it + 1)
-    Int(nh[]), rs, cs
+"`k` rounds with ONE host synchronisation (stf_fit_rounds); returns the per-round length(colist) and the positions after the last round"
+function fit_rounds!(d::DeviceQTrees, k::Integer, labels=nothing; optimiser=(t, Δ) -> Δ ./ 6, partial=false, level=1)
+    _setopt!(d, optimiser)
+    lb, nl = _lb(labels); nh = Vector{Int64}(undef, k); seed, it = d.clock
+    rs = Vector{Int32}(undef, d.n); cs = Vector{Int32}(undef, d.n)
+    check(d, ccall((:stf_fit_rounds, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, UInt64, UInt64, Int32, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{Int32}, Ptr{Int32}),
+                   d.h, partial ? 1 : 0, nl, lb, seed, it, k, nh, C_NULL, level, rs, cs))
+    d.clock = (seed, it + k)
+    Int.(nh), collect(zip(Int.(rs), Int.(cs)))
 end
 
-# src/fit.jl:235-266 — one root BFS per pair of the pool (misses report -level: the nearness score), hits are stepped
-function filttrain!(d::DeviceQTrees, inpool::Vector{Tuple{Int,Int}}, outpool, nearlevel2; optimiser=nothing)
-    isempty(inpool) && return 0
-    L = Int(ccall((:stf_num_levels, LIB), Int32, (Ptr{Cvoid},), d.h))
-    items = [StfItem(i1, i2, L, 1, 1) for (i1, i2) in inpool]; out = similar(items)
-    check(d, ccall((:stf_collision_bfs, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{StfItem}, Ptr{StfItem}), d.h, length(items), items, out))
-    near = [o.l >= nearlevel2 for o in out]
-    outpool === nothing || append!(outpool, inpool[near])
-    colist = CoItem[CoItem(o) for (o, k) in zip(out, near) if k && o.l > 0]
-    batchsteps!(d, colist, optimiser)
-    length(colist)
-end
+# ------------------------------------------------------------------------------------------------ trainers (fit.jl:77-233) — host policy over device rounds
+# The reference's trainepoch_* functions only call totalcollisions / dynamiccollisions / batchsteps! on their `qtrees`
+# argument, so they run UNCHANGED on a DeviceQTrees through the methods above; train!/fit! (fit.jl:450-552) likewise
+# (its `resource` Dict is passed through; `:spqtree`/`:queue`/`:itemlist`/`:pairlist` entries are accepted and ignored by
+# the keyword shims, `:moved` must be a DeviceColliders for trainepoch_D!).  Two resource constructors need a device twin:
+trainepoch_D_resource(d::DeviceQTrees) = Dict(:colist => Vector{CoItem}(), :moved => DeviceColliders(d), :loops => 10)
 
-# src/qtree_functions.jl:452-518 — the ground place!/reposition! search: deepcopy(mask) + every tree not in `inds`,
-# composed on the device; findroom_uniform (the reference's own, unchanged) then runs on the downloaded ground
-function ground_level(d::DeviceQTrees, l::Integer)
-    info = Vector{Int32}(undef, 5)
-    check(d, ccall((:stf_ground_level, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Ptr{Int32}), d.h, l, C_NULL, info))
-    m = Matrix{UInt8}(undef, info[1], info[2])
-    check(d, ccall((:stf_ground_level, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Ptr{Int32}), d.h, l, m, info))
-    m, (Int(info[3]), Int(info[4]))                       # payload and (rshift, cshift): fill a PaddedMat with it
+# ------------------------------------------------------------------------------------------------ several GPUs from one process
+"One context per device holding the same scene; rounds are split by candidate records, the GPUs exchange their hit lists
+over NVLink peer memory themselves (include/stuffing_b200.h: stf_group_*)."
+mutable struct GpuGroup
+    h::Ptr{Cvoid}
+    replicas::Vector{DeviceQTrees}
 end
-function place!(d::DeviceQTrees, host_ground, qts, inds; kargs...)   # host_ground: a ShiftedQTree shaped like the mask
-    ex = Int32.(collect(inds))
-    check(d, ccall((:stf_ground_compose, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}), d.h, 1, length(ex), ex))
-    for l in 1:length(host_ground)
-        m, _ = ground_level(d, l); host_ground[l].kernel[2:size(m, 1) + 1, 2:size(m, 2) + 1] .= m
+function GpuGroup(qts::AbstractVector, devices::AbstractVector{<:Integer}; seed::Integer=0)
+    h = Ref{Ptr{Cvoid}}(C_NULL); dv = Int32.(collect(devices))
+    rc = ccall((:stf_group_create, LIB), Int32, (Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}), length(dv), dv, h)
+    rc == 0 || error("stf_group_create failed ($rc)")
+    reps = DeviceQTrees[]
+    for i in 0:length(dv)-1
+        d = ccall(:jl_new_struct_uninit, Any, (Any,), DeviceQTrees)::DeviceQTrees    # adopt the group's context: no finalizer, the group owns it
+        d.h = ccall((:stf_group_ctx, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), h[], i); d.n = 0; d.L = 0; d.clock = (UInt64(seed), UInt64(0))
+        push!(reps, upload!(d, qts))
     end
-    ind = nothing; Q = Vector{Tuple{Int,Int,Int}}()
-    for i in inds                                           # the reference's loop, qtree_functions.jl:512-517
-        ind = Main.Stuffing.QTrees.place!(host_ground, qts[i], Q; kargs...)
-        ind === nothing && return ind
-        Main.Stuffing.QTrees.overlap!(host_ground, qts[i])
-    end
-    rs = Int32[qts[i][1].rshift for i in inds]; cs = Int32[qts[i][1].cshift for i in inds]
-    check(d, ccall((:stf_set_shifts, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Int32), d.h, length(ex), ex, 1, rs, cs, 0))
-    ind
+    g = GpuGroup(h[], reps)
+    finalizer(x -> ccall((:stf_group_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), g)
 end
-
-# item-parallel sharding of one scene (INTEGRATION.md "Multi-GPU from Julia"): the three calls around the all-gather
-function shard_collide!(d::DeviceQTrees, rank, nranks; labels=nothing, partial=false)
-    lb, nl = _labels(labels); n = Ref{Int64}(0)
-    check(d, ccall((:stf_shard_collide, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int32, Int32, Ptr{Int64}), d.h, partial ? 1 : 0, nl, lb, rank, nranks, n))
-    Int(n[])
-end
-shard_pack!(d::DeviceQTrees, send_dev, stride) = check(d, ccall((:stf_shard_pack, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), d.h, send_dev, stride))
-function shard_step!(d::DeviceQTrees, recv_dev, nranks, stride)
-    nh = Ref{Int64}(0); seed, it = _clock[]
-    check(d, ccall((:stf_shard_step, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, UInt64, UInt64, Ptr{Int64}), d.h, recv_dev, nranks, stride, seed, it, nh))
-    _clock[] = (seed, it + 1)
+function fit_round!(g::GpuGroup, labels=nothing; optimiser=(t, Δ) -> Δ ./ 6, partial=false)
+    foreach(d -> _setopt!(d, optimiser), g.replicas)
+    lb, nl = _lb(labels); nh = Ref{Int64}(0); seed, it = g.replicas[1].clock
+    rc = ccall((:stf_group_fit_round, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, UInt64, UInt64, Ptr{Int64}), g.h, partial ? 1 : 0, nl, lb, seed, it, nh)
+    rc == 0 || error(unsafe_string(ccall((:stf_group_last_error, LIB), Cstring, (Ptr{Cvoid},), g.h)))
+    foreach(d -> d.clock = (seed, it + 1), g.replicas)
     Int(nh[])
 end
 end # module

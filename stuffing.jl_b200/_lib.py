@@ -58,11 +58,19 @@ EXPORTS = {
     "stf_batchsteps": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64, C.c_uint64]),
     "stf_fit_round": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "stf_fit_round_positions": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "stf_fit_rounds": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "stf_ground_compose": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "stf_ground_level": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "stf_shard_collide": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "stf_shard_pack": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64]),
     "stf_shard_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "stf_group_create": (C.c_int32, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "stf_group_destroy": (None, [C.c_void_p]),
+    "stf_group_size": (C.c_int32, [C.c_void_p]),
+    "stf_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "stf_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "stf_group_fit_round": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "stf_group_nvlink_bytes": (C.c_int64, [C.c_void_p]),
     "stf_counters": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "stf_launch_count": (C.c_int64, [C.c_void_p]),
     "stf_profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -25,8 +25,9 @@ namespace cg = cooperative_groups;
 #define LOC_THREADS 128
 __global__ void __launch_bounds__(LOC_THREADS) k_locate(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
                          int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                         int* __restrict__ err, unsigned long long* __restrict__ n_append) {
+                         int* __restrict__ err, unsigned long long* __restrict__ n_append, const unsigned long long* __restrict__ cancel = nullptr) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
+    if (cancel && *cancel) return; // a cancelled round of a multi-round call (stf_fit_rounds): no records, so every later kernel finds empty lists
     const unsigned FULLM = 0xffffffffu;
     const int lane = threadIdx.x & 31, gl = lane & 3, g0 = lane & ~3;
     const int j = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
@@ -111,8 +112,9 @@ __global__ void __launch_bounds__(LOC_THREADS) k_locate(const uint32_t* __restri
 //   reproduces the insertion order of the reference's Dict of Vectors (qtrees.jl:411-415) whatever the append order.
 __global__ void k_locate_wide(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
                          int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                         int* __restrict__ err, unsigned long long* __restrict__ n_append) {
+                         int* __restrict__ err, unsigned long long* __restrict__ n_append, const unsigned long long* __restrict__ cancel = nullptr) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
+    if (cancel && *cancel) return;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0; uint64_t ck[4]; int o = 0, slot = 0;
     if (j < nl) {
@@ -161,8 +163,10 @@ __global__ void k_locate_wide(const uint32_t* __restrict__ words, const LevelMet
 }
 // LinkedSpacialQTree table (4 slots per object) -> compact (key, label) records, unordered
 __global__ void k_compact_records(const uint64_t* __restrict__ tk, const uint32_t* __restrict__ tv, int64_t nslots,
-                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_append) {
+                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_append,
+                                  const unsigned long long* __restrict__ cancel = nullptr) {
     pdl_sync();
+    if (cancel && *cancel) return;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t k = i < nslots ? tk[i] : STF_KEY_INVALID;
     bool v = k != STF_KEY_INVALID;
@@ -876,4 +880,59 @@ __global__ void k_shard_unpack(const Item16* __restrict__ recv, int nranks, int6
     int64_t base = 0, mine = 0;
     for (int q = 0; q <= s; q++) { Item16 h = recv[(int64_t)q * stride]; int64_t c = (int64_t)(uint32_t)h.i1 | ((int64_t)(uint32_t)h.i2l << 31); if (q < s) base += c; else mine = c; }
     if (k - 1 < mine && base + k - 1 < cap) hits[base + k - 1] = recv[i];
+}
+
+// ---- item-parallel group of GPUs driven by ONE process (stf_group_*): device-side exchange of the local hit lists over
+// NVLink peer memory.  After its share of the narrow phase, GPU `rank` copies its hits into segment `rank` of EVERY peer's
+// gather buffer with plain peer stores, fences at system scope, and the last block publishes (count | cancel bit, epoch)
+// to every peer's flag slots with a system-scope release.  k_shard_gather then spins on the flags of all peers
+// (system-scope acquire: a device-side barrier, no host involvement), ORs the cancel bits into the local status and
+// compacts the segments, in rank order, into the local hit list.  Every GPU ends up with the same union.
+#define STF_MAX_GROUP 16
+struct PeerSet { Item16* gather[STF_MAX_GROUP]; unsigned long long* flags[STF_MAX_GROUP]; int n; };
+__global__ void __launch_bounds__(256) k_shard_push(const Item16* __restrict__ hits, const unsigned long long* __restrict__ nh_dev, int64_t seg_cap,
+                                                    PeerSet P, int rank, unsigned long long epoch, const int* __restrict__ status,
+                                                    const unsigned long long* __restrict__ n_list_dev, int64_t list_cap, unsigned int* __restrict__ blocks_done) {
+    pdl_sync();
+    const int64_t nh = (int64_t)*nh_dev;
+    const int64_t n = min(nh, seg_cap);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Item16 h = hits[i];
+        for (int p = 0; p < P.n; p++) P.gather[p][(int64_t)rank * seg_cap + i] = h;
+    }
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(blocks_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *blocks_done = 0u;
+    if ((int)threadIdx.x < P.n) {
+        // cancel bit: this GPU's part of the round cannot be used (a list overflowed, too many hits): every peer must drop the round too
+        const bool bad = *status != 0 || nh > seg_cap || (n_list_dev && (int64_t)*n_list_dev > list_cap);
+        unsigned long long* f = P.flags[threadIdx.x] + 2 * rank;
+        f[0] = (unsigned long long)n | (bad ? (1ull << 63) : 0ull);
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f + 1), "l"(epoch) : "memory");
+    }
+}
+__global__ void __launch_bounds__(256) k_shard_gather(const Item16* __restrict__ gather, const unsigned long long* __restrict__ flags, int nranks, int64_t seg_cap,
+                                                      unsigned long long epoch, Item16* __restrict__ hits, int64_t hits_cap, unsigned long long* __restrict__ nhits, int* __restrict__ status) {
+    pdl_sync();
+    __shared__ long long s_cnt[STF_MAX_GROUP], s_base[STF_MAX_GROUP + 1];
+    if ((int)threadIdx.x < nranks) { // device-side barrier: wait until peer `threadIdx.x` has published this round
+        const unsigned long long* f = flags + 2 * threadIdx.x;
+        unsigned long long e;
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(e) : "l"(f + 1) : "memory"); } while (e < epoch);
+        unsigned long long v = *((volatile const unsigned long long*)f);
+        s_cnt[threadIdx.x] = (long long)(v & 0x7FFFFFFFFFFFFFFFull);
+        if ((v >> 63) && blockIdx.x == 0) atomicOr(status, 1 /* STF_ST_RETRY_GROW: drop the round everywhere */);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { long long b = 0; for (int r = 0; r < nranks; r++) { s_base[r] = b; b += s_cnt[r]; } s_base[nranks] = b; if (blockIdx.x == 0) *nhits = (unsigned long long)b; }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)nranks * seg_cap; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / seg_cap); const int64_t k = i - (int64_t)r * seg_cap;
+        if (k < s_cnt[r] && s_base[r] + k < hits_cap) hits[s_base[r] + k] = gather[i];
+    }
 }

@@ -57,11 +57,14 @@ struct stf_ctx {
     int64_t last_result = 0, last_items = 0; bool items_valid = false;
     int64_t big_cap = 0; int big_ctas = 1;
     int ground_of = -1; // object whose copy the ground pyramid currently is (stf_ground_compose)
-    int shard_rank = 0, shard_n = 1; // item-parallel sharding of the candidate generation (stf_shard_*)
+    int shard_rank = 0, shard_n = 1; // item-parallel sharding of the candidate generation (stf_shard_*, stf_group_*)
+    DevBuf gather, gflags, gdone;    // stf_group_*: segments the peers push their hits into, their (count, epoch) flags, push bookkeeping
     bool force_big = false; // the single-CTA latency path overflowed once: stay on the multi-launch path
     int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
     int64_t hint_surv = 0;  // pairs the word-parallel narrow phase handed to the frontier kernel in the previous round
     bool fused_narrow = false; // STF_FUSED_NARROW=1: candidates are tested inside the candidate kernel and never stored (measured slower: DESIGN.md)
+    bool in_rounds = false; // stf_fit_rounds is enqueueing: k_round_begin resets the counters (not a host memset) and a raised C_STOP cancels a round
+    DevBuf rounds_rec;      // stf_fit_rounds: per-round records (hits, items, node tests, moves)
     bool keep_items = false; // stf_set_keep_items: the candidate list (the reference's `itemlist`) must be fetchable: never the fused variant
     stf_counters_t ctr = {};
     int64_t launches = 0; // kernels launched by this context (bench.py gpu_launches)
@@ -185,7 +188,7 @@ static inline int nblk(int64_t n, int t) { return (int)std::max<int64_t>(1, (n +
 // entries per warp of the grouped rebuild kernels: one per warp while the GPU has warps to spare, up to 32 beyond that
 static inline int rebuild_group(int64_t n) { int64_t g = n / (148 * 64); return g < 4 ? 1 : (int)std::min<int64_t>(32, g); }
 
-enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_SURV = 13, C_STATUS = 14 /* path status bits (int) */, C_ERR = 15 /* error bits (int) */, C_CURSOR = 16, C_N = 17 };
+enum { C_ITEMS = 0, C_DIRECT = 1, C_OVERFLOW = 2, C_VISITED = 3, C_MOVES = 4, C_KEPT = 5, C_NHITS = 6, C_ZEROED = 7, /* not reset by zero_counts: */ C_NVALID = 7, C_TICKET = 8, C_NEP = 9, C_NSTEPS = 10, C_NREC = 11, C_VARY = 12, C_SURV = 13, C_STATUS = 14 /* path status bits (int) */, C_ERR = 15 /* error bits (int) */, C_CURSOR = 16, C_STOP = 17 /* multi-round calls: != 0 cancels the remaining rounds */, C_N = 18 };
 #define ERRP(ctx) reinterpret_cast<int*>((ctx)->counts.as<unsigned long long>() + C_ERR)
 #define STATUSP(ctx) reinterpret_cast<int*>((ctx)->counts.as<unsigned long long>() + C_STATUS)
 
@@ -272,7 +275,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from, &ctx->gather, &ctx->gflags, &ctx->gdone, &ctx->rounds_rec };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) free(ctx->h_err);
@@ -916,13 +919,14 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     unsigned long long* nvalid = ctx->counts.as<unsigned long long>() + C_NVALID;
     unsigned long long* nappend = ctx->counts.as<unsigned long long>() + C_NREC;
     if (fast) {
+        const unsigned long long* cancel = ctx->in_rounds ? ctx->counts.as<unsigned long long>() + C_STOP : nullptr;
         if (linked) {
             if (nl > 0) LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
-                                                                   ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
-            LAUNCH_PDL(ctx, k_compact_records, nblk(nrec, 256), 256, 0, ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), nrec, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend);
+                                                                   ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr, cancel);
+            LAUNCH_PDL(ctx, k_compact_records, nblk(nrec, 256), 256, 0, ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), nrec, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), nappend, cancel);
         } else if (nl > 0) {
             LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
-                                                        ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ERRP(ctx), nappend);
+                                                        ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ERRP(ctx), nappend, cancel);
         }
         KCHECK();
         stage_begin(ctx, STF_STAGE_SORT);
@@ -940,12 +944,12 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
     if (linked) {
         if (nl > 0) LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
-                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
+                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr, (const unsigned long long*)nullptr);
         CK(cudaMemcpyAsync(ctx->rk.p, ctx->lkk.p, sizeof(uint64_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->rv.p, ctx->lkv.p, sizeof(uint32_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
     } else if (nl > 0) {
         LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
-                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ERRP(ctx), nullptr);
+                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ERRP(ctx), nullptr, (const unsigned long long*)nullptr);
     }
     KCHECK();
     stage_begin(ctx, STF_STAGE_SORT);
@@ -1006,7 +1010,7 @@ extern "C" int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* la
     if (nl <= 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
     LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
-                                                ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr);
+                                                ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr, (const unsigned long long*)nullptr);
     KCHECK();
     return sync_counts(ctx);
 }
@@ -1090,7 +1094,8 @@ static int32_t spacial_core_fast(stf_ctx* ctx, int32_t nl, const int32_t* labels
     const int32_t* moved_pos = nullptr;
     if (linked) { r = upload_moved_pos(ctx, nl, labels, &moved_pos); if (r) return r; }
     int64_t nrec; uint64_t* keys; uint32_t* vals;
-    CK(cudaMemsetAsync(ctx->counts.p, 0, C_ERR * sizeof(unsigned long long), ctx->st)); // every counter and the status; pending error bits stay until a sync reads them
+    if (!ctx->in_rounds) CK(cudaMemsetAsync(ctx->counts.p, 0, C_ERR * sizeof(unsigned long long), ctx->st)); // every counter and the status; pending error bits stay until a sync reads them
+    // (inside stf_fit_rounds k_round_begin resets the counters and keeps the status: a raised bit cancels the rounds that follow)
     r = locate_and_sort(ctx, nl, dl, linked, true, &nrec, &keys, &vals); if (r) return r;
     CK(ctx->hits.ensure(sizeof(Item16) * (size_t)(BS_CAP + 1024))); // more hits than BS_CAP leave the fast path anyway
     if (ctx->fused_narrow && !ctx->keep_items) { // fused: candidates are tested where they are generated; only the undecided pairs are stored
@@ -1326,6 +1331,28 @@ static void pos_deliver(stf_ctx* ctx) {
     const size_t nb = sizeof(int32_t) * (size_t)ctx->n;
     memcpy(ctx->pos_rs, ctx->h_out, nb); memcpy(ctx->pos_cs, ctx->h_out + nb, nb);
 }
+// second half of a latency-path round: the unordered hit list (ctx->hits, count on the device) -> canonical order + step
+// links (one cluster kernel) -> batchsteps + materialisation.  Enqueue only.  cancel_on_status: a status bit raised before
+// (by this GPU, or by a peer of an item-parallel group) cancels the round.
+static int32_t fast_round_tail(stf_ctx* ctx, uint64_t seed, uint64_t iteration, bool cancel_on_status) {
+    CK(ctx->hits2.ensure(sizeof(Item16) * (size_t)(BS_CAP + 1024)));
+    CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)(BS_CAP + 1024))); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)(BS_CAP + 1024)));
+    stage_begin(ctx, STF_STAGE_RESULT);
+    FinalizeArgs F = {};
+    F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
+    set_overflow_check(ctx, F);
+    F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = 0; F.out5 = nullptr; F.kept = nullptr;
+    F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
+    F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
+    F.status = STATUSP(ctx); F.abort_on_status = cancel_on_status ? 1 : 0;
+    if (ctx->no_cluster) LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
+    else {
+        CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)(CS_CAP + 1024)));
+        LAUNCH_PDL(ctx, k_finalize_prep_cl, CS_CTAS, CS_THREADS, CS_SMEM_BYTES, F, ctx->hk.as<uint64_t>());
+    }
+    KCHECK();
+    return launch_steps(ctx, ctx->hits2.as<Item16>(), std::max<int64_t>(ctx->ctr.hits, 2048), ctx->counts.as<unsigned long long>() + C_NSTEPS, seed, iteration);
+}
 extern "C" int32_t stf_fit_round_positions(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits,
                                            int32_t level, int32_t* rs, int32_t* cs) {
     NEED_OBJS();
@@ -1346,23 +1373,7 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
     int linked = mode == 1;
     for (int attempt = 0; attempt < 4 && fast_path_ok(ctx, linked ? ctx->n : nl); attempt++) {
         int32_t r = spacial_core_fast(ctx, nl, labels, linked); if (r) return r;
-        CK(ctx->hits2.ensure(sizeof(Item16) * (size_t)(BS_CAP + 1024)));
-        CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)(BS_CAP + 1024))); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)(BS_CAP + 1024)));
-        stage_begin(ctx, STF_STAGE_RESULT);
-        FinalizeArgs F = {};
-        F.hits = ctx->hits.as<Item16>(); F.nh_dev = ctx->counts.as<unsigned long long>() + C_NHITS; F.hits_cap = (int64_t)(ctx->hits.cap / sizeof(Item16));
-        set_overflow_check(ctx, F);
-        F.sorted = ctx->hits2.as<Item16>(); F.label_bits = ctx->label_bits; F.unique = 0; F.out5 = nullptr; F.kept = nullptr;
-        F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
-        F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
-        F.status = STATUSP(ctx);
-        if (ctx->no_cluster) LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
-        else {
-            CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)(CS_CAP + 1024)));
-            LAUNCH_PDL(ctx, k_finalize_prep_cl, CS_CTAS, CS_THREADS, CS_SMEM_BYTES, F, ctx->hk.as<uint64_t>());
-        }
-        KCHECK();
-        r = launch_steps(ctx, ctx->hits2.as<Item16>(), std::max<int64_t>(ctx->ctr.hits, 2048), ctx->counts.as<unsigned long long>() + C_NSTEPS, seed, iteration); if (r) return r;
+        r = fast_round_tail(ctx, seed, iteration, false); if (r) return r;
         const bool fold = ctx->pos_level > 0 && ctx->n <= 65536;
         if (fold) { r = pos_enqueue(ctx); if (r) return r; }
         r = sync_counts(ctx); if (r) return r;
@@ -1379,6 +1390,97 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
     if (nhits) *nhits = nh;
     return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
 }
+// ---- several fit rounds without a host round trip in between (the inner loop of the trainers,
+// fit.jl:85-99, stays on the device).  Every round is enqueued blindly; k_round_begin resets the round's counters on the
+// device and cancels the round (C_STOP) when an earlier round raised a status bit (a list was too small / the scene left the
+// latency path) — a cancelled round's locate produces no records, so all its kernels find empty lists; k_round_end records
+// (hits, items, node tests, moves) of the round.  ONE synchronisation per call.
+#define ROUND_REC 4
+__global__ void k_round_begin(unsigned long long* __restrict__ counts) {
+    pdl_sync();
+    const int t = threadIdx.x;
+    const int status = (int)counts[C_STATUS];
+    const bool stop = status != 0 || counts[C_STOP] != 0ull;
+    __syncwarp();
+    if (t == 0 && stop) counts[C_STOP] = 2ull; // a previous round failed: nothing of what follows may run
+    // a cancelled round only empties the lists (its kernels find nothing to do); the counters of the failed round stay: the
+    // host sizes the buffers of the re-run from them
+    if (stop) { if (t == C_NREC || t == C_NVALID || t == C_NHITS || t == C_NSTEPS || t == C_SURV) counts[t] = 0ull; return; }
+    if (t < C_STATUS) counts[t] = 0ull;
+}
+__global__ void k_round_end(unsigned long long* __restrict__ counts, unsigned long long* __restrict__ rec, int k) {
+    pdl_sync();
+    if (threadIdx.x != 0) return;
+    if (counts[C_STOP] != 0ull) return;                 // cancelled round: no record
+    if ((int)counts[C_STATUS] != 0) { counts[C_STOP] = 2ull; return; } // this round raised a bit (its steps did not run)
+    unsigned long long* r = rec + (size_t)ROUND_REC * (k + 1);
+    r[0] = counts[C_NHITS]; r[1] = counts[C_ITEMS] + counts[C_DIRECT]; r[2] = counts[C_VISITED]; r[3] = counts[C_MOVES];
+    rec[0] = (unsigned long long)(k + 1);               // rounds done
+    rec[1] = counts[C_NVALID];
+}
+extern "C" int32_t stf_fit_rounds(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration0, int32_t n_rounds,
+                                  int64_t* nhits_per_round, stf_counters_t* totals, int32_t level, int32_t* rs, int32_t* cs) {
+    NEED_OBJS();
+    if (n_rounds < 0 || (level != 0 && (level < 1 || level > ctx->L || !rs || !cs))) FAIL(STF_E_ARG, "bad round count, level or output arrays");
+    if (!labels) nl = ctx->n;
+    stf_counters_t tot = {};
+    for (int k = 0; k < n_rounds; k++) if (nhits_per_round) nhits_per_round[k] = 0;
+    const int linked = mode == 1;
+    int done = 0;
+    if (ctx->n > 1 && nl > 0) {
+        CK(ctx->rounds_rec.ensure(sizeof(unsigned long long) * ROUND_REC * (size_t)(n_rounds + 2)));
+        std::vector<unsigned long long> rec((size_t)ROUND_REC * (n_rounds + 2));
+        while (done < n_rounds) {
+            if (!fast_path_ok(ctx, linked ? ctx->n : nl)) { // scenes beyond the latency path: one host-driven round at a time
+                int64_t nh = 0;
+                int32_t r = stf_fit_round(ctx, mode, nl, labels, seed, iteration0 + done, &nh); if (r) return r;
+                if (nhits_per_round) nhits_per_round[done] = nh;
+                tot.hits += nh; tot.items += ctx->ctr.items; tot.direct += ctx->ctr.direct; tot.visited += ctx->ctr.visited; tot.moved += nh ? ctx->ctr.moved : 0; tot.records = ctx->ctr.records;
+                done++;
+                continue;
+            }
+            const int todo = n_rounds - done;
+            CK(cudaMemsetAsync(ctx->rounds_rec.p, 0, sizeof(unsigned long long) * ROUND_REC * (size_t)(todo + 2), ctx->st));
+            CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_STATUS, 0, sizeof(unsigned long long), ctx->st));
+            CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_STOP, 0, sizeof(unsigned long long), ctx->st));
+            ctx->in_rounds = true;
+            int32_t r = STF_OK;
+            for (int k = 0; k < todo && !r; k++) {
+                LAUNCH_PDL(ctx, k_round_begin, 1, 32, 0, ctx->counts.as<unsigned long long>());
+                r = spacial_core_fast(ctx, nl, labels, linked);
+                if (!r) r = fast_round_tail(ctx, seed, iteration0 + done + k, true);
+                if (!r) LAUNCH_PDL(ctx, k_round_end, 1, 32, 0, ctx->counts.as<unsigned long long>(), ctx->rounds_rec.as<unsigned long long>(), k);
+            }
+            ctx->in_rounds = false;
+            if (r) return r;
+            const bool fold = level > 0 && ctx->n <= 65536;
+            if (fold) { ctx->pos_level = level; ctx->pos_rs = rs; ctx->pos_cs = cs; r = pos_enqueue(ctx); if (r) { ctx->pos_level = 0; return r; } }
+            CK(cudaMemcpyAsync(rec.data(), ctx->rounds_rec.p, sizeof(unsigned long long) * ROUND_REC * (size_t)(todo + 2), cudaMemcpyDeviceToHost, ctx->st));
+            r = sync_counts(ctx);
+            ctx->pos_level = 0;
+            if (r) return r;
+            const int ran = (int)rec[0];
+            for (int k = 0; k < ran; k++) {
+                const unsigned long long* q = rec.data() + (size_t)ROUND_REC * (k + 1);
+                if (nhits_per_round) nhits_per_round[done + k] = (int64_t)q[0];
+                tot.hits += (int64_t)q[0]; tot.items += (int64_t)q[1]; tot.visited += (int64_t)q[2]; tot.moved += q[0] ? (int64_t)q[3] : 0;
+            }
+            tot.records = (int64_t)rec[1];
+            done += ran;
+            CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_STOP, 0, sizeof(unsigned long long), ctx->st));
+            if (ran < todo) { // round `done` raised a status bit: grow / switch path, then go on from there
+                if (!fast_round_verdict(ctx)) FAIL(STF_E_CUDA, "internal: a round was cancelled without a status bit");
+                continue;
+            }
+            if (fold) { pos_deliver(ctx); level = 0; }
+        }
+    } else done = n_rounds;
+    ctx->ctr.hits = nhits_per_round && n_rounds > 0 ? nhits_per_round[n_rounds - 1] : 0;
+    if (totals) *totals = tot;
+    if (level > 0) return stf_get_shifts(ctx, ctx->n, nullptr, level, rs, cs); // paths without a folded read-back
+    return STF_OK;
+}
+
 // ---- ground composition for place!/reposition!: deepcopy(mask) with every other tree overlapped
 // (qtree_functions.jl:505-518 `for i in 1:length(sortedtrees) if i in indexes continue end; overlap!(ground, sortedtrees[i])`).
 // The parallel part of place! runs on the device; the sequential, RNG-driven room search reads the result on the host.
@@ -1493,6 +1595,118 @@ extern "C" int32_t stf_shard_step(stf_ctx* ctx, const void* recv_dev, int32_t nr
     ctx->ctr.hits = nh;
     return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
 }
+// ------------------------------------------------------------------------------------------------ group of GPUs, one process
+// SURVEY §8b threading row / §8e-2: ONE host thread drives one context per GPU (the way a Julia host would); the scene is
+// replicated, every fit round is split by candidate records, and the local hit lists are exchanged by the GPUs themselves:
+// peer stores over NVLink + a device-side flag barrier (k_shard_push / k_shard_gather).  The host only enqueues: no
+// collective call, no host synchronisation between the halves of a round — one synchronisation per GPU at the end.
+struct stf_group {
+    std::vector<stf_ctx*> ctx; std::string err;
+    unsigned long long epoch = 0; int64_t seg_cap = 0;
+    int64_t nvlink_bytes = 0; // bytes pushed to peer GPUs by the last round (hit records + flags, excluding the local copy)
+};
+extern "C" int32_t stf_group_create(int32_t n, const int32_t* devices, stf_group** out) {
+    if (!out || n < 1 || n > STF_MAX_GROUP || !devices) return STF_E_ARG;
+    *out = nullptr;
+    stf_group* g = new stf_group();
+    for (int i = 0; i < n; i++) {
+        stf_ctx* c = nullptr;
+        int32_t r = stf_create(devices[i], &c);
+        if (r) { for (stf_ctx* x : g->ctx) stf_destroy(x); delete g; return r; }
+        g->ctx.push_back(c);
+    }
+    for (int i = 0; i < n; i++) // peer access both ways between every pair of distinct devices
+        for (int j = 0; j < n; j++) {
+            if (devices[i] == devices[j]) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+            cudaSetDevice(devices[i]);
+            cudaError_t e = can ? cudaDeviceEnablePeerAccess(devices[j], 0) : cudaErrorPeerAccessUnsupported;
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) { for (stf_ctx* x : g->ctx) stf_destroy(x); delete g; return STF_E_CUDA; }
+        }
+    g->seg_cap = BS_CAP + 1024;
+    for (int i = 0; i < n; i++) {
+        stf_ctx* ctx = g->ctx[i];
+        cudaSetDevice(ctx->device);
+        if (ctx->gather.ensure(sizeof(Item16) * (size_t)n * g->seg_cap) != cudaSuccess || ctx->gflags.ensure(sizeof(unsigned long long) * 2 * STF_MAX_GROUP) != cudaSuccess ||
+            ctx->gdone.ensure(sizeof(unsigned int) * 4) != cudaSuccess) { for (stf_ctx* x : g->ctx) stf_destroy(x); delete g; return STF_E_CUDA; }
+        cudaMemset(ctx->gflags.p, 0, sizeof(unsigned long long) * 2 * STF_MAX_GROUP); cudaMemset(ctx->gdone.p, 0, sizeof(unsigned int) * 4);
+    }
+    *out = g;
+    return STF_OK;
+}
+extern "C" void stf_group_destroy(stf_group* g) {
+    if (!g) return;
+    for (stf_ctx* x : g->ctx) stf_destroy(x);
+    delete g;
+}
+extern "C" int32_t stf_group_size(const stf_group* g) { return g ? (int32_t)g->ctx.size() : 0; }
+extern "C" stf_ctx* stf_group_ctx(stf_group* g, int32_t i) { return (g && i >= 0 && i < (int32_t)g->ctx.size()) ? g->ctx[i] : nullptr; }
+extern "C" const char* stf_group_last_error(const stf_group* g) { return g ? g->err.c_str() : "no group"; }
+extern "C" int64_t stf_group_nvlink_bytes(const stf_group* g) { return g ? g->nvlink_bytes : 0; }
+
+#define GFAIL(code, msg) do { g->err = (msg); return (code); } while (0)
+extern "C" int32_t stf_group_fit_round(stf_group* g, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits) {
+    if (!g) return STF_E_ARG;
+    if (nhits) *nhits = 0;
+    const int n = (int)g->ctx.size();
+    stf_ctx* c0 = g->ctx[0];
+    for (stf_ctx* c : g->ctx) if (c->L == 0 || c->n != c0->n || c->L != c0->L) GFAIL(STF_E_STATE, "every context of the group must hold the same uploaded scene");
+    if (!labels) nl = c0->n;
+    if (c0->n <= 1 || nl <= 0) return STF_OK;
+    const int linked = mode == 1;
+    PeerSet P = {}; P.n = n;
+    for (int i = 0; i < n; i++) { P.gather[i] = g->ctx[i]->gather.as<Item16>(); P.flags[i] = g->ctx[i]->gflags.as<unsigned long long>(); }
+    for (int attempt = 0; attempt < 4; attempt++) {
+        if (!fast_path_ok(c0, linked ? c0->n : nl)) GFAIL(STF_E_STATE, "scene too large for the item-parallel latency path of a group (use scene-parallel contexts)");
+        const unsigned long long epoch = ++g->epoch;
+        // ---- phase A on every GPU: broad phase + narrow phase over its share of the records, then push the local hits to all peers
+        for (int i = 0; i < n; i++) {
+            stf_ctx* ctx = g->ctx[i];
+            if (cudaSetDevice(ctx->device) != cudaSuccess) GFAIL(STF_E_CUDA, "cudaSetDevice failed");
+            stage_reset(ctx); ctx->after_kernel = false; ctx->last_result = 0;
+            ctx->shard_rank = i; ctx->shard_n = n;
+            int32_t r = spacial_core_fast(ctx, nl, labels, linked);
+            ctx->shard_rank = 0; ctx->shard_n = 1;
+            if (r) GFAIL(r, ctx->err);
+            FinalizeArgs F = {}; set_overflow_check(ctx, F);
+            LAUNCH_PDL(ctx, k_shard_push, 8, 256, 0, (const Item16*)ctx->hits.as<Item16>(), (const unsigned long long*)(ctx->counts.as<unsigned long long>() + C_NHITS), g->seg_cap, P, i, epoch,
+                       (const int*)STATUSP(ctx), F.n_items_dev, F.item_cap, ctx->gdone.as<unsigned int>());
+            if (cudaGetLastError() != cudaSuccess) GFAIL(STF_E_CUDA, "k_shard_push launch failed");
+        }
+        // ---- phase B on every GPU: wait for all peers (device-side), union of the hit lists, canonical order, batchsteps
+        for (int i = 0; i < n; i++) {
+            stf_ctx* ctx = g->ctx[i];
+            cudaSetDevice(ctx->device);
+            if (ctx->hits.ensure(sizeof(Item16) * (size_t)n * g->seg_cap, true, ctx->st) != cudaSuccess) GFAIL(STF_E_CUDA, "hit buffer allocation failed");
+            LAUNCH_PDL(ctx, k_shard_gather, 16, 256, 0, (const Item16*)ctx->gather.as<Item16>(), (const unsigned long long*)ctx->gflags.as<unsigned long long>(), n, g->seg_cap, epoch,
+                       ctx->hits.as<Item16>(), (int64_t)(ctx->hits.cap / sizeof(Item16)), ctx->counts.as<unsigned long long>() + C_NHITS, STATUSP(ctx));
+            if (cudaGetLastError() != cudaSuccess) GFAIL(STF_E_CUDA, "k_shard_gather launch failed");
+            int32_t r = fast_round_tail(ctx, seed, iteration, true); if (r) GFAIL(r, ctx->err);
+        }
+        // ---- one synchronisation per GPU
+        bool again = false; int32_t rc = STF_OK;
+        int64_t local_sum = 0;
+        for (int i = 0; i < n; i++) {
+            stf_ctx* ctx = g->ctx[i];
+            cudaSetDevice(ctx->device);
+            int32_t r = sync_counts(ctx); if (r && !rc) { rc = r; g->err = ctx->err; }
+            if (fast_round_verdict(ctx)) again = true;
+        }
+        if (rc) return rc;
+        if (again) { // a list was too small somewhere (every GPU dropped the round: the cancel bit travels with the hits): sizes are grown, run it again
+            for (stf_ctx* c : g->ctx) if (c->force_big) GFAIL(STF_E_STATE, "scene too large for the item-parallel latency path of a group (use scene-parallel contexts)");
+            continue;
+        }
+        for (int i = 0; i < n; i++) { stf_ctx* ctx = g->ctx[i]; read_round_counters(ctx); ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES]; local_sum += 0; }
+        if (nhits) *nhits = c0->ctr.hits; // the union: identical on every GPU
+        g->nvlink_bytes = (int64_t)(n - 1) * ((int64_t)sizeof(Item16) * c0->ctr.hits + 16ll * n); // every hit travels to n-1 peers; 16 B of flags per (source, peer)
+        return STF_OK;
+    }
+    GFAIL(STF_E_CUDA, "internal: the group round did not converge");
+}
+
 extern "C" int32_t stf_counters(stf_ctx* ctx, stf_counters_t* out) {
     if (!ctx || !out) return STF_E_ARG;
     *out = ctx->ctr;

@@ -104,3 +104,55 @@ class ShardedFit:
         nh = C.c_int64(0)
         d._ck(d.lib.stf_shard_step(d.h, recv.data_ptr(), self.world, stride, seed, iteration, C.byref(nh)))
         return nh.value
+
+
+class GpuGroup:
+    """Several GPUs driven from ONE process (stf_group_*): one context per device holding the same scene; fit rounds are
+    split by candidate records and the GPUs exchange their hit lists themselves over NVLink peer memory (device-side flag
+    barrier), so a round costs one host synchronisation per GPU and no collective call.  `replicas[i]` is the DeviceQTrees
+    view of GPU i (state changes such as setshift must be applied to every replica: `each(fn)`)."""
+
+    def __init__(self, trees, devices, is_mask=None, scene=None):
+        from . import _lib
+        from .qtrees import DeviceQTrees
+        self.lib = _lib.load()
+        devs = np.ascontiguousarray(np.asarray(list(devices), np.int32))
+        self.h = C.c_void_p()
+        rc = self.lib.stf_group_create(len(devs), devs.ctypes.data, C.byref(self.h))
+        if rc != 0:
+            raise _lib.StuffingError(rc, "stf_group_create failed (no CUDA device, or no peer access between the listed devices)")
+        trees = list(trees)
+        self.replicas = [DeviceQTrees(trees, device=int(dv), is_mask=is_mask, scene=scene, handle=self.lib.stf_group_ctx(self.h, i)) for i, dv in enumerate(devs)]
+        self.devices = [int(x) for x in devs]
+
+    def __len__(self):
+        return len(self.replicas)
+
+    def each(self, fn):
+        return [fn(d) for d in self.replicas]
+
+    def fit_round(self, seed: int, iteration: int, labels=None, partial: bool = False) -> int:
+        lb = None if labels is None else np.ascontiguousarray(np.asarray(list(labels), np.int32))
+        nh = C.c_int64(0)
+        rc = self.lib.stf_group_fit_round(self.h, 1 if partial else 0, 0 if lb is None else len(lb), None if lb is None else lb.ctypes.data, seed, iteration, C.byref(nh))
+        if rc != 0:
+            from . import _lib
+            raise _lib.StuffingError(rc, self.lib.stf_group_last_error(self.h).decode())
+        return nh.value
+
+    @property
+    def nvlink_bytes(self) -> int:
+        return int(self.lib.stf_group_nvlink_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            for d in self.replicas:
+                d.h = None
+            self.lib.stf_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -159,13 +159,18 @@ class DeviceTree:
 class DeviceQTrees:
     """Vector{U8SQTree} resident on one GPU: a context of the C ABI."""
 
-    def __init__(self, trees, device: int = 0, is_mask=None, scene=None):
+    def __init__(self, trees, device: int = 0, is_mask=None, scene=None, handle=None):
+        """`handle`: upload into an existing context (one of a GpuGroup's) instead of creating one; the group owns it"""
         self.lib = _lib.load()
         trees = list(trees)
-        self.h = C.c_void_p()
-        rc = self.lib.stf_create(device, C.byref(self.h))
-        if rc != 0:
-            raise StuffingError(rc, "stf_create failed: no CUDA device (there is no CPU fallback)")
+        self._owns = handle is None
+        if handle is not None:
+            self.h = C.c_void_p(handle)
+        else:
+            self.h = C.c_void_p()
+            rc = self.lib.stf_create(device, C.byref(self.h))
+            if rc != 0:
+                raise StuffingError(rc, "stf_create failed: no CUDA device (there is no CPU fallback)")
         self.n = len(trees)
         self.device = device
         self.defaults = [t.default for t in trees]
@@ -194,6 +199,7 @@ class DeviceQTrees:
         batches of scenes.  `payload_dev_ptr`: the payload already lives in HBM (needs 32 bytes of zeroed slack)."""
         self = cls.__new__(cls)
         self.lib = _lib.load()
+        self._owns = True
         self.h = C.c_void_p()
         rc = self.lib.stf_create(device, C.byref(self.h))
         if rc != 0:
@@ -218,7 +224,7 @@ class DeviceQTrees:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and getattr(self, "_owns", True):
                 self.lib.stf_destroy(self.h)
                 self.h = None
         except Exception:

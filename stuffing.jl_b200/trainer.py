@@ -117,6 +117,24 @@ def fit_round_positions(qts, labels=None, optimiser=None, clock: StepClock | Non
     return nh.value, rs, cs
 
 
+def fit_rounds(qts, n_rounds, labels=None, optimiser=None, clock: StepClock | None = None, partial=False, positions=False, level=1):
+    """`n_rounds` device-resident rounds of totalcollisions(qtrees[, labels]; unique=false) → batchsteps! with ONE host
+    synchronisation (stf_fit_rounds); returns (per-round length(colist), totals dict[, rs, cs])"""
+    d = _dev(qts)
+    clock = clock or _default_clock
+    _set_opt(d, optimiser)
+    lb = None if labels is None else i32(list(labels))
+    nh = np.zeros(max(1, n_rounds), np.int64)
+    tot = np.zeros(8, np.int64)
+    rs = np.zeros(d.n, np.int32) if positions else None
+    cs = np.zeros(d.n, np.int32) if positions else None
+    d._ck(d.lib.stf_fit_rounds(d.h, 1 if partial else 0, 0 if lb is None else len(lb), ptr(lb), clock.seed, clock.iteration, n_rounds, ptr(nh), ptr(tot),
+                               level if positions else 0, ptr(rs), ptr(cs)))
+    clock.iteration += n_rounds
+    totals = dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in tot)))
+    return (nh[:n_rounds], totals, rs, cs) if positions else (nh[:n_rounds], totals)
+
+
 def _labels_of(colist):
     seen, out = set(), []
     for r in colist:

@@ -153,3 +153,102 @@ def test_two_rank_gloo_shard_exchange(tmp_path):
                           "--master-port", "29543", str(script)], env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "SHARD-OK 1237 768" in out.stdout
+
+
+def _julia_ccalls():
+    """(name, return type, [argument types]) of every `ccall((:name, LIB), Ret, (Args...), ...)` in julia/StuffingB200.jl"""
+    import re
+    src = open(os.path.join(ROOT, "julia", "StuffingB200.jl")).read()
+    out = []
+    for m in re.finditer(r"ccall\(\(:(\w+), LIB\),\s*([\w{}]+),\s*\(", src):
+        i, depth = m.end(), 1
+        while depth:                      # the argument-type tuple, with nested braces/parentheses
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        tup = src[m.end():i - 1]
+        args, cur, lvl = [], "", 0
+        for ch in tup:
+            if ch == "," and lvl == 0:
+                args.append(cur.strip()); cur = ""
+            else:
+                lvl += {"{": 1, "}": -1}.get(ch, 0); cur += ch
+        if cur.strip():
+            args.append(cur.strip())
+        out.append((m.group(1), m.group(2), args))
+    return out
+
+
+def test_julia_glue_ccalls_match_the_library_exports():
+    """the Julia binding cannot run here (no Julia in the image): every ccall in it is checked statically against the
+    ctypes declarations of the same export — name, arity, and the C type class of the result and of every argument"""
+    import ctypes as C
+    S = product()
+    jl2c = {"Int32": C.c_int32, "Int64": C.c_int64, "UInt64": C.c_uint64, "Float64": C.c_double, "Cstring": C.c_char_p, "Cvoid": None}
+    calls = _julia_ccalls()
+    assert len(calls) >= 30
+    seen = set()
+    for name, ret, args in calls:
+        assert name in S._lib.EXPORTS, f"{name}: not an export of the library"
+        cres, cargs = S._lib.EXPORTS[name]
+        assert len(args) == len(cargs), (name, args, cargs)
+        want_ret = C.c_void_p if ret.startswith("Ptr{") else jl2c[ret]
+        assert want_ret == cres, (name, ret, cres)
+        for a, ca in zip(args, cargs):
+            if a.startswith("Ptr{"):
+                assert ca in (C.c_void_p, C.c_char_p) or hasattr(ca, "contents") or "LP_" in getattr(ca, "__name__", ""), (name, a, ca)
+            else:
+                assert jl2c[a] == ca, (name, a, ca)
+        seen.add(name)
+    # the hot-path surface of SURVEY §8b is bound
+    for must in ("stf_upload_objects", "stf_collision", "stf_totalcollisions_spacial", "stf_totalcollisions_native", "stf_partialcollisions", "stf_locate",
+                 "stf_linked_locate", "stf_grad2d", "stf_batchsteps", "stf_fit_round", "stf_fit_rounds", "stf_set_shifts", "stf_get_shifts", "stf_download_trees",
+                 "stf_group_create", "stf_group_fit_round"):
+        assert must in seen, must
+
+
+def test_narrow_bit_helpers_on_the_host(tmp_path):
+    """the pure bit helpers of the word-parallel narrow phase (stf_narrow.cuh: raster -> Morton order, frontier spreading,
+    field squeezing) compiled for the HOST with nvcc and checked exhaustively / on random masks"""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = tmp_path / "t.cu"
+    src.write_text(r'''
+#include "%s/stuffing.jl_b200/csrc/stf_narrow.cuh"
+#include <cstdio>
+#include <cstdlib>
+int main() {
+    int bad = 0;
+    for (int d = 1; d <= 3; d++) {
+        int n = 1 << d;
+        for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+            int be = n - 1 - j, al = n - 1 - i, key = 0;
+            for (int t = d - 1; t >= 0; t--) key = (key << 2) | ((((be >> t) & 1) << 1) | ((al >> t) & 1));
+            uint64_t r = 1ull << (j * n + i), m;
+            if (d == 1) m = nw_morton1((uint32_t)r); else if (d == 2) m = nw_morton2((uint32_t)r); else m = nw_morton3(r);
+            if (m != (1ull << key)) bad++;
+            int a2, b2; nw_unkey((uint32_t)key, &a2, &b2);
+            if (a2 != al || b2 != be) bad++;
+        }
+    }
+    srand(1);
+    for (int it = 0; it < 1000; it++) {
+        uint64_t r = ((uint64_t)rand() << 40) ^ ((uint64_t)rand() << 20) ^ rand(), w = 0;
+        for (int p = 0; p < 64; p++) if ((r >> p) & 1) w |= nw_morton3(1ull << p);
+        if (w != nw_morton3(r)) bad++;
+        uint32_t r16 = r & 0xFFFF, w16 = 0;
+        for (int p = 0; p < 16; p++) if ((r16 >> p) & 1) w16 |= nw_morton2(1u << p);
+        if (w16 != nw_morton2(r16)) bad++;
+    }
+    for (uint32_t m = 0; m < 16; m++) { uint32_t w = 0; for (int k = 0; k < 4; k++) if ((m >> k) & 1) w |= 0xFu << (4 * k); if (w != nw_children16(m)) bad++; }
+    for (uint32_t m = 0; m < 65536; m++) { uint64_t w = 0; for (int k = 0; k < 16; k++) if ((m >> k) & 1) w |= 0xFull << (4 * k); if (w != nw_children64(m)) bad++; }
+    for (int it = 0; it < 100000; it++) { uint32_t x = ((uint32_t)rand() << 16) ^ rand(), w = 0; for (int i = 0; i < 16; i++) if ((x >> (2 * i + 1)) & 1) w |= 1u << i; if (w != nw_squeeze_odd(x)) bad++; }
+    printf("bad = %%d\n", bad);
+    return bad != 0;
+}
+''' % ROOT)
+    exe = tmp_path / "t"
+    subprocess.check_call([nvcc, "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", str(exe), str(src)])
+    assert subprocess.run([str(exe)], capture_output=True, text=True).returncode == 0

@@ -93,6 +93,39 @@ def test_c2_fit_loop_1k_rects_1024_canvas(S, orc):
     assert_same_trees(d, qo, labels=list(range(1, 1002, 7)))
 
 
+def test_c2_fit_rounds_one_sync_equals_round_by_round(S, orc):
+    """stf_fit_rounds: 50 device-resident rounds with one host synchronisation == 50 calls of stf_fit_round == the golden
+    vector; a fresh context starts with buffers that are too small, so the cancel-and-continue path runs as well"""
+    W = workloads.load_workload("c2")
+    d = workloads.device_scene(S, W)
+    clock = S.trainer.StepClock(seed=W["seed"])
+    nh, tot, rs, cs = S.trainer.fit_rounds(d, W["rounds"], None, S.Momentum(0.25, 0.5), clock, positions=True)
+    assert nh.tolist() == W["round_hits"].tolist() and clock.iteration == W["rounds"]
+    assert np.array_equal(rs, W["final_rs"]) and np.array_equal(cs, W["final_cs"])
+    assert tot["items"] == int(W["round_items"].sum()) and tot["hits"] == int(W["round_hits"].sum()) and tot["visited"] == int(W["round_visited"].sum())
+    # a second pass from the restored layout, in chunks, partial mode over every movable label (same collisions: :65-69)
+    lab = np.arange(2, len(d) + 1, dtype=np.int32)
+    d.setshift(lab, 1, W["rs"][1:], W["cs"][1:])
+    d._ck(d.lib.stf_reset_velocity(d.h, 0, None))
+    S.locate(d, None, S.linked_spacial_qtree(d))
+    clock = S.trainer.StepClock(seed=W["seed"])
+    got = []
+    for chunk in (1, 7, 30, 12):
+        nh, _ = S.trainer.fit_rounds(d, chunk, lab, S.Momentum(0.25, 0.5), clock, partial=True)
+        got += nh.tolist()
+    rs2, cs2 = d.getshifts()
+    qo = workloads.oracle_scene(orc, W)
+    tree_o = orc.LinkedTree(qo); tree_o.locate(qo)
+    opt = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    want = []
+    for k in range(50):
+        hs, _ = _sorted_hits(orc, qo, lab, tree_o)
+        want.append(len(hs))
+        orc.batchsteps(qo, hs, opt, seed=W["seed"], iteration=k)
+    ro, co = orc.getshifts(qo)
+    assert got == want and np.array_equal(rs2, ro) and np.array_equal(cs2, co)
+
+
 def _orc_trainepoch_E(orc, qo, opt, seed, it0):
     """trainepoch_E! (fit.jl:85-99) on the oracle in canonical mode, the twin of trainer.trainepoch_E"""
     def total(labels=None):  # the dispatcher (qtree_functions.jl:270-276): native below the threshold, spacial above
@@ -192,6 +225,54 @@ def test_two_contexts_in_one_process(S, orc):
     for it in range(2):
         res = [S.trainer.fit_round_positions(d, None, S.Momentum(0.25, 0.5), clock[k]) for k, d in enumerate(ds)]
         assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
+def test_gpu_group_item_parallel_rounds(S, orc):
+    """stf_group_*: one process drives several contexts; every round is split by candidate records and the hit lists are
+    exchanged by the GPUs themselves (peer stores + device-side flag barrier).  Replicas must stay bit-identical to each
+    other, to a single-context stf_fit_round, and to the oracle.  On a one-GPU box the group's contexts share device 0."""
+    import torch
+    from stuffing_b200 import parallel
+    ndev = torch.cuda.device_count()
+    devices = list(range(min(ndev, 4))) if ndev > 1 else [0, 0, 0]
+    W = workloads.load_workload("c1k")
+    qo = workloads.oracle_scene(orc, W)
+    s = W["mask_side"]
+    trees = [S.maskqtree(np.ones((s, s), bool))] + [S.qtree(o, W["canvas"]) for o in W["objs"]]
+    for t, r, c in zip(trees, W["rs"], W["cs"]):
+        t.shift1 = (int(r), int(c))
+    g = parallel.GpuGroup(trees, devices)
+    single = S.DeviceQTrees(trees)
+    opt = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    g.each(lambda d: S.trainer._set_opt(d, S.Momentum(0.25, 0.5)))
+    clock = S.trainer.StepClock(seed=5)
+    for it in range(5):
+        hs, info = _sorted_hits(orc, qo)
+        nh_g = g.fit_round(5, it)
+        nh_s = S.trainer.fit_round(single, None, S.Momentum(0.25, 0.5), clock)
+        assert nh_g == nh_s == len(hs), (it, nh_g, nh_s, len(hs))
+        assert sum(d.counters()["items"] + d.counters()["direct"] for d in g.replicas) == info["n_items"] + info["n_direct"]  # the shares add up
+        orc.batchsteps(qo, hs, opt, seed=5, iteration=it)
+        ro, co = orc.getshifts(qo)
+        rs, cs = single.getshifts()
+        assert np.array_equal(rs, ro) and np.array_equal(cs, co)
+        for d in g.replicas:
+            r2, c2 = d.getshifts()
+            assert np.array_equal(r2, ro) and np.array_equal(c2, co), it
+        assert g.nvlink_bytes == (len(devices) - 1) * (16 * nh_g + 16 * len(devices))
+    # partialcollisions mode over a moved subset
+    labels = list(range(2, 400))
+    for d in g.replicas + [single]:
+        S.locate(d, None, S.linked_spacial_qtree(d))
+    nh_g = g.fit_round(5, 9, labels=labels, partial=True)
+    clock9 = S.trainer.StepClock(seed=5); clock9.iteration = 9
+    nh_s = S.trainer.fit_round(single, labels, S.Momentum(0.25, 0.5), clock9, partial=True)
+    assert nh_g == nh_s
+    rs, cs = single.getshifts()
+    for d in g.replicas:
+        r2, c2 = d.getshifts()
+        assert np.array_equal(r2, rs) and np.array_equal(c2, cs)
+    g.close()
 
 
 def test_c4_100k_objects_16384_canvas(S, orc):
