@@ -15,3 +15,5 @@ from . import trainer  # noqa: F401
 from .trainer import Momentum, SGD, batchsteps, fit, fit_round, grad2d, train  # noqa: F401
 from . import place as placement  # noqa: F401
 from .place import place, overlap_ground  # noqa: F401
+from . import io  # noqa: F401,E402
+from .io import charimage, charmat, load_scene, packing, save_scene  # noqa: F401,E402

@@ -252,3 +252,28 @@ int main() {
     exe = tmp_path / "t"
     subprocess.check_call([nvcc, "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", str(exe), str(src)])
     assert subprocess.run([str(exe)], capture_output=True, text=True).returncode == 0
+
+
+def test_charimage_and_npy_scene_exchange(tmp_path):
+    """f-4 wire formats on the host: charimage glyphs and elision as src/qtrees.jl:308-345; save_scene/load_scene round
+    trip through plain .npy files in Fortran order (what julia/NpyIO.jl reads)"""
+    S = product()
+    m = np.array([[1, 2, 3], [2, 2, 9]], np.uint8)
+    assert S.charimage(m) == "░▓▒\n▓▓▞\n"
+    big = np.full((60, 10), 1, np.uint8); big[0, 0] = 2
+    rows = S.charimage(big, maxlen=9).split("\n")[:-1]
+    assert len(rows) == 4 + 1 + 4 and rows[0][0] == "▓" and rows[4][0] == "⋮" and len(rows[4]) == 9   # 4 rows, an elision row, 4 rows
+    wide = np.full((3, 60), 3, np.uint8)
+    rows = S.charimage(wide, maxlen=9).split("\n")[:-1]
+    assert all(len(r) == 9 and r[4] == "…" for r in rows)
+    rng = np.random.default_rng(0)
+    trees = [S.maskqtree(np.ones((40, 50), bool))] + [S.qtree(rng.random((int(rng.integers(3, 12)), int(rng.integers(3, 12)))) < 0.6, 128) for _ in range(5)]
+    for k, t in enumerate(trees[1:]):
+        t.shift1 = (3 * k + 1, 40 - 5 * k)
+    S.save_scene(str(tmp_path / "scene"), trees)
+    hdr = open(tmp_path / "scene" / "tree_00002.npy", "rb").read(128)
+    assert hdr[:6] == b"\x93NUMPY" and b"'fortran_order': True" in hdr and b"|u1" in hdr
+    back = S.load_scene(str(tmp_path / "scene"))
+    assert len(back) == len(trees)
+    for a, b in zip(trees, back):
+        assert np.array_equal(a.codes, b.codes) and a.shift1 == b.shift1 and a.default == b.default and a.canvas == b.canvas
