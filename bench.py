@@ -555,6 +555,43 @@ def run_ours(args):
             hits_job = float(hits)        # the hit list is the union, identical on every rank
     else:                                 # replicas: N copies of the same job
         items_job, hits_job = float(items) * world, float(hits) * world
+    # ---- the sharded configurations of the path, next to the replica headline: (1) C5, the 4096 scenes split
+    # over the ranks (strong scaling, no data-path collective); (2) C1 item-parallel: rank 0 drives ALL GPUs of the box from
+    # one process through stf_group_* (hit lists exchanged by the GPUs over NVLink peer memory).  Both are timed at every N,
+    # N = 1 included, so the driver's per-N files carry the speed-ups.
+    sharded = None
+    if which == "c1" and not args.no_sharded:
+        sharded = {}
+        try:
+            sc5 = DevScene(S, torch, "c5", local, rank, world, False, dist)
+            for _ in range(3):
+                sc5.step(True)
+            sc5.step(True, count=True)
+            bracket()
+            tot5 = 0.0
+            for _ in range(5):
+                with torch.cuda.stream(sc5.stream):
+                    flush.zero_()
+                a5, b5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a5.record(sc5.stream); sc5.step(True); b5.record(sc5.stream); b5.synchronize()
+                tot5 += a5.elapsed_time(b5)
+            t5 = torch.tensor([tot5 / 5, float(sc5.tot["items"])], dtype=torch.float64, device="cuda")
+            t5max = t5.clone()
+            if dist is not None:
+                dist.all_reduce(t5max, op=dist.ReduceOp.MAX); dist.all_reduce(t5, op=dist.ReduceOp.SUM)
+            sharded["c5_scene_split"] = {"workload": NAMES["c5"], "gpus": world, "scaling": "strong", "ms_per_step": float(t5max[0]), "items_per_step": int(float(t5[1])),
+                                         "items_per_s": float(t5[1]) / (float(t5max[0]) * 1e-3), "scene_iterations_per_s": 4096e3 / float(t5max[0]), "collective": "none (independent scenes)"}
+            del sc5
+        except Exception as e:  # reporting only
+            sharded["c5_scene_split"] = {"error": str(e)}
+        bracket()
+        if rank == 0:
+            try:
+                ndev = min(world, torch.cuda.device_count())
+                sharded["c1_item_parallel_group"] = group_bench(S, torch, "c1", list(range(ndev)), 10, 3)
+            except Exception as e:
+                sharded["c1_item_parallel_group"] = {"error": str(e)}
+        bracket()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -620,6 +657,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     if collide_only:
         line["collide_only"] = collide_only
+    if sharded:
+        line["sharded"] = sharded
     if sc.sharded is not None:
         line["nvlink_bytes_per_step"] = int(sc.sharded.bytes_exchanged / max(1, 2 * (args.steps + warm)))
     print(json.dumps(line), flush=True)
@@ -649,9 +688,8 @@ def group_bench(S, torch, which, devices, steps, warm):
         lib.stf_set_optimiser(d.h, 2, 0.25, 0.5)
 
     def step():
-        for d in g.replicas:
-            d._ck(lib.stf_set_shifts(d.h, len(movable), movable.ctypes.data, 1, rs.ctypes.data, cs.ctypes.data, 0))
-            d._ck(lib.stf_reset_velocity(d.h, 0, None))
+        g.setshift(movable, 1, rs, cs)
+        g.reset_velocity()
         return g.fit_round(SEED, ITERATION)
 
     for _ in range(warm):
@@ -814,6 +852,7 @@ def main():
     ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--shard", default="scenes", choices=["scenes", "items"])
     ap.add_argument("--no-build-roofline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded records (C5 scene split, C1 item-parallel group) of the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

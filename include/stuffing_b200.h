@@ -223,14 +223,18 @@ int32_t stf_shard_step(stf_ctx* ctx, const void* recv_dev, int32_t nranks, int64
  * stf_set_optimiser, ...) to every context.  stf_group_fit_round = stf_fit_round over the group: GPU i generates and tests
  * the candidate pairs of the sorted records i, i+n, ..., the GPUs exchange their hit lists THEMSELVES (peer stores over
  * NVLink into every peer's gather buffer + a device-side flag barrier, no collective call and no host synchronisation in
- * between), and every GPU runs the same canonical batchsteps on the union, so the replicas stay bit-identical.  One host
- * synchronisation per GPU and round.  *nhits = length(colist).  Needs a scene that fits the single-scene latency path. */
+ * between), and every GPU runs the same canonical batchsteps on the union, so the replicas stay bit-identical.  Inside the
+ * library every GPU has its own (persistent) host thread, so the GPUs are enqueued in parallel; one host synchronisation
+ * per GPU and round.  *nhits = length(colist).  Needs a scene that fits the single-scene latency path. */
 typedef struct stf_group stf_group;
 int32_t stf_group_create(int32_t n, const int32_t* devices, stf_group** out);
 void stf_group_destroy(stf_group* g);
 int32_t stf_group_size(const stf_group* g);
 stf_ctx* stf_group_ctx(stf_group* g, int32_t i);
 const char* stf_group_last_error(const stf_group* g);
+/* setshift!/shift! (stf_set_shifts with host arrays) and reset!(optimiser) on every replica, the GPUs driven in parallel */
+int32_t stf_group_set_shifts(stf_group* g, int32_t n, const int32_t* labels, int32_t level, const int32_t* rs, const int32_t* cs, int32_t mode);
+int32_t stf_group_reset_velocity(stf_group* g, int32_t n, const int32_t* labels);
 int32_t stf_group_fit_round(stf_group* g, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits);
 /* bytes the last stf_group_fit_round moved between GPUs (hit records and flags pushed to peers) */
 int64_t stf_group_nvlink_bytes(const stf_group* g);

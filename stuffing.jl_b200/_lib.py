@@ -69,6 +69,8 @@ EXPORTS = {
     "stf_group_size": (C.c_int32, [C.c_void_p]),
     "stf_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "stf_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "stf_group_set_shifts": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
+    "stf_group_reset_velocity": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "stf_group_fit_round": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "stf_group_nvlink_bytes": (C.c_int64, [C.c_void_p]),
     "stf_counters": (C.c_int32, [C.c_void_p, C.c_void_p]),

@@ -916,6 +916,16 @@ __global__ void __launch_bounds__(256) k_shard_push(const Item16* __restrict__ h
         asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f + 1), "l"(epoch) : "memory");
     }
 }
+// a GPU that cannot run its part of the round (an allocation failed on the host side) still answers: empty list + cancel bit,
+// so that no peer waits for it forever
+__global__ void k_shard_poison(PeerSet P, int rank, unsigned long long epoch) {
+    if ((int)threadIdx.x < P.n) {
+        unsigned long long* f = P.flags[threadIdx.x] + 2 * rank;
+        f[0] = 1ull << 63;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f + 1), "l"(epoch) : "memory");
+    }
+}
 __global__ void __launch_bounds__(256) k_shard_gather(const Item16* __restrict__ gather, const unsigned long long* __restrict__ flags, int nranks, int64_t seg_cap,
                                                       unsigned long long epoch, Item16* __restrict__ hits, int64_t hits_cap, unsigned long long* __restrict__ nhits, int* __restrict__ status) {
     pdl_sync();

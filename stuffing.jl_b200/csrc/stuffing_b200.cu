@@ -10,6 +10,12 @@
 #include "stf_step.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -1600,10 +1606,55 @@ extern "C" int32_t stf_shard_step(stf_ctx* ctx, const void* recv_dev, int32_t nr
 // replicated, every fit round is split by candidate records, and the local hit lists are exchanged by the GPUs themselves:
 // peer stores over NVLink + a device-side flag barrier (k_shard_push / k_shard_gather).  The host only enqueues: no
 // collective call, no host synchronisation between the halves of a round — one synchronisation per GPU at the end.
+// One HOST THREAD per GPU of the group: enqueueing a round is ~15 launches per device, so a single thread would serialise
+// the GPUs on the host side (measured: 2 GPUs slower than 1).  The workers are persistent; a job is a function of the
+// device index; after a job a worker spins briefly (the next round usually follows at once) before it sleeps on a
+// condition variable.  Thread 0 is the caller's own thread.
+struct GroupPool {
+    std::vector<std::thread> th;
+    std::mutex mu; std::condition_variable cv;
+    std::function<void(int)> job;
+    std::atomic<unsigned long long> gen{0}; std::atomic<int> pending{0}; std::atomic<bool> quit{false};
+    void start(int n) {
+        for (int i = 1; i < n; i++) th.emplace_back([this, i] {
+            unsigned long long seen = 0;
+            for (;;) {
+                auto t0 = std::chrono::steady_clock::now();
+                while (gen.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_acquire)) {
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return gen.load(std::memory_order_acquire) != seen || quit.load(std::memory_order_acquire); });
+                        break;
+                    }
+                }
+                if (quit.load(std::memory_order_acquire)) return;
+                seen = gen.load(std::memory_order_acquire);
+                job(i);
+                pending.fetch_sub(1, std::memory_order_acq_rel);
+            }
+        });
+    }
+    void run(int n, const std::function<void(int)>& f) { // f(i) for every device i, f(0) on the calling thread
+        if (n == 1) { f(0); return; }
+        job = f;
+        pending.store(n - 1, std::memory_order_release);
+        { std::lock_guard<std::mutex> lk(mu); gen.fetch_add(1, std::memory_order_acq_rel); }
+        cv.notify_all();
+        f(0);
+        while (pending.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu); quit.store(true, std::memory_order_release); }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+};
 struct stf_group {
     std::vector<stf_ctx*> ctx; std::string err;
     unsigned long long epoch = 0; int64_t seg_cap = 0;
     int64_t nvlink_bytes = 0; // bytes pushed to peer GPUs by the last round (hit records + flags, excluding the local copy)
+    GroupPool pool;
 };
 extern "C" int32_t stf_group_create(int32_t n, const int32_t* devices, stf_group** out) {
     if (!out || n < 1 || n > STF_MAX_GROUP || !devices) return STF_E_ARG;
@@ -1633,11 +1684,13 @@ extern "C" int32_t stf_group_create(int32_t n, const int32_t* devices, stf_group
             ctx->gdone.ensure(sizeof(unsigned int) * 4) != cudaSuccess) { for (stf_ctx* x : g->ctx) stf_destroy(x); delete g; return STF_E_CUDA; }
         cudaMemset(ctx->gflags.p, 0, sizeof(unsigned long long) * 2 * STF_MAX_GROUP); cudaMemset(ctx->gdone.p, 0, sizeof(unsigned int) * 4);
     }
+    g->pool.start(n);
     *out = g;
     return STF_OK;
 }
 extern "C" void stf_group_destroy(stf_group* g) {
     if (!g) return;
+    g->pool.stop();
     for (stf_ctx* x : g->ctx) stf_destroy(x);
     delete g;
 }
@@ -1645,6 +1698,22 @@ extern "C" int32_t stf_group_size(const stf_group* g) { return g ? (int32_t)g->c
 extern "C" stf_ctx* stf_group_ctx(stf_group* g, int32_t i) { return (g && i >= 0 && i < (int32_t)g->ctx.size()) ? g->ctx[i] : nullptr; }
 extern "C" const char* stf_group_last_error(const stf_group* g) { return g ? g->err.c_str() : "no group"; }
 extern "C" int64_t stf_group_nvlink_bytes(const stf_group* g) { return g ? g->nvlink_bytes : 0; }
+// the same state change on every replica, the GPUs driven in parallel: setshift!/shift! (stf_set_shifts) and reset!(optimiser)
+extern "C" int32_t stf_group_set_shifts(stf_group* g, int32_t n, const int32_t* labels, int32_t level, const int32_t* rs, const int32_t* cs, int32_t mode) {
+    if (!g) return STF_E_ARG;
+    if (mode & (STF_SHIFT_DEVICE_ARRAYS | STF_SHIFT_DEVICE_LABELS)) { g->err = "group calls take host arrays"; return STF_E_ARG; }
+    std::vector<int32_t> rc(g->ctx.size(), STF_OK);
+    g->pool.run((int)g->ctx.size(), [&](int i) { rc[i] = stf_set_shifts(g->ctx[i], n, labels, level, rs, cs, mode); });
+    for (size_t i = 0; i < rc.size(); i++) if (rc[i]) { g->err = g->ctx[i]->err; return rc[i]; }
+    return STF_OK;
+}
+extern "C" int32_t stf_group_reset_velocity(stf_group* g, int32_t n, const int32_t* labels) {
+    if (!g) return STF_E_ARG;
+    std::vector<int32_t> rc(g->ctx.size(), STF_OK);
+    g->pool.run((int)g->ctx.size(), [&](int i) { rc[i] = stf_reset_velocity(g->ctx[i], n, labels); });
+    for (size_t i = 0; i < rc.size(); i++) if (rc[i]) { g->err = g->ctx[i]->err; return rc[i]; }
+    return STF_OK;
+}
 
 #define GFAIL(code, msg) do { g->err = (msg); return (code); } while (0)
 extern "C" int32_t stf_group_fit_round(stf_group* g, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits) {
@@ -1661,45 +1730,44 @@ extern "C" int32_t stf_group_fit_round(stf_group* g, int32_t mode, int32_t nl, c
     for (int attempt = 0; attempt < 4; attempt++) {
         if (!fast_path_ok(c0, linked ? c0->n : nl)) GFAIL(STF_E_STATE, "scene too large for the item-parallel latency path of a group (use scene-parallel contexts)");
         const unsigned long long epoch = ++g->epoch;
-        // ---- phase A on every GPU: broad phase + narrow phase over its share of the records, then push the local hits to all peers
-        for (int i = 0; i < n; i++) {
+        std::vector<int32_t> rcs(n, STF_OK);
+        // every GPU on its own host thread.  Phase A: broad phase + narrow phase over its share of the records, then the local
+        // hits are pushed to all peers.  Phase B: wait for all peers ON THE DEVICE, union of the hit lists, canonical order,
+        // batchsteps.  Then the GPU's one synchronisation.
+        g->pool.run(n, [&](int i) {
             stf_ctx* ctx = g->ctx[i];
-            if (cudaSetDevice(ctx->device) != cudaSuccess) GFAIL(STF_E_CUDA, "cudaSetDevice failed");
+            bool pushed = false;
+            auto fail = [&](int32_t code, const char* msg) {
+                if (msg) ctx->err = msg;
+                rcs[i] = code;
+                if (!pushed) { ctx->launches++; k_shard_poison<<<1, 32, 0, ctx->st>>>(P, i, epoch); cudaStreamSynchronize(ctx->st); } // the peers must not wait for this GPU forever
+            };
+            if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(STF_E_CUDA, "cudaSetDevice failed");
             stage_reset(ctx); ctx->after_kernel = false; ctx->last_result = 0;
             ctx->shard_rank = i; ctx->shard_n = n;
             int32_t r = spacial_core_fast(ctx, nl, labels, linked);
             ctx->shard_rank = 0; ctx->shard_n = 1;
-            if (r) GFAIL(r, ctx->err);
+            if (r) return fail(r, nullptr);
             FinalizeArgs F = {}; set_overflow_check(ctx, F);
             LAUNCH_PDL(ctx, k_shard_push, 8, 256, 0, (const Item16*)ctx->hits.as<Item16>(), (const unsigned long long*)(ctx->counts.as<unsigned long long>() + C_NHITS), g->seg_cap, P, i, epoch,
                        (const int*)STATUSP(ctx), F.n_items_dev, F.item_cap, ctx->gdone.as<unsigned int>());
-            if (cudaGetLastError() != cudaSuccess) GFAIL(STF_E_CUDA, "k_shard_push launch failed");
-        }
-        // ---- phase B on every GPU: wait for all peers (device-side), union of the hit lists, canonical order, batchsteps
-        for (int i = 0; i < n; i++) {
-            stf_ctx* ctx = g->ctx[i];
-            cudaSetDevice(ctx->device);
-            if (ctx->hits.ensure(sizeof(Item16) * (size_t)n * g->seg_cap, true, ctx->st) != cudaSuccess) GFAIL(STF_E_CUDA, "hit buffer allocation failed");
+            if (cudaGetLastError() != cudaSuccess) return fail(STF_E_CUDA, "k_shard_push launch failed");
+            pushed = true;
+            if (ctx->hits.ensure(sizeof(Item16) * (size_t)n * g->seg_cap, true, ctx->st) != cudaSuccess) return fail(STF_E_CUDA, "hit buffer allocation failed");
             LAUNCH_PDL(ctx, k_shard_gather, 16, 256, 0, (const Item16*)ctx->gather.as<Item16>(), (const unsigned long long*)ctx->gflags.as<unsigned long long>(), n, g->seg_cap, epoch,
                        ctx->hits.as<Item16>(), (int64_t)(ctx->hits.cap / sizeof(Item16)), ctx->counts.as<unsigned long long>() + C_NHITS, STATUSP(ctx));
-            if (cudaGetLastError() != cudaSuccess) GFAIL(STF_E_CUDA, "k_shard_gather launch failed");
-            int32_t r = fast_round_tail(ctx, seed, iteration, true); if (r) GFAIL(r, ctx->err);
-        }
-        // ---- one synchronisation per GPU
-        bool again = false; int32_t rc = STF_OK;
-        int64_t local_sum = 0;
-        for (int i = 0; i < n; i++) {
-            stf_ctx* ctx = g->ctx[i];
-            cudaSetDevice(ctx->device);
-            int32_t r = sync_counts(ctx); if (r && !rc) { rc = r; g->err = ctx->err; }
-            if (fast_round_verdict(ctx)) again = true;
-        }
-        if (rc) return rc;
+            if (cudaGetLastError() != cudaSuccess) return fail(STF_E_CUDA, "k_shard_gather launch failed");
+            r = fast_round_tail(ctx, seed, iteration, true); if (r) return fail(r, nullptr);
+            r = sync_counts(ctx); if (r) return fail(r, nullptr);
+        });
+        bool again = false;
+        for (int i = 0; i < n; i++) if (rcs[i]) GFAIL(rcs[i], g->ctx[i]->err); // (a failed enqueue on one GPU leaves its peers' gather kernels without its flag only if the push never ran: every error above happens after the push or before any launch of the round)
+        for (int i = 0; i < n; i++) { cudaSetDevice(g->ctx[i]->device); if (fast_round_verdict(g->ctx[i])) again = true; }
         if (again) { // a list was too small somewhere (every GPU dropped the round: the cancel bit travels with the hits): sizes are grown, run it again
             for (stf_ctx* c : g->ctx) if (c->force_big) GFAIL(STF_E_STATE, "scene too large for the item-parallel latency path of a group (use scene-parallel contexts)");
             continue;
         }
-        for (int i = 0; i < n; i++) { stf_ctx* ctx = g->ctx[i]; read_round_counters(ctx); ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES]; local_sum += 0; }
+        for (int i = 0; i < n; i++) { stf_ctx* ctx = g->ctx[i]; read_round_counters(ctx); ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES]; }
         if (nhits) *nhits = c0->ctr.hits; // the union: identical on every GPU
         g->nvlink_bytes = (int64_t)(n - 1) * ((int64_t)sizeof(Item16) * c0->ctr.hits + 16ll * n); // every hit travels to n-1 peers; 16 B of flags per (source, peer)
         return STF_OK;

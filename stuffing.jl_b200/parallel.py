@@ -131,6 +131,19 @@ class GpuGroup:
     def each(self, fn):
         return [fn(d) for d in self.replicas]
 
+    def _ck(self, rc):
+        if rc != 0:
+            from . import _lib
+            raise _lib.StuffingError(rc, self.lib.stf_group_last_error(self.h).decode())
+
+    def setshift(self, labels, level, s1, s2, relative: bool = False):
+        """setshift!/shift! of the listed trees on every replica (the GPUs driven in parallel)"""
+        lb = np.ascontiguousarray(np.asarray(labels, np.int32)); s1 = np.ascontiguousarray(np.asarray(s1, np.int32)); s2 = np.ascontiguousarray(np.asarray(s2, np.int32))
+        self._ck(self.lib.stf_group_set_shifts(self.h, len(lb), lb.ctypes.data, level, s1.ctypes.data, s2.ctypes.data, 1 if relative else 0))
+
+    def reset_velocity(self):
+        self._ck(self.lib.stf_group_reset_velocity(self.h, 0, None))
+
     def fit_round(self, seed: int, iteration: int, labels=None, partial: bool = False) -> int:
         lb = None if labels is None else np.ascontiguousarray(np.asarray(list(labels), np.int32))
         nh = C.c_int64(0)
