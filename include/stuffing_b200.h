@@ -257,6 +257,9 @@ int64_t stf_launch_count(const stf_ctx* ctx);
 int32_t stf_profile_enable(stf_ctx* ctx, int32_t on);
 /* accumulated milliseconds and number of timed intervals per stage since the last reset */
 int32_t stf_profile_read(stf_ctx* ctx, double* ms, int64_t* calls, int32_t reset);
+/* the last upload (profiling on), each build kernel timed alone by its own event pair: ms4 = k_pack_build_small,
+ * k_pack_build_mid<128>, k_pack_build_mid<512>, the mask-sized path (k_pack_level1 + wide level builds) */
+int32_t stf_profile_build_kernels(stf_ctx* ctx, double* ms4);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ EXPORTS = {
     "stf_counters": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "stf_launch_count": (C.c_int64, [C.c_void_p]),
     "stf_profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "stf_profile_build_kernels": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "stf_profile_read": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
 }
 STAGES = ("shift_rebuild", "locate", "sort", "emit", "narrow", "result", "step_prep", "step", "build")

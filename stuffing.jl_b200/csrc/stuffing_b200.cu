@@ -80,6 +80,7 @@ struct stf_ctx {
     std::vector<ProfRec> prof_pending; std::vector<cudaEvent_t> prof_pool;
     double prof_ms[STF_NSTAGES] = {}; int64_t prof_calls[STF_NSTAGES] = {};
     int prof_open = -1; cudaEvent_t prof_open_ev = nullptr;
+    double build_ms[4] = {}; // last upload, profiling on: k_pack_build_small, k_pack_build_mid<128>, k_pack_build_mid<512>, mask-sized path (each launch timed alone)
     // pinned staging for small host inputs (labels, shifts): the caller's buffer is only read during the call,
     // the H2D copy is a true async DMA, and calls without outputs need no stream synchronisation
     int pos_level = 0; int32_t *pos_rs = nullptr, *pos_cs = nullptr; // stf_fit_round_positions: read-back folded into the round's one sync
@@ -430,6 +431,9 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
         CK(cudaMemcpyAsync(ctx->woff1.p, big_woff.data(), sizeof(uint64_t) * big_woff.size(), cudaMemcpyHostToDevice, ctx->st));
     }
     stage_begin(ctx, STF_STAGE_BUILD);
+    cudaEvent_t bev[5] = {};
+    auto mark = [&](int i) { if (ctx->prof) { if (!bev[i]) cudaEventCreate(&bev[i]); cudaEventRecord(bev[i], ctx->st); } };
+    mark(0);
     // buildqtree!(t) for every object, fused with the level-1 pack: a warp per small object, a CTA per mid-size object;
     // big objects (mask-sized) are packed by a wide launch and built level by level with wide launches
     if (!l_small.empty()) {
@@ -437,6 +441,7 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
         int blocks = std::min(nblk(((int64_t)l_small.size() + grp - 1) / grp * 32, 256), 148 * 8);
         ctx->launches++, k_pack_build_small<<<blocks, 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list, (int)l_small.size(), ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, ERRP(ctx), grp);
     }
+    mark(1);
     for (int k = 0; k < 2; k++) { // a CTA per mid-size object: 128 threads for a few KB, 512 for mask-sized ones
         size_t cnt = k ? l_mid.size() - n_mid1 : n_mid1;
         if (!cnt) continue;
@@ -445,7 +450,10 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
         size_t smem = sizeof(uint32_t) * (size_t)(aw + bw);
         if (k == 0) ctx->launches++, k_pack_build_mid<128><<<(int)cnt, 128, smem, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), lst, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, aw, ERRP(ctx));
         else ctx->launches++, k_pack_build_mid<512><<<(int)cnt, 512, smem, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), lst, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), L, aw, ERRP(ctx));
+        mark(2 + k);
     }
+    if (ctx->prof && !bev[2]) { bev[2] = bev[1]; }
+    if (ctx->prof && !bev[3]) { bev[3] = bev[2]; }
     if (!l_big.empty()) {
         uint64_t tw = big_woff.back();
         ctx->launches++, k_pack_level1<<<nblk((int64_t)tw, 256), 256, 0, ctx->st>>>(d_payload, ctx->poff.as<uint64_t>(), d_list + l_small.size() + l_mid.size(), ctx->woff1.as<uint64_t>(), (int)l_big.size(),
@@ -453,8 +461,13 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     }
     KCHECK();
     for (int o : ctx->big_objs) { int32_t r = build_big(ctx, o, 1); if (r) return r; }
+    mark(4);
     stage_end(ctx);
     int32_t r = sync_counts(ctx); // staging must outlive the copy; also surfaces bad codes
+    if (ctx->prof && !r) {
+        for (int i = 0; i < 4; i++) { float t = 0.f; ctx->build_ms[i] = (bev[i] != bev[i + 1] && cudaEventElapsedTime(&t, bev[i], bev[i + 1]) == cudaSuccess) ? t : 0.0; }
+    }
+    for (int i = 0; i < 5; i++) { bool dup = false; for (int j2 = 0; j2 < i; j2++) dup |= bev[j2] == bev[i]; if (bev[i] && !dup) cudaEventDestroy(bev[i]); }
     return r;
 }
 
@@ -1804,6 +1817,11 @@ extern "C" int32_t stf_profile_read(stf_ctx* ctx, double* ms, int64_t* calls, in
     return STF_OK;
 }
 
+extern "C" int32_t stf_profile_build_kernels(stf_ctx* ctx, double* ms4) {
+    if (!ctx || !ms4) return STF_E_ARG;
+    for (int i = 0; i < 4; i++) ms4[i] = ctx->build_ms[i];
+    return STF_OK;
+}
 extern "C" int64_t stf_launch_count(const stf_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // debug: timeline of the last k_batchsteps launch (STF_DEBUG_STEP & 16): 4 x u64 nanosecond stamps per step

@@ -8,13 +8,13 @@ s = W["mask_side"]
 trees = [S.maskqtree(np.ones((s, s), bool))] + [S.qtree(o, W["canvas"]) for o in W["objs"]]
 for t, r, c in zip(trees, W["rs"], W["cs"]):
     t.shift1 = (int(r), int(c))
+os.environ["STF_DEBUG_STEP"] = sys.argv[1] if len(sys.argv) > 1 else "16"  # read once, at stf_create
 d = S.DeviceQTrees(trees); lib, h = d.lib, d.h
 n_all = len(d); movable = np.arange(2, n_all + 1, dtype=np.int32)
 rs, cs = W["rs"][1:].copy(), W["cs"][1:].copy()
 lib.stf_set_optimiser(h, 2, 0.25, 0.5)
 hits = S.totalcollisions_spacial(d, unique=False, raw=True)
 print("hits", len(hits))
-os.environ["STF_DEBUG_STEP"] = sys.argv[1] if len(sys.argv) > 1 else "16"
 for it in range(3):
     d._ck(lib.stf_set_shifts(h, len(movable), movable.ctypes.data, 1, rs.ctypes.data, cs.ctypes.data, 0))
     d._ck(lib.stf_reset_velocity(h, 0, None))
