@@ -785,6 +785,7 @@ def run_c3(args):
     S.locate(d, None, tree)
     moved = list(range(2, n_all + 1))
     tot = dict(items=0, hits=0, moved=0, ms=0.0, h2d=0, d2h=0)
+    nh, nm, moved_buf = C.c_int64(0), C.c_int32(0), np.zeros(n_all, np.int32)
     warm = max(3, args.warmup)
     script = c3_script(n_all, warm + args.steps)
     l0 = 0
@@ -801,16 +802,17 @@ def run_c3(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         d.shift(jit, 1, dr, dc)
-        labels = list(dict.fromkeys(moved + jit.tolist()))
-        colist = S.partialcollisions(d, tree, labels, unique=False, raw=True)
-        c = d.counters()
-        d._ck(lib.stf_batchsteps(h, len(colist), colist.ctypes.data, SEED, step))
+        labels = np.asarray(list(dict.fromkeys(moved + jit.tolist())), np.int32)
+        # ONE call: partialcollisions over `labels` + batchsteps! on the device; only the labels of the result come back
+        d._ck(lib.stf_fit_round_moved(h, 1, len(labels), labels.ctypes.data, SEED, step, C.byref(nh), moved_buf.ctypes.data, len(moved_buf), C.byref(nm)))
         b.record(stream)
         b.synchronize()
-        moved = labels_of_result(colist)
+        c = d.counters()
+        res = moved_buf[: nm.value]
+        moved = res[res != 1].tolist()
         if timed:
-            tot["ms"] += a.elapsed_time(b); tot["items"] += c["items"] + c["direct"]; tot["hits"] += len(colist); tot["moved"] += len(labels)
-            tot["h2d"] += 4 * len(labels) + 12 * len(jit) + 20 * len(colist); tot["d2h"] += 20 * len(colist) + 128
+            tot["ms"] += a.elapsed_time(b); tot["items"] += c["items"] + c["direct"]; tot["hits"] += nh.value; tot["moved"] += len(labels)
+            tot["h2d"] += 4 * len(labels) + 12 * len(jit); tot["d2h"] += 4 * nm.value + 136
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -836,7 +838,7 @@ def run_c3(args):
             "e2e": {"value": world * items / (ms * 1e-3), "unit": "items/s", "ms_per_step": ms, "h2d_bytes_per_step": int(tot["h2d"] / args.steps), "d2h_bytes_per_step": int(tot["d2h"] / args.steps)},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole dynamic step", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "peak_source": peak_src, "note": "latency-bound host-driven loop: two C-ABI calls with host lists per step"},
+                         "peak_source": peak_src, "note": "latency-bound loop: per step one shift! call (no sync) and one stf_fit_round_moved call (one sync); the hit list stays on the device"},
             "cpu_baseline": {"value": None, "unit": "items/s", "cores": 0, "kind": "port", "sample": "run `bench.py --impl reference --workload c3`: the same scripted dynamic steps on the C restatement"}}
     print(json.dumps(line), flush=True)
     if dist is not None:

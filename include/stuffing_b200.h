@@ -177,6 +177,12 @@ int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colist, uint64_t
  * partialcollisions over `labels`.  *nhits = length(colist). */
 int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels,
                       uint64_t seed, uint64_t iteration, int64_t* nhits);
+/* the same round, returning the distinct labels of its colist in ascending order instead of the list itself: the
+ * `moved := labels of the result` of dynamiccollisions (qtree_functions.jl:354-355) and the `inds` of the element-wise
+ * trainers (fit.jl:90: there in order of first appearance) — a dynamic loop then needs ONE call and one synchronisation per
+ * step and ships a few hundred labels instead of the hit list.  Two-call pattern on cap / *nmoved. */
+int32_t stf_fit_round_moved(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration,
+                            int64_t* nhits, int32_t* moved_out, int32_t cap, int32_t* nmoved);
 /* the same round followed by getshift(t, level) of EVERY tree (qtrees.jl:135-141): rs/cs (n each) receive the positions
  * after the round.  On the single-scene path the read-back rides on the round's one synchronisation instead of a
  * second call; otherwise it equals stf_fit_round + stf_get_shifts. */

@@ -57,6 +57,7 @@ EXPORTS = {
     "stf_get_velocity": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "stf_batchsteps": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64, C.c_uint64]),
     "stf_fit_round": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "stf_fit_round_moved": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "stf_fit_round_positions": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "stf_fit_rounds": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "stf_ground_compose": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

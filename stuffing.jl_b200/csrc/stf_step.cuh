@@ -294,3 +294,33 @@ __global__ void __launch_bounds__(256) k_materialize(uint32_t* __restrict__ word
         __syncwarp();
     }
 }
+
+// union!(moved, first.(colist) |> Iterators.flatten) (qtree_functions.jl:354-355) on the device: the distinct labels of a hit
+// list in ascending order.  One CTA: endpoints stamp mark[label] with this call's epoch (no clearing between calls), then
+// the labels 1..n are compacted in order (block scan per 1024-label slab).  out[0] = count, out[1..] = labels.
+__global__ void __launch_bounds__(1024) k_result_labels(const Item16* __restrict__ hits, const unsigned long long* __restrict__ n_dev, int64_t n_cap,
+                                                        uint32_t* __restrict__ mark, int n_obj, uint32_t epoch, int32_t* __restrict__ out, int out_cap) {
+    pdl_sync();
+    __shared__ int wsum[32];
+    __shared__ int base;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int64_t n = min((int64_t)*n_dev, n_cap);
+    for (int64_t e = t; e < 2 * n; e += 1024) { const Item16 h = hits[e >> 1]; mark[((e & 1) ? item_i2(h) : h.i1) - 1] = epoch; }
+    if (t == 0) base = 0;
+    __syncthreads();
+    for (int o0 = 0; o0 < n_obj; o0 += 1024) {
+        const int o = o0 + t;
+        const bool m = o < n_obj && mark[o] == epoch;
+        const unsigned bal = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int i = 0; i < w; i++) off += wsum[i];
+        const int pos = off + __popc(bal & ((1u << lane) - 1u));
+        if (m && 1 + pos < out_cap) out[1 + pos] = o + 1;
+        __syncthreads();
+        if (t == 0) { int sum = 0; for (int i = 0; i < 32; i++) sum += wsum[i]; base += sum; }
+        __syncthreads();
+    }
+    if (t == 0) out[0] = base;
+}

@@ -70,6 +70,7 @@ struct stf_ctx {
     int64_t hint_surv = 0;  // pairs the word-parallel narrow phase handed to the frontier kernel in the previous round
     bool fused_narrow = false; // STF_FUSED_NARROW=1: candidates are tested inside the candidate kernel and never stored (measured slower: DESIGN.md)
     bool in_rounds = false; // stf_fit_rounds is enqueueing: k_round_begin resets the counters (not a host memset) and a raised C_STOP cancels a round
+    DevBuf lab_mark; uint32_t lab_epoch = 0; bool want_moved = false; // stf_fit_round_moved: epoch-stamped label marks; fold the label list into the round's sync
     DevBuf rounds_rec;      // stf_fit_rounds: per-round records (hits, items, node tests, moves)
     bool keep_items = false; // stf_set_keep_items: the candidate list (the reference's `itemlist`) must be fetchable: never the fused variant
     stf_counters_t ctr = {};
@@ -282,7 +283,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from, &ctx->gather, &ctx->gflags, &ctx->gdone, &ctx->rounds_rec };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from, &ctx->gather, &ctx->gflags, &ctx->gdone, &ctx->rounds_rec, &ctx->lab_mark };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) free(ctx->h_err);
@@ -1383,6 +1384,37 @@ extern "C" int32_t stf_fit_round_positions(stf_ctx* ctx, int32_t mode, int32_t n
     if (r) return r;
     return delivered ? STF_OK : stf_get_shifts(ctx, ctx->n, nullptr, level, rs, cs); // paths without a folded read-back
 }
+// the round + the distinct labels of its colist: `moved := labels of the result` of dynamiccollisions (qtree_functions.jl:354-355)
+// and `inds` of the element-wise trainers (fit.jl:90) without shipping the hit list to the host.  Ascending label order.
+extern "C" int32_t stf_fit_round_moved(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits,
+                                       int32_t* moved_out, int32_t cap, int32_t* nmoved) {
+    if (!ctx) return STF_E_ARG;
+    if (nmoved) *nmoved = 0;
+    const bool device_list = ctx->L > 0 && ctx->n <= 65536;
+    ctx->want_moved = device_list;
+    if (ctx->lab_mark.p && ctx->lab_mark.cap < sizeof(uint32_t) * (size_t)ctx->n) ctx->lab_mark.release();
+    int64_t nh = 0;
+    int32_t r = stf_fit_round(ctx, mode, nl, labels, seed, iteration, &nh);
+    const bool folded = ctx->want_moved == false && device_list; // stf_fit_round clears the flag when the latency path delivered the list
+    ctx->want_moved = false;
+    if (r) return r;
+    if (nhits) *nhits = nh;
+    std::vector<int32_t> lab;
+    if (folded) {
+        const int32_t* src = reinterpret_cast<const int32_t*>(ctx->h_out);
+        lab.assign(src + 1, src + 1 + src[0]);
+    } else if (nh > 0) { // throughput path: the sorted hit list is still on the device (ctx->hits2)
+        std::vector<Item16> h((size_t)nh);
+        CK(cudaMemcpyAsync(h.data(), ctx->hits2.p, sizeof(Item16) * (size_t)nh, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        for (const Item16& x : h) { lab.push_back(x.i1); lab.push_back(item_i2(x)); }
+        std::sort(lab.begin(), lab.end()); lab.erase(std::unique(lab.begin(), lab.end()), lab.end());
+    }
+    if (nmoved) *nmoved = (int32_t)lab.size();
+    if ((int64_t)lab.size() > cap) FAIL(STF_E_CAPACITY, "label buffer too small");
+    if (!lab.empty()) { if (!moved_out) FAIL(STF_E_ARG, "null output buffer"); memcpy(moved_out, lab.data(), sizeof(int32_t) * lab.size()); }
+    return STF_OK;
+}
 extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration, int64_t* nhits) {
     NEED_OBJS();
     if (nhits) *nhits = 0;
@@ -1393,11 +1425,20 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
     for (int attempt = 0; attempt < 4 && fast_path_ok(ctx, linked ? ctx->n : nl); attempt++) {
         int32_t r = spacial_core_fast(ctx, nl, labels, linked); if (r) return r;
         r = fast_round_tail(ctx, seed, iteration, false); if (r) return r;
-        const bool fold = ctx->pos_level > 0 && ctx->n <= 65536;
+        if (ctx->want_moved) { // the labels of the colist (ascending), written straight into the pinned landing area
+            const size_t need = sizeof(int32_t) * (size_t)(ctx->n + 1);
+            if (ctx->h_out_cap < need) { if (ctx->h_out) cudaFreeHost(ctx->h_out); ctx->h_out = nullptr; ctx->h_out_cap = 0; CK(cudaMallocHost(&ctx->h_out, 2 * need)); ctx->h_out_cap = 2 * need; }
+            if (!ctx->lab_mark.p) { CK(ctx->lab_mark.ensure(sizeof(uint32_t) * (size_t)ctx->n)); CK(cudaMemsetAsync(ctx->lab_mark.p, 0, sizeof(uint32_t) * (size_t)ctx->n, ctx->st)); ctx->lab_epoch = 0; }
+            LAUNCH_PDL(ctx, k_result_labels, 1, 1024, 0, (const Item16*)ctx->hits2.as<Item16>(), (const unsigned long long*)(ctx->counts.as<unsigned long long>() + C_NSTEPS), (int64_t)BS_CAP,
+                       ctx->lab_mark.as<uint32_t>(), ctx->n, ++ctx->lab_epoch, reinterpret_cast<int32_t*>(ctx->h_out), ctx->n + 1);
+            KCHECK();
+        }
+        const bool fold = ctx->pos_level > 0 && ctx->n <= 65536 && !ctx->want_moved;
         if (fold) { r = pos_enqueue(ctx); if (r) return r; }
         r = sync_counts(ctx); if (r) return r;
         if (fast_round_verdict(ctx)) continue; // no step ran (n_steps == 0): nothing to undo
         if (fold) { pos_deliver(ctx); ctx->pos_level = 0; }
+        ctx->want_moved = false; // (delivered: the caller reads the label list from the landing area)
         read_round_counters(ctx);
         ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES];
         if (nhits) *nhits = ctx->ctr.hits;

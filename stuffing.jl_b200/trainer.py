@@ -102,6 +102,20 @@ def fit_round(qts, labels=None, optimiser=None, clock: StepClock | None = None, 
     return nh.value
 
 
+def fit_round_moved(qts, labels=None, optimiser=None, clock: StepClock | None = None, partial=False):
+    """fit_round that also returns the distinct labels of its colist, ascending (stf_fit_round_moved): the next `moved` set of
+    a dynamic loop without shipping the hit list; returns (length(colist), labels)"""
+    d = _dev(qts)
+    clock = clock or _default_clock
+    _set_opt(d, optimiser)
+    lb = None if labels is None else i32(list(labels))
+    nh, nm = C.c_int64(0), C.c_int32(0)
+    out = np.zeros(d.n, np.int32)
+    d._ck(d.lib.stf_fit_round_moved(d.h, 1 if partial else 0, 0 if lb is None else len(lb), ptr(lb), clock.seed, clock.iteration, C.byref(nh), ptr(out), len(out), C.byref(nm)))
+    clock.iteration += 1
+    return nh.value, out[: nm.value].copy()
+
+
 def fit_round_positions(qts, labels=None, optimiser=None, clock: StepClock | None = None, partial=False, level=1):
     """fit_round followed by getshift(t, level) of every tree, read back with the round's own synchronisation;
     returns (length(colist), rs, cs)"""

@@ -207,6 +207,27 @@ def test_c3_dynamic_loop_10k(S, orc):
         moved = bench.labels_of_result(got)
         total_hits += len(got)
     assert total_hits > 5000 and len(moved) < n_all // 2
+    # the same loop as ONE call per step (stf_fit_round_moved: the hit list stays on the device, the labels of the result
+    # come back): same hit counts, same moved sets, same positions as the two-call loop above
+    d2 = workloads.device_scene(S, W)
+    S.locate(d2, None, S.linked_spacial_qtree(d2))
+    clock = S.trainer.StepClock(seed=1)
+    qo2 = workloads.oracle_scene(orc, W)
+    tree_o2 = orc.LinkedTree(qo2); tree_o2.locate(qo2)
+    opt2 = orc.Opt("momentum", 0.25, 0.5, n_all)
+    moved = list(range(2, n_all + 1))
+    for step, (jit, dr, dc) in enumerate(bench.c3_script(n_all, 8)):
+        d2.shift(jit, 1, dr, dc)
+        for lb, a, b in zip(jit.tolist(), dr.tolist(), dc.tolist()):
+            qo2[lb - 1].shift(1, a, b)
+        labels = list(dict.fromkeys(moved + jit.tolist()))
+        nh, mv = S.trainer.fit_round_moved(d2, labels, S.Momentum(0.25, 0.5), clock, partial=True)
+        want, _ = _sorted_hits(orc, qo2, labels, tree_o2)
+        orc.batchsteps(qo2, want, opt2, seed=1, iteration=step)
+        assert nh == len(want) and mv.tolist() == sorted(set(want["i1"].tolist()) | set(want["i2"].tolist())), step
+        rs, cs = d2.getshifts(); ro, co = orc.getshifts(qo2)
+        assert np.array_equal(rs, ro) and np.array_equal(cs, co), step
+        moved = [x for x in mv.tolist() if x != 1]
 
 
 def test_two_contexts_in_one_process(S, orc):
