@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstuffing_b200.so")
+LIB_PATH = os.environ.get("STUFFING_B200_LIB", os.path.join(_HERE, "libstuffing_b200.so"))  # (the same override as julia/StuffingB200.jl)
 
 STF_OK, STF_E_CUDA, STF_E_ARG, STF_E_CAPACITY, STF_E_BADCODE, STF_E_RANGE, STF_E_STATE = 0, -1, -2, -3, -4, -5, -6
 

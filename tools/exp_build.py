@@ -40,6 +40,8 @@ def run(name, payload, kh, kw, dflt, is_mask, scene, canvas, reps=5):
         assert rc == 0, lib.stf_last_error(h)
         wall = time.perf_counter() - t0
         lib.stf_profile_read(h, ms.ctypes.data, calls.ctypes.data, 1)
+        k4 = np.zeros(4); lib.stf_profile_build_kernels(h, k4.ctypes.data)
+        print("   per kernel (us): small %.1f  mid128 %.1f  mid512 %.1f  mask path %.1f" % tuple(k4 * 1e3), flush=True)
         print(f"{name}: n={n} payload={up/1e6:.1f} MB algorithmic={alg/1e6:.1f} MB  build kernels {ms[8]*1e3:.1f} us -> {alg/ms[8]/1e6:.1f} GB/s ({alg/ms[8]/1e6/6534.8*100:.1f}% of measured HBM peak); whole call {wall*1e3:.1f} ms", flush=True)
     lib.stf_destroy(h)
 
