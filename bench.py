@@ -585,12 +585,18 @@ def run_ours(args):
         except Exception as e:  # reporting only
             sharded["c5_scene_split"] = {"error": str(e)}
         bracket()
+        # rank 0 now drives every GPU of the box from its own process; the other ranks must leave their GPUs ALONE meanwhile
+        # (an NCCL barrier would park a spinning kernel on each of them and time-slice against rank 0's work): they wait in a
+        # host-side (gloo) barrier
+        host_group = dist.new_group(backend="gloo") if dist is not None else None
         if rank == 0:
             try:
                 ndev = min(world, torch.cuda.device_count())
                 sharded["c1_item_parallel_group"] = group_bench(S, torch, "c1", list(range(ndev)), 10, 3)
             except Exception as e:
                 sharded["c1_item_parallel_group"] = {"error": str(e)}
+        if host_group is not None:
+            dist.barrier(group=host_group)
         bracket()
     if rank != 0:
         if dist is not None:
@@ -733,6 +739,7 @@ def run_group(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     line = None
+    host_group = dist.new_group(backend="gloo") if dist is not None else None
     if rank == 0:
         n = max(world, args.gpus)
         n = min(n, torch.cuda.device_count())
@@ -752,7 +759,7 @@ def run_group(args):
                              "note": "latency-bound round; see the default bench line for the per-stage roofline"},
                 "cpu_baseline": {"value": None, "unit": "items/s", "cores": 0, "kind": "port", "sample": "see the default bench line"}}
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=host_group)  # host-side: no kernel may sit on the other GPUs while rank 0 drives them
         dist.destroy_process_group()
     if line:
         print(json.dumps(line), flush=True)
