@@ -131,6 +131,13 @@ int32_t stf_collision_dfs(stf_ctx* ctx, int64_t n, const stf_item* items, stf_it
 /* _totalcollisions_native(qtrees, coitems, colist)  qtree_functions.jl:89-110: hits only */
 int32_t stf_collide_items(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out, int64_t cap, int64_t* count);
 
+/* the pool test of the pairwise trainers: filttrain!(qtrees, inpool, outpool, nearlevel2)  fit.jl:235-266.  `pairs` =
+ * n_pairs x 2 labels, or NULL = all pairs i < j of the objects, generated ON THE DEVICE in the reference's order (fit.jl:279;
+ * 5e7 pairs at 10 k objects never cross the boundary).  Every pair is tested from the root (L,1,1), no bounds pre-check;
+ * the pairs whose result level is >= nearlevel come back as (i1,i2) => (l,a,b) in pool order (l > 0: a collision to step;
+ * nearlevel <= l < 0: a near miss, -l = level of the deepest node still MIX in both trees).  Two-call pattern on cap. */
+int32_t stf_filter_pairs(stf_ctx* ctx, int64_t n_pairs, const int32_t* pairs, int32_t nearlevel, stf_item* out, int64_t cap, int64_t* count);
+
 /* ---- many-body collision ---- */
 /* totalcollisions_native(qtrees, labels)  qtree_functions.jl:111-131 (labels == NULL: 1..n) */
 int32_t stf_totalcollisions_native(stf_ctx* ctx, int32_t nl, const int32_t* labels, stf_item* out, int64_t cap, int64_t* count);

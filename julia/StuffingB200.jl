@@ -283,6 +283,19 @@ function fit_rounds!(d::DeviceQTrees, k::Integer, labels=nothing; optimiser=(t, 
     Int.(nh), collect(zip(Int.(rs), Int.(cs)))
 end
 
+"filttrain!(qtrees, inpool, outpool, nearlevel2; optimiser)  fit.jl:235-266 — the pool test runs on the device; `inpool === nothing`
+stands for ALL pairs i < j in the reference's order (fit.jl:279), generated on the device instead of being enumerated here"
+function filttrain!(d::DeviceQTrees, inpool, outpool, nearlevel2; optimiser=(t, Δ) -> Δ ./ 6, kargs...)
+    pairs = inpool === nothing ? C_NULL : Int32[x for p in inpool for x in p]
+    np = inpool === nothing ? 0 : length(inpool)
+    near = _list(d, Vector{CoItem}(), (buf, cap, cnt) -> ccall((:stf_filter_pairs, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Int32, Ptr{StfItem}, Int64, Ptr{Int64}),
+                                                                d.h, np, pairs, Int32(ceil(nearlevel2)), buf, cap, cnt))
+    outpool === nothing || append!(outpool, first.(near))
+    colist = CoItem[c for c in near if c.second[1] > 0]
+    batchsteps!(d, colist, optimiser)
+    length(colist)
+end
+
 # ------------------------------------------------------------------------------------------------ trainers (fit.jl:77-233) — host policy over device rounds
 # The reference's trainepoch_* functions only call totalcollisions / dynamiccollisions / batchsteps! on their `qtrees`
 # argument, so they run UNCHANGED on a DeviceQTrees through the methods above; train!/fit! (fit.jl:450-552) likewise

@@ -946,3 +946,40 @@ __global__ void __launch_bounds__(256) k_shard_gather(const Item16* __restrict__
         if (k < s_cnt[r] && s_base[r] + k < hits_cap) hits[s_base[r] + k] = gather[i];
     }
 }
+
+// ---- pair pools of the pairwise trainers (filttrain!, fit.jl:235-266): every pair is tested from the root (L,1,1) without
+// a bounds pre-check; the pairs whose result level is >= nearlevel survive, in pool order.
+// all pairs (i, j), i < j, of objects 1..n in the reference's order `for i in 1:n for j in i+1:n` (fit.jl:279): one thread per
+// (i, j) of the square; item index = i*(2n-i-1)/2 + (j-i-1) (0-based)
+__global__ void k_allpairs_items(int n, int L, Item16* __restrict__ items) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = t / n, j = t - i * n;
+    if (i < j && j < n) items[i * (2 * (int64_t)n - i - 1) / 2 + (j - i - 1)] = make_item((int)i + 1, (int)j + 1, L, 1, 1);
+}
+__global__ void k_pairs_items(const int32_t* __restrict__ pairs, int64_t n, int L, Item16* __restrict__ items) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) items[t] = make_item(pairs[2 * t], pairs[2 * t + 1], L, 1, 1);
+}
+// order-preserving compaction of the results with level >= nearlevel: count per block, (k_scan_u32 over the block counts), write
+#define FP_BLOCK 256
+__global__ void __launch_bounds__(FP_BLOCK) k_near_count(const int4* __restrict__ res, int64_t n, int nearlevel, uint32_t* __restrict__ bcount) {
+    int64_t i = (int64_t)blockIdx.x * FP_BLOCK + threadIdx.x;
+    bool keep = i < n && res[i].x >= nearlevel;
+    int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) bcount[blockIdx.x] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(FP_BLOCK) k_near_write(const Item16* __restrict__ items, const int4* __restrict__ res, int64_t n, int nearlevel,
+                                                         const uint32_t* __restrict__ boff, int32_t* __restrict__ out5) {
+    __shared__ int wcnt[FP_BLOCK / 32];
+    int64_t i = (int64_t)blockIdx.x * FP_BLOCK + threadIdx.x;
+    bool keep = i < n && res[i].x >= nearlevel;
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wcnt[w] = __popc(bal);
+    __syncthreads();
+    if (!keep) return;
+    int off = 0;
+    for (int k = 0; k < w; k++) off += wcnt[k];
+    int32_t* o = out5 + 5 * ((size_t)boff[blockIdx.x] + off + __popc(bal & ((1u << lane) - 1u)));
+    o[0] = items[i].i1; o[1] = item_i2(items[i]); o[2] = res[i].x; o[3] = res[i].y; o[4] = res[i].z;
+}

@@ -883,6 +883,49 @@ static int32_t collide_and_collect(stf_ctx* ctx, int64_t n, int64_t nd, int64_t*
     return STF_OK;
 }
 
+// filttrain!'s pool test on the device (fit.jl:235-266): the pool is `pairs` (n_pairs x 2 labels, host) or —
+// pairs == NULL — ALL pairs i < j of the objects, generated on the device in the reference's order (fit.jl:279: at 10 k
+// objects that is 5e7 pairs, never enumerated or shipped by the host).  Every pair is tested from the root (L,1,1); the
+// pairs with result level >= nearlevel come back as (i1,i2) => (l,a,b) in pool order: level > 0 = a collision to step,
+// level in [nearlevel, 0) = a near miss for the next pool.
+extern "C" int32_t stf_filter_pairs(stf_ctx* ctx, int64_t n_pairs, const int32_t* pairs, int32_t nearlevel, stf_item* out, int64_t cap, int64_t* count) {
+    NEED_OBJS();
+    if (count) *count = 0;
+    ctx->last_result = 0;
+    if (ctx->multi_scene) FAIL(STF_E_STATE, "pair pools are defined for one scene");
+    const int64_t n = pairs ? n_pairs : (int64_t)ctx->n * (ctx->n - 1) / 2;
+    if (n <= 0) return STF_OK;
+    if (ctx->L < 2) FAIL(STF_E_STATE, "_collision_randbfs needs a start level >= 2");
+    CK(ctx->items.ensure(sizeof(Item16) * (size_t)n));
+    ctx->items_valid = false;
+    if (pairs) {
+        for (int64_t i = 0; i < 2 * n; i++) CHECK_LABEL(pairs[i]);
+        CK(ctx->out32.ensure(sizeof(int32_t) * 2 * (size_t)n));
+        CK(cudaMemcpyAsync(ctx->out32.p, pairs, sizeof(int32_t) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+        ctx->launches++, k_pairs_items<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->out32.as<int32_t>(), n, ctx->L, ctx->items.as<Item16>());
+    } else {
+        ctx->launches++, k_allpairs_items<<<nblk((int64_t)ctx->n * ctx->n, 256), 256, 0, ctx->st>>>(ctx->n, ctx->L, ctx->items.as<Item16>());
+    }
+    KCHECK();
+    int32_t r = zero_counts(ctx); if (r) return r;
+    r = narrow_phase(ctx, n, n, true, false); if (r) return r;
+    const int nb = nblk(n, FP_BLOCK);
+    CK(ctx->keep.ensure(sizeof(uint32_t) * (size_t)(nb + 16)));
+    ctx->launches++, k_near_count<<<nb, FP_BLOCK, 0, ctx->st>>>(ctx->res.as<int4>(), n, nearlevel, ctx->keep.as<uint32_t>());
+    ctx->after_kernel = false;
+    LAUNCH_PDL(ctx, k_scan_u32, 1, 1024, 0, ctx->keep.as<uint32_t>(), (int64_t)nb, reinterpret_cast<uint32_t*>(ctx->counts.as<unsigned long long>() + C_KEPT));
+    KCHECK();
+    r = sync_counts(ctx); if (r) return r;
+    const int64_t kept = (int64_t)(uint32_t)ctx->h_counts[C_KEPT];
+    ctx->ctr.items = n; ctx->ctr.direct = 0; ctx->ctr.hits = 0; ctx->ctr.overflow = (int64_t)ctx->h_counts[C_OVERFLOW]; ctx->ctr.visited = (int64_t)ctx->h_counts[C_VISITED];
+    CK(ctx->out32.ensure(sizeof(int32_t) * 5 * (size_t)std::max<int64_t>(1, kept)));
+    if (kept > 0) {
+        ctx->launches++, k_near_write<<<nb, FP_BLOCK, 0, ctx->st>>>(ctx->items.as<Item16>(), ctx->res.as<int4>(), n, nearlevel, ctx->keep.as<uint32_t>(), ctx->out32.as<int32_t>());
+        KCHECK();
+    }
+    return deliver(ctx, kept, out, cap, count);
+}
+
 extern "C" int32_t stf_collide_items(stf_ctx* ctx, int64_t n, const stf_item* items, stf_item* out, int64_t cap, int64_t* count) {
     NEED_OBJS();
     if (count) *count = 0;

@@ -8,6 +8,7 @@ include/stuffing_b200_rng.h, keyed (seed, iteration, k); `iteration` advances on
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -260,20 +261,31 @@ def filttrain(qts, inpool, outpool, nearlevel2, optimiser=None, clock=None):
     -level of the deepest node still MIX in both trees: the nearness score), hits (cp[1] > 0) are stepped.  Canonical
     mode: pool order instead of shuffle!(inpool), colist in pool order.  One stf_collision_bfs call for the whole pool."""
     d = _dev(qts)
-    if len(inpool) == 0:
+    if inpool is not ALLPAIRS and len(inpool) == 0:
         return 0
-    L = d.nlevels
-    arr = np.zeros(len(inpool), _lib.ITEM_DT)
-    pool = np.asarray(inpool, np.int32).reshape(-1, 2)
-    arr["i1"], arr["i2"], arr["l"], arr["a"], arr["b"] = pool[:, 0], pool[:, 1], L, 1, 1
-    out = np.zeros(len(arr), _lib.ITEM_DT)
-    d._ck(d.lib.stf_collision_bfs(d.h, len(arr), ptr(arr), ptr(out)))
-    near = out["l"] >= nearlevel2
+    if inpool is ALLPAIRS:  # every pair i < j, generated on the device in the reference's order (fit.jl:279)
+        near = d._call_list(d.lib.stf_filter_pairs, 0, None, int(math.ceil(nearlevel2)))
+    else:
+        pool = np.ascontiguousarray(np.asarray(inpool, np.int32).reshape(-1, 2))
+        near = d._call_list(d.lib.stf_filter_pairs, len(pool), ptr(pool), int(math.ceil(nearlevel2)))
     if outpool is not None:
-        outpool.extend((int(a), int(b)) for a, b in pool[near])
-    colist = out[near & (out["l"] > 0)]
+        outpool.extend(zip(near["i1"].tolist(), near["i2"].tolist()))
+    colist = near[near["l"] > 0]
     batchsteps(d, colist, optimiser, clock)
     return len(colist)
+
+
+class _AllPairs:
+    """the pool `[(i, j) for i in 1:n for j in i+1:n]` (fit.jl:279) without enumerating it on the host"""
+
+    def __init__(self):
+        self.n = 0
+
+    def __len__(self):
+        return self.n * (self.n - 1) // 2
+
+
+ALLPAIRS = _AllPairs()
 
 
 def _allpairs(n):
@@ -284,7 +296,8 @@ def trainepoch_P(qts, optimiser=None, clock=None, nearlevel=None, last=None, **_
     """pairwise trainer  fit.jl:268-296"""
     d = _dev(qts)
     nearlevel = min(-1, -d.nlevels / 2 if nearlevel is None else nearlevel)
-    indpairs, nearlist, colist = _allpairs(len(d)), [], []
+    ALLPAIRS.n = len(d)
+    indpairs, nearlist, colist = ALLPAIRS, [], []
     _note(last, colist)
     nc = filttrain(d, indpairs, nearlist, nearlevel, optimiser, clock)
     if nc == 0:
@@ -306,7 +319,8 @@ def trainepoch_P2(qts, optimiser=None, clock=None, nearlevel1=None, nearlevel2=N
     d = _dev(qts)
     nearlevel1 = min(-1, -d.nlevels * 0.75 if nearlevel1 is None else nearlevel1)
     nearlevel2 = min(-1, -d.nlevels * 0.5 if nearlevel2 is None else nearlevel2)
-    indpairs, nearlist1, nearlist2, colist = _allpairs(len(d)), [], [], []
+    ALLPAIRS.n = len(d)
+    indpairs, nearlist1, nearlist2, colist = ALLPAIRS, [], [], []
     _note(_kw.get("last"), colist)
     nc = filttrain(d, indpairs, nearlist1, nearlevel1, optimiser, clock)
     if nc == 0:

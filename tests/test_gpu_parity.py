@@ -518,6 +518,16 @@ def test_pairwise_trainers_filttrain_parity_and_convergence(S, orc):
         pool = out_dev
         if not pool:
             break
+    # the all-pairs pool generated ON THE DEVICE (stf_filter_pairs with pairs == NULL, the reference's order of fit.jl:279)
+    # gives what the explicit pool gives: same near pairs in the same order, same hits, same steps
+    qo = rect_scene(orc, 30, 23, sz=70, masksize=(400, 400))
+    d1, d2 = device_from_oracle(S, qo), device_from_oracle(S, qo)
+    t.ALLPAIRS.n = len(qo)
+    out1, out2 = [], []
+    c1, c2 = t.StepClock(seed=4), t.StepClock(seed=4)
+    assert t.filttrain(d1, pairs, out1, -L / 2, S.Momentum(0.25, 0.5), c1) == t.filttrain(d2, t.ALLPAIRS, out2, -L / 2, S.Momentum(0.25, 0.5), c2) > 0
+    assert out1 == out2 and len(out1) < len(pairs) and d2.counters()["items"] == len(pairs)
+    assert all(np.array_equal(x, y) for x, y in zip(d1.getshifts(), d2.getshifts()))
     for trainer in (t.trainepoch_P, t.trainepoch_P2, t.trainepoch_Px):
         qo = rect_scene(orc, 24, 15, sz=60, masksize=(400, 600))
         d = device_from_oracle(S, qo)
