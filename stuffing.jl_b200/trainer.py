@@ -200,14 +200,28 @@ class LRU:
         return r if firstn is None else r[:firstn]
 
 
-def _em(qts, widen, optimiser, clock, memory: LRU, last=None):
-    """the shared shape of trainepoch_EM!/EM2!/EM3!  fit.jl:110-212: nested rounds on LRU-widened label sets"""
-    d = _dev(qts)
-    colist = _note(last, totalcollisions(d, unique=False, raw=True))
+class _DeviceOps:
+    """what a trainer needs from its trees: their number, a many-body collision call, a batchsteps! call"""
+
+    def __init__(self, qts, optimiser, clock):
+        self.d, self.optimiser, self.clock = _dev(qts), optimiser, clock
+        self.n = len(self.d)
+
+    def total(self, labels=None):
+        return totalcollisions(self.d, labels, unique=False, raw=True)
+
+    def steps(self, colist):
+        batchsteps(self.d, colist, self.optimiser, self.clock)
+
+
+def em_epoch(ops, widen, memory: LRU, last=None):
+    """the shared shape of trainepoch_EM!/EM2!/EM3!  fit.jl:110-212: nested rounds on LRU-widened label sets.  `ops` supplies
+    n, total(labels) and steps(colist) (the device by default; the parity tests run the same policy over the oracle)"""
+    colist = _note(last, ops.total())
     nc = len(colist)
     if nc == 0:
         return nc
-    batchsteps(d, colist, optimiser, clock)
+    ops.steps(colist)
 
     def level(depth, parent_len, inds_src):
         inds = inds_src
@@ -216,8 +230,8 @@ def _em(qts, widen, optimiser, clock, memory: LRU, last=None):
                 memory.push(x)
             inds = memory.collect(len(inds) * widen[depth])
         for ni in range(1, 2 * parent_len // max(1, len(inds)) + 1):
-            cl = _note(last, totalcollisions(d, inds, unique=False, raw=True))
-            batchsteps(d, cl, optimiser, clock)
+            cl = _note(last, ops.total(inds))
+            ops.steps(cl)
             if ni > 2 * len(cl):
                 break
             if depth + 1 <= len(widen):
@@ -225,8 +239,12 @@ def _em(qts, widen, optimiser, clock, memory: LRU, last=None):
                 if sub:
                     level(depth + 1, len(inds), sub)
 
-    level(0, len(d), _labels_of(colist))
+    level(0, ops.n, _labels_of(colist))
     return nc
+
+
+def _em(qts, widen, optimiser, clock, memory: LRU, last=None):
+    return em_epoch(_DeviceOps(qts, optimiser, clock or _default_clock), widen, memory, last)
 
 
 def trainepoch_EM(qts, optimiser=None, clock=None, memory=None, last=None, **_kw):

@@ -175,6 +175,44 @@ def test_c2_trainepoch_E_policy_parity(S, orc):
     assert nc_o < W["round_hits"][0] // 4
 
 
+class _OracleOps:
+    """the trainer back end over the oracle: same dispatcher (native below the threshold), canonical list order"""
+
+    def __init__(self, orc, qo, opt, seed):
+        self.orc, self.qo, self.opt, self.seed, self.it, self.n = orc, qo, opt, seed, 0, len(qo)
+
+    def total(self, labels=None):
+        h = self.orc.items_array(self.orc.totalcollisions(self.qo, labels, unique=False))
+        self.orc.lib().orc_sort_unique(h.ctypes.data, C.byref(C.c_int64(len(h))), 0)
+        return h
+
+    def steps(self, colist):
+        self.orc.batchsteps(self.qo, colist, self.opt, seed=self.seed, iteration=self.it)
+        self.it += 1
+
+
+def test_c2_default_trainer_EM2_policy_parity(S, orc):
+    """the reference's DEFAULT trainer (train!'s trainepoch_EM2!, fit.jl:137-171: LRU-widened label sets x4 / x2, three
+    nested round loops) at the C2 size: the same policy code runs once over the device and once over the oracle; collision
+    counts, number of rounds and every position must agree epoch by epoch (label lists in LRU order, native/spacial
+    dispatch included)"""
+    W = workloads.load_workload("c2")
+    qo = workloads.oracle_scene(orc, W)
+    d = workloads.device_scene(S, W)
+    t = S.trainer
+    ops_o = _OracleOps(orc, qo, orc.Opt("momentum", 0.25, 0.5, len(qo)), 11)
+    clock = t.StepClock(seed=11)
+    mem_d, mem_o = t.LRU(), t.LRU()
+    for ep in range(4):
+        nc_o = t.em_epoch(ops_o, [4, 2], mem_o)
+        nc_d = t.trainepoch_EM2(d, S.Momentum(0.25, 0.5), clock, memory=mem_d)
+        assert nc_d == nc_o and clock.iteration == ops_o.it, (ep, nc_d, nc_o, clock.iteration, ops_o.it)
+        rs, cs = d.getshifts()
+        ro, co = orc.getshifts(qo)
+        assert np.array_equal(rs, ro) and np.array_equal(cs, co), ep
+    assert clock.iteration > 12 and nc_o < W["round_hits"][0] // 2
+
+
 def test_c3_dynamic_loop_10k(S, orc):
     """BASELINE configs[2]: 20 steps of the scripted dynamic loop of bench.py --workload c3 on the 10k scene — per step the
     partialcollisions result through the linked tree and every position after batchsteps, against the oracle"""
