@@ -207,6 +207,18 @@ int32_t stf_fit_round_positions(stf_ctx* ctx, int32_t mode, int32_t nl, const in
 int32_t stf_fit_rounds(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* labels, uint64_t seed, uint64_t iteration0,
                        int32_t n_rounds, int64_t* nhits_per_round, stf_counters_t* totals, int32_t level, int32_t* rs, int32_t* cs);
 
+/* trainepoch_E!(qtrees; optimiser)  fit.jl:85-99 with its round loop ON THE DEVICE: round 0 = totalcollisions(qtrees) ->
+ * batchsteps!; inds := the labels of its colist in order of first appearance (:90) and the limit length(qtrees) ÷
+ * length(inds) are built on the device; rounds ni = 1.. run totalcollisions(qtrees, inds) -> batchsteps! until the round with
+ * ni > 8 length(colist) (:96) or ni == limit.  Rounds are enqueued blindly (at most max_rounds per call), ONE
+ * synchronisation per call; round k uses the draws of iteration0 + k.  first_round = 0 starts an epoch, > 0 resumes it.
+ * state_out = {reason, ni, length(inds), limit}: reason 1 = epoch finished; 0 = max_rounds ran out (call again with
+ * first_round = rounds done so far in this epoch); 3 = length(inds) <= 10 = SPACIAL_ENABLE_THRESHOLD (qtree_functions.jl:265,
+ * one thread): the dispatcher's native all-pairs path takes over — the caller runs the remaining rounds itself over inds_out.
+ * nhits_per_round[0] is the epoch's nc.  Needs a scene on the single-scene latency path. */
+int32_t stf_fit_epoch_E(stf_ctx* ctx, uint64_t seed, uint64_t iteration0, int32_t first_round, int32_t max_rounds,
+                        int64_t* nhits_per_round, int32_t* rounds_done, int32_t state_out[4], int32_t* inds_out, int32_t inds_cap);
+
 /* ---- ground composition for place! / reposition! (qtree_functions.jl:452-518, fit.jl:420-436).
  * ground = deepcopy(qtrees[mask_label]) with every other tree overlap!-ed except the `excl_labels` (the trees about to be
  * re-placed).  The room search itself (findroom_uniform: a sequential BFS driven by one RNG stream) stays on the host

@@ -18,7 +18,7 @@ import ..QTrees: AbstractStackedQTree, U8SQTree, CoItem, Index, collision, colli
                  totalcollisions_spacial, partialcollisions, dynamiccollisions, locate!, hash_spacial_qtree, linked_spacial_qtree,
                  shift!, setshift!, setcenter!, getshift, getcenter, kernelsize, buildqtree!, inkernelbounds, EMPTY, FULL, MIX
 import ..Trainer: grad2d, batchsteps!, Momentum, SGD, eta, eta!, reset!
-export DeviceQTrees, DeviceTree, DeviceHashTree, DeviceLinkedTree, DeviceColliders, sync_to_host!, fit_round!, fit_rounds!, GpuGroup
+export DeviceQTrees, DeviceTree, DeviceHashTree, DeviceLinkedTree, DeviceColliders, sync_to_host!, fit_round!, fit_rounds!, trainepoch_E_device!, filttrain!, GpuGroup
 
 const LIB = get(ENV, "STUFFING_B200_LIB", joinpath(@__DIR__, "..", "stuffing.jl_b200", "libstuffing_b200.so"))
 
@@ -294,6 +294,33 @@ function filttrain!(d::DeviceQTrees, inpool, outpool, nearlevel2; optimiser=(t, 
     colist = CoItem[c for c in near if c.second[1] > 0]
     batchsteps!(d, colist, optimiser)
     length(colist)
+end
+
+"trainepoch_E!(qtrees; optimiser)  fit.jl:85-99 with the round loop on the device (stf_fit_epoch_E): `inds`, the round limit and the
+stop rule `ni > 8length(colist)` are evaluated there; one host synchronisation per `chunk` rounds.  Small label sets (<= the
+dispatcher's threshold) finish through the host dispatcher, as in the reference."
+function trainepoch_E_device!(d::DeviceQTrees; optimiser=(t, Δ) -> Δ ./ 6, chunk::Integer=8, kargs...)
+    _setopt!(d, optimiser)
+    nh = Vector{Int64}(undef, chunk); state = Vector{Int32}(undef, 4); inds = Vector{Int32}(undef, d.n)
+    first = 0; nc = 0
+    while true
+        rd = Ref{Int32}(0); seed, it = d.clock
+        check(d, ccall((:stf_fit_epoch_E, LIB), Int32, (Ptr{Cvoid}, UInt64, UInt64, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32),
+                       d.h, seed, it, first, chunk, nh, rd, state, inds, length(inds)))
+        first == 0 && rd[] > 0 && (nc = Int(nh[1]))
+        (first == 0 && rd[] == 1 && nc == 0) || (d.clock = (seed, it + rd[]))
+        first += rd[]
+        (state[1] != 0 || rd[] == 0) && break
+    end
+    if state[1] == 3                                    # the native dispatcher path takes over for a small label set
+        lb = Int.(inds[1:state[3]])
+        for ni in state[2]+1:state[4]
+            colist = totalcollisions(d, lb; unique=false)
+            batchsteps!(d, colist, optimiser)
+            ni > 8length(colist) && break
+        end
+    end
+    nc
 end
 
 # ------------------------------------------------------------------------------------------------ trainers (fit.jl:77-233) — host policy over device rounds

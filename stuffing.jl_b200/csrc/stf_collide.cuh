@@ -23,11 +23,16 @@ namespace cg = cooperative_groups;
 //   (key, tie) with tie = position in `labels` (or the label itself when labels == NULL); a sort by (key, tie)
 //   reproduces the insertion order of the reference's Dict of Vectors (qtrees.jl:411-415) whatever the append order.
 #define LOC_THREADS 128
+// device-side control of a round inside a multi-round call (stf_fit_rounds, stf_fit_epoch_E): `stop` != 0 cancels the round
+// (no records are produced, so every later kernel finds empty lists); `nl_dev` = the number of labels when the label list
+// was produced on the device (the labels of the previous round's colist)
+struct RoundCtl { const unsigned long long* stop; const int* nl_dev; };
 __global__ void __launch_bounds__(LOC_THREADS) k_locate(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
                          int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                         int* __restrict__ err, unsigned long long* __restrict__ n_append, const unsigned long long* __restrict__ cancel = nullptr) {
+                         int* __restrict__ err, unsigned long long* __restrict__ n_append, RoundCtl ctl) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
-    if (cancel && *cancel) return; // a cancelled round of a multi-round call (stf_fit_rounds): no records, so every later kernel finds empty lists
+    if (ctl.stop && *ctl.stop) return; // a cancelled round of a multi-round call: no records, so every later kernel finds empty lists
+    if (ctl.nl_dev) nl = min(nl, *ctl.nl_dev);
     const unsigned FULLM = 0xffffffffu;
     const int lane = threadIdx.x & 31, gl = lane & 3, g0 = lane & ~3;
     const int j = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
@@ -112,9 +117,10 @@ __global__ void __launch_bounds__(LOC_THREADS) k_locate(const uint32_t* __restri
 //   reproduces the insertion order of the reference's Dict of Vectors (qtrees.jl:411-415) whatever the append order.
 __global__ void k_locate_wide(const uint32_t* __restrict__ words, const LevelMeta* __restrict__ lm, const ObjMeta* __restrict__ om, int L,
                          int nl, const int32_t* __restrict__ labels, int linked, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                         int* __restrict__ err, unsigned long long* __restrict__ n_append, const unsigned long long* __restrict__ cancel = nullptr) {
+                         int* __restrict__ err, unsigned long long* __restrict__ n_append, RoundCtl ctl) {
     pdl_sync(); // programmatic dependent launch: scheduled while the previous kernel drains; nothing global before this
-    if (cancel && *cancel) return;
+    if (ctl.stop && *ctl.stop) return;
+    if (ctl.nl_dev) nl = min(nl, *ctl.nl_dev);
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0; uint64_t ck[4]; int o = 0, slot = 0;
     if (j < nl) {
@@ -164,9 +170,9 @@ __global__ void k_locate_wide(const uint32_t* __restrict__ words, const LevelMet
 // LinkedSpacialQTree table (4 slots per object) -> compact (key, label) records, unordered
 __global__ void k_compact_records(const uint64_t* __restrict__ tk, const uint32_t* __restrict__ tv, int64_t nslots,
                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_append,
-                                  const unsigned long long* __restrict__ cancel = nullptr) {
+                                  RoundCtl ctl) {
     pdl_sync();
-    if (cancel && *cancel) return;
+    if (ctl.stop && *ctl.stop) return;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t k = i < nslots ? tk[i] : STF_KEY_INVALID;
     bool v = k != STF_KEY_INVALID;

@@ -87,6 +87,7 @@ struct FinalizeArgs {
     int do_prep; const ObjMeta* om; uint32_t* prev; uint32_t* done;             // optional step-dependency links
     unsigned long long* ticket; unsigned long long* n_steps;
     int* status;
+    const unsigned long long* stop; // optional: != 0 cancels the round as well (a multi-round call that has ended)
     int abort_on_status;   // != 0: a status bit that is already raised (by an earlier kernel of the round, by a peer GPU of an
                            // item-parallel group, or by an earlier round of a multi-round call) cancels the round: no step runs
 };
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_finalize_hits(FinalizeArgs A) {
     int64_t nh64 = (int64_t)*A.nh_dev;
     bool grow = nh64 > A.hits_cap || (A.n_items_dev && (int64_t)*A.n_items_dev > A.item_cap);
     bool big = nh64 > (A.do_prep ? BS_CAP / 2 : BS_CAP);
-    if (A.abort_on_status && *A.status != 0 && !grow && !big) { // cancelled from outside: keep the bits as they are
+    if (((A.abort_on_status && *A.status != 0) || (A.stop && *A.stop != 0ull)) && !grow && !big) { // cancelled from outside: keep the bits as they are
         if (threadIdx.x == 0) { if (A.n_steps) *A.n_steps = 0; if (A.ticket) *A.ticket = 0; if (A.kept) *A.kept = 0; }
         return;
     }
@@ -241,7 +242,7 @@ __global__ void __cluster_dims__(CS_CTAS, 1, 1) __launch_bounds__(CS_THREADS) k_
     int64_t nh64 = (int64_t)*A.nh_dev;
     bool grow = nh64 > A.hits_cap || (A.n_items_dev && (int64_t)*A.n_items_dev > A.item_cap);
     bool big = nh64 > CS_CAP / 2;
-    if (A.abort_on_status && *A.status != 0 && !grow && !big) { // cancelled from outside: keep the bits as they are
+    if (((A.abort_on_status && *A.status != 0) || (A.stop && *A.stop != 0ull)) && !grow && !big) { // cancelled from outside: keep the bits as they are
         if (c == 0 && threadIdx.x == 0) { *A.n_steps = 0; *A.ticket = 0; }
         return;
     }

@@ -324,3 +324,65 @@ __global__ void __launch_bounds__(1024) k_result_labels(const Item16* __restrict
     }
     if (t == 0) out[0] = base;
 }
+
+// ---- trainepoch_E! on the device (fit.jl:85-99): the end-of-round kernel of stf_fit_epoch_E.
+// Round 0 ran over every label: `inds := union!(empty!(moved), first.(colist) |> Iterators.flatten)` — the distinct labels of
+// the colist in order of FIRST APPEARANCE (IntSet keeps insertion order, common_datatypes.jl:227-237) — is built here
+// (atomicMin of the endpoint index per label, then an ordered compaction over the endpoints), together with the round
+// limit length(qtrees) ÷ length(inds).  Rounds ni >= 1 ran over `inds`: the epoch ends after the round with
+// ni > 8 length(colist) (:96) or with ni == limit.  ctl = {ninds, limit, ni, reason}; reason 1 = epoch finished,
+// 3 = `inds` is at or below the dispatcher's threshold (qtree_functions.jl:265-276: the native all-pairs path takes over,
+// driven by the host).  *stop != 0 cancels every round enqueued after this one.
+#define EPOCH_E_THRESHOLD 10
+__global__ void __launch_bounds__(1024) k_epoch_e_end(unsigned long long* __restrict__ counts, int c_stop, int c_status, int c_nhits, int c_items, int c_direct, int c_visited, int c_moves, int c_nvalid,
+                                                      unsigned long long* __restrict__ rec, int k_rec, int ni, const Item16* __restrict__ hits, int64_t hits_cap,
+                                                      int* __restrict__ firstpos, int n_obj, int32_t* __restrict__ inds, int* __restrict__ ctl) {
+    pdl_sync();
+    __shared__ int wsum[32];
+    __shared__ int base, s_go;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) {
+        int go = 1;
+        if (counts[c_stop] != 0ull) go = 0;                                        // cancelled round: no record
+        else if ((int)counts[c_status] != 0) { counts[c_stop] = 2ull; go = 0; }    // this round raised a bit (its steps did not run)
+        if (go) {
+            unsigned long long* r = rec + (size_t)4 * (k_rec + 1);
+            r[0] = counts[c_nhits]; r[1] = counts[c_items] + counts[c_direct]; r[2] = counts[c_visited]; r[3] = counts[c_moves];
+            rec[0] = (unsigned long long)(k_rec + 1); rec[1] = counts[c_nvalid];
+        }
+        s_go = go; base = 0;
+    }
+    __syncthreads();
+    if (!s_go) return;
+    const int64_t nh = min((int64_t)counts[c_nhits], hits_cap);
+    if (ni > 0) { // a round over `inds`
+        if (t == 0) { ctl[2] = ni; if ((int64_t)ni > 8 * nh || ni >= ctl[1]) { ctl[3] = 1; counts[c_stop] = 1ull; } }
+        return;
+    }
+    if (nh == 0) { if (t == 0) { ctl[0] = 0; ctl[1] = 0; ctl[2] = 0; ctl[3] = 1; counts[c_stop] = 1ull; } return; } // nc == 0: return nc (:89)
+    const int64_t ne = 2 * nh;
+    for (int64_t e = t; e < ne; e += 1024) { const Item16 h = hits[e >> 1]; firstpos[((e & 1) ? item_i2(h) : h.i1) - 1] = 0x7fffffff; }
+    __syncthreads();
+    for (int64_t e = t; e < ne; e += 1024) { const Item16 h = hits[e >> 1]; atomicMin(firstpos + (((e & 1) ? item_i2(h) : h.i1) - 1), (int)e); }
+    __syncthreads();
+    for (int64_t e0 = 0; e0 < ne; e0 += 1024) {
+        const int64_t e = e0 + t;
+        int label = 0; bool first = false;
+        if (e < ne) { const Item16 h = hits[e >> 1]; label = (e & 1) ? item_i2(h) : h.i1; first = firstpos[label - 1] == (int)e; }
+        const unsigned bal = __ballot_sync(0xffffffffu, first);
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int i = 0; i < w; i++) off += wsum[i];
+        if (first) inds[off + __popc(bal & ((1u << lane) - 1u))] = label;
+        __syncthreads();
+        if (t == 0) { int sum = 0; for (int i = 0; i < 32; i++) sum += wsum[i]; base += sum; }
+        __syncthreads();
+    }
+    if (t == 0) {
+        const int ninds = base;
+        ctl[0] = ninds; ctl[1] = n_obj / ninds; ctl[2] = 0; ctl[3] = 0;
+        if (ctl[1] < 1) { ctl[3] = 1; counts[c_stop] = 1ull; }                    // for ni in 1:0 — no inner round
+        else if (ninds <= EPOCH_E_THRESHOLD) { ctl[3] = 3; counts[c_stop] = 3ull; } // the native path takes over (host)
+    }
+}

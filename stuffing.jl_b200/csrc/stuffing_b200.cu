@@ -69,6 +69,8 @@ struct stf_ctx {
     int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
     int64_t hint_surv = 0;  // pairs the word-parallel narrow phase handed to the frontier kernel in the previous round
     bool fused_narrow = false; // STF_FUSED_NARROW=1: candidates are tested inside the candidate kernel and never stored (measured slower: DESIGN.md)
+    const int32_t* dev_labels = nullptr; const int* dev_nl = nullptr; // stf_fit_epoch_E: the label list of the round lives on the device (the labels of an earlier colist)
+    DevBuf inds, epoch_ctl; // that list and the epoch's control block
     bool in_rounds = false; // stf_fit_rounds is enqueueing: k_round_begin resets the counters (not a host memset) and a raised C_STOP cancels a round
     DevBuf lab_mark; uint32_t lab_epoch = 0; bool want_moved = false; // stf_fit_round_moved: epoch-stamped label marks; fold the label list into the round's sync
     DevBuf rounds_rec;      // stf_fit_rounds: per-round records (hits, items, node tests, moves)
@@ -283,7 +285,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from, &ctx->gather, &ctx->gflags, &ctx->gdone, &ctx->rounds_rec, &ctx->lab_mark };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from, &ctx->gather, &ctx->gflags, &ctx->gdone, &ctx->rounds_rec, &ctx->lab_mark, &ctx->inds, &ctx->epoch_ctl };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) free(ctx->h_err);
@@ -982,7 +984,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     unsigned long long* nvalid = ctx->counts.as<unsigned long long>() + C_NVALID;
     unsigned long long* nappend = ctx->counts.as<unsigned long long>() + C_NREC;
     if (fast) {
-        const unsigned long long* cancel = ctx->in_rounds ? ctx->counts.as<unsigned long long>() + C_STOP : nullptr;
+        const RoundCtl cancel = { ctx->in_rounds ? ctx->counts.as<unsigned long long>() + C_STOP : nullptr, ctx->dev_nl };
         if (linked) {
             if (nl > 0) LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
                                                                    ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr, cancel);
@@ -1007,12 +1009,12 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
     CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(std::max<int64_t>(1, nrec))));
     if (linked) {
         if (nl > 0) LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1,
-                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr, (const unsigned long long*)nullptr);
+                                                               ctx->lkk.as<uint64_t>(), ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr, RoundCtl{ nullptr, nullptr });
         CK(cudaMemcpyAsync(ctx->rk.p, ctx->lkk.p, sizeof(uint64_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->rv.p, ctx->lkv.p, sizeof(uint32_t) * (size_t)nrec, cudaMemcpyDeviceToDevice, ctx->st));
     } else if (nl > 0) {
         LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 0,
-                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ERRP(ctx), nullptr, (const unsigned long long*)nullptr);
+                                                    ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), ERRP(ctx), nullptr, RoundCtl{ nullptr, nullptr });
     }
     KCHECK();
     stage_begin(ctx, STF_STAGE_SORT);
@@ -1073,7 +1075,7 @@ extern "C" int32_t stf_linked_locate(stf_ctx* ctx, int32_t nl, const int32_t* la
     if (nl <= 0) return STF_OK;
     const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
     LAUNCH_LOCATE(ctx, nl, ctx->words.as<uint32_t>(), ctx->lm.as<LevelMeta>(), ctx->om.as<ObjMeta>(), ctx->L, nl, dl, 1, ctx->lkk.as<uint64_t>(),
-                                                ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr, (const unsigned long long*)nullptr);
+                                                ctx->lkv.as<uint32_t>(), ERRP(ctx), nullptr, RoundCtl{ nullptr, nullptr });
     KCHECK();
     return sync_counts(ctx);
 }
@@ -1153,7 +1155,9 @@ static void set_overflow_check(stf_ctx* ctx, FinalizeArgs& F) {
 // in counts[C_NHITS].  Buffer sizes come from the previous round; the finalize kernel raises RETRY bits if one was too
 // small or the scene is too large for the single-CTA kernels, and the caller re-runs.
 static int32_t spacial_core_fast(stf_ctx* ctx, int32_t nl, const int32_t* labels, int linked) {
-    const int32_t* dl; int32_t r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r;
+    const int32_t* dl; int32_t r = STF_OK;
+    if (ctx->dev_labels) dl = ctx->dev_labels; // the list was produced on the device; nl = its capacity, the count is read by k_locate
+    else { r = upload_labels(ctx, ctx->lab, nl, labels, &dl); if (r) return r; }
     const int32_t* moved_pos = nullptr;
     if (linked) { r = upload_moved_pos(ctx, nl, labels, &moved_pos); if (r) return r; }
     int64_t nrec; uint64_t* keys; uint32_t* vals;
@@ -1408,6 +1412,7 @@ static int32_t fast_round_tail(stf_ctx* ctx, uint64_t seed, uint64_t iteration, 
     F.do_prep = 1; F.om = ctx->om.as<ObjMeta>(); F.prev = ctx->prev.as<uint32_t>(); F.done = ctx->done.as<uint32_t>();
     F.ticket = ctx->counts.as<unsigned long long>() + C_TICKET; F.n_steps = ctx->counts.as<unsigned long long>() + C_NSTEPS;
     F.status = STATUSP(ctx); F.abort_on_status = cancel_on_status ? 1 : 0;
+    F.stop = ctx->in_rounds ? ctx->counts.as<unsigned long long>() + C_STOP : nullptr;
     if (ctx->no_cluster) LAUNCH_PDL(ctx, k_finalize_hits, 1, BS_THREADS, BS_SMEM_BYTES, F);
     else {
         CK(ctx->hk.ensure(sizeof(uint64_t) * (size_t)(CS_CAP + 1024)));
@@ -1505,10 +1510,11 @@ __global__ void k_round_begin(unsigned long long* __restrict__ counts) {
     const int status = (int)counts[C_STATUS];
     const bool stop = status != 0 || counts[C_STOP] != 0ull;
     __syncwarp();
-    if (t == 0 && stop) counts[C_STOP] = 2ull; // a previous round failed: nothing of what follows may run
+    if (t == 0 && stop && counts[C_STOP] == 0ull) counts[C_STOP] = 2ull; // a previous round failed: nothing of what follows may run (other stop codes stay)
     // a cancelled round only empties the lists (its kernels find nothing to do); the counters of the failed round stay: the
     // host sizes the buffers of the re-run from them
-    if (stop) { if (t == C_NREC || t == C_NVALID || t == C_NHITS || t == C_NSTEPS || t == C_SURV) counts[t] = 0ull; return; }
+    // (an epoch that simply ended — no status bit — also drops the stale candidate list: nothing may be tested or stepped again)
+    if (stop) { if (t == C_NREC || t == C_NVALID || t == C_NHITS || t == C_NSTEPS || t == C_SURV || (t == C_ITEMS && status == 0)) counts[t] = 0ull; return; }
     if (t < C_STATUS) counts[t] = 0ull;
 }
 __global__ void k_round_end(unsigned long long* __restrict__ counts, unsigned long long* __restrict__ rec, int k) {
@@ -1582,6 +1588,75 @@ extern "C" int32_t stf_fit_rounds(stf_ctx* ctx, int32_t mode, int32_t nl, const 
     if (totals) *totals = tot;
     if (level > 0) return stf_get_shifts(ctx, ctx->n, nullptr, level, rs, cs); // paths without a folded read-back
     return STF_OK;
+}
+
+// trainepoch_E! (fit.jl:85-99) with its round loop on the device: round 0 over every label, `inds` (the labels of its
+// colist, first-appearance order) and the round limit built on the device, then rounds over `inds` until the reference's
+// stop rule fires — all enqueued blindly, ONE synchronisation per call.  first_round = 0 starts an epoch; > 0 resumes the
+// epoch whose state is still on the device at that round (after max_rounds ran out).  state_out = {reason, ni, ninds,
+// limit}: reason 0 = max_rounds ran out (call again with first_round = rounds done so far), 1 = the epoch is finished,
+// 3 = `inds` (returned in inds_out) is at or below SPACIAL_ENABLE_THRESHOLD = 10: the dispatcher's native path takes over
+// and the caller runs the remaining rounds ni+1.. through totalcollisions(qtrees, inds) + batchsteps! itself.
+extern "C" int32_t stf_fit_epoch_E(stf_ctx* ctx, uint64_t seed, uint64_t iteration0, int32_t first_round, int32_t max_rounds,
+                                   int64_t* nhits_per_round, int32_t* rounds_done, int32_t state_out[4], int32_t* inds_out, int32_t inds_cap) {
+    NEED_OBJS();
+    if (rounds_done) *rounds_done = 0;
+    if (max_rounds < 1 || first_round < 0 || !state_out) FAIL(STF_E_ARG, "bad round counts or null state");
+    if (ctx->n <= 1) { state_out[0] = 1; state_out[1] = state_out[2] = state_out[3] = 0; return STF_OK; }
+    if (!fast_path_ok(ctx, ctx->n)) FAIL(STF_E_STATE, "stf_fit_epoch_E needs a scene on the single-scene latency path (use the host trainer over stf_fit_round)");
+    CK(ctx->rounds_rec.ensure(sizeof(unsigned long long) * ROUND_REC * (size_t)(max_rounds + 2)));
+    CK(ctx->inds.ensure(sizeof(int32_t) * (size_t)ctx->n)); CK(ctx->epoch_ctl.ensure(sizeof(int) * 8));
+    if (ctx->lab_mark.cap < sizeof(uint32_t) * (size_t)ctx->n) { ctx->lab_mark.release(); CK(ctx->lab_mark.ensure(sizeof(uint32_t) * (size_t)ctx->n)); CK(cudaMemsetAsync(ctx->lab_mark.p, 0, sizeof(uint32_t) * (size_t)ctx->n, ctx->st)); ctx->lab_epoch = 0; }
+    std::vector<unsigned long long> rec((size_t)ROUND_REC * (max_rounds + 2));
+    int ctl[4] = {};
+    int done = 0, round = first_round;
+    unsigned long long* C0 = ctx->counts.as<unsigned long long>();
+    for (int attempt = 0; attempt < 6; attempt++) {
+        const int todo = max_rounds - done;
+        CK(cudaMemsetAsync(ctx->rounds_rec.p, 0, sizeof(unsigned long long) * ROUND_REC * (size_t)(todo + 2), ctx->st));
+        CK(cudaMemsetAsync(C0 + C_STATUS, 0, sizeof(unsigned long long), ctx->st));
+        CK(cudaMemsetAsync(C0 + C_STOP, 0, sizeof(unsigned long long), ctx->st));
+        ctx->in_rounds = true;
+        int32_t r = STF_OK;
+        for (int k = 0; k < todo && !r; k++) {
+            const int ni = round + k;
+            LAUNCH_PDL(ctx, k_round_begin, 1, 32, 0, C0);
+            if (ni > 0) { ctx->dev_labels = ctx->inds.as<int32_t>(); ctx->dev_nl = ctx->epoch_ctl.as<int>(); }
+            r = spacial_core_fast(ctx, ctx->n, nullptr, 0);
+            ctx->dev_labels = nullptr; ctx->dev_nl = nullptr;
+            if (!r) r = fast_round_tail(ctx, seed, iteration0 + done + k, true);
+            if (!r) LAUNCH_PDL(ctx, k_epoch_e_end, 1, 1024, 0, C0, (int)C_STOP, (int)C_STATUS, (int)C_NHITS, (int)C_ITEMS, (int)C_DIRECT, (int)C_VISITED, (int)C_MOVES, (int)C_NVALID,
+                               ctx->rounds_rec.as<unsigned long long>(), k, ni, (const Item16*)ctx->hits2.as<Item16>(), (int64_t)BS_CAP,
+                               reinterpret_cast<int*>(ctx->lab_mark.as<uint32_t>()), ctx->n, ctx->inds.as<int32_t>(), ctx->epoch_ctl.as<int>());
+        }
+        ctx->in_rounds = false;
+        if (r) return r;
+        CK(cudaMemcpyAsync(rec.data(), ctx->rounds_rec.p, sizeof(unsigned long long) * ROUND_REC * (size_t)(todo + 2), cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(ctl, ctx->epoch_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, ctx->st));
+        r = sync_counts(ctx); if (r) return r;
+        const int ran = (int)rec[0];
+        for (int k = 0; k < ran; k++) if (nhits_per_round) nhits_per_round[done + k] = (int64_t)rec[(size_t)ROUND_REC * (k + 1)];
+        done += ran; round += ran;
+        const int stop = (int)ctx->h_counts[C_STOP];
+        CK(cudaMemsetAsync(C0 + C_STOP, 0, sizeof(unsigned long long), ctx->st));
+        ctx->lab_epoch = 0; CK(cudaMemsetAsync(ctx->lab_mark.p, 0, sizeof(uint32_t) * (size_t)ctx->n, ctx->st)); // (the marks were used as first positions)
+        if (stop == 2) { // a round needs larger buffers (or the scene left the latency path): grow, go on from that round
+            if (!fast_round_verdict(ctx)) FAIL(STF_E_CUDA, "internal: a round was cancelled without a status bit");
+            if (ctx->force_big) FAIL(STF_E_STATE, "the scene left the single-scene latency path inside stf_fit_epoch_E");
+            if (done < max_rounds) continue;
+        }
+        if (rounds_done) *rounds_done = done;
+        state_out[0] = stop == 2 ? 0 : ctl[3]; state_out[1] = ctl[2]; state_out[2] = ctl[0]; state_out[3] = ctl[1];
+        if (round == 0) { state_out[0] = 0; state_out[1] = state_out[2] = state_out[3] = 0; } // not even round 0 ran
+        if (inds_out && ctl[0] > 0 && round > 0) {
+            if (ctl[0] > inds_cap) FAIL(STF_E_CAPACITY, "label buffer too small");
+            CK(cudaMemcpyAsync(inds_out, ctx->inds.p, sizeof(int32_t) * (size_t)ctl[0], cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+        }
+        ctx->ctr.hits = done > 0 && nhits_per_round ? nhits_per_round[done - 1] : 0;
+        return STF_OK;
+    }
+    FAIL(STF_E_CUDA, "internal: stf_fit_epoch_E did not converge");
 }
 
 // ---- ground composition for place!/reposition!: deepcopy(mask) with every other tree overlapped

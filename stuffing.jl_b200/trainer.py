@@ -184,6 +184,39 @@ def trainepoch_E(qts, optimiser=None, clock=None, last=None, **_kw):
     return nc
 
 
+def trainepoch_E_device(qts, optimiser=None, clock=None, last=None, chunk=8, **_kw):
+    """trainepoch_E! (fit.jl:85-99) with its round loop on the device (stf_fit_epoch_E): round 0, the label set `inds` of its
+    colist, the round limit and the stop rule ni > 8 length(colist) are all evaluated there; the host synchronises once per
+    `chunk` rounds.  When `inds` is at or below the dispatcher's threshold the remaining rounds run through the host
+    dispatcher (native all-pairs path), exactly as trainepoch_E does.  Same result as trainepoch_E."""
+    d = _dev(qts)
+    clock = clock or _default_clock
+    _set_opt(d, optimiser)
+    nh = np.zeros(chunk, np.int64)
+    state, inds = np.zeros(4, np.int32), np.zeros(d.n, np.int32)
+    first, nc = 0, 0
+    while True:
+        rd = C.c_int32(0)
+        d._ck(d.lib.stf_fit_epoch_E(d.h, clock.seed, clock.iteration, first, chunk, ptr(nh), C.byref(rd), ptr(state), ptr(inds), len(inds)))
+        if first == 0 and rd.value > 0:
+            nc = int(nh[0])
+        if not (first == 0 and rd.value == 1 and nc == 0):  # (trainepoch_E returns before batchsteps! when nc == 0: no tick)
+            clock.iteration += rd.value
+        first += rd.value
+        if state[0] != 0 or rd.value == 0:
+            break
+    if last is not None:
+        last["colist"] = None  # the colist stays on the device; train!'s policy re-queries when it needs it
+    if state[0] == 3:  # the native dispatcher path takes over for a small label set
+        inds_l = inds[: state[2]].tolist()
+        for ni in range(int(state[1]) + 1, int(state[3]) + 1):
+            colist = _note(last, totalcollisions(d, inds_l, unique=False, raw=True))
+            batchsteps(d, colist, optimiser, clock)
+            if ni > 8 * len(colist):
+                break
+    return nc
+
+
 class LRU:
     """LRU{Int} over labels  fit_helper.jl:80-102: most recently pushed first"""
 

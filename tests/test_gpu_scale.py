@@ -173,6 +173,21 @@ def test_c2_trainepoch_E_policy_parity(S, orc):
         ro, co = orc.getshifts(qo)
         assert np.array_equal(rs, ro) and np.array_equal(cs, co), ep
     assert nc_o < W["round_hits"][0] // 4
+    # the same epochs with the round loop ON THE DEVICE (stf_fit_epoch_E: inds, round limit and stop rule evaluated there, one
+    # synchronisation per chunk of rounds; small label sets fall back to the host dispatcher): same counts, rounds, positions
+    for chunk in (8, 2):
+        qo2 = workloads.oracle_scene(orc, W)
+        d2 = workloads.device_scene(S, W)
+        opt2 = orc.Opt("momentum", 0.25, 0.5, len(qo2))
+        clock2 = S.trainer.StepClock(seed=7)
+        it = 0
+        for ep in range(6):
+            nc_o, it = _orc_trainepoch_E(orc, qo2, opt2, 7, it)
+            nc_d = S.trainer.trainepoch_E_device(d2, S.Momentum(0.25, 0.5), clock2, chunk=chunk)
+            assert nc_d == nc_o and clock2.iteration == it, (chunk, ep, nc_d, nc_o, clock2.iteration, it)
+            rs, cs = d2.getshifts()
+            ro, co = orc.getshifts(qo2)
+            assert np.array_equal(rs, ro) and np.array_equal(cs, co), (chunk, ep)
 
 
 class _OracleOps:
