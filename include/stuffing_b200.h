@@ -216,7 +216,7 @@ int32_t stf_fit_rounds(stf_ctx* ctx, int32_t mode, int32_t nl, const int32_t* la
  * first_round = rounds done so far in this epoch); 3 = length(inds) <= 10 = SPACIAL_ENABLE_THRESHOLD (qtree_functions.jl:265,
  * one thread): the dispatcher's native all-pairs path takes over — the caller runs the remaining rounds itself over inds_out.
  * nhits_per_round[0] is the epoch's nc.  Needs a scene on the single-scene latency path. */
-int32_t stf_fit_epoch_E(stf_ctx* ctx, uint64_t seed, uint64_t iteration0, int32_t first_round, int32_t max_rounds,
+int32_t stf_fit_epoch_e(stf_ctx* ctx, uint64_t seed, uint64_t iteration0, int32_t first_round, int32_t max_rounds,
                         int64_t* nhits_per_round, int32_t* rounds_done, int32_t state_out[4], int32_t* inds_out, int32_t inds_cap);
 
 /* ---- ground composition for place! / reposition! (qtree_functions.jl:452-518, fit.jl:420-436).

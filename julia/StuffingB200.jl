@@ -296,7 +296,7 @@ function filttrain!(d::DeviceQTrees, inpool, outpool, nearlevel2; optimiser=(t, 
     length(colist)
 end
 
-"trainepoch_E!(qtrees; optimiser)  fit.jl:85-99 with the round loop on the device (stf_fit_epoch_E): `inds`, the round limit and the
+"trainepoch_E!(qtrees; optimiser)  fit.jl:85-99 with the round loop on the device (stf_fit_epoch_e): `inds`, the round limit and the
 stop rule `ni > 8length(colist)` are evaluated there; one host synchronisation per `chunk` rounds.  Small label sets (<= the
 dispatcher's threshold) finish through the host dispatcher, as in the reference."
 function trainepoch_E_device!(d::DeviceQTrees; optimiser=(t, Δ) -> Δ ./ 6, chunk::Integer=8, kargs...)
@@ -305,7 +305,7 @@ function trainepoch_E_device!(d::DeviceQTrees; optimiser=(t, Δ) -> Δ ./ 6, chu
     first = 0; nc = 0
     while true
         rd = Ref{Int32}(0); seed, it = d.clock
-        check(d, ccall((:stf_fit_epoch_E, LIB), Int32, (Ptr{Cvoid}, UInt64, UInt64, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32),
+        check(d, ccall((:stf_fit_epoch_e, LIB), Int32, (Ptr{Cvoid}, UInt64, UInt64, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32),
                        d.h, seed, it, first, chunk, nh, rd, state, inds, length(inds)))
         first == 0 && rd[] > 0 && (nc = Int(nh[1]))
         (first == 0 && rd[] == 1 && nc == 0) || (d.clock = (seed, it + rd[]))

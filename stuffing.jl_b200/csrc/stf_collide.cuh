@@ -23,7 +23,7 @@ namespace cg = cooperative_groups;
 //   (key, tie) with tie = position in `labels` (or the label itself when labels == NULL); a sort by (key, tie)
 //   reproduces the insertion order of the reference's Dict of Vectors (qtrees.jl:411-415) whatever the append order.
 #define LOC_THREADS 128
-// device-side control of a round inside a multi-round call (stf_fit_rounds, stf_fit_epoch_E): `stop` != 0 cancels the round
+// device-side control of a round inside a multi-round call (stf_fit_rounds, stf_fit_epoch_e): `stop` != 0 cancels the round
 // (no records are produced, so every later kernel finds empty lists); `nl_dev` = the number of labels when the label list
 // was produced on the device (the labels of the previous round's colist)
 struct RoundCtl { const unsigned long long* stop; const int* nl_dev; };

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(1024) k_result_labels(const Item16* __restrict
     if (t == 0) out[0] = base;
 }
 
-// ---- trainepoch_E! on the device (fit.jl:85-99): the end-of-round kernel of stf_fit_epoch_E.
+// ---- trainepoch_E! on the device (fit.jl:85-99): the end-of-round kernel of stf_fit_epoch_e.
 // Round 0 ran over every label: `inds := union!(empty!(moved), first.(colist) |> Iterators.flatten)` — the distinct labels of
 // the colist in order of FIRST APPEARANCE (IntSet keeps insertion order, common_datatypes.jl:227-237) — is built here
 // (atomicMin of the endpoint index per label, then an ordered compaction over the endpoints), together with the round

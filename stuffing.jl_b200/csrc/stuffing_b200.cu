@@ -69,7 +69,7 @@ struct stf_ctx {
     int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
     int64_t hint_surv = 0;  // pairs the word-parallel narrow phase handed to the frontier kernel in the previous round
     bool fused_narrow = false; // STF_FUSED_NARROW=1: candidates are tested inside the candidate kernel and never stored (measured slower: DESIGN.md)
-    const int32_t* dev_labels = nullptr; const int* dev_nl = nullptr; // stf_fit_epoch_E: the label list of the round lives on the device (the labels of an earlier colist)
+    const int32_t* dev_labels = nullptr; const int* dev_nl = nullptr; // stf_fit_epoch_e: the label list of the round lives on the device (the labels of an earlier colist)
     DevBuf inds, epoch_ctl; // that list and the epoch's control block
     bool in_rounds = false; // stf_fit_rounds is enqueueing: k_round_begin resets the counters (not a host memset) and a raised C_STOP cancels a round
     DevBuf lab_mark; uint32_t lab_epoch = 0; bool want_moved = false; // stf_fit_round_moved: epoch-stamped label marks; fold the label list into the round's sync
@@ -1597,13 +1597,13 @@ extern "C" int32_t stf_fit_rounds(stf_ctx* ctx, int32_t mode, int32_t nl, const 
 // limit}: reason 0 = max_rounds ran out (call again with first_round = rounds done so far), 1 = the epoch is finished,
 // 3 = `inds` (returned in inds_out) is at or below SPACIAL_ENABLE_THRESHOLD = 10: the dispatcher's native path takes over
 // and the caller runs the remaining rounds ni+1.. through totalcollisions(qtrees, inds) + batchsteps! itself.
-extern "C" int32_t stf_fit_epoch_E(stf_ctx* ctx, uint64_t seed, uint64_t iteration0, int32_t first_round, int32_t max_rounds,
+extern "C" int32_t stf_fit_epoch_e(stf_ctx* ctx, uint64_t seed, uint64_t iteration0, int32_t first_round, int32_t max_rounds,
                                    int64_t* nhits_per_round, int32_t* rounds_done, int32_t state_out[4], int32_t* inds_out, int32_t inds_cap) {
     NEED_OBJS();
     if (rounds_done) *rounds_done = 0;
     if (max_rounds < 1 || first_round < 0 || !state_out) FAIL(STF_E_ARG, "bad round counts or null state");
     if (ctx->n <= 1) { state_out[0] = 1; state_out[1] = state_out[2] = state_out[3] = 0; return STF_OK; }
-    if (!fast_path_ok(ctx, ctx->n)) FAIL(STF_E_STATE, "stf_fit_epoch_E needs a scene on the single-scene latency path (use the host trainer over stf_fit_round)");
+    if (!fast_path_ok(ctx, ctx->n)) FAIL(STF_E_STATE, "stf_fit_epoch_e needs a scene on the single-scene latency path (use the host trainer over stf_fit_round)");
     CK(ctx->rounds_rec.ensure(sizeof(unsigned long long) * ROUND_REC * (size_t)(max_rounds + 2)));
     CK(ctx->inds.ensure(sizeof(int32_t) * (size_t)ctx->n)); CK(ctx->epoch_ctl.ensure(sizeof(int) * 8));
     if (ctx->lab_mark.cap < sizeof(uint32_t) * (size_t)ctx->n) { ctx->lab_mark.release(); CK(ctx->lab_mark.ensure(sizeof(uint32_t) * (size_t)ctx->n)); CK(cudaMemsetAsync(ctx->lab_mark.p, 0, sizeof(uint32_t) * (size_t)ctx->n, ctx->st)); ctx->lab_epoch = 0; }
@@ -1642,7 +1642,7 @@ extern "C" int32_t stf_fit_epoch_E(stf_ctx* ctx, uint64_t seed, uint64_t iterati
         ctx->lab_epoch = 0; CK(cudaMemsetAsync(ctx->lab_mark.p, 0, sizeof(uint32_t) * (size_t)ctx->n, ctx->st)); // (the marks were used as first positions)
         if (stop == 2) { // a round needs larger buffers (or the scene left the latency path): grow, go on from that round
             if (!fast_round_verdict(ctx)) FAIL(STF_E_CUDA, "internal: a round was cancelled without a status bit");
-            if (ctx->force_big) FAIL(STF_E_STATE, "the scene left the single-scene latency path inside stf_fit_epoch_E");
+            if (ctx->force_big) FAIL(STF_E_STATE, "the scene left the single-scene latency path inside stf_fit_epoch_e");
             if (done < max_rounds) continue;
         }
         if (rounds_done) *rounds_done = done;
@@ -1656,7 +1656,7 @@ extern "C" int32_t stf_fit_epoch_E(stf_ctx* ctx, uint64_t seed, uint64_t iterati
         ctx->ctr.hits = done > 0 && nhits_per_round ? nhits_per_round[done - 1] : 0;
         return STF_OK;
     }
-    FAIL(STF_E_CUDA, "internal: stf_fit_epoch_E did not converge");
+    FAIL(STF_E_CUDA, "internal: stf_fit_epoch_e did not converge");
 }
 
 // ---- ground composition for place!/reposition!: deepcopy(mask) with every other tree overlapped

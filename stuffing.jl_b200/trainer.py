@@ -185,7 +185,7 @@ def trainepoch_E(qts, optimiser=None, clock=None, last=None, **_kw):
 
 
 def trainepoch_E_device(qts, optimiser=None, clock=None, last=None, chunk=8, **_kw):
-    """trainepoch_E! (fit.jl:85-99) with its round loop on the device (stf_fit_epoch_E): round 0, the label set `inds` of its
+    """trainepoch_E! (fit.jl:85-99) with its round loop on the device (stf_fit_epoch_e): round 0, the label set `inds` of its
     colist, the round limit and the stop rule ni > 8 length(colist) are all evaluated there; the host synchronises once per
     `chunk` rounds.  When `inds` is at or below the dispatcher's threshold the remaining rounds run through the host
     dispatcher (native all-pairs path), exactly as trainepoch_E does.  Same result as trainepoch_E."""
@@ -197,7 +197,7 @@ def trainepoch_E_device(qts, optimiser=None, clock=None, last=None, chunk=8, **_
     first, nc = 0, 0
     while True:
         rd = C.c_int32(0)
-        d._ck(d.lib.stf_fit_epoch_E(d.h, clock.seed, clock.iteration, first, chunk, ptr(nh), C.byref(rd), ptr(state), ptr(inds), len(inds)))
+        d._ck(d.lib.stf_fit_epoch_e(d.h, clock.seed, clock.iteration, first, chunk, ptr(nh), C.byref(rd), ptr(state), ptr(inds), len(inds)))
         if first == 0 and rd.value > 0:
             nc = int(nh[0])
         if not (first == 0 and rd.value == 1 and nc == 0):  # (trainepoch_E returns before batchsteps! when nc == 0: no tick)

@@ -173,7 +173,7 @@ def test_c2_trainepoch_E_policy_parity(S, orc):
         ro, co = orc.getshifts(qo)
         assert np.array_equal(rs, ro) and np.array_equal(cs, co), ep
     assert nc_o < W["round_hits"][0] // 4
-    # the same epochs with the round loop ON THE DEVICE (stf_fit_epoch_E: inds, round limit and stop rule evaluated there, one
+    # the same epochs with the round loop ON THE DEVICE (stf_fit_epoch_e: inds, round limit and stop rule evaluated there, one
     # synchronisation per chunk of rounds; small label sets fall back to the host dispatcher): same counts, rounds, positions
     for chunk in (8, 2):
         qo2 = workloads.oracle_scene(orc, W)
