@@ -378,7 +378,7 @@ class DevScene:
         self.S, self.which, self.torch = S, which, torch
         t_up = time.perf_counter()
         if which == "c5":
-            my = parallel.shard_range(4096, rank, world)
+            my = parallel.shard_range(int(os.environ.get("STF_BENCH_C5_SCENES", "4096")), rank, world)  # (env: a rank's share of a larger split, for analysis)
             B = scene_batch(S, my)
             self.d = S.DeviceQTrees.from_packed(B["payload"], B["kh"], B["kw"], B["rs"], B["cs"], B["dflt"], B["canvas"], B["is_mask"], B["scene"], device=local)
             rs0, cs0 = B["rs"], B["cs"]
