@@ -51,6 +51,37 @@ __global__ void k_step_level(const uint32_t* __restrict__ prev, const uint32_t* 
     if (p1) l = max(l, lin[p1 - 1] + 1);
     lout[k] = l;
 }
+// The same dependency depth, EXACT, by ONE CTA in one launch (mid-size lists: 16 relaxation launches cost ~50 us whatever
+// the work).  A predecessor always has the smaller index, so the list is processed in chunks of 1024 steps in order: the
+// depths of earlier chunks are final, the chunk's own are relaxed in shared memory until nothing changes (as many sweeps as
+// the longest chain inside the chunk).  Depths are clamped to 63 (one 6-bit radix pass): (level, k) stays a topological order.
+__global__ void __launch_bounds__(1024) k_step_depth_cta(const uint32_t* __restrict__ prev, uint32_t* __restrict__ lvl, int64_t n) {
+    pdl_sync();
+    __shared__ uint32_t s_l[1024];
+    const int t = threadIdx.x;
+    for (int64_t c0 = 0; c0 < n; c0 += 1024) {
+        const int64_t k = c0 + t;
+        uint32_t p0 = 0, p1 = 0, base = 0;
+        if (k < n) {
+            p0 = prev[2 * k]; p1 = prev[2 * k + 1];
+            if (p0 && (int64_t)(p0 - 1) < c0) { base = min(63u, lvl[p0 - 1] + 1); p0 = 0; }  // predecessor in an earlier chunk: final
+            if (p1 && (int64_t)(p1 - 1) < c0) { base = max(base, min(63u, lvl[p1 - 1] + 1)); p1 = 0; }
+        }
+        s_l[t] = base;
+        __syncthreads();
+        for (;;) {
+            uint32_t l = base;
+            if (p0) l = max(l, min(63u, s_l[p0 - 1 - c0] + 1));
+            if (p1) l = max(l, min(63u, s_l[p1 - 1 - c0] + 1));
+            const int changed = __syncthreads_or(l != s_l[t]);
+            s_l[t] = l;
+            __syncthreads();
+            if (!changed) break;
+        }
+        if (k < n) lvl[k] = s_l[t];
+        __syncthreads(); // (the next chunk reads lvl[] of this one from global memory)
+    }
+}
 __global__ void k_step_level_keys(const uint32_t* __restrict__ lvl, int64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     pdl_sync();
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -68,6 +68,7 @@ struct stf_ctx {
     bool force_big = false; // the single-CTA latency path overflowed once: stay on the multi-launch path
     int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
     int64_t hint_surv = 0;  // pairs the word-parallel narrow phase handed to the frontier kernel in the previous round
+    bool sort3 = false;        // STF_SORT_3LAUNCH=1: always the three-launch radix passes and the 16 level sweeps (comparison / tests)
     bool fused_narrow = false; // STF_FUSED_NARROW=1: candidates are tested inside the candidate kernel and never stored (measured slower: DESIGN.md)
     const int32_t* dev_labels = nullptr; const int* dev_nl = nullptr; // stf_fit_epoch_e: the label list of the round lives on the device (the labels of an earlier colist)
     DevBuf inds, epoch_ctl; // that list and the epoch's control block
@@ -268,6 +269,7 @@ extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
     ctx->env_force_big = getenv("STF_FORCE_BIG") != nullptr;
     ctx->no_cluster = getenv("STF_NO_CLUSTER") != nullptr;
     ctx->fused_narrow = getenv("STF_FUSED_NARROW") != nullptr;
+    ctx->sort3 = getenv("STF_SORT_3LAUNCH") != nullptr;
     { const char* e = getenv("STF_DEBUG_STEP"); ctx->dbg_step = e ? atoi(e) : 0; }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || (ctx->h_err = (int*)calloc(2, sizeof(int))) == nullptr ||
@@ -815,7 +817,7 @@ static int32_t finalize_hits(stf_ctx* ctx, int64_t nh, int unique, bool export_h
     uint64_t* ks; uint32_t* vs;
     { // (i1, i2) = bits [32, 32+lb) and [0, lb): one LSD sort over exactly those bits
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), nh,
-                                 bit_range(0, ctx->label_bits) | bit_range(32, 32 + ctx->label_bits), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
+                                 bit_range(0, ctx->label_bits) | bit_range(32, 32 + ctx->label_bits), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel, ctx->sort3);
         ks = f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(); vs = f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
     }
     LAUNCH_PDL(ctx, k_gather_hits, nblk(nh, 256), 256, 0, ctx->hits.as<Item16>(), vs, nh, ctx->hits2.as<Item16>());
@@ -1032,7 +1034,7 @@ static int32_t locate_and_sort(stf_ctx* ctx, int32_t nl, const int32_t* dl, int 
         int64_t nv = (int64_t)ctx->h_counts[C_NVALID];
         ctx->ctr.records = nv; // valid (cell, label) records
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->rk2.as<uint64_t>(), ctx->rv2.as<uint32_t>(), ctx->rk.as<uint64_t>(), ctx->rv.as<uint32_t>(), nv,
-                                 (uint64_t)ctx->h_counts[C_VARY] & bit_range(0, bits), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
+                                 (uint64_t)ctx->h_counts[C_VARY] & bit_range(0, bits), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel, ctx->sort3);
         *keys = f ? ctx->rk.as<uint64_t>() : ctx->rk2.as<uint64_t>();
         *vals = f ? ctx->rv.as<uint32_t>() : ctx->rv2.as<uint32_t>();
     }
@@ -1346,17 +1348,23 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
         CK(ctx->hist.ensure(sizeof(uint32_t) * radix_sort_hist_words(m)));
         LAUNCH_PDL(ctx, k_step_endpoints, nblk(m, 256), 256, 0, hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->prev.p, 0, sizeof(uint32_t) * (size_t)m, ctx->st));
-        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, bit_range(0, ctx->label_bits + 1), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
+        int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, bit_range(0, ctx->label_bits + 1), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel, ctx->sort3);
         LAUNCH_PDL(ctx, k_step_prev, nblk(m, 256), 256, 0, f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
         CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
         if (n >= 16384) { // many chains (a batch of scenes): claim the steps level by level
             CK(ctx->keep.ensure(sizeof(uint32_t) * 2 * (size_t)n));
             uint32_t* la = ctx->keep.as<uint32_t>(); uint32_t* lb = la + n;
-            CK(cudaMemsetAsync(la, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
-            for (int sweep = 0; sweep < 16; sweep++) { LAUNCH_PDL(ctx, k_step_level, nblk(n, 256), 256, 0, ctx->prev.as<uint32_t>(), la, lb, n); std::swap(la, lb); }
+            int level_bits = 5;
+            if (n <= 32768 && !ctx->sort3) { // one launch: exact depths (clamped to 63) by one CTA
+                LAUNCH_PDL(ctx, k_step_depth_cta, 1, 1024, 0, (const uint32_t*)ctx->prev.as<uint32_t>(), la, n);
+                level_bits = 6;
+            } else {
+                CK(cudaMemsetAsync(la, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
+                for (int sweep = 0; sweep < 16; sweep++) { LAUNCH_PDL(ctx, k_step_level, nblk(n, 256), 256, 0, ctx->prev.as<uint32_t>(), la, lb, n); std::swap(la, lb); }
+            }
             LAUNCH_PDL(ctx, k_step_level_keys, nblk(n, 256), 256, 0, la, n, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
-            int f2 = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), n, bit_range(0, 5), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel);
+            int f2 = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), n, bit_range(0, level_bits), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel, ctx->sort3);
             order = f2 ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>();
         }
     }
@@ -1826,6 +1834,7 @@ struct stf_group {
     std::vector<stf_ctx*> ctx; std::string err;
     unsigned long long epoch = 0; int64_t seg_cap = 0;
     int64_t nvlink_bytes = 0; // bytes pushed to peer GPUs by the last round (hit records + flags, excluding the local copy)
+    bool shared_device = false; // two contexts of the group sit on the same GPU (one-GPU test boxes): see stf_group_fit_round
     GroupPool pool;
 };
 extern "C" int32_t stf_group_create(int32_t n, const int32_t* devices, stf_group** out) {
@@ -1848,6 +1857,7 @@ extern "C" int32_t stf_group_create(int32_t n, const int32_t* devices, stf_group
             if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
             if (e != cudaSuccess) { for (stf_ctx* x : g->ctx) stf_destroy(x); delete g; return STF_E_CUDA; }
         }
+    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) if (devices[i] == devices[j]) g->shared_device = true;
     g->seg_cap = BS_CAP + 1024;
     for (int i = 0; i < n; i++) {
         stf_ctx* ctx = g->ctx[i];
@@ -1906,14 +1916,22 @@ extern "C" int32_t stf_group_fit_round(stf_group* g, int32_t mode, int32_t nl, c
         // every GPU on its own host thread.  Phase A: broad phase + narrow phase over its share of the records, then the local
         // hits are pushed to all peers.  Phase B: wait for all peers ON THE DEVICE, union of the hit lists, canonical order,
         // batchsteps.  Then the GPU's one synchronisation.
-        g->pool.run(n, [&](int i) {
-            stf_ctx* ctx = g->ctx[i];
-            bool pushed = false;
-            auto fail = [&](int32_t code, const char* msg) {
+        // Contexts that SHARE a device (a group listed as {0, 0, 0} on a one-GPU box) cannot use the device-side barrier: a
+        // spinning gather kernel only ends if the other contexts' kernels run beside it, and kernels of different streams of one
+        // device may be serialised (streams aliased onto one hardware queue).  There the halves are separated by a host
+        // synchronisation of every context, so the flags are already set when the gather kernels start.
+        std::vector<char> pushed_v(n, 0);
+        auto fail_of = [&](int i) {
+            return [&, i](int32_t code, const char* msg) {
+                stf_ctx* ctx = g->ctx[i];
                 if (msg) ctx->err = msg;
                 rcs[i] = code;
-                if (!pushed) { ctx->launches++; k_shard_poison<<<1, 32, 0, ctx->st>>>(P, i, epoch); cudaStreamSynchronize(ctx->st); } // the peers must not wait for this GPU forever
+                if (!pushed_v[i]) { ctx->launches++; k_shard_poison<<<1, 32, 0, ctx->st>>>(P, i, epoch); cudaStreamSynchronize(ctx->st); } // the peers must not wait for this GPU forever
             };
+        };
+        auto phase_a = [&](int i) {
+            stf_ctx* ctx = g->ctx[i];
+            auto fail = fail_of(i);
             if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(STF_E_CUDA, "cudaSetDevice failed");
             stage_reset(ctx); ctx->after_kernel = false; ctx->last_result = 0;
             ctx->shard_rank = i; ctx->shard_n = n;
@@ -1924,14 +1942,25 @@ extern "C" int32_t stf_group_fit_round(stf_group* g, int32_t mode, int32_t nl, c
             LAUNCH_PDL(ctx, k_shard_push, 8, 256, 0, (const Item16*)ctx->hits.as<Item16>(), (const unsigned long long*)(ctx->counts.as<unsigned long long>() + C_NHITS), g->seg_cap, P, i, epoch,
                        (const int*)STATUSP(ctx), F.n_items_dev, F.item_cap, ctx->gdone.as<unsigned int>());
             if (cudaGetLastError() != cudaSuccess) return fail(STF_E_CUDA, "k_shard_push launch failed");
-            pushed = true;
+            pushed_v[i] = 1;
+            if (g->shared_device && cudaStreamSynchronize(ctx->st) != cudaSuccess) return fail(STF_E_CUDA, "synchronisation failed");
+        };
+        auto phase_b = [&](int i) {
+            stf_ctx* ctx = g->ctx[i];
+            auto fail = fail_of(i);
+            if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(STF_E_CUDA, "cudaSetDevice failed");
+            int32_t r = STF_OK;
             if (ctx->hits.ensure(sizeof(Item16) * (size_t)n * g->seg_cap, true, ctx->st) != cudaSuccess) return fail(STF_E_CUDA, "hit buffer allocation failed");
             LAUNCH_PDL(ctx, k_shard_gather, 16, 256, 0, (const Item16*)ctx->gather.as<Item16>(), (const unsigned long long*)ctx->gflags.as<unsigned long long>(), n, g->seg_cap, epoch,
                        ctx->hits.as<Item16>(), (int64_t)(ctx->hits.cap / sizeof(Item16)), ctx->counts.as<unsigned long long>() + C_NHITS, STATUSP(ctx));
             if (cudaGetLastError() != cudaSuccess) return fail(STF_E_CUDA, "k_shard_gather launch failed");
             r = fast_round_tail(ctx, seed, iteration, true); if (r) return fail(r, nullptr);
             r = sync_counts(ctx); if (r) return fail(r, nullptr);
-        });
+        };
+        if (g->shared_device) {
+            g->pool.run(n, phase_a);
+            g->pool.run(n, [&](int i) { if (pushed_v[i]) phase_b(i); });
+        } else g->pool.run(n, [&](int i) { phase_a(i); if (!rcs[i]) phase_b(i); });
         bool again = false;
         for (int i = 0; i < n; i++) if (rcs[i]) GFAIL(rcs[i], g->ctx[i]->err); // (a failed enqueue on one GPU leaves its peers' gather kernels without its flag only if the push never ran: every error above happens after the push or before any launch of the round)
         for (int i = 0; i < n; i++) { cudaSetDevice(g->ctx[i]->device); if (fast_round_verdict(g->ctx[i])) again = true; }

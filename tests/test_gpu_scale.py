@@ -397,7 +397,27 @@ def _scene_batch(S, n_scenes, per_scene, seed):
 
 
 def test_c5_4096_scene_batch(S, orc):
-    n_scenes, per = 4096, 128
+    _check_scene_batch(S, orc, 4096, [0, 1, 777, 2048, 4095], 777)
+
+
+def test_c5_mid_size_batch_400_scenes(S, orc):
+    """a rank's share of a split batch: ~50 k records and ~26 k hits per step — the sizes at which the one-launch radix
+    passes (decoupled look-back) and the single-CTA step-depth kernel are used instead of the multi-launch versions"""
+    d = _check_scene_batch(S, orc, 400, [0, 1, 123, 399], 123)
+    # the multi-launch versions (three launches per radix pass, 16 level sweeps) must leave exactly the same state
+    import os
+    os.environ["STF_SORT_3LAUNCH"] = "1"
+    try:
+        d3 = _check_scene_batch(S, orc, 400, [0], 0)
+    finally:
+        del os.environ["STF_SORT_3LAUNCH"]
+    for l in (1, 3):
+        a, b = d.getshifts(level=l), d3.getshifts(level=l)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def _check_scene_batch(S, orc, n_scenes, sample, probe):
+    per = 128
     trees, scene, is_mask = _scene_batch(S, n_scenes, per, 5)
     d = S.DeviceQTrees(trees, is_mask=is_mask, scene=scene)
     assert len(d) == n_scenes * (per + 1) and d.nlevels == 10
@@ -411,7 +431,6 @@ def test_c5_4096_scene_batch(S, orc):
     c1 = d.read_nodes(sub["i1"], sub["l"], sub["a"], sub["b"]); c2 = d.read_nodes(sub["i2"], sub["l"], sub["a"], sub["b"])
     assert np.all((c1 & c2) == S.FULL)
     # (d) sampled scenes against the oracle, bit for bit, before and after two batched fit iterations
-    sample = [0, 1, 777, 2048, 4095]
     stride = per + 1
 
     def oracle_scene(s):
@@ -436,9 +455,10 @@ def test_c5_4096_scene_batch(S, orc):
     for s in sample:
         assert device_scene_hits(hits, s) == sorted(orc.totalcollisions_spacial(oracle_scene(s), unique=False))
     # the pyramids of a moved scene are consistent with a from-scratch build at the fitted shifts
-    s = 777
+    s = probe
     qo = oracle_scene(s)
     lo = s * stride
     for k in range(stride):
         for l in (2, 3, 5, 10):
             assert np.array_equal(d[lo + k].level(l), qo[k].level(l)) and d[lo + k].info(l) == qo[k].info(l)
+    return d
