@@ -242,15 +242,23 @@ __device__ __forceinline__ int decode2(uint32_t c) { return (int)((0x60u >> ((c 
 // lane i = window column i, one 64-bit register = the rows of that column; each level is two shuffles, a pair-OR
 // compress and the clip against that level's kernel window (outside -> default).  Needs l - m <= 3 (24 columns).
 // `meta_at(j)` returns the LevelMeta of level j (warp-uniform).  Whole warp must call.
-template <bool CG, class MetaAt> __device__ __forceinline__ int2 grad_lazy(const uint32_t* __restrict__ words, MetaAt meta_at, int l, int a, int b, int m, int lane) {
+// Two halves, so that a caller can issue the loads of several windows before it consumes any of them:
+// lazy_window_load = the only memory access (level m's fields, lane = window column), lazy_window_reduce = shuffles only.
+template <bool CG> __device__ __forceinline__ uint64_t lazy_window_load(const uint32_t* __restrict__ words, const LevelMeta& mm, int l, int a, int b, int m, int lane) {
+    int k = l - m;
+    int rlo = a - 1, clo = b - 1;
+    for (int i = 0; i < k; i++) { rlo = 2 * rlo - 1; clo = 2 * clo - 1; }
+    int n = 3 << k;
+    uint64_t x = 0;
+    if (lane < n) x = fields64_at<CG>(words, mm, clo + lane - mm.cs - 1, rlo - mm.rs - 1);
+    return x;
+}
+template <class MetaAt> __device__ __forceinline__ int2 lazy_window_reduce(uint64_t x, MetaAt meta_at, int l, int a, int b, int m, int lane) {
     const unsigned FULLM = 0xffffffffu;
     int k = l - m;
     int rlo = a - 1, clo = b - 1;
     for (int i = 0; i < k; i++) { rlo = 2 * rlo - 1; clo = 2 * clo - 1; }
     int n = 3 << k;
-    LevelMeta mm = meta_at(m);
-    uint64_t x = 0;
-    if (lane < n) x = fields64_at<CG>(words, mm, clo + lane - mm.cs - 1, rlo - mm.rs - 1);
     for (int j = m + 1; j <= l; j++) {
         rlo = (rlo + 1) >> 1; clo = (clo + 1) >> 1; n >>= 1; // exact: lo_{j-1} = 2*lo_j - 1
         uint64_t y = __shfl_sync(FULLM, x, (2 * lane) & 31) | __shfl_sync(FULLM, x, (2 * lane + 1) & 31);
@@ -267,6 +275,11 @@ template <bool CG, class MetaAt> __device__ __forceinline__ int2 grad_lazy(const
     int gh = __shfl_sync(FULLM, rowdiff, 0) + __shfl_sync(FULLM, rowdiff, 1) + __shfl_sync(FULLM, rowdiff, 2);
     int gw = __shfl_sync(FULLM, colsum, 2) - __shfl_sync(FULLM, colsum, 0);
     return make_int2(gh, gw);
+}
+template <bool CG, class MetaAt> __device__ __forceinline__ int2 grad_lazy(const uint32_t* __restrict__ words, MetaAt meta_at, int l, int a, int b, int m, int lane) {
+    LevelMeta mm = meta_at(m);
+    uint64_t x = lazy_window_load<CG>(words, mm, l, a, b, m, lane);
+    return lazy_window_reduce(x, meta_at, l, a, b, m, lane);
 }
 
 // ---- spatial cell keys: scene | level | a+bias | b+bias ----

@@ -200,7 +200,6 @@ __global__ void __launch_bounds__(128, MINB) k_batchsteps(StepArgs A) {
         // ---- round trip 1: tree state
         LevelMeta mine = {};
         if (hl < A.L) mine = ldmeta<true>(A.lm + (size_t)oh * A.L + hl);
-        LevelMeta q = ldmeta<true>(A.lm + (size_t)oh * A.L + (l - 1));
         int dmh = __ldcg(A.dirty + oh), dmo = __ldcg(A.dirty + oo); // levels > dirty are stale in memory
         int hasA = 0, hasB = 0; double2 vA = make_double2(0, 0), vB = make_double2(0, 0);
         if (A.opt.kind == 2) {
@@ -210,37 +209,42 @@ __global__ void __launch_bounds__(128, MINB) k_batchsteps(StepArgs A) {
         }
         int dmA = half ? dmo : dmh, dmB = half ? dmh : dmo;
         s_shift[wib][lane] = make_int2(mine.rs, mine.cs);
-        if (A.dbg & 16) asm volatile("mov.u64 %0, %%clock64;" : "=l"(s1) : "r"(mine.off), "r"(q.off), "r"(dmh), "r"(dmo), "d"(vB.y), "d"(vA.x), "r"(hasB));
-        // ---- round trip 2: grad2d (fit_helper.jl:51-66), 8 neighbours per tree, one per lane; sums by ballot + popc
-        uint32_t dv = 0;
-        if (hl < 8 && l <= dmh) {
-            int idx = hl < 4 ? hl : hl + 1; int dr = idx / 3 - 1, dc = idx % 3 - 1;
-            dv = (uint32_t)decode2(node_code<true>(A.words, q, a + dr, b + dc));
-        }
-        uint32_t b0 = __ballot_sync(FULLM, dv & 1u), b1 = __ballot_sync(FULLM, dv & 2u);
-        // lanes hl = 0..7 hold window cells (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
-#define STF_GSUM(B0, B1, P, M) ((__popc((B0) & (P)) + 2 * __popc((B1) & (P))) - (__popc((B0) & (M)) + 2 * __popc((B1) & (M))))
-        int g1x = STF_GSUM(b0, b1, 0xE0u, 0x07u), g1y = STF_GSUM(b0, b1, 0x94u, 0x29u);
-        int g2x = STF_GSUM(b0 >> 16, b1 >> 16, 0xE0u, 0x07u), g2y = STF_GSUM(b0 >> 16, b1 >> 16, 0x94u, 0x29u);
-#undef STF_GSUM
-        if (A.dbg & 16) asm volatile("mov.u64 %0, %%clock64;" : "=l"(s2) : "r"(g1x), "r"(g2y));
-        if (l > dmA || l > dmB) { // stale level (the tree moved earlier in this batch): derive the window from the lowest valid level
+        if (A.dbg & 16) asm volatile("mov.u64 %0, %%clock64;" : "=l"(s1) : "r"(mine.off), "r"(dmh), "r"(dmo), "d"(vB.y), "d"(vA.x), "r"(hasB));
+        // ---- round trip 2: grad2d (fit_helper.jl:51-66).  A tree that moved earlier in this batch has stale rasters above
+        // dirty[o]: its 3x3 window is derived from the lowest valid level (lazy window); the level metas it needs are the ones
+        // the lanes already hold (shuffles, no further memory round trips), and the loads of both trees and of the direct
+        // nodes are issued before anything is consumed.  The rarely executed parts are kept as ONE loop body each: a step on
+        // the dependent chain usually meets this code cold in the instruction cache, so its size is latency.
+        if (l - dmA > 3 || l - dmB > 3) { // window too wide: materialise that tree now (rare), then read it directly
 #pragma unroll 1
             for (int t = 0; t < 2; t++) {
                 int dmt = t ? dmB : dmA, ot = t ? o2 : o1;
-                if (l <= dmt) continue;
-                const LevelMeta* tl = A.lm + (size_t)ot * A.L;
-                if (l - dmt > 3) { // window too wide: materialise this tree now (rare), then read it
-                    LevelMeta tm = {};
-                    if (lane < A.L) tm = ldmeta<true>(tl + lane);
-                    warp_rebuild<true, true>(A.words, tm, A.L, dmt, lane, sbuf[wib]);
-                    if (lane == 0) A.built_from[ot] = dmt - 1;
-                    __syncwarp();
-                    dmt = A.L; if (t) dmB = dmt; else dmA = dmt;
-                }
-                int2 g = grad_lazy<true>(A.words, [&](int j) { return ldmeta<true>(tl + (j - 1)); }, l, a, b, min(dmt, l), lane);
-                if (t) { g2x = g.x; g2y = g.y; } else { g1x = g.x; g1y = g.y; }
+                if (l - dmt <= 3) continue;
+                LevelMeta tm = {};
+                if (lane < A.L) tm = ldmeta<true>(A.lm + (size_t)ot * A.L + lane);
+                warp_rebuild<true, true>(A.words, tm, A.L, dmt, lane, sbuf[wib]);
+                if (lane == 0) A.built_from[ot] = dmt - 1;
+                __syncwarp();
+                if (t) dmB = A.L; else dmA = A.L;
             }
+        }
+        // every tree goes through the window code (k = 0 for a valid level: the 3 columns of the 3x3 window are read directly),
+        // so the dependent chain never meets a code path that no earlier warp of the SM has executed
+        uint64_t xA = 0, xB = 0;
+#pragma unroll 1
+        for (int t = 0; t < 2; t++) {
+            const int mt = min(t ? dmB : dmA, l);
+            LevelMeta mm = shfl_meta(mine, 16 * t + mt - 1);
+            uint64_t x = lazy_window_load<true>(A.words, mm, l, a, b, mt, lane);
+            if (t) xB = x; else xA = x;
+        }
+        int g1x = 0, g1y = 0, g2x = 0, g2y = 0;
+        if (A.dbg & 16) asm volatile("mov.u64 %0, %%clock64;" : "=l"(s2) : "l"(xA), "l"(xB));
+#pragma unroll 1
+        for (int t = 0; t < 2; t++) {
+            const int mt = min(t ? dmB : dmA, l);
+            int2 g = lazy_window_reduce(t ? xB : xA, [&](int j) { return shfl_meta(mine, 16 * t + j - 1); }, l, a, b, mt, lane);
+            if (t) { g2x = g.x; g2y = g.y; } else { g1x = g.x; g1y = g.y; }
         }
         // ---- step!/step_mask! (fit.jl:25-56): every lane runs the same scalar arithmetic
         int3 mvA = make_int3(0, 0, 0), mvB = make_int3(0, 0, 0); int oA = -1, oB = -1;
@@ -296,6 +300,230 @@ __global__ void __launch_bounds__(128, MINB) k_batchsteps(StepArgs A) {
             if (A.dbg & 16) { unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end)); A.dbg_t[4 * k] = (unsigned long long)(((s1 - s0) >> 4) & 0xfff) | ((unsigned long long)(((s2 - s1) >> 4) & 0xfff) << 12) | ((unsigned long long)(((s3 - s2) >> 4) & 0xfff) << 24) | ((unsigned long long)(((s4 - s3) >> 4) & 0xfff) << 36) | ((unsigned long long)(((s5 - s4) >> 4) & 0xfff) << 48); A.dbg_t[4 * k + 1] = t_ready; A.dbg_t[4 * k + 2] = t_decided; A.dbg_t[4 * k + 3] = t_end; }
         }
         if (hl == 0 && moves) { A.moved_flag[oh] = 1; atomicAdd(A.counts + 4, 1ull); } // off the chain: only read after the kernel
+    }
+}
+
+// ---- scene-local batchsteps (batches of scenes) -------------------------------------------------------------------
+// The same canonical result, organised around shared memory instead of global tickets and flags.  The scenes of a batch
+// never interact, and when scene ids ascend with the labels the hits of a scene are CONTIGUOUS in the canonical order
+// (k_scene_ranges).  A CTA claims a scene (one global ticket per scene, not per step), loads its hits, links and object
+// sizes in one coalesced round trip, computes the exact dependency depth of every step (relaxation in shared memory) and
+// runs the scene LEVEL BY LEVEL: the steps of one depth touch disjoint trees, so they run concurrently, one warp per step,
+// and a CTA barrier separates the levels — no flag, no gpu-scope fence and no poll between dependent steps (that hop
+// costs ~2 us per dependent step in k_batchsteps), no global depth sweeps and no sort of the steps by depth.  A scene
+// with more than CAP hits is run in consecutive pieces of CAP steps by the same CTA (earlier pieces are complete).
+__global__ void k_scene_ranges(const Item16* __restrict__ hits, int64_t n, const ObjMeta* __restrict__ om, uint32_t* __restrict__ rng) {
+    pdl_sync();
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int sc = om[hits[k].i1 - 1].scene;
+    if (k == 0 || om[hits[k - 1].i1 - 1].scene != sc) rng[2 * sc] = (uint32_t)k;
+    if (k == n - 1 || om[hits[k + 1].i1 - 1].scene != sc) rng[2 * sc + 1] = (uint32_t)(k + 1);
+}
+__device__ __forceinline__ void step_core(const StepArgs& A, const unsigned long long k, const Item16 h, const int sz1, const int sz2,
+                                          const uint64_t hbase, const int lane, uint64_t* __restrict__ s_rnd, int2* __restrict__ s_shift, uint32_t* __restrict__ s_sbuf, int* __restrict__ s_lock) {
+    const int half = lane >> 4, hl = lane & 15;
+    const int o1 = h.i1 - 1, o2 = item_i2(h) - 1;
+    const int l = item_l(h), a = h.a, b = h.b;
+    if (lane < 8) s_rnd[lane] = stf_mix64(hbase + (k << 3) + (uint64_t)lane);
+    __syncwarp();
+    uint64_t R[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) R[j] = s_rnd[j];
+    const bool m1 = sz1 < 0, m2 = sz2 < 0;
+    bool move1 = false, move2 = false;
+    if (!(m1 || m2)) { // step!  fit.jl:33-35
+        double s1 = (double)sz1, s2 = (double)sz2;
+        double ks1 = s1 * s1 * s1, ks2 = s2 * s2 * s2;
+        move1 = u64_to_unit(R[0]) < ks2 / ks1;
+        move2 = u64_to_unit(R[1]) < ks1 / ks2;
+    }
+    const double ll = (double)(1ll << (l - 1));
+    const int oh = half ? o2 : o1, oo = half ? o1 : o2;
+    // ---- round trip 1: tree state
+    LevelMeta mine = {};
+    if (hl < A.L) mine = ldmeta<true>(A.lm + (size_t)oh * A.L + hl);
+    int dmh = __ldcg(A.dirty + oh), dmo = __ldcg(A.dirty + oo); // levels > dirty are stale in memory
+    int hasA = 0, hasB = 0; double2 vA = make_double2(0, 0), vB = make_double2(0, 0);
+    if (A.opt.kind == 2) {
+        hasA = __ldcg(A.has_vel + o1); hasB = __ldcg(A.has_vel + o2);
+        vA = __ldcg(reinterpret_cast<const double2*>(A.vel + 2 * (size_t)o1));
+        vB = __ldcg(reinterpret_cast<const double2*>(A.vel + 2 * (size_t)o2));
+    }
+    int dmA = half ? dmo : dmh, dmB = half ? dmh : dmo;
+    s_shift[lane] = make_int2(mine.rs, mine.cs);
+    // ---- round trip 2: grad2d (fit_helper.jl:51-66); stale trees through the lazy window (see k_batchsteps)
+    if (l - dmA > 3 || l - dmB > 3) { // window too wide: materialise that tree now (rare); one scratch buffer per CTA
+#pragma unroll 1
+        for (int t = 0; t < 2; t++) {
+            int dmt = t ? dmB : dmA, ot = t ? o2 : o1;
+            if (l - dmt <= 3) continue;
+            LevelMeta tm = {};
+            if (lane < A.L) tm = ldmeta<true>(A.lm + (size_t)ot * A.L + lane);
+            if (lane == 0) while (atomicCAS(s_lock, 0, 1) != 0) { }
+            __syncwarp();
+            warp_rebuild<true, true>(A.words, tm, A.L, dmt, lane, s_sbuf);
+            __syncwarp();
+            if (lane == 0) { A.built_from[ot] = dmt - 1; __threadfence_block(); atomicExch(s_lock, 0); }
+            __syncwarp();
+            if (t) dmB = A.L; else dmA = A.L;
+        }
+    }
+    uint64_t xA = 0, xB = 0; // (every tree through the window code, k = 0 for a valid level: see k_batchsteps)
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        const int mt = min(t ? dmB : dmA, l);
+        LevelMeta mm = shfl_meta(mine, 16 * t + mt - 1);
+        uint64_t x = lazy_window_load<true>(A.words, mm, l, a, b, mt, lane);
+        if (t) xB = x; else xA = x;
+    }
+    int g1x = 0, g1y = 0, g2x = 0, g2y = 0;
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        const int mt = min(t ? dmB : dmA, l);
+        int2 g = lazy_window_reduce(t ? xB : xA, [&](int j) { return shfl_meta(mine, 16 * t + j - 1); }, l, a, b, mt, lane);
+        if (t) { g2x = g.x; g2y = g.y; } else { g1x = g.x; g1y = g.y; }
+    }
+    // ---- step!/step_mask! (fit.jl:25-56): every lane runs the same scalar arithmetic
+    int3 mvA = make_int3(0, 0, 0), mvB = make_int3(0, 0, 0); int oA = -1, oB = -1;
+    const bool st = lane == 0; // the lane that stores the optimiser state
+    {
+        double d1x = ll * g1x, d1y = ll * g1y, d2x = ll * g2x, d2y = ll * g2y;
+        if (m1 || m2) { // step_mask!  fit.jl:49-56 (i1 == 1 first, then i2 == 1: fit.jl:60-63)
+            int ot = m1 ? o2 : o1;
+            double dx = m1 ? (d2x - d1x) / 2 : (d1x - d2x) / 2, dy = m1 ? (d2y - d1y) / 2 : (d1y - d2y) / 2;
+            if (m1) opt_apply_dev(A, ot, dx, dy, hasB, vB.x, vB.y, st); else opt_apply_dev(A, ot, dx, dy, hasA, vA.x, vA.y, st);
+            mvA = move_decide(A, dx, dy, R[2], R[3], R[4]); oA = ot;
+        } else { // step!  fit.jl:25-48
+            int slot = 2;
+            if (move1) {
+                double dx = d1x, dy = d1y;
+                if (!move2) { dx -= d2x; dy -= d2y; }
+                opt_apply_dev(A, o1, dx, dy, hasA, vA.x, vA.y, st);
+                mvA = move_decide(A, dx, dy, R[2], R[3], R[4]); oA = o1; slot += 3;
+            }
+            if (move2) {
+                double dx = d2x, dy = d2y;
+                if (!move1) { dx -= d1x; dy -= d1y; }
+                opt_apply_dev(A, o2, dx, dy, hasB, vB.x, vB.y, st);
+                int3 mv = slot == 2 ? move_decide(A, dx, dy, R[2], R[3], R[4]) : move_decide(A, dx, dy, R[5], R[6], R[7]);
+                if (oA < 0) { mvA = mv; oA = o2; } else { mvB = mv; oB = o2; }
+            }
+        }
+    }
+    // ---- shift! on the metas only (qtrees.jl:267-275); both halves at once, half h holds tree (h ? o2 : o1)
+    const bool isA = oA == oh, isB = oB == oh; // o1 != o2; a tree moves at most once per step
+    const bool moves = isA || isB;
+    const int3 mv = isA ? mvA : mvB;
+    const int lv = moves ? mv.x : 1;
+    __syncwarp();
+    const int2 base = s_shift[half * 16 + lv - 1];
+    if (moves && hl < A.L) {
+        if (hl < lv) { int f = 1 << (lv - 1 - hl); mine.rs += mv.y * f; mine.cs += mv.z * f; }
+        else { // levels above lv: (new shift of level lv) ÷ 2^sh toward zero (qtrees.jl:225-226 composed)
+            int sh = hl + 1 - lv, brs = base.x + mv.y, bcs = base.y + mv.z;
+            mine.rs = brs >= 0 ? (brs >> sh) : -((-brs) >> sh); mine.cs = bcs >= 0 ? (bcs >> sh) : -((-bcs) >> sh);
+        }
+        stmeta<true>(A.lm + (size_t)oh * A.L + hl, mine);
+    }
+    const int dcur = half ? dmB : dmA;
+    if (hl == 0) { int nd = moves ? min(dcur, lv) : dcur; if (nd != dmh) __stcg(A.dirty + oh, nd); }
+    if (hl == 0 && moves) { A.moved_flag[oh] = 1; atomicAdd(A.counts + 4, 1ull); } // only read after the kernel
+    __syncwarp();
+}
+
+template <int NT, int CAP, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_batchsteps_scene(StepArgs A, const uint32_t* __restrict__ rng, int nscenes) {
+    pdl_sync(); // programmatic dependent launch: nothing global before this
+    constexpr int NW = NT / 32;
+    const unsigned FULLM = 0xffffffffu;
+    __shared__ Item16 s_hit[CAP];
+    __shared__ int s_sz[2 * CAP];      // kh1 + kw1 of the object on each side of the hit; -1 = the mask
+    __shared__ uint16_t s_p0[CAP], s_p1[CAP]; // links inside the piece: local index + 1, 0 = none (or already complete)
+    __shared__ uint16_t s_depth[CAP], s_order[CAP];
+    __shared__ int s_lstart[CAP + 1], s_cur[CAP];
+    __shared__ uint64_t s_rnd[NW][8];
+    __shared__ int2 s_shift[NW][32];
+    __shared__ uint32_t s_sbuf[2 * RB_HALF];
+    __shared__ int s_lock, s_nlev, s_scene;
+    const int t = threadIdx.x, lane = t & 31, wib = t >> 5;
+    const uint64_t hbase = stf_mix64(stf_mix64(A.seed ^ 0x5354554646494E47ull) + A.iter); // stf_rand_u64 without the per-draw part
+    if (t == 0) s_lock = 0;
+    for (;;) {
+        __syncthreads(); // the previous scene's shared arrays are no longer read
+        if (t == 0) s_scene = (int)atomicAdd(A.ticket, 1ull);
+        __syncthreads();
+        const int sc = s_scene;
+        if (sc >= nscenes) return;
+        const int64_t lo = rng[2 * sc], hi = rng[2 * sc + 1];
+        for (int64_t c0 = lo; c0 < hi; c0 += CAP) {
+            const int m = (int)min((int64_t)CAP, hi - c0);
+            // ---- one coalesced round trip: hits, links, object sizes
+            for (int i = t; i < m; i += NT) {
+                const Item16 h = A.hits[c0 + i];
+                const uint2 pv = *reinterpret_cast<const uint2*>(A.prev + 2 * (c0 + i));
+                const ObjMeta a = A.om[h.i1 - 1], b = A.om[item_i2(h) - 1];
+                s_hit[i] = h;
+                s_sz[2 * i] = a.is_mask ? -1 : a.kh1 + a.kw1; s_sz[2 * i + 1] = b.is_mask ? -1 : b.kh1 + b.kw1;
+                s_p0[i] = (pv.x && (int64_t)(pv.x - 1) >= c0) ? (uint16_t)(pv.x - c0) : (uint16_t)0;
+                s_p1[i] = (pv.y && (int64_t)(pv.y - 1) >= c0) ? (uint16_t)(pv.y - c0) : (uint16_t)0;
+                s_depth[i] = 0; s_cur[i] = 0;
+            }
+            for (int i = t; i <= CAP; i += NT) s_lstart[i] = 0;
+            __syncthreads();
+            // ---- exact depth inside the piece: relax until nothing changes (as many sweeps as the longest chain)
+            for (;;) {
+                int changed = 0;
+                uint32_t nl[(CAP + NT - 1) / NT];
+#pragma unroll
+                for (int j = 0; j < (CAP + NT - 1) / NT; j++) {
+                    const int i = t + j * NT;
+                    uint32_t l = 0;
+                    if (i < m) {
+                        const int p0 = s_p0[i], p1 = s_p1[i];
+                        if (p0) l = s_depth[p0 - 1] + 1u;
+                        if (p1) l = max(l, (uint32_t)s_depth[p1 - 1] + 1u);
+                        changed |= l != s_depth[i];
+                    }
+                    nl[j] = l;
+                }
+                changed = __syncthreads_or(changed);
+#pragma unroll
+                for (int j = 0; j < (CAP + NT - 1) / NT; j++) { const int i = t + j * NT; if (i < m) s_depth[i] = (uint16_t)nl[j]; }
+                __syncthreads();
+                if (!changed) break;
+            }
+            // ---- counting sort by depth: s_order = the steps level by level, s_lstart[d] = first slot of depth d
+            for (int i = t; i < m; i += NT) atomicAdd(&s_lstart[s_depth[i] + 1], 1);
+            __syncthreads();
+            if (wib == 0) {
+                int run = 0, nlev = 0;
+                for (int base = 0; base < CAP && run < m; base += 32) {
+                    const int v = s_lstart[base + lane + 1];
+                    int inc = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(FULLM, inc, o); if (lane >= o) inc += u; }
+                    s_lstart[base + lane + 1] = run + inc; // end of depth base+lane = start of the next depth
+                    const unsigned nz = __ballot_sync(FULLM, v != 0);
+                    if (nz) nlev = base + 32 - __clz(nz);
+                    run += __shfl_sync(FULLM, inc, 31);
+                }
+                if (lane == 0) s_nlev = nlev;
+            }
+            __syncthreads();
+            for (int i = t; i < m; i += NT) { const int d = s_depth[i]; s_order[s_lstart[d] + atomicAdd(&s_cur[d], 1)] = (uint16_t)i; }
+            __syncthreads();
+            // ---- the piece, level by level
+            const int nlev = s_nlev;
+            for (int d = 0; d < nlev; d++) {
+                const int l0 = s_lstart[d], l1 = s_lstart[d + 1];
+                for (int j = l0 + wib; j < l1; j += NW) {
+                    const int tl = s_order[j];
+                    step_core(A, (unsigned long long)(c0 + tl), s_hit[tl], s_sz[2 * tl], s_sz[2 * tl + 1], hbase, lane, s_rnd[wib], s_shift[wib], s_sbuf, &s_lock);
+                }
+                __syncthreads(); // the stores of this level (L2-scope) are ordered before the reads of the next one
+            }
+        }
     }
 }
 

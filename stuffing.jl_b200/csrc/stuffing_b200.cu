@@ -68,6 +68,9 @@ struct stf_ctx {
     bool force_big = false; // the single-CTA latency path overflowed once: stay on the multi-launch path
     int64_t hint_items = 0; // candidate-list size of the previous round (buffer sizing without a host round trip)
     int64_t hint_surv = 0;  // pairs the word-parallel narrow phase handed to the frontier kernel in the previous round
+    bool step_global = false;  // STF_STEP_GLOBAL=1: batches of scenes also step through k_batchsteps (global tickets and flags, depth-ordered) instead of k_batchsteps_scene
+    bool scene_sorted = false; int n_scenes = 1; // scene ids ascend with the labels: the hits of a scene are contiguous in the canonical order
+    DevBuf scene_rng;
     bool sort3 = false;        // STF_SORT_3LAUNCH=1: always the three-launch radix passes and the 16 level sweeps (comparison / tests)
     bool fused_narrow = false; // STF_FUSED_NARROW=1: candidates are tested inside the candidate kernel and never stored (measured slower: DESIGN.md)
     const int32_t* dev_labels = nullptr; const int* dev_nl = nullptr; // stf_fit_epoch_e: the label list of the round lives on the device (the labels of an earlier colist)
@@ -270,6 +273,7 @@ extern "C" int32_t stf_create(int32_t device, stf_ctx** out) {
     ctx->no_cluster = getenv("STF_NO_CLUSTER") != nullptr;
     ctx->fused_narrow = getenv("STF_FUSED_NARROW") != nullptr;
     ctx->sort3 = getenv("STF_SORT_3LAUNCH") != nullptr;
+    ctx->step_global = getenv("STF_STEP_GLOBAL") != nullptr;
     { const char* e = getenv("STF_DEBUG_STEP"); ctx->dbg_step = e ? atoi(e) : 0; }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counts, C_N * sizeof(unsigned long long)) != cudaSuccess || (ctx->h_err = (int*)calloc(2, sizeof(int))) == nullptr ||
@@ -287,7 +291,7 @@ extern "C" void stf_destroy(stf_ctx* ctx) {
     DevBuf* all[] = { &ctx->words, &ctx->lm, &ctx->om, &ctx->payload, &ctx->poff, &ctx->woff1, &ctx->work, &ctx->lab, &ctx->lab2, &ctx->lab3, &ctx->lab4, &ctx->bytes_tmp,
                       &ctx->rk, &ctx->rv, &ctx->rk2, &ctx->rv2, &ctx->hist, &ctx->lkk, &ctx->lkv, &ctx->items, &ctx->direct, &ctx->res, &ctx->overflow,
                       &ctx->hits, &ctx->hits2, &ctx->hk, &ctx->hv, &ctx->hk2, &ctx->hv2, &ctx->keep, &ctx->out32, &ctx->scratch, &ctx->counts, &ctx->errflag,
-                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from, &ctx->gather, &ctx->gflags, &ctx->gdone, &ctx->rounds_rec, &ctx->lab_mark, &ctx->inds, &ctx->epoch_ctl };
+                      &ctx->vel, &ctx->has_vel, &ctx->moved_flag, &ctx->moved_pos, &ctx->prev, &ctx->done, &ctx->nat_flt, &ctx->nat_m, &ctx->dirty, &ctx->dbg_t, &ctx->surv, &ctx->gwords, &ctx->glm, &ctx->lvlidx, &ctx->built_from, &ctx->gather, &ctx->gflags, &ctx->gdone, &ctx->rounds_rec, &ctx->lab_mark, &ctx->inds, &ctx->epoch_ctl, &ctx->scene_rng };
     for (DevBuf* b : all) b->release();
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_err) free(ctx->h_err);
@@ -373,7 +377,9 @@ static int32_t upload_common(stf_ctx* ctx, int32_t n, const uint8_t* const* pics
     }
     ctx->has_big = !ctx->big_objs.empty();
     ctx->total_words = words;
-    ctx->multi_scene = max_scene > 0;
+    ctx->multi_scene = max_scene > 0; ctx->n_scenes = max_scene + 1;
+    ctx->scene_sorted = true;
+    for (int o = 1; o < n && ctx->scene_sorted; o++) if (scene && scene[o] < scene[o - 1]) ctx->scene_sorted = false;
     ctx->scene_bits = 0; while ((1ll << ctx->scene_bits) <= max_scene) ctx->scene_bits++;
     if (!ctx->multi_scene) ctx->scene_bits = 0;
     if (ctx->scene_bits > 64 - 5 - 2 * STF_CELL_W) FAIL(STF_E_ARG, "too many scenes");
@@ -1310,7 +1316,7 @@ extern "C" int32_t stf_get_velocity(stf_ctx* ctx, int32_t n, const int32_t* labe
     return STF_OK;
 }
 // k_batchsteps + k_materialize over `hits`; the step count is host-known (n_dev == NULL) or lives on the device
-static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, const unsigned long long* n_dev, uint64_t seed, uint64_t iter, const uint32_t* order = nullptr) {
+static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, const unsigned long long* n_dev, uint64_t seed, uint64_t iter, const uint32_t* order = nullptr, bool by_scene = false) {
     StepArgs A;
     A.words = ctx->words.as<uint32_t>(); A.lm = ctx->lm.as<LevelMeta>(); A.om = ctx->om.as<ObjMeta>(); A.L = ctx->L;
     A.hits = hits; A.n = n_host; A.n_dev = n_dev; A.prev = ctx->prev.as<uint32_t>(); A.done = ctx->done.as<uint32_t>();
@@ -1322,7 +1328,9 @@ static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, co
     if (A.dbg & 16) { CK(ctx->dbg_t.ensure(sizeof(unsigned long long) * 4 * (size_t)std::max<int64_t>(n_host, BS_CAP))); A.dbg_t = ctx->dbg_t.as<unsigned long long>(); }
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (n_host + 3) / 4), 148 * 8);
     stage_begin(ctx, STF_STAGE_STEP);
-    if (n_host > 32768) LAUNCH_PDL(ctx, k_batchsteps<6>, blocks, 128, 0, A);
+#define K_STEPS_SCENE k_batchsteps_scene<128, 256, 6>
+    if (by_scene) LAUNCH_PDL(ctx, K_STEPS_SCENE, std::min(ctx->n_scenes, 148 * 6), 128, 0, A, (const uint32_t*)ctx->scene_rng.as<uint32_t>(), ctx->n_scenes);
+    else if (n_host > 32768) LAUNCH_PDL(ctx, k_batchsteps<6>, blocks, 128, 0, A);
     else LAUNCH_PDL(ctx, k_batchsteps<4>, blocks, 128, 0, A);
     // the steps only moved the shifts: materialise the rasters of every moved tree once
     { int grp = rebuild_group(ctx->n);
@@ -1336,7 +1344,7 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
     if (n == 0) { ctx->ctr.moved = 0; return STF_OK; }
     int64_t m = 2 * n;
     CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)n));
-    const uint32_t* order = nullptr;
+    const uint32_t* order = nullptr; bool by_scene = false;
     stage_begin(ctx, STF_STAGE_STEP_PREP);
     CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_MOVES, 0, sizeof(unsigned long long), ctx->st));
     if (m <= BS_CAP && ctx->label_bits + 1 + FIN_IDX_BITS <= 64) { // one CTA: endpoints, sort, links
@@ -1349,10 +1357,15 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
         LAUNCH_PDL(ctx, k_step_endpoints, nblk(m, 256), 256, 0, hits, n, ctx->om.as<ObjMeta>(), ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->prev.p, 0, sizeof(uint32_t) * (size_t)m, ctx->st));
         int f = radix_sort_pairs(ctx->st, &ctx->launches, ctx->hk.as<uint64_t>(), ctx->hv.as<uint32_t>(), ctx->hk2.as<uint64_t>(), ctx->hv2.as<uint32_t>(), m, bit_range(0, ctx->label_bits + 1), ctx->hist.as<uint32_t>(), ctx->pdl, &ctx->after_kernel, ctx->sort3);
-        LAUNCH_PDL(ctx, k_step_prev, nblk(m, 256), 256, 0, f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
         CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
         CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
-        if (n >= 16384) { // many chains (a batch of scenes): claim the steps level by level
+        LAUNCH_PDL(ctx, k_step_prev, nblk(m, 256), 256, 0, f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
+        if (n >= 16384 && ctx->multi_scene && ctx->scene_sorted && !ctx->step_global) { // a batch of scenes: one CTA per scene, levels separated by CTA barriers
+            CK(ctx->scene_rng.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->n_scenes));
+            CK(cudaMemsetAsync(ctx->scene_rng.p, 0, sizeof(uint32_t) * 2 * (size_t)ctx->n_scenes, ctx->st));
+            LAUNCH_PDL(ctx, k_scene_ranges, nblk(n, 256), 256, 0, hits, n, ctx->om.as<ObjMeta>(), ctx->scene_rng.as<uint32_t>());
+            by_scene = true;
+        } else if (n >= 16384) { // many chains (a batch of scenes): claim the steps level by level
             CK(ctx->keep.ensure(sizeof(uint32_t) * 2 * (size_t)n));
             uint32_t* la = ctx->keep.as<uint32_t>(); uint32_t* lb = la + n;
             int level_bits = 5;
@@ -1369,7 +1382,7 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
         }
     }
     KCHECK();
-    int32_t r = launch_steps(ctx, hits, n, nullptr, seed, iter, order); if (r) return r;
+    int32_t r = launch_steps(ctx, hits, n, nullptr, seed, iter, order, by_scene); if (r) return r;
     r = sync_counts(ctx); if (r) return r;
     ctx->ctr.moved = (int64_t)ctx->h_counts[C_MOVES];
     return STF_OK;
