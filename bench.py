@@ -489,8 +489,9 @@ def run_ours(args):
     def timed(resident, steps):
         tot = 0.0
         for _ in range(steps):
-            with torch.cuda.stream(stream):
-                flush.zero_()  # L2 flush between timed iterations, outside the event pair
+            if not os.environ.get("STF_BENCH_NOFLUSH"):  # (experiments only: the reported lines always flush)
+                with torch.cuda.stream(stream):
+                    flush.zero_()  # L2 flush between timed iterations, outside the event pair
             if sc.sharded is not None:
                 torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -373,6 +373,27 @@ def test_fit_round_matches_host_loop(S, orc):
     assert_same_trees(d, qo)
 
 
+def test_small_scene_with_many_hits_moves_to_the_cluster_sorts(S, orc):
+    """small scenes (<= 2048 objects) sort on one CTA; a hit list beyond what that kernel holds (5 632) re-runs the round on
+    the cluster kernels (<= 8 192) without leaving the latency path: 115 rects on top of each other = 6 555 hits"""
+    qo = rect_scene(orc, 115, 3, sz=60, masksize=(500, 500), place=False)
+    for k, t in enumerate(qo[1:]):
+        t.setshift(1, 270 + k % 3, 270 + k % 2)
+    d = device_from_oracle(S, qo)
+    oo = orc.Opt("momentum", 0.25, 0.5, len(qo))
+    clock = S.trainer.StepClock(seed=2)
+    seen = []
+    for it in range(3):
+        hits = sorted(orc.totalcollisions_spacial(qo, unique=False))
+        nh, rs, cs = S.trainer.fit_round_positions(d, optimiser=S.Momentum(0.25, 0.5), clock=clock)
+        seen.append(nh)
+        assert nh == len(hits), (it, nh, len(hits))
+        orc.batchsteps(qo, hits, oo, seed=2, iteration=it)
+        assert [tuple(x) for x in zip(rs, cs)] == [t.getshift() for t in qo]
+    assert 5632 < seen[0] <= 8192, seen
+    assert_same_trees(d, qo)
+
+
 def test_dynamic_loops(S, orc):
     # test/test_qtrees.jl:71-113 on the device, checked against the oracle step by step
     qo = rect_scene(orc, 200, 14)

@@ -402,7 +402,7 @@ def test_c5_4096_scene_batch(S, orc):
 
 def test_c5_mid_size_batch_400_scenes(S, orc):
     """a rank's share of a split batch: ~50 k records and ~26 k hits per step — the sizes at which the one-launch radix
-    passes (decoupled look-back) and the single-CTA step-depth kernel are used instead of the multi-launch versions"""
+    passes (decoupled look-back) and the scene-by-scene step kernel are used instead of the multi-launch versions"""
     d = _check_scene_batch(S, orc, 400, [0, 1, 123, 399], 123)
     # the multi-launch versions (three launches per radix pass, 16 level sweeps) must leave exactly the same state
     import os
@@ -413,6 +413,16 @@ def test_c5_mid_size_batch_400_scenes(S, orc):
         del os.environ["STF_SORT_3LAUNCH"]
     for l in (1, 3):
         a, b = d.getshifts(level=l), d3.getshifts(level=l)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # ... and so must the steps through global tickets and flags in depth order (the path of batches whose scene ids do not
+    # ascend with the labels) instead of scene by scene (k_batchsteps_scene)
+    os.environ["STF_STEP_GLOBAL"] = "1"
+    try:
+        dg = _check_scene_batch(S, orc, 400, [0], 0)
+    finally:
+        del os.environ["STF_STEP_GLOBAL"]
+    for l in (1, 3):
+        a, b = d.getshifts(level=l), dg.getshifts(level=l)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
