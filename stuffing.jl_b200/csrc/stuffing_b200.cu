@@ -1333,8 +1333,12 @@ static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, co
     if (A.dbg & 16) { CK(ctx->dbg_t.ensure(sizeof(unsigned long long) * 4 * (size_t)std::max<int64_t>(n_host, BS_CAP))); A.dbg_t = ctx->dbg_t.as<unsigned long long>(); }
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(1, (n_host + 3) / 4), 148 * 8);
     stage_begin(ctx, STF_STAGE_STEP);
-#define K_STEPS_SCENE k_batchsteps_scene<128, 256, 6>
-    if (by_scene) LAUNCH_PDL(ctx, K_STEPS_SCENE, std::min(ctx->n_scenes, 148 * 6), 128, 0, A, (const uint32_t*)ctx->scene_rng.as<uint32_t>(), ctx->n_scenes);
+#ifndef STF_SCENE_NT
+#define STF_SCENE_NT 128
+#define STF_SCENE_MINB 6
+#endif
+#define K_STEPS_SCENE k_batchsteps_scene<STF_SCENE_NT, 256, STF_SCENE_MINB>
+    if (by_scene) LAUNCH_PDL(ctx, K_STEPS_SCENE, std::min(ctx->n_scenes, 148 * STF_SCENE_MINB), STF_SCENE_NT, 0, A, (const uint32_t*)ctx->scene_rng.as<uint32_t>(), ctx->n_scenes);
     else if (n_host > 32768) LAUNCH_PDL(ctx, k_batchsteps<6>, blocks, 128, 0, A);
     else LAUNCH_PDL(ctx, k_batchsteps<4>, blocks, 128, 0, A);
     // the steps only moved the shifts: materialise the rasters of every moved tree once

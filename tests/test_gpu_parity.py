@@ -373,10 +373,13 @@ def test_fit_round_matches_host_loop(S, orc):
     assert_same_trees(d, qo)
 
 
-def test_small_scene_with_many_hits_moves_to_the_cluster_sorts(S, orc):
-    """small scenes (<= 2048 objects) sort on one CTA; a hit list beyond what that kernel holds (5 632) re-runs the round on
-    the cluster kernels (<= 8 192) without leaving the latency path: 115 rects on top of each other = 6 555 hits"""
-    qo = rect_scene(orc, 115, 3, sz=60, masksize=(500, 500), place=False)
+@pytest.mark.parametrize("n,lo,hi", [(106, 5000, 5632), (115, 5632, 8192), (130, 8192, 16384), (200, 16384, 10**9)])
+def test_crowded_scene_across_the_capacity_steps(S, orc, n, lo, hi):
+    """n rects on top of each other: every pair collides (n(n-1)/2 hits) and every tree is stepped ~n times in one round —
+    the longest dependency chains the step kernels see.  The four sizes sit on either side of the capacity steps of the
+    latency path: <= 5 632 hits the single-CTA finalize of small scenes, <= 8 192 the cluster finalize (the round is re-run
+    there, the scene stays on the latency path), beyond that the throughput path, from 16 384 steps on in depth order"""
+    qo = rect_scene(orc, n, 3, sz=60, masksize=(500, 500), place=False)
     for k, t in enumerate(qo[1:]):
         t.setshift(1, 270 + k % 3, 270 + k % 2)
     d = device_from_oracle(S, qo)
@@ -389,8 +392,8 @@ def test_small_scene_with_many_hits_moves_to_the_cluster_sorts(S, orc):
         seen.append(nh)
         assert nh == len(hits), (it, nh, len(hits))
         orc.batchsteps(qo, hits, oo, seed=2, iteration=it)
-        assert [tuple(x) for x in zip(rs, cs)] == [t.getshift() for t in qo]
-    assert 5632 < seen[0] <= 8192, seen
+        assert [(int(a), int(b)) for a, b in zip(rs, cs)] == [t.getshift() for t in qo], it
+    assert lo < seen[0] <= hi, seen
     assert_same_trees(d, qo)
 
 
