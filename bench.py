@@ -30,6 +30,7 @@ N > 1    : c1 / c2 / c3 / c4 — scene replicas ("weak"); c5 — the 4096 scenes
 """
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import shutil
@@ -87,7 +88,7 @@ class ClockSampler:
     def __init__(self, gpu):
         self.rows, self.p = [], None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("STF_BENCH_CLOCK_MS", "200")],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -488,6 +489,14 @@ def run_ours(args):
 
     def timed(resident, steps):
         tot = 0.0
+        gc.collect(); gc.disable()  # (a collector pause on one rank is a straggler in the max over ranks)
+        try:
+            return _timed(resident, steps)
+        finally:
+            gc.enable()
+
+    def _timed(resident, steps):
+        tot = 0.0
         for _ in range(steps):
             if not os.environ.get("STF_BENCH_NOFLUSH"):  # (experiments only: the reported lines always flush)
                 with torch.cuda.stream(stream):
@@ -522,7 +531,7 @@ def run_ours(args):
         assert np.array_equal(sc.out_rs.numpy(), sc.W["final_rs"]) and np.array_equal(sc.out_cs.numpy(), sc.W["final_cs"]), "c2: fitted positions differ from the golden vector"
         assert items == int(sc.W["round_items"].sum())
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("STF_BENCH_NOSAMPLER") else None
     l0 = lib.stf_launch_count(h)
     bracket()
     ms_res = timed(True, args.steps)
@@ -544,6 +553,8 @@ def run_ours(args):
     if sc.sharded is None:
         assert sc.tot["items"] == items and sc.tot["hits"] == hits, "steps must do identical work"
 
+    if os.environ.get("STF_BENCH_DEBUG_RANKS"):
+        print(f"[rank {rank}] resident {ms_res / args.steps:.4f} ms  e2e {ms_e2e / args.steps:.4f} ms", file=sys.stderr, flush=True)
     t = torch.tensor([ms_res, ms_e2e, float(items), float(hits), float(T["visited"])], dtype=torch.float64, device="cuda")
     tmax = t.clone()
     if dist is not None:
