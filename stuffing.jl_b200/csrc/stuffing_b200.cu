@@ -1349,7 +1349,9 @@ static int32_t launch_steps(stf_ctx* ctx, const Item16* hits, int64_t n_host, co
     return STF_OK;
 }
 // batchsteps! over hits[0..n) (device, list order, host-known n)
-static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, uint64_t seed, uint64_t iter) {
+// scenes_contiguous: the steps of one scene are consecutive in the list (true for the canonical order of a batch whose scene
+// ids ascend with the labels; a caller's own list is checked on the host): the precondition of the scene-by-scene step kernel
+static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, uint64_t seed, uint64_t iter, bool scenes_contiguous) {
     if (n == 0) { ctx->ctr.moved = 0; return STF_OK; }
     int64_t m = 2 * n;
     CK(ctx->prev.ensure(sizeof(uint32_t) * (size_t)m)); CK(ctx->done.ensure(sizeof(uint32_t) * (size_t)n));
@@ -1369,7 +1371,7 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
         CK(cudaMemsetAsync(ctx->done.p, 0, sizeof(uint32_t) * (size_t)n, ctx->st));
         CK(cudaMemsetAsync(ctx->counts.as<unsigned long long>() + C_TICKET, 0, sizeof(unsigned long long), ctx->st));
         LAUNCH_PDL(ctx, k_step_prev, nblk(m, 256), 256, 0, f ? ctx->hk2.as<uint64_t>() : ctx->hk.as<uint64_t>(), f ? ctx->hv2.as<uint32_t>() : ctx->hv.as<uint32_t>(), nullptr, m, ctx->prev.as<uint32_t>());
-        if (n >= 16384 && ctx->multi_scene && ctx->scene_sorted && !ctx->step_global) { // a batch of scenes: one CTA per scene, levels separated by CTA barriers
+        if (n >= 16384 && ctx->multi_scene && scenes_contiguous && !ctx->step_global) { // a batch of scenes: one CTA per scene, levels separated by CTA barriers
             CK(ctx->scene_rng.ensure(sizeof(uint32_t) * 2 * (size_t)ctx->n_scenes));
             CK(cudaMemsetAsync(ctx->scene_rng.p, 0, sizeof(uint32_t) * 2 * (size_t)ctx->n_scenes, ctx->st));
             LAUNCH_PDL(ctx, k_scene_ranges, nblk(n, 256), 256, 0, hits, n, ctx->om.as<ObjMeta>(), ctx->scene_rng.as<uint32_t>());
@@ -1399,9 +1401,19 @@ static int32_t batchsteps_device(stf_ctx* ctx, const Item16* hits, int64_t n, ui
 extern "C" int32_t stf_batchsteps(stf_ctx* ctx, int64_t n, const stf_item* colist, uint64_t seed, uint64_t iteration) {
     NEED_OBJS();
     if (n <= 0) return STF_OK;
-    for (int64_t i = 0; i < n; i++) if (colist[i].l < 1) FAIL(STF_E_ARG, "collision point level must be >= 1");
+    bool contiguous = ctx->multi_scene; int last_scene = -1; // (a caller's list is stepped in ITS order: scene by scene only if it is grouped by scene)
+    for (int64_t i = 0; i < n; i++) {
+        if (colist[i].l < 1) FAIL(STF_E_ARG, "collision point level must be >= 1");
+        if (contiguous) {
+            const int32_t a = colist[i].i1, b = colist[i].i2;
+            if (a < 1 || a > ctx->n || b < 1 || b > ctx->n) { contiguous = false; continue; } // (import_items reports the bad label)
+            const int sa = ctx->h_om[a - 1].scene, sb = ctx->h_om[b - 1].scene;
+            if (sa != sb || sa < last_scene) contiguous = false;
+            last_scene = sa;
+        }
+    }
     int32_t r = import_items(ctx, n, colist, ctx->hits2); if (r) return r;
-    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), n, seed, iteration);
+    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), n, seed, iteration, contiguous);
 }
 // One fit iteration on the device: many-body collision detection over the active labels, then batchsteps! on the result
 // (canonical list order = sorted by ((i1,i2),(l,a,b))).  Latency path: ~10 launches, ONE host synchronisation.
@@ -1526,7 +1538,7 @@ extern "C" int32_t stf_fit_round(stf_ctx* ctx, int32_t mode, int32_t nl, const i
     int32_t r = spacial_core(ctx, nl, labels, linked, &nh); if (r) return r;
     r = finalize_hits(ctx, nh, 0, false, &nout); if (r) return r; // canonical list order = sorted, stays on the device
     if (nhits) *nhits = nh;
-    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
+    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration, ctx->scene_sorted);
 }
 // ---- several fit rounds without a host round trip in between (the inner loop of the trainers,
 // fit.jl:85-99, stays on the device).  Every round is enqueued blindly; k_round_begin resets the round's counters on the
@@ -1805,7 +1817,7 @@ extern "C" int32_t stf_shard_step(stf_ctx* ctx, const void* recv_dev, int32_t nr
     r = finalize_hits(ctx, nh, 0, false, &nout); if (r) return r; // canonical list order = sorted: identical on every rank
     if (nhits) *nhits = nh;
     ctx->ctr.hits = nh;
-    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration);
+    return batchsteps_device(ctx, ctx->hits2.as<Item16>(), nh, seed, iteration, ctx->scene_sorted);
 }
 // ------------------------------------------------------------------------------------------------ group of GPUs, one process
 // SURVEY §8b threading row / §8e-2: ONE host thread drives one context per GPU (the way a Julia host would); the scene is
