@@ -272,6 +272,27 @@ function fit_round!(d::DeviceQTrees, labels=nothing; optimiser=(t, Δ) -> Δ ./ 
     d.clock = (seed, it + 1)
     Int(nh[])
 end
+"the same round + getshift of every tree at `level` in the round's one synchronisation (stf_fit_round_positions)"
+function fit_round_positions!(d::DeviceQTrees, labels=nothing; optimiser=(t, Δ) -> Δ ./ 6, partial=false, level=1)
+    _setopt!(d, optimiser)
+    lb, nl = _lb(labels); nh = Ref{Int64}(0); seed, it = d.clock
+    rs = Vector{Int32}(undef, d.n); cs = Vector{Int32}(undef, d.n)
+    check(d, ccall((:stf_fit_round_positions, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, UInt64, UInt64, Ptr{Int64}, Int32, Ptr{Int32}, Ptr{Int32}),
+                   d.h, partial ? 1 : 0, nl, lb, seed, it, nh, level, rs, cs))
+    d.clock = (seed, it + 1)
+    Int(nh[]), collect(zip(Int.(rs), Int.(cs)))
+end
+"a round that returns `moved := the labels of its colist` (qtree_functions.jl:354-355; the trainers' `inds`, fit.jl:90) instead of the list:
+the step of a dynamic loop is ONE call and one synchronisation (stf_fit_round_moved)"
+function fit_round_moved!(d::DeviceQTrees, labels=nothing; optimiser=(t, Δ) -> Δ ./ 6, partial=true)
+    _setopt!(d, optimiser)
+    lb, nl = _lb(labels); nh = Ref{Int64}(0); nm = Ref{Int32}(0); seed, it = d.clock
+    moved = Vector{Int32}(undef, d.n)
+    check(d, ccall((:stf_fit_round_moved, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, UInt64, UInt64, Ptr{Int64}, Ptr{Int32}, Int32, Ptr{Int32}),
+                   d.h, partial ? 1 : 0, nl, lb, seed, it, nh, moved, length(moved), nm))
+    d.clock = (seed, it + 1)
+    Int(nh[]), Int.(moved[1:nm[]])
+end
 "`k` rounds with ONE host synchronisation (stf_fit_rounds); returns the per-round length(colist) and the positions after the last round"
 function fit_rounds!(d::DeviceQTrees, k::Integer, labels=nothing; optimiser=(t, Δ) -> Δ ./ 6, partial=false, level=1)
     _setopt!(d, optimiser)
@@ -333,6 +354,76 @@ trainepoch_D_resource(d::DeviceQTrees) = Dict(:colist => Vector{CoItem}(), :move
 # ------------------------------------------------------------------------------------------------ several GPUs from one process
 "One context per device holding the same scene; rounds are split by candidate records, the GPUs exchange their hit lists
 over NVLink peer memory themselves (include/stuffing_b200.h: stf_group_*)."
+# ---- the rest of the boundary: narrow phase over an explicit item list, the linked tree's own operations, level shifts of
+# one PaddedMat, the optimiser's velocities, ground composition for place!, counters
+"_totalcollisions_native(qtrees, coitems, colist)  qtree_functions.jl:89-110: the narrow phase over an explicit item list"
+function totalcollisions_native(d::DeviceQTrees, coitems::Vector{CoItem}, colist=Vector{CoItem}())
+    items = StfItem.(coitems)
+    _list(d, colist, (buf, cap, cnt) -> ccall((:stf_collide_items, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{StfItem}, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, length(items), items, buf, cap, cnt))
+end
+"the itemlist of the last many-body call (the `itemlist` keyword of totalcollisions_spacial / partialcollisions)"
+function itemlist(d::DeviceQTrees)
+    _list(d, Vector{CoItem}(), (buf, cap, cnt) -> ccall((:stf_fetch_items, LIB), Int32, (Ptr{Cvoid}, Ptr{StfItem}, Int64, Ptr{Int64}), d.h, buf, cap, cnt))
+end
+keep_itemlist!(d::DeviceQTrees, on::Bool=true) = check(d, ccall((:stf_set_keep_items, LIB), Int32, (Ptr{Cvoid}, Int32), d.h, on ? 1 : 0))
+"clear!(t::LinkedSpacialQTree, label) for a label list  qtrees.jl:538-545"
+function clear!(t::DeviceLinkedTree, labels)
+    lb, nl = _lb(labels)
+    check(t.owner, ccall((:stf_linked_clear, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}), t.owner.h, nl, lb)); t
+end
+"collect_tree(t::LinkedSpacialQTree)  qtrees.jl:546-552 — (index, label) of every list node"
+function collect_tree(t::DeviceLinkedTree)
+    cnt = Ref{Int64}(0)
+    ccall((:stf_linked_collect, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int64, Ptr{Int64}), t.owner.h, C_NULL, 0, cnt)
+    buf = Vector{Int32}(undef, 4 * cnt[])                                    # stf_cellrec = (l, a, b, label)
+    check(t.owner, ccall((:stf_linked_collect, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int64, Ptr{Int64}), t.owner.h, buf, cnt[], cnt))
+    [(Int(buf[4i+1]), Int(buf[4i+2]), Int(buf[4i+3])) => Int(buf[4i+4]) for i in 0:cnt[]-1]
+end
+"setrshift!/setcshift!(t[l]::PaddedMat, …)  qtrees.jl:134-135: the shift of ONE level, no rebuild (the caller rebuilds with buildqtree!)"
+setlevelshift!(t::DeviceTree, l::Integer, rs::Integer, cs::Integer) =
+    check(t.owner, ccall((:stf_set_level_shift, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Int32), t.owner.h, t.label, l, rs, cs))
+"the Momentum velocity of a list of trees (fit_helper.jl:19-33): (v, has) — what `optimiser.velocity[t]` holds"
+function velocity(d::DeviceQTrees, labels=1:d.n)
+    lb = Int32.(collect(labels)); v = Vector{Float64}(undef, 2 * length(lb)); has = Vector{UInt8}(undef, length(lb))
+    check(d, ccall((:stf_get_velocity, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{UInt8}), d.h, length(lb), lb, v, has))
+    [(v[2i-1], v[2i]) for i in 1:length(lb)], has .!= 0
+end
+"overlap!(ground, trees) of place!(ground, sortedtrees, indexes)  qtree_functions.jl:452-518: ground = the mask with every tree except
+`excluded` composed into it, on the device; `groundlevel(d, l)` is the level the host-side findroom reads"
+function compose_ground!(d::DeviceQTrees, mask_label::Integer=1, excluded=Int[])
+    ex = Int32.(collect(excluded))
+    check(d, ccall((:stf_ground_compose, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}), d.h, mask_label, length(ex), ex)); d
+end
+function groundlevel(d::DeviceQTrees, l::Integer)
+    info = Vector{Int32}(undef, 5)
+    check(d, ccall((:stf_ground_level, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Ptr{Int32}), d.h, l, C_NULL, info))   # sizes first
+    m = Matrix{UInt8}(undef, info[1], info[2])
+    check(d, ccall((:stf_ground_level, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Ptr{Int32}), d.h, l, m, info))
+    m, (Int(info[3]), Int(info[4])), Int(info[5])                            # kernel, (rshift, cshift), canvas size of the level
+end
+"counters of the last many-body call (records, items, direct, hits, overflow, moved, visited)"
+function counters(d::DeviceQTrees)
+    c = Vector{Int64}(undef, 8)
+    check(d, ccall((:stf_counters, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}), d.h, c))
+    (records=c[1], items=c[2], direct=c[3], hits=c[4], overflow=c[5], moved=c[6], visited=c[7])
+end
+
+# ---- item-parallel rounds with ONE PROCESS PER GPU (MPI.jl / NCCL.jl own the all-gather; SURVEY §8e-2): collide over this rank's
+# share, pack the local hits into a fixed-stride device buffer, (caller: all-gather send -> recv), step on the union
+function shard_collide!(d::DeviceQTrees, rank::Integer, nranks::Integer, labels=nothing; partial=false)
+    lb, nl = _lb(labels); nloc = Ref{Int64}(0)
+    check(d, ccall((:stf_shard_collide, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int32, Int32, Ptr{Int64}), d.h, partial ? 1 : 0, nl, lb, rank, nranks, nloc))
+    Int(nloc[])
+end
+shard_pack!(d::DeviceQTrees, send_dev::Ptr{Cvoid}, stride::Integer) =
+    check(d, ccall((:stf_shard_pack, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), d.h, send_dev, stride))
+function shard_step!(d::DeviceQTrees, recv_dev::Ptr{Cvoid}, nranks::Integer, stride::Integer)
+    nh = Ref{Int64}(0); seed, it = d.clock
+    check(d, ccall((:stf_shard_step, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, UInt64, UInt64, Ptr{Int64}), d.h, recv_dev, nranks, stride, seed, it, nh))
+    d.clock = (seed, it + 1)
+    Int(nh[])
+end
+
 mutable struct GpuGroup
     h::Ptr{Cvoid}
     replicas::Vector{DeviceQTrees}
@@ -350,6 +441,20 @@ function GpuGroup(qts::AbstractVector, devices::AbstractVector{<:Integer}; seed:
     g = GpuGroup(h[], reps)
     finalizer(x -> ccall((:stf_group_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), g)
 end
+"setshift! of the listed trees on EVERY replica (the GPUs driven in parallel)  qtrees.jl:276-288"
+function setshift!(g::GpuGroup, labels, l::Integer, s1, s2)
+    lb = Int32.(collect(labels)); rs = Int32.(collect(s1)); cs = Int32.(collect(s2))
+    rc = ccall((:stf_group_set_shifts, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Int32), g.h, length(lb), lb, l, rs, cs, 0)
+    rc == 0 || error(unsafe_string(ccall((:stf_group_last_error, LIB), Cstring, (Ptr{Cvoid},), g.h))); g
+end
+function reset!(o::Momentum, g::GpuGroup, labels=nothing)
+    lb, nl = _lb(labels)
+    rc = ccall((:stf_group_reset_velocity, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}), g.h, nl, lb)
+    rc == 0 || error(unsafe_string(ccall((:stf_group_last_error, LIB), Cstring, (Ptr{Cvoid},), g.h))); o
+end
+Base.length(g::GpuGroup) = Int(ccall((:stf_group_size, LIB), Int32, (Ptr{Cvoid},), g.h))
+"bytes pushed to peer GPUs over NVLink by the last round"
+nvlink_bytes(g::GpuGroup) = Int(ccall((:stf_group_nvlink_bytes, LIB), Int64, (Ptr{Cvoid},), g.h))
 function fit_round!(g::GpuGroup, labels=nothing; optimiser=(t, Δ) -> Δ ./ 6, partial=false)
     foreach(d -> _setopt!(d, optimiser), g.replicas)
     lb, nl = _lb(labels); nh = Ref{Int64}(0); seed, it = g.replicas[1].clock

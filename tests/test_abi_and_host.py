@@ -202,7 +202,9 @@ def test_julia_glue_ccalls_match_the_library_exports():
     # the hot-path surface of SURVEY §8b is bound
     for must in ("stf_upload_objects", "stf_collision", "stf_totalcollisions_spacial", "stf_totalcollisions_native", "stf_partialcollisions", "stf_locate",
                  "stf_linked_locate", "stf_grad2d", "stf_batchsteps", "stf_fit_round", "stf_fit_rounds", "stf_set_shifts", "stf_get_shifts", "stf_download_trees",
-                 "stf_group_create", "stf_group_fit_round"):
+                 "stf_group_create", "stf_group_fit_round", "stf_fit_round_positions", "stf_fit_round_moved", "stf_fit_epoch_e", "stf_filter_pairs", "stf_collide_items",
+                 "stf_ground_compose", "stf_ground_level", "stf_shard_collide", "stf_shard_pack", "stf_shard_step", "stf_linked_clear", "stf_linked_collect",
+                 "stf_get_velocity", "stf_set_level_shift", "stf_counters", "stf_group_set_shifts"):
         assert must in seen, must
 
 
